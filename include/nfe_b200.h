@@ -1,0 +1,179 @@
+/*
+ * nfe_b200.h — C ABI of libnfe_b200.so: the sm_100a kernels behind NeRFFaceEditing's tri-plane
+ * volume-rendering hot path.
+ *
+ * The reference has no FFI for this path (it is a composition of ATen ops); its operator
+ * convention is torch_utils/custom_ops.py:61-157 (JIT-built plugin, tensors in, TORCH_CHECK ->
+ * RuntimeError, outputs allocated by the caller's framework, work enqueued on the current
+ * stream).  This header is what a binding for the path would target instead: plain device
+ * pointers and sizes, an explicit stream, no torch types.  Each entry cites the reference
+ * code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; nfe_last_error() then holds a
+ *     message (thread-local).  Nothing throws, nothing allocates device memory: outputs and
+ *     workspaces are passed in by the caller (size them with the *_workspace_bytes queries);
+ *   - all pointers are DEVICE pointers on the current device unless named `host_*`;
+ *     tensors are contiguous fp32 unless stated; `stream` is a cudaStream_t;
+ *   - work is only enqueued: no call synchronises the device;
+ *   - re-entrant; the only global state is an atomic launch counter.
+ */
+#ifndef NFE_B200_H
+#define NFE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* nfe_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int nfe_version(void);
+const char* nfe_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+uint64_t nfe_launch_count(void);
+
+/* ---- plane statistics: TriPlaneGenerator.compute_mean_var / normalize_plane /
+ *      denormalize_plane, training/triplane.py:56-68 (twins utils.py:146-158) ---------------
+ * planes is [n_slabs, hw] (a slab = one (batch, channel) image).  std is sqrt of the unbiased
+ * variance.  normalize: (x-mean)/(std+1e-8).  denormalize: x*std'+mean' with slab s using
+ * statistics entry s % stat_slabs (per-item stats, or one item's stats for the whole batch,
+ * triplane.py:100-101). */
+int nfe_plane_stats(const float* planes, int64_t n_slabs, int64_t hw, float* mean, float* std_out,
+                    nfe_stream_t stream);
+int nfe_plane_normalize(const float* planes, const float* mean, const float* std_in, int64_t n_slabs,
+                        int64_t hw, float* out, nfe_stream_t stream);
+int nfe_plane_denormalize(const float* norm, const float* mean, const float* std_in, int64_t n_slabs,
+                          int64_t stat_slabs, int64_t hw, float* out, nfe_stream_t stream);
+/* Layout staging for the gather: [n_img, C, hw] (reference NCHW, triplane.py:114-115) ->
+ * channel-last [n_img, hw, C] so that one bilinear tap is one contiguous C*4-byte line. */
+int nfe_planes_to_channel_last(const float* planes, int64_t n_img, int channels, int64_t hw, float* out,
+                               nfe_stream_t stream);
+
+/* ---- rays: RaySampler.forward, training/volumetric_rendering/ray_sampler.py:24-63 -------- */
+int nfe_generate_rays(const float* cam2world /*[n,4,4]*/, const float* intrinsics /*[n,3,3]*/, int n,
+                      int resolution, float* origins /*[n,res*res,3]*/, float* dirs, nfe_stream_t stream);
+/* math_utils.get_ray_limits_box, training/volumetric_rendering/math_utils.py:46-98 */
+int nfe_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays, float box_side_length,
+                       float* tmin, float* tmax, nfe_stream_t stream);
+
+/* ---- coarse depths: ImportanceRenderer.sample_stratified, renderer.py:169-192 ------------
+ * mode 0: scalar limits, t = table[s] + u*delta;  mode 1: per-ray limits (math_utils.linspace,
+ * math_utils.py:101-118);  mode 2: disparity space.  `table` is torch.linspace evaluated on the
+ * host ([s_c] device floats); ray_start/ray_end are the Python doubles of rendering_options.  u comes from `jitter` ([n_rays,s_c]) if non-NULL, else from the
+ * in-kernel Philox stream (seed, offset) if stochastic != 0, else u = 0 (parity mode). */
+int nfe_sample_stratified(int64_t n_rays, int s_c, int mode, const float* table, double ray_start,
+                          double ray_end, const float* start_per_ray, const float* end_per_ray,
+                          const float* jitter, int stochastic, uint64_t seed, uint64_t offset,
+                          float* depths /*[n_rays,s_c]*/, nfe_stream_t stream);
+
+/* ---- tri-plane gather: sample_from_planes, renderer.py:55-65 (+ generate_planes /
+ *      project_onto_planes :23-53) -----------------------------------------------------------
+ * planes_cl is channel-last [plane_batch,3,H,W,C] (see nfe_planes_to_channel_last); plane_batch
+ * is n or 1 (one plane set shared by the whole ray batch).  out is [n,3,m,C]. */
+int nfe_sample_planes_fwd(const float* planes_cl, int plane_batch, int channels, int height, int width,
+                          const float* coords /*[n,m,3]*/, int n, int64_t m, float box_warp, float* out,
+                          nfe_stream_t stream);
+
+/* ---- decoders: OSGDecoder / SegmentationOSGDecoder / DisentangledOSGDecoder,
+ *      training/triplane.py:167-270 over FullyConnectedLayer, networks_stylegan2.py:96-127 ---
+ * An nfe_mlp is FC(in->hidden) . Softplus . FC(hidden->out) given by the RAW parameters and
+ * the layer gains (w_eff = weight*wgain, b_eff = bias*bgain), read on every call. */
+typedef struct {
+    const float* w1; const float* b1; /* [hidden,in], [hidden] */
+    const float* w2; const float* b2; /* [out,hidden], [out]   */
+    int in_dim, hidden, out_dim;
+    float wgain1, bgain1, wgain2, bgain2;
+} nfe_mlp;
+
+enum { NFE_DEC_OSG = 0, NFE_DEC_DISENTANGLED = 1, NFE_DEC_SEGMENTATION = 2 };
+
+/* decoder(sampled_features[n,3,m,C], ray_directions) stand-alone.  feat_norm may be NULL for
+ * OSG / Segmentation (which ignore it).  rgb [n,m,color_dim], sigma [n,m], seg [n,m,seg_dim]. */
+int nfe_decoder_fwd(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* feat_norm,
+                    const float* feat_denorm, int n, int64_t m, int channels, float* rgb, float* sigma,
+                    float* seg, nfe_stream_t stream);
+
+/* ---- ray marching: MipRayMarcher2 / SegMipRayMarcher2.run_forward, ray_marcher.py:25-57,68-101
+ * colors [n_rays,S,cc], segs [n_rays,S,cs] (NULL when cs == 0), sigma/depths [n_rays,S].
+ * weights [n_rays,S-1] and wsum [n_rays] may be NULL.  depth is clamped to the min/max of the
+ * whole depths tensor; minmax_ws is a 2-float device scratch. */
+int nfe_composite_fwd(const float* colors, const float* segs, const float* sigma, const float* depths,
+                      int64_t n_rays, int S, int cc, int cs, int white_back, float* rgb, float* seg,
+                      float* depth, float* weights, float* wsum, float* minmax_ws, nfe_stream_t stream);
+
+/* ---- importance resampling: sample_importance + sample_pdf, renderer.py:194-253 -----------
+ * z_vals [n_rays,S], weights [n_rays,S-1] -> out [n_rays,s_f].  u: explicit ([s_f] if
+ * u_per_ray == 0 else [n_rays,s_f]); NULL -> Philox U[0,1) (seed, offset) as the reference's
+ * torch.rand (sample_pdf det=False).  below/above (int32, optional) expose the bin indices. */
+int nfe_importance_resample(const float* z_vals, const float* weights, int64_t n_rays, int S, int s_f,
+                            const float* u, int u_per_ray, uint64_t seed, uint64_t offset, float* out,
+                            int32_t* below, int32_t* above, nfe_stream_t stream);
+
+/* sample_pdf alone, renderer.py:214-253: bins [n_rays,n_bins], weights [n_rays,n_weights]
+ * (n_weights < n_bins) -> out [n_rays,s_f]; eps is the reference's `eps` argument (1e-5). */
+int nfe_sample_pdf(const float* bins, const float* weights, int64_t n_rays, int n_bins, int n_weights, int s_f,
+                   const float* u, int u_per_ray, uint64_t seed, uint64_t offset, float eps, float* out,
+                   nfe_stream_t stream);
+
+/* ---- merge: unify_samples / sort_samples, renderer.py:150-167,288-300 ---------------------
+ * Sorts the concatenation [coarse | fine] of one ray's samples by depth and permutes every
+ * attribute.  Inputs [n_rays,s1,*] and [n_rays,s2,*]; outputs [n_rays,s1+s2,*].  s2 may be 0
+ * (sort_samples).  segs may be NULL when cs == 0. */
+int nfe_unify_samples(const float* depths1, const float* colors1, const float* segs1, const float* sigma1,
+                      const float* depths2, const float* colors2, const float* segs2, const float* sigma2,
+                      int64_t n_rays, int s1, int s2, int cc, int cs, float* depths, float* colors,
+                      float* segs, float* sigma, nfe_stream_t stream);
+
+/* ---- fused forward: ImportanceRenderer.forward / DisentangledImportanceRenderer.forward,
+ *      renderer.py:88-148,301-363, and .run_model, :142-148,259-287 -------------------------- */
+typedef struct {
+    int kind;                /* NFE_DEC_* */
+    int channels, height, width;
+    int s_c, s_f;            /* depth_resolution, depth_resolution_importance (0: single pass) */
+    int color_dim, seg_dim;  /* 32, 15 (0 for OSG) */
+    int white_back;
+    float box_warp;
+    float density_noise;     /* sigma += N(0,1)*density_noise when > 0 (renderer.py:146-147) */
+    int stochastic;          /* 0: parity mode (u_fine = linspace table); 1: Philox jitter */
+    uint64_t seed, offset;   /* Philox stream for stochastic mode / density noise */
+    int precision;           /* NFE_PREC_* : arithmetic of the decoder MLPs */
+} nfe_render_cfg;
+
+enum { NFE_PREC_FP32 = 0, NFE_PREC_BF16X3 = 1, NFE_PREC_BF16 = 2 };
+
+/* bytes of device workspace nfe_render_fwd needs for n*n_rays rays with this cfg */
+int64_t nfe_render_workspace_bytes(const nfe_render_cfg* cfg, int n, int64_t n_rays);
+
+/* planes_*_cl: channel-last [plane_batch,3,H,W,C]; planes_norm_cl NULL for OSG/Segmentation.
+ * depths_coarse [n,n_rays,s_c] (from nfe_sample_stratified); u_fine [s_f] table (parity mode)
+ * or NULL.  Outputs rgb [n,n_rays,color_dim], seg [n,n_rays,seg_dim] (NULL if seg_dim == 0),
+ * depth [n,n_rays], wsum [n,n_rays].  The depth clamp needs the min/max over ALL sample depths
+ * (ray_marcher.py:49-50,93-94): they are accumulated into minmax_out (device float[2], optional)
+ * and applied when finish_depth != 0.  A ray-sharded render passes finish_depth = 0, all-reduces
+ * minmax_out across ranks (MIN / MAX) and then calls nfe_finish_depth.  depths_fine_out /
+ * weights_coarse_out are optional stage taps ([n,n_rays,s_f], [n,n_rays,s_c-1]). */
+int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, const nfe_mlp* net_b,
+                   const float* planes_norm_cl, const float* planes_denorm_cl, int plane_batch,
+                   const float* origins, const float* dirs, int n, int64_t n_rays,
+                   const float* depths_coarse, const float* u_fine, float* rgb, float* seg, float* depth,
+                   float* wsum, float* minmax_out, int finish_depth, float* depths_fine_out,
+                   float* weights_coarse_out, void* workspace, int64_t workspace_bytes, nfe_stream_t stream);
+
+/* Depth clamp split out for sharded renders: depth = clamp(nan_to_num(depth, +inf), min, max)
+ * with {min,max} read from device memory (ray_marcher.py:49-50,93-94). */
+int nfe_finish_depth(float* depth, int64_t n_rays, const float* minmax_dev, nfe_stream_t stream);
+
+/* run_model: gather + decode at explicit points.  coords [n,m,3] -> rgb [n,m,color_dim],
+ * sigma [n,m], seg [n,m,seg_dim]. */
+int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, const nfe_mlp* net_b,
+                      const float* planes_norm_cl, const float* planes_denorm_cl, int plane_batch,
+                      const float* coords, int n, int64_t m, float* rgb, float* sigma, float* seg,
+                      void* workspace, int64_t workspace_bytes, nfe_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NFE_B200_H */

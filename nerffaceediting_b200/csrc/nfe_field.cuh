@@ -1,0 +1,153 @@
+// Device-side building blocks of the radiance-field evaluation: channel-last tri-plane gather and
+// the decoder MLPs (fp32 SIMT path).  Shared by the stage kernels (nfe_field.cu) and the fused
+// renderer (nfe_render.cu).
+#pragma once
+#include "nfe_common.cuh"
+
+namespace nfe {
+
+constexpr int FEAT = 32;    // n_features of every decoder (triplane.py:48-50: 32 channels per plane)
+constexpr int HIDDEN = 64;  // self.hidden_dim (triplane.py:170,195,235)
+
+// Effective (gain-folded) parameters of one MLP in shared memory.
+//   w1  [HIDDEN][FEAT]      row-major, read as broadcast float4 over k
+//   b1  [HIDDEN]
+//   w2t [HIDDEN][OUT_PAD]   transposed so that one hidden unit updates all outputs with float4 reads
+//   b2  [OUT_PAD]
+template <int OUT_PAD>
+struct MlpParams {
+    float w1[HIDDEN * FEAT];
+    float b1[HIDDEN];
+    float w2t[HIDDEN * OUT_PAD];
+    float b2[OUT_PAD];
+};
+
+constexpr int pad4(int x) { return (x + 3) / 4 * 4; }
+
+// Block-cooperative: fold the FullyConnectedLayer gains (networks_stylegan2.py:115-120:
+// w = weight*weight_gain, b = bias*bias_gain only when the gain is not 1) and lay the
+// parameters out for the kernel.  Re-read from global on every launch: training updates them.
+template <int OUT_PAD>
+__device__ void load_mlp(MlpParams<OUT_PAD>& dst, const nfe_mlp& src)
+{
+    for (int i = threadIdx.x; i < HIDDEN * FEAT; i += blockDim.x) dst.w1[i] = __fmul_rn(__ldg(src.w1 + i), src.wgain1);
+    for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x)
+        dst.b1[i] = src.bgain1 != 1.0f ? __fmul_rn(__ldg(src.b1 + i), src.bgain1) : __ldg(src.b1 + i);
+    for (int i = threadIdx.x; i < HIDDEN * OUT_PAD; i += blockDim.x) {
+        const int j = i / OUT_PAD, o = i % OUT_PAD;
+        dst.w2t[i] = o < src.out_dim ? __fmul_rn(__ldg(src.w2 + o * HIDDEN + j), src.wgain2) : 0.0f;
+    }
+    for (int i = threadIdx.x; i < OUT_PAD; i += blockDim.x)
+        dst.b2[i] = i < src.out_dim ? (src.bgain2 != 1.0f ? __fmul_rn(__ldg(src.b2 + i), src.bgain2) : __ldg(src.b2 + i)) : 0.0f;
+}
+
+// Softplus for the hidden layer: max(x,0) + log(1 + exp(-|x|)) on the SFU (ex2/lg2.approx).
+// Absolute error ~1e-7 (threshold-20 branch of torch.nn.Softplus differs from this by < 3e-9).
+__device__ __forceinline__ float softplus_fast(float x)
+{
+    const float e = __expf(-fabsf(x));
+    return fmaxf(x, 0.0f) + __logf(1.0f + e);
+}
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+
+// One sample per lane: out = b2 + W2 * softplus(b1 + W1 * x).  The hidden loop is kept rolled
+// (code size); k and o loops are unrolled so x[] / out[] stay in registers.
+template <int OUT_PAD>
+__device__ __forceinline__ void mlp_eval(const MlpParams<OUT_PAD>& p, const float (&x)[FEAT], float (&out)[OUT_PAD])
+{
+#pragma unroll
+    for (int o = 0; o < OUT_PAD; ++o) out[o] = p.b2[o];
+#pragma unroll 2
+    for (int j = 0; j < HIDDEN; ++j) {
+        const float4* w = reinterpret_cast<const float4*>(p.w1 + j * FEAT);
+        float a0 = p.b1[j], a1 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < FEAT / 4; k += 2) {
+            const float4 wa = w[k], wb = w[k + 1];
+            a0 = fmaf(x[4 * k + 0], wa.x, a0); a0 = fmaf(x[4 * k + 1], wa.y, a0);
+            a0 = fmaf(x[4 * k + 2], wa.z, a0); a0 = fmaf(x[4 * k + 3], wa.w, a0);
+            a1 = fmaf(x[4 * k + 4], wb.x, a1); a1 = fmaf(x[4 * k + 5], wb.y, a1);
+            a1 = fmaf(x[4 * k + 6], wb.z, a1); a1 = fmaf(x[4 * k + 7], wb.w, a1);
+        }
+        const float h = softplus_fast(a0 + a1);
+        const float4* w2 = reinterpret_cast<const float4*>(p.w2t + j * OUT_PAD);
+#pragma unroll
+        for (int o = 0; o < OUT_PAD / 4; ++o) {
+            const float4 v = w2[o];
+            out[4 * o + 0] = fmaf(h, v.x, out[4 * o + 0]); out[4 * o + 1] = fmaf(h, v.y, out[4 * o + 1]);
+            out[4 * o + 2] = fmaf(h, v.z, out[4 * o + 2]); out[4 * o + 3] = fmaf(h, v.w, out[4 * o + 3]);
+        }
+    }
+}
+
+// rgb = sigmoid(x)*(1 + 2*0.001) - 0.001   (triplane.py:188,219,269)
+__device__ __forceinline__ float rgb_activation(float x) { return sigmoid_fast(x) * 1.002f - 0.001f; }
+
+// Decoder kinds as compile-time traits: padded output widths of net A / net B and which plane
+// set feeds them.
+template <int KIND> struct DecoderTraits;
+template <> struct DecoderTraits<NFE_DEC_OSG> {            // net: 32->64->33 on the (single) plane set
+    static constexpr int OUT_A = 36, OUT_B = 4, SETS = 1; static constexpr bool HAS_B = false;
+};
+template <> struct DecoderTraits<NFE_DEC_DISENTANGLED> {   // geo_net 32->64->16 (norm), app_net 32->64->32 (denorm)
+    static constexpr int OUT_A = 16, OUT_B = 32, SETS = 2; static constexpr bool HAS_B = true;
+};
+template <> struct DecoderTraits<NFE_DEC_SEGMENTATION> {   // net 32->64->33 and seg_net 32->64->15, both on denorm
+    static constexpr int OUT_A = 36, OUT_B = 16, SETS = 1; static constexpr bool HAS_B = true;
+};
+
+// Bilinear tap sets of the three planes for one point (q = (2/box_warp) * x).
+struct Taps3 { Taps t[3]; };
+
+__device__ __forceinline__ Taps3 taps3(float qx, float qy, float qz, int H, int W)
+{
+    Taps3 r;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        float gx, gy;
+        project(qx, qy, qz, p, gx, gy);
+        r.t[p] = plane_taps(gx, gy, H, W);
+    }
+    return r;
+}
+
+// One point's features from one channel-last plane set ([3,H,W,32] floats): the 8 lanes of a
+// group own 4 channels each and walk the 12 taps (3 planes x 4), so a warp-wide LDG.128 fetches
+// 4 whole 128-byte texels (one per lane group).  Returns the plane MEAN ((f0+f1)+f2)/3
+// (decoders' `.mean(1)`, triplane.py:180,211,251-252) for this lane's 4 channels.
+__device__ __forceinline__ float4 gather_set(const float* __restrict__ set, const Taps3& tp, int H, int W, int c4)
+{
+    float4 f[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        const float* plane = set + (int64_t)p * H * W * FEAT + 4 * c4;
+        const Taps& t = tp.t[p];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = t.x0 + (k & 1), y = t.y0 + (k >> 1);
+            if (x >= 0 && x < W && y >= 0 && y < H) {
+                const float4 v = __ldg(reinterpret_cast<const float4*>(plane + ((int64_t)y * W + x) * FEAT));
+                acc.x = fmaf(v.x, t.w[k], acc.x); acc.y = fmaf(v.y, t.w[k], acc.y);
+                acc.z = fmaf(v.z, t.w[k], acc.z); acc.w = fmaf(v.w, t.w[k], acc.w);
+            }
+        }
+        f[p] = acc;
+    }
+    float4 m;
+    m.x = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].x, f[1].x), f[2].x), 3.0f);
+    m.y = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].y, f[1].y), f[2].y), 3.0f);
+    m.z = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].z, f[1].z), f[2].z), 3.0f);
+    m.w = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].w, f[1].w), f[2].w), 3.0f);
+    return m;
+}
+
+// Per-warp staging tile: 32 samples x 32 features as float4 chunks, chunk index XOR-swizzled
+// with the row so that both the gather's writes (8 lanes = one row) and the MLP's reads (one
+// row per lane) are bank-conflict free.
+__device__ __forceinline__ int tile_chunk(int row, int chunk) { return row * 8 + (chunk ^ (row & 7)); }
+
+constexpr int OUT_STRIDE = 49;  // output tile row stride (floats): 1 sigma + 15/16 seg + 32 rgb, odd -> conflict free
+
+}  // namespace nfe

@@ -1,0 +1,33 @@
+// Host-side launch interface of the fused gather+decode kernel (shared by nfe_field.cu and
+// nfe_render.cu).
+#pragma once
+#include "nfe_common.cuh"
+
+namespace nfe {
+
+constexpr int FIELD_THREADS = 512;
+
+struct FieldArgs {
+    const float* set_norm;    // channel-last [plane_batch,3,H,W,32]; unused unless the decoder is disentangled
+    const float* set_denorm;
+    int plane_batch, H, W;
+    float scale;              // 2 / box_warp
+    // sample positions: explicit points, or rays + per-sample depths (sample idx = ray*s_per_ray + s)
+    const float* coords;      // [n,m,3] or NULL
+    const float* origins;     // [n*R,3]
+    const float* dirs;
+    const float* depths;      // [n*R*s_per_ray]
+    int s_per_ray;
+    int64_t m;                // samples per batch item
+    int64_t total;            // n*m
+    float* sigma;             // [total]
+    float* rgb;               // [total,32]
+    float* seg;               // [total,15]
+    float density_noise;
+    uint64_t seed, offset;
+};
+
+int check_decoder_dims(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, const char* who);
+int launch_field(int kind, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream);
+
+}  // namespace nfe

@@ -1,0 +1,460 @@
+// Per-ray kernels, one warp per ray: alpha compositing (MipRayMarcher2 / SegMipRayMarcher2,
+// ray_marcher.py:25-57,68-101), the coarse+fine merge (unify_samples, renderer.py:150-167,288-300)
+// and inverse-CDF importance resampling (sample_importance/sample_pdf, renderer.py:194-253).
+// Everything a ray needs between samples stays in the warp's shared-memory slice; cross-lane
+// work is shuffle scans.
+#include "nfe_march.cuh"
+
+namespace nfe {
+
+__device__ __forceinline__ double shfl_up_double(double v, int delta)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_up_sync(0xffffffffu, lo, delta);
+    hi = __shfl_up_sync(0xffffffffu, hi, delta);
+    return __hiloint2double(hi, lo);
+}
+__device__ __forceinline__ double shfl_xor_double(double v, int mask)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return __hiloint2double(hi, lo);
+}
+
+// ------------------------------------------------------------------------------------------
+// march_kernel: optional merge-sort of [set1 | set2] by depth, then mid-point compositing.
+//   shared slice per warp: depth[S] sigma[S] weight[S] order[S]
+// ------------------------------------------------------------------------------------------
+template <bool SORT>
+__global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int S = a.s1 + a.s2;
+    float* s_depth = smem + (size_t)warp * 4 * S;
+    float* s_sigma = s_depth + S;
+    float* s_w = s_sigma + S;
+    int* s_order = reinterpret_cast<int*>(s_w + S);
+    float blk_min = __int_as_float(0x7f800000), blk_max = __int_as_float(0xff800000);
+
+    for (int64_t ray = (int64_t)blockIdx.x * warps_per_block + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * warps_per_block) {
+        // ---- load (and merge) depths / densities
+        if (SORT) {
+            // stage the concatenation in s_w (depth) / s_order (sigma bits), then rank-sort (stable:
+            // ties keep concatenation order, i.e. coarse before fine)
+            for (int e = lane; e < S; e += 32) {
+                const bool first = e < a.s1;
+                s_w[e] = first ? a.depths1[ray * a.s1 + e] : a.depths2[ray * a.s2 + (e - a.s1)];
+                s_order[e] = __float_as_int(first ? a.sigma1[ray * a.s1 + e] : a.sigma2[ray * a.s2 + (e - a.s1)]);
+            }
+            __syncwarp();
+            int my_rank[MAX_S / 32];
+            float my_d[MAX_S / 32], my_s[MAX_S / 32];
+#pragma unroll
+            for (int k = 0; k < MAX_S / 32; ++k) {
+                const int e = lane + 32 * k;
+                if (e < S) {
+                    const float d = s_w[e];
+                    int rank = 0;
+                    for (int j = 0; j < S; ++j) {
+                        const float dj = s_w[j];
+                        rank += (dj < d) || (dj == d && j < e);
+                    }
+                    my_rank[k] = rank; my_d[k] = d; my_s[k] = __int_as_float(s_order[e]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < MAX_S / 32; ++k) {
+                const int e = lane + 32 * k;
+                if (e < S) { s_depth[my_rank[k]] = my_d[k]; s_sigma[my_rank[k]] = my_s[k]; s_order[my_rank[k]] = e; }
+            }
+        } else {
+            for (int e = lane; e < S; e += 32) {
+                s_depth[e] = a.depths1[ray * a.s1 + e];
+                s_sigma[e] = a.sigma1[ray * a.s1 + e];
+                s_order[e] = e;
+            }
+        }
+        __syncwarp();
+
+        // ---- weights: each lane owns a contiguous chunk of intervals; transmittance by a
+        //      multiplicative warp scan of the chunk products
+        const int n_int = S - 1;
+        const int chunk = (n_int + 31) / 32;
+        const int i0 = lane * chunk, i1 = min(n_int, i0 + chunk);
+        float prod = 1.0f, dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
+        for (int i = i0; i < i1; ++i) {
+            const float delta = __fsub_rn(s_depth[i + 1], s_depth[i]);
+            const float sig = __fdiv_rn(__fadd_rn(s_sigma[i], s_sigma[i + 1]), 2.0f);
+            const float dens = softplus_ref(__fsub_rn(sig, 1.0f));
+            const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(dens, delta)));
+            s_w[i] = alpha;  // parked; turned into the weight below
+            prod *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+        }
+        for (int e = lane; e < S; e += 32) { dmin = fminf(dmin, s_depth[e]); dmax = fmaxf(dmax, s_depth[e]); }
+        float incl = prod;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const float up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl *= up;
+        }
+        float T = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) T = 1.0f;
+        float wd = 0.0f, wt = 0.0f;
+        for (int i = i0; i < i1; ++i) {
+            const float alpha = s_w[i];
+            const float w = alpha * T;
+            T *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+            s_w[i] = w;
+            wd = fmaf(w, __fdiv_rn(__fadd_rn(s_depth[i], s_depth[i + 1]), 2.0f), wd);
+            wt += w;
+        }
+        wd = warp_sum(wd);
+        wt = warp_sum(wt);
+        dmin = warp_min(dmin);
+        dmax = warp_max(dmax);
+        blk_min = fminf(blk_min, dmin);
+        blk_max = fmaxf(blk_max, dmax);
+        __syncwarp();
+
+        // ---- channel sums: lane = channel, sequential over intervals, rows read coalesced
+        if (a.cc > 0) {
+            for (int c0 = 0; c0 < a.cc; c0 += 32) {
+                const int c = c0 + lane;
+                const bool on = c < a.cc;
+                const bool seg_on = (c0 == 0) && lane < a.cs;
+                float acc = 0.0f, acc_s = 0.0f, prev = 0.0f, prev_s = 0.0f;
+                for (int k = 0; k < S; ++k) {
+                    const int e = s_order[k];
+                    const bool first = e < a.s1;
+                    const int64_t row = first ? ray * a.s1 + e : ray * a.s2 + (e - a.s1);
+                    float cur = 0.0f, cur_s = 0.0f;
+                    if (on) cur = __ldg((first ? a.colors1 : a.colors2) + row * a.cc + c);
+                    if (seg_on) cur_s = __ldg((first ? a.segs1 : a.segs2) + row * a.cs + lane);
+                    if (k > 0) {
+                        const float w = s_w[k - 1];
+                        acc = fmaf(w, (prev + cur) * 0.5f, acc);
+                        acc_s = fmaf(w, (prev_s + cur_s) * 0.5f, acc_s);
+                    }
+                    prev = cur; prev_s = cur_s;
+                }
+                if (on) {
+                    if (a.white_back) acc = acc + 1.0f - wt;
+                    a.rgb[ray * a.cc + c] = acc * 2.0f - 1.0f;
+                }
+                if (seg_on) a.seg[ray * a.cs + lane] = acc_s;
+            }
+            // segs wider than 32 channels are not produced by any decoder of the reference
+        }
+        if (lane == 0) {
+            if (a.depth) a.depth[ray] = __fdiv_rn(wd, wt);  // unclamped; NaN when the ray is empty
+            if (a.wsum) a.wsum[ray] = wt;
+        }
+        if (a.weights) {
+            for (int i = lane; i < n_int; i += 32) a.weights[ray * n_int + i] = s_w[i];
+        }
+        __syncwarp();
+    }
+
+    // ---- global depth range for the clamp: block reduce, then one atomic pair per block
+    if (a.minmax) {
+        __shared__ float red_min[8], red_max[8];
+        if (lane == 0) { red_min[warp] = blk_min; red_max[warp] = blk_max; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < warps_per_block; ++w) { blk_min = fminf(blk_min, red_min[w]); blk_max = fmaxf(blk_max, red_max[w]); }
+            if (blk_min <= blk_max) { atomic_min_float(a.minmax, blk_min); atomic_max_float(a.minmax + 1, blk_max); }
+        }
+    }
+}
+
+__global__ void init_minmax_kernel(float* minmax)
+{
+    minmax[0] = __int_as_float(0x7f800000);
+    minmax[1] = __int_as_float(0xff800000);
+}
+
+// depth = clamp(nan_to_num(depth, nan=+inf), min, max)   (ray_marcher.py:49-50,93-94)
+__global__ void finish_depth_kernel(float* __restrict__ depth, int64_t n, const float* __restrict__ minmax)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float lo = minmax[0], hi = minmax[1];
+    float d = depth[i];
+    if (d != d) d = __int_as_float(0x7f800000);
+    if (d == __int_as_float(0x7f800000)) d = 3.402823466e+38f;
+    if (d == __int_as_float(0xff800000)) d = -3.402823466e+38f;
+    d = fminf(fmaxf(d, lo), hi);
+    depth[i] = d;
+}
+
+// ------------------------------------------------------------------------------------------
+// unify_kernel: stand-alone unify_samples / sort_samples — materialises the sorted attributes.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) unify_kernel(MarchArgs a, float* __restrict__ depths_out, float* __restrict__ colors_out,
+                                                    float* __restrict__ segs_out, float* __restrict__ sigma_out)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int S = a.s1 + a.s2;
+    float* s_d = smem + (size_t)warp * 2 * S;
+    int* s_order = reinterpret_cast<int*>(s_d + S);
+    for (int64_t ray = (int64_t)blockIdx.x * warps_per_block + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * warps_per_block) {
+        for (int e = lane; e < S; e += 32) s_d[e] = e < a.s1 ? a.depths1[ray * a.s1 + e] : a.depths2[ray * a.s2 + (e - a.s1)];
+        __syncwarp();
+        for (int e = lane; e < S; e += 32) {
+            const float d = s_d[e];
+            int rank = 0;
+            for (int j = 0; j < S; ++j) {
+                const float dj = s_d[j];
+                rank += (dj < d) || (dj == d && j < e);
+            }
+            s_order[rank] = e;
+        }
+        __syncwarp();
+        for (int k = lane; k < S; k += 32) {
+            const int e = s_order[k];
+            depths_out[ray * S + k] = s_d[e];
+            sigma_out[ray * S + k] = e < a.s1 ? a.sigma1[ray * a.s1 + e] : a.sigma2[ray * a.s2 + (e - a.s1)];
+        }
+        for (int k = 0; k < S; ++k) {
+            const int e = s_order[k];
+            const bool first = e < a.s1;
+            const int64_t row = first ? ray * a.s1 + e : ray * a.s2 + (e - a.s1);
+            for (int c = lane; c < a.cc; c += 32) colors_out[(ray * S + k) * a.cc + c] = (first ? a.colors1 : a.colors2)[row * a.cc + c];
+            for (int c = lane; c < a.cs; c += 32) segs_out[(ray * S + k) * a.cs + c] = (first ? a.segs1 : a.segs2)[row * a.cs + c];
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// resample_kernel: smoothed coarse weights -> pdf -> cdf -> inverse-CDF samples.
+// NORMATIVE arithmetic (oracle nfo_resample_ray): the normaliser is the exact
+// sum (double; exact for any order because the addends are fp32 of similar magnitude) rounded to
+// fp32, the CDF a double running sum rounded per entry.  No fused multiply-adds.
+//   shared slice per warp: z[S] a[S] bins[S] cdf[S]
+// ------------------------------------------------------------------------------------------
+// SMOOTH = true : sample_importance — inputs are z_vals [S] and raw coarse weights [S-1];
+//                 ns = S-3 pdf entries, bins = the S-1 mid-depths.
+// SMOOTH = false: sample_pdf stand-alone — inputs are bins [S] and weights [ns] as given.
+template <bool SMOOTH>
+__global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a)
+{
+    extern __shared__ __align__(16) float smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const int S = a.S, nw = S - 1, ns = SMOOTH ? S - 3 : a.ns;
+    float* s_z = smem + (size_t)warp * 4 * S;
+    float* s_om = s_z + S;     // omega_j = weight_j + eps, j in [0, ns)
+    float* s_bins = s_om + S;
+    float* s_cdf = s_bins + S;
+    for (int64_t ray = (int64_t)blockIdx.x * warps_per_block + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * warps_per_block) {
+        if (SMOOTH) {
+            for (int e = lane; e < S; e += 32) s_z[e] = a.z_vals[ray * S + e];
+            for (int e = lane; e < nw; e += 32) s_cdf[e] = a.weights[ray * nw + e];  // raw weights parked in s_cdf
+            __syncwarp();
+            // max_pool1d(k=2,s=1,pad=1) then avg_pool1d(k=2,s=1), + 0.01 (renderer.py:205-207); bins = mid-depths;
+            // only smoothed[1:-1] enters the pdf (renderer.py:210)
+            for (int i = lane; i < nw; i += 32) {
+                const float w0 = s_cdf[i];
+                const float m_i = i > 0 ? fmaxf(s_cdf[i - 1], w0) : w0;                // m[i]
+                const float m_n = i + 1 < nw ? fmaxf(w0, s_cdf[i + 1]) : w0;           // m[i+1]
+                const float sm = __fadd_rn(__fdiv_rn(__fadd_rn(m_i, m_n), 2.0f), 0.01f);
+                if (i >= 1 && i <= ns) s_om[i - 1] = __fadd_rn(sm, a.eps);
+                s_bins[i] = __fmul_rn(0.5f, __fadd_rn(s_z[i], s_z[i + 1]));
+            }
+        } else {
+            for (int e = lane; e < S; e += 32) s_bins[e] = a.z_vals[ray * S + e];
+            for (int e = lane; e < ns; e += 32) s_om[e] = __fadd_rn(a.weights[ray * ns + e], a.eps);
+        }
+        __syncwarp();
+        double tot = 0.0;
+        for (int j = lane; j < ns; j += 32) tot += (double)s_om[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += shfl_xor_double(tot, o);
+        const float totf = (float)tot;
+        // cdf: contiguous chunk per lane, exclusive double scan across lanes
+        const int chunk = (ns + 31) / 32;
+        const int j0 = lane * chunk, j1 = min(ns, j0 + chunk);
+        double local = 0.0;
+        for (int j = j0; j < j1; ++j) local += (double)__fdiv_rn(s_om[j], totf);
+        double incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double up = shfl_up_double(incl, o);
+            if (lane >= o) incl += up;
+        }
+        double run = incl - local;
+        __syncwarp();
+        if (lane == 0) s_cdf[0] = 0.0f;
+        for (int j = j0; j < j1; ++j) {
+            run += (double)__fdiv_rn(s_om[j], totf);
+            s_cdf[j + 1] = (float)run;
+        }
+        __syncwarp();
+        // inverse CDF
+        for (int k = lane; k < a.s_f; k += 32) {
+            float u;
+            if (a.u) u = a.u_per_ray ? a.u[ray * a.s_f + k] : a.u[k];
+            else u = u01(philox4x32(a.seed, (uint64_t)(ray * a.s_f + k), a.offset).x);
+            // searchsorted(right=True): number of cdf entries <= u, over cdf[0..ns]
+            int lo = 0, hi = ns + 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_cdf[mid] <= u) lo = mid + 1; else hi = mid;
+            }
+            const int below = max(lo - 1, 0), above = min(lo, ns);
+            float den = __fsub_rn(s_cdf[above], s_cdf[below]);
+            if (den < a.eps) den = 1.0f;
+            const float frac = __fdiv_rn(__fsub_rn(u, s_cdf[below]), den);
+            const float t = __fadd_rn(s_bins[below], __fmul_rn(frac, __fsub_rn(s_bins[above], s_bins[below])));
+            a.out[ray * a.s_f + k] = t;
+            if (a.below) a.below[ray * a.s_f + k] = below;
+            if (a.above) a.above[ray * a.s_f + k] = above;
+        }
+        __syncwarp();
+    }
+}
+
+static int warps_for(int S)
+{
+    // 16*S bytes of shared memory per warp; keep a block under ~96 KB
+    int w = 8;
+    while (w > 1 && (size_t)w * 16 * S > 96 * 1024) w >>= 1;
+    return w;
+}
+
+int launch_march(const MarchArgs& a, bool sort, cudaStream_t stream)
+{
+    const int S = a.s1 + a.s2;
+    NFE_REQUIRE(S >= 2 && S <= MAX_S, "ray march: %d samples per ray unsupported (2..%d)", S, MAX_S);
+    NFE_REQUIRE(a.cs <= 32, "ray march: at most 32 semantic channels (got %d)", a.cs);
+    if (a.n_rays <= 0) return 0;
+    const int warps = warps_for(S);
+    const size_t smem = (size_t)warps * 16 * S;
+    const int64_t blocks = (a.n_rays + warps - 1) / warps;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    if (sort) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        march_kernel<true><<<grid, warps * 32, smem, stream>>>(a);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        march_kernel<false><<<grid, warps * 32, smem, stream>>>(a);
+    }
+    return check_launch("march_kernel");
+}
+
+int launch_init_minmax(float* minmax, cudaStream_t stream)
+{
+    init_minmax_kernel<<<1, 1, 0, stream>>>(minmax);
+    return check_launch("init_minmax_kernel");
+}
+
+int launch_finish_depth(float* depth, int64_t n, const float* minmax, cudaStream_t stream)
+{
+    if (n <= 0) return 0;
+    finish_depth_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(depth, n, minmax);
+    return check_launch("finish_depth_kernel");
+}
+
+int launch_resample(const ResampleArgs& a, cudaStream_t stream)
+{
+    NFE_REQUIRE(a.S >= (a.smooth ? 4 : 2) && a.S <= MAX_S, "importance resampling: %d bins unsupported (%d..%d)", a.S, a.smooth ? 4 : 2, MAX_S);
+    NFE_REQUIRE(a.smooth || (a.ns >= 1 && a.ns < a.S), "sample_pdf: %d weights need at least %d bins (got %d)", a.ns, a.ns + 1, a.S);
+    NFE_REQUIRE(a.s_f >= 1, "importance resampling: need at least one importance sample");
+    if (a.n_rays <= 0) return 0;
+    const int warps = warps_for(a.S);
+    const size_t smem = (size_t)warps * 16 * a.S;
+    const int64_t blocks = (a.n_rays + warps - 1) / warps;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
+    if (a.smooth) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(resample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        resample_kernel<true><<<grid, warps * 32, smem, stream>>>(a);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(resample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        resample_kernel<false><<<grid, warps * 32, smem, stream>>>(a);
+    }
+    return check_launch("resample_kernel");
+}
+
+}  // namespace nfe
+
+using namespace nfe;
+
+NFE_EXPORT int nfe_composite_fwd(const float* colors, const float* segs, const float* sigma, const float* depths, int64_t n_rays, int S,
+                                 int cc, int cs, int white_back, float* rgb, float* seg, float* depth, float* weights, float* wsum,
+                                 float* minmax_ws, nfe_stream_t stream)
+{
+    NFE_REQUIRE(sigma && depths, "nfe_composite_fwd: null sigma/depths");
+    NFE_REQUIRE(cc == 0 || (colors && rgb), "nfe_composite_fwd: colours given without output (or vice versa)");
+    NFE_REQUIRE(cs == 0 || (segs && seg), "nfe_composite_fwd: semantics given without output (or vice versa)");
+    NFE_REQUIRE(!depth || minmax_ws, "nfe_composite_fwd: depth output needs the 2-float minmax workspace");
+    MarchArgs a = {};
+    a.depths1 = depths; a.colors1 = colors; a.segs1 = segs; a.sigma1 = sigma; a.s1 = S; a.s2 = 0;
+    a.n_rays = n_rays; a.cc = cc; a.cs = cs; a.white_back = white_back;
+    a.rgb = rgb; a.seg = seg; a.depth = depth; a.wsum = wsum; a.weights = weights; a.minmax = depth ? minmax_ws : nullptr;
+    if (depth) { if (int rc = launch_init_minmax(minmax_ws, as_stream(stream))) return rc; }
+    if (int rc = launch_march(a, false, as_stream(stream))) return rc;
+    if (depth) return launch_finish_depth(depth, n_rays, minmax_ws, as_stream(stream));
+    return 0;
+}
+
+NFE_EXPORT int nfe_finish_depth(float* depth, int64_t n_rays, const float* minmax_dev, nfe_stream_t stream)
+{
+    NFE_REQUIRE(depth && minmax_dev, "nfe_finish_depth: null pointer");
+    return launch_finish_depth(depth, n_rays, minmax_dev, as_stream(stream));
+}
+
+NFE_EXPORT int nfe_importance_resample(const float* z_vals, const float* weights, int64_t n_rays, int S, int s_f, const float* u,
+                                       int u_per_ray, uint64_t seed, uint64_t offset, float* out, int32_t* below, int32_t* above,
+                                       nfe_stream_t stream)
+{
+    NFE_REQUIRE(z_vals && weights && out, "nfe_importance_resample: null pointer");
+    ResampleArgs a = {};
+    a.z_vals = z_vals; a.weights = weights; a.n_rays = n_rays; a.S = S; a.s_f = s_f; a.u = u; a.u_per_ray = u_per_ray;
+    a.seed = seed; a.offset = offset; a.out = out; a.below = below; a.above = above;
+    a.smooth = 1; a.eps = 1e-5f;
+    return launch_resample(a, as_stream(stream));
+}
+
+NFE_EXPORT int nfe_sample_pdf(const float* bins, const float* weights, int64_t n_rays, int n_bins, int n_weights, int s_f, const float* u,
+                              int u_per_ray, uint64_t seed, uint64_t offset, float eps, float* out, nfe_stream_t stream)
+{
+    NFE_REQUIRE(bins && weights && out, "nfe_sample_pdf: null pointer");
+    ResampleArgs a = {};
+    a.z_vals = bins; a.weights = weights; a.n_rays = n_rays; a.S = n_bins; a.ns = n_weights; a.s_f = s_f; a.u = u; a.u_per_ray = u_per_ray;
+    a.seed = seed; a.offset = offset; a.out = out; a.smooth = 0; a.eps = eps;
+    return launch_resample(a, as_stream(stream));
+}
+
+NFE_EXPORT int nfe_unify_samples(const float* depths1, const float* colors1, const float* segs1, const float* sigma1, const float* depths2,
+                                 const float* colors2, const float* segs2, const float* sigma2, int64_t n_rays, int s1, int s2, int cc, int cs,
+                                 float* depths, float* colors, float* segs, float* sigma, nfe_stream_t stream)
+{
+    NFE_REQUIRE(depths1 && sigma1 && depths && sigma, "nfe_unify_samples: null pointer");
+    NFE_REQUIRE(s2 == 0 || (depths2 && sigma2), "nfe_unify_samples: second sample set missing");
+    NFE_REQUIRE(cc == 0 || (colors1 && colors && (s2 == 0 || colors2)), "nfe_unify_samples: colour pointers missing");
+    NFE_REQUIRE(cs == 0 || (segs1 && segs && (s2 == 0 || segs2)), "nfe_unify_samples: semantic pointers missing");
+    const int S = s1 + s2;
+    NFE_REQUIRE(S >= 1 && S <= MAX_S, "nfe_unify_samples: %d samples per ray unsupported (1..%d)", S, MAX_S);
+    if (n_rays <= 0) return 0;
+    MarchArgs a = {};
+    a.depths1 = depths1; a.colors1 = colors1; a.segs1 = segs1; a.sigma1 = sigma1; a.s1 = s1;
+    a.depths2 = depths2; a.colors2 = colors2; a.segs2 = segs2; a.sigma2 = sigma2; a.s2 = s2;
+    a.n_rays = n_rays; a.cc = cc; a.cs = cs;
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * 8 * S > 48 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * 8 * S;
+    const int64_t blocks = (n_rays + warps - 1) / warps;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    unify_kernel<<<(unsigned)(blocks < cap ? blocks : cap), warps * 32, smem, as_stream(stream)>>>(a, depths, colors, segs, sigma);
+    NFE_LAUNCH_CHECK("unify_kernel");
+    return 0;
+}

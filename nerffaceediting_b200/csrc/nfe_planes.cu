@@ -1,0 +1,205 @@
+// Plane statistics, (de)normalisation and the channel-last staging of the tri-planes.
+// Replaces TriPlaneGenerator.compute_mean_var / normalize_plane / denormalize_plane
+// (training/triplane.py:56-68) — three full passes plus broadcast temporaries in the reference.
+// All four kernels are pure HBM streams: bytes = read 1x (+ write 1x) of the plane tensor.
+#include "nfe_common.cuh"
+
+namespace nfe {
+
+// One CTA per (batch, channel) slab.  Single pass, sum and sum of squares in double: with fp32
+// inputs the double accumulators make the one-pass variance formula safe, and the result is
+// order-independent to ~1e-16, i.e. deterministic after rounding to fp32.
+__global__ void __launch_bounds__(512) plane_stats_kernel(const float* __restrict__ planes, int64_t hw,
+                                                          float* __restrict__ mean, float* __restrict__ std_out)
+{
+    const float* x = planes + (int64_t)blockIdx.x * hw;
+    double s = 0.0, ss = 0.0;
+    const bool vec = (hw % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        const int64_t n4 = hw / 4;
+        for (int64_t i = threadIdx.x; i < n4; i += blockDim.x) {
+            const float4 v = __ldg(x4 + i);
+            // pairwise in fp32 is not exact; keep every add in double
+            s += (double)v.x; s += (double)v.y; s += (double)v.z; s += (double)v.w;
+            ss += (double)v.x * (double)v.x; ss += (double)v.y * (double)v.y;
+            ss += (double)v.z * (double)v.z; ss += (double)v.w * (double)v.w;
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) {
+            const double v = (double)x[i];
+            s += v; ss += v * v;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    }
+    __shared__ double sh_s[16], sh_ss[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh_s[warp] = s; sh_ss[warp] = ss; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        s = lane < nw ? sh_s[lane] : 0.0;
+        ss = lane < nw ? sh_ss[lane] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        }
+        if (lane == 0) {
+            const double n = (double)hw;
+            const double m = s / n;
+            double var = (ss - s * m) / (n - 1.0);
+            if (var < 0.0) var = 0.0;
+            mean[blockIdx.x] = (float)m;
+            std_out[blockIdx.x] = sqrtf((float)var);
+        }
+    }
+}
+
+// (x - mean) / (std + 1e-8), IEEE division to stay bit-comparable with the reference.
+__global__ void __launch_bounds__(256) plane_normalize_kernel(const float* __restrict__ planes, const float* __restrict__ mean,
+                                                              const float* __restrict__ std_in, int64_t hw, int chunks_per_slab,
+                                                              float* __restrict__ out)
+{
+    const int64_t slab = blockIdx.x / chunks_per_slab;
+    const int chunk = blockIdx.x % chunks_per_slab;
+    const float m = mean[slab];
+    const float d = __fadd_rn(std_in[slab], 1e-8f);
+    const int64_t per = (hw + chunks_per_slab - 1) / chunks_per_slab;
+    const int64_t lo = chunk * per, hi = min(hw, lo + per);
+    const float* x = planes + slab * hw;
+    float* y = out + slab * hw;
+    const bool vec = (hw % 4 == 0) && (per % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0);
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* y4 = reinterpret_cast<float4*>(y);
+        for (int64_t i = lo / 4 + threadIdx.x; i < hi / 4; i += blockDim.x) {
+            float4 v = __ldg(x4 + i);
+            v.x = __fdiv_rn(__fsub_rn(v.x, m), d); v.y = __fdiv_rn(__fsub_rn(v.y, m), d);
+            v.z = __fdiv_rn(__fsub_rn(v.z, m), d); v.w = __fdiv_rn(__fsub_rn(v.w, m), d);
+            y4[i] = v;
+        }
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = __fdiv_rn(__fsub_rn(x[i], m), d);
+    }
+}
+
+// x * std' + mean' (mul then add, unfused, as the reference's two ATen kernels)
+__global__ void __launch_bounds__(256) plane_denormalize_kernel(const float* __restrict__ norm, const float* __restrict__ mean,
+                                                                const float* __restrict__ std_in, int64_t stat_slabs, int64_t hw,
+                                                                int chunks_per_slab, float* __restrict__ out)
+{
+    const int64_t slab = blockIdx.x / chunks_per_slab;
+    const int chunk = blockIdx.x % chunks_per_slab;
+    const float m = mean[slab % stat_slabs];
+    const float d = std_in[slab % stat_slabs];
+    const int64_t per = (hw + chunks_per_slab - 1) / chunks_per_slab;
+    const int64_t lo = chunk * per, hi = min(hw, lo + per);
+    const float* x = norm + slab * hw;
+    float* y = out + slab * hw;
+    const bool vec = (hw % 4 == 0) && (per % 4 == 0) && (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0);
+    if (vec) {
+        const float4* x4 = reinterpret_cast<const float4*>(x);
+        float4* y4 = reinterpret_cast<float4*>(y);
+        for (int64_t i = lo / 4 + threadIdx.x; i < hi / 4; i += blockDim.x) {
+            float4 v = __ldg(x4 + i);
+            v.x = __fadd_rn(__fmul_rn(v.x, d), m); v.y = __fadd_rn(__fmul_rn(v.y, d), m);
+            v.z = __fadd_rn(__fmul_rn(v.z, d), m); v.w = __fadd_rn(__fmul_rn(v.w, d), m);
+            y4[i] = v;
+        }
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = __fadd_rn(__fmul_rn(x[i], d), m);
+    }
+}
+
+// [n_img, C, hw] -> [n_img, hw, C] through a padded shared tile.  A CTA moves C x 64 pixels:
+// reads are 256-byte runs per channel, writes are one contiguous 64*C*4-byte span.
+constexpr int CL_PIX = 64;
+__global__ void __launch_bounds__(256) to_channel_last_kernel(const float* __restrict__ planes, int channels, int64_t hw,
+                                                              int64_t tiles_per_img, float* __restrict__ out)
+{
+    extern __shared__ float tile[];  // [channels][CL_PIX + 1]
+    const int64_t img = blockIdx.x / tiles_per_img;
+    const int64_t px0 = (blockIdx.x % tiles_per_img) * CL_PIX;
+    const float* src = planes + img * channels * hw;
+    float* dst = out + img * hw * channels;
+    const int npx = (int)min((int64_t)CL_PIX, hw - px0);
+    for (int i = threadIdx.x; i < channels * CL_PIX; i += blockDim.x) {
+        const int c = i / CL_PIX, p = i % CL_PIX;
+        if (p < npx) tile[c * (CL_PIX + 1) + p] = __ldg(src + (int64_t)c * hw + px0 + p);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < npx * channels; i += blockDim.x) {
+        const int p = i / channels, c = i % channels;
+        dst[(px0 + p) * channels + c] = tile[c * (CL_PIX + 1) + p];
+    }
+}
+
+}  // namespace nfe
+
+using namespace nfe;
+
+static int chunks_for(int64_t n_slabs, int64_t hw)
+{
+    // enough CTAs to fill the machine several times over, each streaming >= 16 KB
+    int64_t c = (int64_t)sm_count() * 16 / (n_slabs > 0 ? n_slabs : 1);
+    const int64_t max_c = hw / 4096 > 0 ? hw / 4096 : 1;
+    if (c > max_c) c = max_c;
+    if (c < 1) c = 1;
+    while (c > 1 && ((hw % c) != 0 || ((hw / c) % 4) != 0)) --c;
+    return (int)c;
+}
+
+NFE_EXPORT int nfe_plane_stats(const float* planes, int64_t n_slabs, int64_t hw, float* mean, float* std_out, nfe_stream_t stream)
+{
+    NFE_REQUIRE(planes && mean && std_out, "nfe_plane_stats: null pointer");
+    NFE_REQUIRE(n_slabs >= 0 && n_slabs < (1ll << 31) && hw >= 2, "nfe_plane_stats: bad sizes (n_slabs=%lld hw=%lld)", (long long)n_slabs, (long long)hw);
+    if (n_slabs == 0) return 0;
+    plane_stats_kernel<<<(unsigned)n_slabs, 512, 0, as_stream(stream)>>>(planes, hw, mean, std_out);
+    NFE_LAUNCH_CHECK("plane_stats_kernel");
+    return 0;
+}
+
+NFE_EXPORT int nfe_plane_normalize(const float* planes, const float* mean, const float* std_in, int64_t n_slabs, int64_t hw,
+                                   float* out, nfe_stream_t stream)
+{
+    NFE_REQUIRE(planes && mean && std_in && out, "nfe_plane_normalize: null pointer");
+    NFE_REQUIRE(n_slabs >= 0 && hw >= 1, "nfe_plane_normalize: bad sizes");
+    if (n_slabs == 0) return 0;
+    const int chunks = chunks_for(n_slabs, hw);
+    NFE_REQUIRE(n_slabs * chunks < (1ll << 31), "nfe_plane_normalize: grid too large");
+    plane_normalize_kernel<<<(unsigned)(n_slabs * chunks), 256, 0, as_stream(stream)>>>(planes, mean, std_in, hw, chunks, out);
+    NFE_LAUNCH_CHECK("plane_normalize_kernel");
+    return 0;
+}
+
+NFE_EXPORT int nfe_plane_denormalize(const float* norm, const float* mean, const float* std_in, int64_t n_slabs, int64_t stat_slabs,
+                                     int64_t hw, float* out, nfe_stream_t stream)
+{
+    NFE_REQUIRE(norm && mean && std_in && out, "nfe_plane_denormalize: null pointer");
+    NFE_REQUIRE(n_slabs >= 0 && hw >= 1 && stat_slabs >= 1, "nfe_plane_denormalize: bad sizes");
+    if (n_slabs == 0) return 0;
+    const int chunks = chunks_for(n_slabs, hw);
+    NFE_REQUIRE(n_slabs * chunks < (1ll << 31), "nfe_plane_denormalize: grid too large");
+    plane_denormalize_kernel<<<(unsigned)(n_slabs * chunks), 256, 0, as_stream(stream)>>>(norm, mean, std_in, stat_slabs, hw, chunks, out);
+    NFE_LAUNCH_CHECK("plane_denormalize_kernel");
+    return 0;
+}
+
+NFE_EXPORT int nfe_planes_to_channel_last(const float* planes, int64_t n_img, int channels, int64_t hw, float* out, nfe_stream_t stream)
+{
+    NFE_REQUIRE(planes && out, "nfe_planes_to_channel_last: null pointer");
+    NFE_REQUIRE(n_img >= 0 && channels >= 1 && channels <= 256 && hw >= 1, "nfe_planes_to_channel_last: bad sizes");
+    if (n_img == 0) return 0;
+    const int64_t tiles = (hw + CL_PIX - 1) / CL_PIX;
+    NFE_REQUIRE(n_img * tiles < (1ll << 31), "nfe_planes_to_channel_last: grid too large");
+    const size_t smem = (size_t)channels * (CL_PIX + 1) * sizeof(float);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(to_channel_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    to_channel_last_kernel<<<(unsigned)(n_img * tiles), 256, smem, as_stream(stream)>>>(planes, channels, hw, tiles, out);
+    NFE_LAUNCH_CHECK("to_channel_last_kernel");
+    return 0;
+}

@@ -152,7 +152,7 @@ NFO_API void nfo_ray_limits_box(const float* origins, const float* dirs, int64_t
  * ---------------------------------------------------------------------------------------- */
 NFO_API void nfo_sample_stratified(int64_t n_rays, int s_c, int mode /*0 scalar,1 per-ray,2 disparity*/,
                                    const float* table /*[S] for modes 0,2*/,
-                                   float ray_start, float ray_end,
+                                   double ray_start, double ray_end,
                                    const float* start_per_ray, const float* end_per_ray,
                                    const float* jitter /*[n_rays,S] or NULL*/, float* depths /*[n_rays,S]*/)
 {
@@ -161,7 +161,7 @@ NFO_API void nfo_sample_stratified(int64_t n_rays, int s_c, int mode /*0 scalar,
             const float u = jitter ? jitter[r * s_c + s] : 0.0f;
             float t;
             if (mode == 0) {
-                const float delta = (float)(((double)ray_end - (double)ray_start) / (double)(s_c - 1));
+                const float delta = (float)((ray_end - ray_start) / (double)(s_c - 1));
                 t = table[s] + u * delta;
             } else if (mode == 1) {
                 const float a = start_per_ray[r], b = end_per_ray[r];
@@ -172,7 +172,7 @@ NFO_API void nfo_sample_stratified(int64_t n_rays, int s_c, int mode /*0 scalar,
             } else {
                 const float delta = (float)(1.0 / (double)(s_c - 1));
                 const float sp = table[s] + u * delta;
-                const float ia = (float)(1.0 / (double)ray_start), ib = (float)(1.0 / (double)ray_end);
+                const float ia = (float)(1.0 / ray_start), ib = (float)(1.0 / ray_end);
                 t = 1.0f / (ia * (1.0f - sp) + ib * sp);
             }
             depths[r * s_c + s] = t;

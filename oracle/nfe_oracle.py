@@ -166,8 +166,8 @@ def sample_stratified(n, r, s_c, table=None, ray_start=0.0, ray_end=0.0, start_p
     sp = _f(start_per_ray) if start_per_ray is not None else None
     ep = _f(end_per_ray) if end_per_ray is not None else None
     jt = _f(jitter) if jitter is not None else None
-    lib().nfo_sample_stratified(ctypes.c_int64(n * r), int(s_c), mode, _p(tb), ctypes.c_float(ray_start),
-                                ctypes.c_float(ray_end), _p(sp), _p(ep), _p(jt), _p(out))
+    lib().nfo_sample_stratified(ctypes.c_int64(n * r), int(s_c), mode, _p(tb), ctypes.c_double(ray_start),
+                                ctypes.c_double(ray_end), _p(sp), _p(ep), _p(jt), _p(out))
     return out
 
 
