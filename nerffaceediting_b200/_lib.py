@@ -42,6 +42,8 @@ SIGNATURES = {
     "nfe_version": (c_int, []),
     "nfe_last_error": (ctypes.c_char_p, []),
     "nfe_launch_count": (c_u64, []),
+    "nfe_timing_enable": (c_int, [c_int]),
+    "nfe_timing_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(c_i64), c_int, c_int]),
     "nfe_plane_stats": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "nfe_plane_normalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "nfe_plane_denormalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
@@ -91,3 +93,18 @@ def check(rc, what):
 
 def launch_count():
     return int(load().nfe_launch_count())
+
+
+STAGES = ("field_coarse", "march_coarse", "resample", "field_fine", "march_final", "run_model")
+
+
+def timing_enable(on=True):
+    check(load().nfe_timing_enable(int(bool(on))), "nfe_timing_enable")
+
+
+def timing_read(reset=True):
+    """{stage: (total_ms, launches)} of the stages recorded since the last reset (waits for them)."""
+    ms = (c_double * len(STAGES))()
+    cnt = (c_i64 * len(STAGES))()
+    check(load().nfe_timing_read(ms, cnt, len(STAGES), int(bool(reset))), "nfe_timing_read")
+    return {name: (float(ms[i]), int(cnt[i])) for i, name in enumerate(STAGES)}

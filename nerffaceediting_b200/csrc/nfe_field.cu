@@ -272,6 +272,7 @@ using namespace nfe;
 NFE_EXPORT int nfe_sample_planes_fwd(const float* planes_cl, int plane_batch, int channels, int height, int width, const float* coords,
                                      int n, int64_t m, float box_warp, float* out, nfe_stream_t stream)
 {
+    if ((int64_t)n * m == 0) return 0;  // empty tensors carry null pointers
     NFE_REQUIRE(planes_cl && coords && out, "nfe_sample_planes_fwd: null pointer");
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_sample_planes_fwd: plane batch %d does not match coordinate batch %d", plane_batch, n);
     NFE_REQUIRE(channels >= 1 && height >= 1 && width >= 1 && n >= 0 && m >= 0, "nfe_sample_planes_fwd: bad sizes");
@@ -311,6 +312,7 @@ NFE_EXPORT int nfe_decoder_fwd(int kind, const nfe_mlp* net_a, const nfe_mlp* ne
 {
     if (int rc = check_decoder_dims(kind, net_a, net_b, "nfe_decoder_fwd")) return rc;
     NFE_REQUIRE(channels == FEAT, "nfe_decoder_fwd: features must have %d channels (got %d)", FEAT, channels);
+    if ((int64_t)n * m == 0) return 0;
     NFE_REQUIRE(feat_denorm && rgb && sigma, "nfe_decoder_fwd: null pointer");
     NFE_REQUIRE(kind != NFE_DEC_DISENTANGLED || feat_norm, "nfe_decoder_fwd: the disentangled decoder needs feat_norm");
     NFE_REQUIRE(kind == NFE_DEC_OSG || seg, "nfe_decoder_fwd: seg output missing");
@@ -331,6 +333,7 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     NFE_REQUIRE(cfg, "nfe_run_model_fwd: null cfg");
     if (int rc = check_decoder_dims(cfg->kind, net_a, net_b, "nfe_run_model_fwd")) return rc;
     NFE_REQUIRE(cfg->channels == FEAT, "nfe_run_model_fwd: planes must have %d channels (got %d)", FEAT, cfg->channels);
+    if ((int64_t)n * m == 0) return 0;
     NFE_REQUIRE(planes_denorm_cl && coords && rgb && sigma, "nfe_run_model_fwd: null pointer");
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_run_model_fwd: the disentangled decoder needs the normalised planes");
     NFE_REQUIRE(cfg->kind == NFE_DEC_OSG || seg, "nfe_run_model_fwd: seg output missing");
@@ -342,5 +345,6 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     a.coords = coords; a.m = m; a.total = (int64_t)n * m; a.s_per_ray = 1;
     a.sigma = sigma; a.rgb = rgb; a.seg = seg;
     a.density_noise = cfg->density_noise; a.seed = cfg->seed; a.offset = cfg->offset;
+    StageScope t(STAGE_RUN_MODEL, as_stream(stream));
     return launch_field(cfg->kind, a, net_a, net_b, as_stream(stream));
 }

@@ -392,6 +392,7 @@ NFE_EXPORT int nfe_composite_fwd(const float* colors, const float* segs, const f
                                  int cc, int cs, int white_back, float* rgb, float* seg, float* depth, float* weights, float* wsum,
                                  float* minmax_ws, nfe_stream_t stream)
 {
+    if (n_rays <= 0) return 0;
     NFE_REQUIRE(sigma && depths, "nfe_composite_fwd: null sigma/depths");
     NFE_REQUIRE(cc == 0 || (colors && rgb), "nfe_composite_fwd: colours given without output (or vice versa)");
     NFE_REQUIRE(cs == 0 || (segs && seg), "nfe_composite_fwd: semantics given without output (or vice versa)");
@@ -408,6 +409,7 @@ NFE_EXPORT int nfe_composite_fwd(const float* colors, const float* segs, const f
 
 NFE_EXPORT int nfe_finish_depth(float* depth, int64_t n_rays, const float* minmax_dev, nfe_stream_t stream)
 {
+    if (n_rays <= 0) return 0;
     NFE_REQUIRE(depth && minmax_dev, "nfe_finish_depth: null pointer");
     return launch_finish_depth(depth, n_rays, minmax_dev, as_stream(stream));
 }
@@ -416,6 +418,7 @@ NFE_EXPORT int nfe_importance_resample(const float* z_vals, const float* weights
                                        int u_per_ray, uint64_t seed, uint64_t offset, float* out, int32_t* below, int32_t* above,
                                        nfe_stream_t stream)
 {
+    if (n_rays <= 0) return 0;
     NFE_REQUIRE(z_vals && weights && out, "nfe_importance_resample: null pointer");
     ResampleArgs a = {};
     a.z_vals = z_vals; a.weights = weights; a.n_rays = n_rays; a.S = S; a.s_f = s_f; a.u = u; a.u_per_ray = u_per_ray;
@@ -427,6 +430,7 @@ NFE_EXPORT int nfe_importance_resample(const float* z_vals, const float* weights
 NFE_EXPORT int nfe_sample_pdf(const float* bins, const float* weights, int64_t n_rays, int n_bins, int n_weights, int s_f, const float* u,
                               int u_per_ray, uint64_t seed, uint64_t offset, float eps, float* out, nfe_stream_t stream)
 {
+    if (n_rays <= 0) return 0;
     NFE_REQUIRE(bins && weights && out, "nfe_sample_pdf: null pointer");
     ResampleArgs a = {};
     a.z_vals = bins; a.weights = weights; a.n_rays = n_rays; a.S = n_bins; a.ns = n_weights; a.s_f = s_f; a.u = u; a.u_per_ray = u_per_ray;
@@ -438,6 +442,7 @@ NFE_EXPORT int nfe_unify_samples(const float* depths1, const float* colors1, con
                                  const float* colors2, const float* segs2, const float* sigma2, int64_t n_rays, int s1, int s2, int cc, int cs,
                                  float* depths, float* colors, float* segs, float* sigma, nfe_stream_t stream)
 {
+    if (n_rays <= 0) return 0;
     NFE_REQUIRE(depths1 && sigma1 && depths && sigma, "nfe_unify_samples: null pointer");
     NFE_REQUIRE(s2 == 0 || (depths2 && sigma2), "nfe_unify_samples: second sample set missing");
     NFE_REQUIRE(cc == 0 || (colors1 && colors && (s2 == 0 || colors2)), "nfe_unify_samples: colour pointers missing");

@@ -156,6 +156,7 @@ static int chunks_for(int64_t n_slabs, int64_t hw)
 
 NFE_EXPORT int nfe_plane_stats(const float* planes, int64_t n_slabs, int64_t hw, float* mean, float* std_out, nfe_stream_t stream)
 {
+    if (n_slabs == 0) return 0;
     NFE_REQUIRE(planes && mean && std_out, "nfe_plane_stats: null pointer");
     NFE_REQUIRE(n_slabs >= 0 && n_slabs < (1ll << 31) && hw >= 2, "nfe_plane_stats: bad sizes (n_slabs=%lld hw=%lld)", (long long)n_slabs, (long long)hw);
     if (n_slabs == 0) return 0;
@@ -167,6 +168,7 @@ NFE_EXPORT int nfe_plane_stats(const float* planes, int64_t n_slabs, int64_t hw,
 NFE_EXPORT int nfe_plane_normalize(const float* planes, const float* mean, const float* std_in, int64_t n_slabs, int64_t hw,
                                    float* out, nfe_stream_t stream)
 {
+    if (n_slabs == 0 || hw == 0) return 0;
     NFE_REQUIRE(planes && mean && std_in && out, "nfe_plane_normalize: null pointer");
     NFE_REQUIRE(n_slabs >= 0 && hw >= 1, "nfe_plane_normalize: bad sizes");
     if (n_slabs == 0) return 0;
@@ -180,6 +182,7 @@ NFE_EXPORT int nfe_plane_normalize(const float* planes, const float* mean, const
 NFE_EXPORT int nfe_plane_denormalize(const float* norm, const float* mean, const float* std_in, int64_t n_slabs, int64_t stat_slabs,
                                      int64_t hw, float* out, nfe_stream_t stream)
 {
+    if (n_slabs == 0 || hw == 0) return 0;
     NFE_REQUIRE(norm && mean && std_in && out, "nfe_plane_denormalize: null pointer");
     NFE_REQUIRE(n_slabs >= 0 && hw >= 1 && stat_slabs >= 1, "nfe_plane_denormalize: bad sizes");
     if (n_slabs == 0) return 0;
@@ -192,6 +195,7 @@ NFE_EXPORT int nfe_plane_denormalize(const float* norm, const float* mean, const
 
 NFE_EXPORT int nfe_planes_to_channel_last(const float* planes, int64_t n_img, int channels, int64_t hw, float* out, nfe_stream_t stream)
 {
+    if (n_img == 0 || hw == 0) return 0;
     NFE_REQUIRE(planes && out, "nfe_planes_to_channel_last: null pointer");
     NFE_REQUIRE(n_img >= 0 && channels >= 1 && channels <= 256 && hw >= 1, "nfe_planes_to_channel_last: bad sizes");
     if (n_img == 0) return 0;

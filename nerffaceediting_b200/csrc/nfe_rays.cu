@@ -109,6 +109,7 @@ using namespace nfe;
 NFE_EXPORT int nfe_generate_rays(const float* cam2world, const float* intrinsics, int n, int resolution, float* origins, float* dirs,
                                  nfe_stream_t stream)
 {
+    if (n == 0) return 0;
     NFE_REQUIRE(cam2world && intrinsics && origins && dirs, "nfe_generate_rays: null pointer");
     NFE_REQUIRE(n >= 0 && resolution >= 1 && resolution <= 16384, "nfe_generate_rays: bad sizes");
     const int64_t total = (int64_t)n * resolution * resolution;
@@ -121,6 +122,7 @@ NFE_EXPORT int nfe_generate_rays(const float* cam2world, const float* intrinsics
 NFE_EXPORT int nfe_ray_limits_box(const float* origins, const float* dirs, int64_t n_rays, float box_side_length, float* tmin, float* tmax,
                                   nfe_stream_t stream)
 {
+    if (n_rays <= 0) return 0;
     NFE_REQUIRE(origins && dirs && tmin && tmax, "nfe_ray_limits_box: null pointer");
     if (n_rays <= 0) return 0;
     const float hi = 1.0f * (box_side_length / 2.0f), lo = -1.0f * (box_side_length / 2.0f);
@@ -133,6 +135,7 @@ NFE_EXPORT int nfe_sample_stratified(int64_t n_rays, int s_c, int mode, const fl
                                      const float* start_per_ray, const float* end_per_ray, const float* jitter, int stochastic,
                                      uint64_t seed, uint64_t offset, float* depths, nfe_stream_t stream)
 {
+    if (n_rays <= 0) return 0;
     NFE_REQUIRE(depths, "nfe_sample_stratified: null output");
     NFE_REQUIRE(s_c >= 2, "nfe_sample_stratified: depth_resolution must be >= 2 (got %d)", s_c);
     NFE_REQUIRE(mode >= 0 && mode <= 2, "nfe_sample_stratified: bad mode %d", mode);

@@ -79,6 +79,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
 {
     if (int rc = check_cfg(cfg, "nfe_render_fwd")) return rc;
     if (int rc = check_decoder_dims(cfg->kind, net_a, net_b, "nfe_render_fwd")) return rc;
+    if ((int64_t)n * n_rays == 0) return 0;  // empty tensors carry null pointers
     NFE_REQUIRE(planes_denorm_cl && origins && dirs && depths_coarse && rgb && depth && wsum, "nfe_render_fwd: null pointer");
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_render_fwd: the disentangled decoder needs the normalised planes");
     NFE_REQUIRE(cfg->seg_dim == 0 || seg, "nfe_render_fwd: seg output missing");
@@ -101,7 +102,10 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
     f.m = n_rays * sc; f.total = rays * sc;
     f.sigma = w.sigma_c; f.rgb = w.rgb_c; f.seg = w.seg_c;
     f.density_noise = cfg->density_noise; f.seed = cfg->seed; f.offset = cfg->offset + 1;
-    if (int rc = launch_field(cfg->kind, f, net_a, net_b, stream)) return rc;
+    {
+        StageScope t(STAGE_FIELD_COARSE, stream);
+        if (int rc = launch_field(cfg->kind, f, net_a, net_b, stream)) return rc;
+    }
 
     if (int rc = launch_init_minmax(minmax, stream)) return rc;
     MarchArgs m = {};
@@ -110,21 +114,31 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
         // ---- coarse weights (renderer.py:118,340) and importance resampling (:120,342)
         float* wc = weights_coarse_out ? weights_coarse_out : w.w_c;
         m.depths1 = depths_coarse; m.sigma1 = w.sigma_c; m.s1 = sc; m.s2 = 0; m.cc = 0; m.cs = 0; m.weights = wc;
-        if (int rc = launch_march(m, false, stream)) return rc;
+        {
+            StageScope t(STAGE_MARCH_COARSE, stream);
+            if (int rc = launch_march(m, false, stream)) return rc;
+        }
         float* df = depths_fine_out ? depths_fine_out : w.depths_f;
         ResampleArgs r = {};
         r.z_vals = depths_coarse; r.weights = wc; r.n_rays = rays; r.S = sc; r.s_f = sf; r.smooth = 1; r.eps = 1e-5f;
         r.u = cfg->stochastic ? nullptr : u_fine; r.u_per_ray = 0; r.seed = cfg->seed; r.offset = cfg->offset + 2; r.out = df;
-        if (int rc = launch_resample(r, stream)) return rc;
+        {
+            StageScope t(STAGE_RESAMPLE, stream);
+            if (int rc = launch_resample(r, stream)) return rc;
+        }
         // ---- fine pass (renderer.py:122-129,344-353)
         f.depths = df; f.s_per_ray = sf; f.m = n_rays * sf; f.total = rays * sf;
         f.sigma = w.sigma_f; f.rgb = w.rgb_f; f.seg = w.seg_f; f.offset = cfg->offset + 3;
-        if (int rc = launch_field(cfg->kind, f, net_a, net_b, stream)) return rc;
+        {
+            StageScope t(STAGE_FIELD_FINE, stream);
+            if (int rc = launch_field(cfg->kind, f, net_a, net_b, stream)) return rc;
+        }
         // ---- merge + composite (renderer.py:131-135,355-359)
         m.depths2 = df; m.colors2 = w.rgb_f; m.segs2 = w.seg_f; m.sigma2 = w.sigma_f; m.s2 = sf;
     }
     m.depths1 = depths_coarse; m.colors1 = w.rgb_c; m.segs1 = w.seg_c; m.sigma1 = w.sigma_c; m.s1 = sc;
     m.cc = 32; m.cs = cfg->seg_dim; m.rgb = rgb; m.seg = seg; m.depth = depth; m.wsum = wsum; m.weights = nullptr; m.minmax = minmax;
+    StageScope t(STAGE_MARCH_FINAL, stream);
     if (int rc = launch_march(m, sf > 0, stream)) return rc;
     if (finish_depth) return launch_finish_depth(depth, rays, minmax, stream);
     return 0;

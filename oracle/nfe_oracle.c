@@ -265,7 +265,8 @@ static inline float nfo_softplus(float x) { return x > 20.0f ? x : log1pf(expf(x
 static inline float nfo_sigmoid(float x) { return 1.0f / (1.0f + expf(-x)); }
 
 /* y[out] = FC2(Softplus(FC1(x[in])));  gains applied to the parameters in fp32 first. */
-static void nfo_mlp_eval(const nfo_mlp* p, const float* x, float* y)
+/* Normative definition, kept for reading; the callers below use nfo_mlp_eval_fast. */
+static __attribute__((unused)) void nfo_mlp_eval(const nfo_mlp* p, const float* x, float* y)
 {
     float h[256];
     for (int j = 0; j < p->hidden; ++j) {
@@ -280,6 +281,54 @@ static void nfo_mlp_eval(const nfo_mlp* p, const float* x, float* y)
         const float b = p->bgain2 != 1.0f ? p->b2[o] * p->bgain2 : p->b2[o];
         y[o] = b + acc;
     }
+}
+
+/* The same arithmetic, laid out for speed (the CPU-baseline legs of bench.py time this file):
+ * gains folded once, weights transposed so that the loops over hidden units / outputs are the
+ * contiguous (vectorisable) ones.  Every output still accumulates its products in ascending
+ * k (resp. j) order starting from 0, so results are bit-identical to nfo_mlp_eval. */
+typedef struct {
+    float w1t[64 * 256];   /* [in][hidden]  */
+    float b1[256];
+    float w2t[256 * 64];   /* [hidden][out] */
+    float b2[64];
+    int in_dim, hidden, out_dim;
+} nfo_mlp_fast;
+
+static int nfo_mlp_prepare(const nfo_mlp* p, nfo_mlp_fast* f)
+{
+    if (!p) { f->in_dim = f->hidden = f->out_dim = 0; return 0; }
+    if (p->in_dim > 64 || p->hidden > 256 || p->out_dim > 64) return 1;
+    f->in_dim = p->in_dim; f->hidden = p->hidden; f->out_dim = p->out_dim;
+    for (int j = 0; j < p->hidden; ++j) {
+        for (int k = 0; k < p->in_dim; ++k) f->w1t[k * p->hidden + j] = p->w1[j * p->in_dim + k] * p->wgain1;
+        f->b1[j] = p->bgain1 != 1.0f ? p->b1[j] * p->bgain1 : p->b1[j];
+    }
+    for (int o = 0; o < p->out_dim; ++o) {
+        for (int j = 0; j < p->hidden; ++j) f->w2t[j * p->out_dim + o] = p->w2[o * p->hidden + j] * p->wgain2;
+        f->b2[o] = p->bgain2 != 1.0f ? p->b2[o] * p->bgain2 : p->b2[o];
+    }
+    return 0;
+}
+
+static void nfo_mlp_eval_fast(const nfo_mlp_fast* f, const float* x, float* y)
+{
+    float h[256], acc[256];
+    const int H = f->hidden, O = f->out_dim;
+    for (int j = 0; j < H; ++j) acc[j] = 0.0f;
+    for (int k = 0; k < f->in_dim; ++k) {
+        const float xk = x[k];
+        const float* w = f->w1t + k * H;
+        for (int j = 0; j < H; ++j) acc[j] += xk * w[j];
+    }
+    for (int j = 0; j < H; ++j) h[j] = nfo_softplus(f->b1[j] + acc[j]);
+    for (int o = 0; o < O; ++o) acc[o] = 0.0f;
+    for (int j = 0; j < H; ++j) {
+        const float hj = h[j];
+        const float* w = f->w2t + j * O;
+        for (int o = 0; o < O; ++o) acc[o] += hj * w[o];
+    }
+    for (int o = 0; o < O; ++o) y[o] = f->b2[o] + acc[o];
 }
 
 NFO_API void nfo_fc(const float* x, int64_t rows, int in_dim, int out_dim, const float* weight,
@@ -303,24 +352,24 @@ enum { NFO_DEC_OSG = 0, NFO_DEC_DISENTANGLED = 1, NFO_DEC_SEGMENTATION = 2 };
  *                                         app_net(f_denorm)  -> rgb = sig(a)
  *   Segmentation   (triplane.py:209-230): net(f_denorm) as OSG; seg_net(f_denorm) -> seg
  * For OSG the single feature tensor is passed as f_denorm. */
-static inline void nfo_decode_sample(int kind, const nfo_mlp* net_a, const nfo_mlp* net_b,
+static inline void nfo_decode_sample(int kind, const nfo_mlp_fast* net_a, const nfo_mlp_fast* net_b,
                                      const float* f_norm, const float* f_denorm,
                                      float* sigma, float* rgb, float* seg)
 {
     float y[256];
     if (kind == NFO_DEC_OSG || kind == NFO_DEC_SEGMENTATION) {
-        nfo_mlp_eval(net_a, f_denorm, y);
+        nfo_mlp_eval_fast(net_a, f_denorm, y);
         *sigma = y[0];
         for (int c = 1; c < net_a->out_dim; ++c) rgb[c - 1] = nfo_sigmoid(y[c]) * 1.002f - 0.001f;
         if (kind == NFO_DEC_SEGMENTATION) {
-            nfo_mlp_eval(net_b, f_denorm, y);
+            nfo_mlp_eval_fast(net_b, f_denorm, y);
             for (int c = 0; c < net_b->out_dim; ++c) seg[c] = y[c];
         }
     } else {
-        nfo_mlp_eval(net_a, f_norm, y);          /* geo_net */
+        nfo_mlp_eval_fast(net_a, f_norm, y);     /* geo_net */
         *sigma = y[0];
         for (int c = 1; c < net_a->out_dim; ++c) seg[c - 1] = y[c];
-        nfo_mlp_eval(net_b, f_denorm, y);        /* app_net */
+        nfo_mlp_eval_fast(net_b, f_denorm, y);   /* app_net */
         for (int c = 0; c < net_b->out_dim; ++c) rgb[c] = nfo_sigmoid(y[c]) * 1.002f - 0.001f;
     }
 }
@@ -336,6 +385,9 @@ NFO_API void nfo_decoder(int kind, const nfo_mlp* net_a, const nfo_mlp* net_b,
                          int n, int64_t m, int C, int color_dim, int seg_dim,
                          float* rgb /*[N,M,color]*/, float* sigma /*[N,M]*/, float* seg /*[N,M,seg]*/)
 {
+    nfo_mlp_fast* fa = (nfo_mlp_fast*)malloc(2 * sizeof(nfo_mlp_fast));
+    nfo_mlp_fast* fb = fa + 1;
+    if (nfo_mlp_prepare(net_a, fa) || nfo_mlp_prepare(net_b, fb)) { free(fa); return; }
 #pragma omp parallel for collapse(2) schedule(static)
     for (int b = 0; b < n; ++b) {
         for (int64_t i = 0; i < m; ++i) {
@@ -347,10 +399,11 @@ NFO_API void nfo_decoder(int kind, const nfo_mlp* net_a, const nfo_mlp* net_b,
             nfo_plane_mean(feat_denorm + (base + i) * C, feat_denorm + (base + m + i) * C,
                            feat_denorm + (base + 2 * m + i) * C, C, fd);
             const int64_t s = (int64_t)b * m + i;
-            nfo_decode_sample(kind, net_a, net_b, fn, fd, sigma + s, rgb + s * color_dim,
+            nfo_decode_sample(kind, fa, fb, fn, fd, sigma + s, rgb + s * color_dim,
                               seg ? seg + s * seg_dim : NULL);
         }
     }
+    free(fa);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -519,7 +572,7 @@ typedef struct {
     float density_noise;      /* must be 0 here: the oracle has no RNG */
 } nfo_render_cfg;
 
-static void nfo_eval_point(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const nfo_mlp* net_b,
+static void nfo_eval_point(const nfo_render_cfg* cfg, const nfo_mlp_fast* net_a, const nfo_mlp_fast* net_b,
                            const float* pl_norm /*channel-last [3,H,W,C] or NULL*/, const float* pl_denorm,
                            const float x[3], float* sigma, float* rgb, float* seg)
 {
@@ -564,6 +617,9 @@ NFO_API int nfo_render(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const nf
     const int S_c = cfg->s_c, S_f = cfg->s_f, S_all = S_c + S_f;
     const int cc = cfg->color_dim, cs = cfg->seg_dim;
     if (S_all > 768 || cc > 64 || cs > 64 || cfg->C > 64) return 1;
+    nfo_mlp_fast* fa = (nfo_mlp_fast*)malloc(2 * sizeof(nfo_mlp_fast));
+    nfo_mlp_fast* fb = fa + 1;
+    if (nfo_mlp_prepare(net_a, fa) || nfo_mlp_prepare(net_b, fb)) { free(fa); return 1; }
     const int64_t hw = (int64_t)cfg->H * cfg->W;
     float* cl_norm = planes_norm ? nfo_to_channel_last(planes_norm, (int64_t)plane_batch * 3, cfg->C, hw) : NULL;
     float* cl_denorm = nfo_to_channel_last(planes_denorm, (int64_t)plane_batch * 3, cfg->C, hw);
@@ -589,7 +645,7 @@ NFO_API int nfo_render(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const nf
             const float t = depths_coarse[ray * S_c + s];
             t_all[s] = t;
             const float x[3] = { o[0] + t * d[0], o[1] + t * d[1], o[2] + t * d[2] };
-            nfo_eval_point(cfg, net_a, net_b, pn, pd, x, sg_all + s, col_all + (size_t)s * cc, seg_all + (size_t)s * cs);
+            nfo_eval_point(cfg, fa, fb, pn, pd, x, sg_all + s, col_all + (size_t)s * cc, seg_all + (size_t)s * cs);
         }
         int S = S_c;
         float rgbv[64], segv[64], dep, ws;
@@ -601,7 +657,7 @@ NFO_API int nfo_render(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const nf
             for (int s = S_c; s < S_all; ++s) {
                 const float t = t_all[s];
                 const float x[3] = { o[0] + t * d[0], o[1] + t * d[1], o[2] + t * d[2] };
-                nfo_eval_point(cfg, net_a, net_b, pn, pd, x, sg_all + s, col_all + (size_t)s * cc, seg_all + (size_t)s * cs);
+                nfo_eval_point(cfg, fa, fb, pn, pd, x, sg_all + s, col_all + (size_t)s * cc, seg_all + (size_t)s * cs);
             }
             S = S_all;
             /* unify_samples: permute everything into depth order */
@@ -630,7 +686,7 @@ NFO_API int nfo_render(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const nf
         free(t_all);
     }
     for (int64_t ray = 0; ray < total; ++ray) depth[ray] = nfo_finish_depth(depth[ray], gmin, gmax);
-    free(cl_norm); free(cl_denorm);
+    free(cl_norm); free(cl_denorm); free(fa);
     return 0;
 }
 
@@ -641,6 +697,9 @@ NFO_API int nfo_run_model(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const
                           float* rgb, float* sigma, float* seg)
 {
     if (cfg->color_dim > 64 || cfg->seg_dim > 64 || cfg->C > 64) return 1;
+    nfo_mlp_fast* fa = (nfo_mlp_fast*)malloc(2 * sizeof(nfo_mlp_fast));
+    nfo_mlp_fast* fb = fa + 1;
+    if (nfo_mlp_prepare(net_a, fa) || nfo_mlp_prepare(net_b, fb)) { free(fa); return 1; }
     const int64_t hw = (int64_t)cfg->H * cfg->W;
     float* cl_norm = planes_norm ? nfo_to_channel_last(planes_norm, (int64_t)plane_batch * 3, cfg->C, hw) : NULL;
     float* cl_denorm = nfo_to_channel_last(planes_denorm, (int64_t)plane_batch * 3, cfg->C, hw);
@@ -649,10 +708,10 @@ NFO_API int nfo_run_model(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const
     for (int64_t i = 0; i < (int64_t)n * m; ++i) {
         const int pb = plane_batch == 1 ? 0 : (int)(i / m);
         float segv[64];
-        nfo_eval_point(cfg, net_a, net_b, cl_norm ? cl_norm + pb * set_sz : NULL, cl_denorm + pb * set_sz,
+        nfo_eval_point(cfg, fa, fb, cl_norm ? cl_norm + pb * set_sz : NULL, cl_denorm + pb * set_sz,
                        coords + i * 3, sigma + i, rgb + i * cfg->color_dim, seg ? seg + i * cfg->seg_dim : segv);
     }
-    free(cl_norm); free(cl_denorm);
+    free(cl_norm); free(cl_denorm); free(fa);
     return 0;
 }
 
