@@ -33,43 +33,35 @@ __global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int S = a.s1 + a.s2;
-    float* s_depth = smem + (size_t)warp * 4 * S;
+    float* s_depth = smem + (size_t)warp * MARCH_SMEM_FLOATS_PER_SAMPLE * S;
     float* s_sigma = s_depth + S;
     float* s_w = s_sigma + S;
     int* s_order = reinterpret_cast<int*>(s_w + S);
+    float* s_raw = s_w + 2 * S;  // unsorted sigma while ranking
     float blk_min = __int_as_float(0x7f800000), blk_max = __int_as_float(0xff800000);
 
     for (int64_t ray = (int64_t)blockIdx.x * warps_per_block + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * warps_per_block) {
         // ---- load (and merge) depths / densities
         if (SORT) {
-            // stage the concatenation in s_w (depth) / s_order (sigma bits), then rank-sort (stable:
-            // ties keep concatenation order, i.e. coarse before fine)
+            // stage the concatenation in s_w (depth) / s_raw (sigma), then rank-sort (stable: ties keep
+            // concatenation order, i.e. coarse before fine).  The coarse list is already sorted and, in
+            // parity mode, so is the fine list; a rank sort is also right for the stochastic mode's
+            // unsorted fine depths (renderer.py:237).
             for (int e = lane; e < S; e += 32) {
                 const bool first = e < a.s1;
                 s_w[e] = first ? a.depths1[ray * a.s1 + e] : a.depths2[ray * a.s2 + (e - a.s1)];
-                s_order[e] = __float_as_int(first ? a.sigma1[ray * a.s1 + e] : a.sigma2[ray * a.s2 + (e - a.s1)]);
+                s_raw[e] = first ? a.sigma1[ray * a.s1 + e] : a.sigma2[ray * a.s2 + (e - a.s1)];
             }
             __syncwarp();
-            int my_rank[MAX_S / 32];
-            float my_d[MAX_S / 32], my_s[MAX_S / 32];
-#pragma unroll
-            for (int k = 0; k < MAX_S / 32; ++k) {
-                const int e = lane + 32 * k;
-                if (e < S) {
-                    const float d = s_w[e];
-                    int rank = 0;
-                    for (int j = 0; j < S; ++j) {
-                        const float dj = s_w[j];
-                        rank += (dj < d) || (dj == d && j < e);
-                    }
-                    my_rank[k] = rank; my_d[k] = d; my_s[k] = __int_as_float(s_order[e]);
+            for (int e = lane; e < S; e += 32) {
+                const float d = s_w[e];
+                int rank = 0;
+#pragma unroll 4
+                for (int j = 0; j < S; ++j) {
+                    const float dj = s_w[j];
+                    rank += (dj < d) || (dj == d && j < e);
                 }
-            }
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < MAX_S / 32; ++k) {
-                const int e = lane + 32 * k;
-                if (e < S) { s_depth[my_rank[k]] = my_d[k]; s_sigma[my_rank[k]] = my_s[k]; s_order[my_rank[k]] = e; }
+                s_depth[rank] = d; s_sigma[rank] = s_raw[e]; s_order[rank] = e;
             }
         } else {
             for (int e = lane; e < S; e += 32) {
@@ -127,19 +119,31 @@ __global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
                 const bool on = c < a.cc;
                 const bool seg_on = (c0 == 0) && lane < a.cs;
                 float acc = 0.0f, acc_s = 0.0f, prev = 0.0f, prev_s = 0.0f;
-                for (int k = 0; k < S; ++k) {
-                    const int e = s_order[k];
-                    const bool first = e < a.s1;
-                    const int64_t row = first ? ray * a.s1 + e : ray * a.s2 + (e - a.s1);
-                    float cur = 0.0f, cur_s = 0.0f;
-                    if (on) cur = __ldg((first ? a.colors1 : a.colors2) + row * a.cc + c);
-                    if (seg_on) cur_s = __ldg((first ? a.segs1 : a.segs2) + row * a.cs + lane);
-                    if (k > 0) {
-                        const float w = s_w[k - 1];
-                        acc = fmaf(w, (prev + cur) * 0.5f, acc);
-                        acc_s = fmaf(w, (prev_s + cur_s) * 0.5f, acc_s);
+                constexpr int UN = 8;  // rows fetched together: the loads are independent, only the sums chain
+                for (int k0 = 0; k0 < S; k0 += UN) {
+                    float cur[UN], cur_s[UN];
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        const int k = k0 + u;
+                        cur[u] = 0.0f; cur_s[u] = 0.0f;
+                        if (k < S) {
+                            const int e = s_order[k];
+                            const bool first = e < a.s1;
+                            const int64_t row = first ? ray * a.s1 + e : ray * a.s2 + (e - a.s1);
+                            if (on) cur[u] = __ldg((first ? a.colors1 : a.colors2) + row * a.cc + c);
+                            if (seg_on) cur_s[u] = __ldg((first ? a.segs1 : a.segs2) + row * a.cs + lane);
+                        }
                     }
-                    prev = cur; prev_s = cur_s;
+#pragma unroll
+                    for (int u = 0; u < UN; ++u) {
+                        const int k = k0 + u;
+                        if (k > 0 && k < S) {
+                            const float w = s_w[k - 1];
+                            acc = fmaf(w, (prev + cur[u]) * 0.5f, acc);
+                            acc_s = fmaf(w, (prev_s + cur_s[u]) * 0.5f, acc_s);
+                        }
+                        prev = cur[u]; prev_s = cur_s[u];
+                    }
                 }
                 if (on) {
                     if (a.white_back) acc = acc + 1.0f - wt;
@@ -321,13 +325,16 @@ __global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a)
     }
 }
 
-static int warps_for(int S)
+static int warps_for(int S, int floats_per_sample)
 {
-    // 16*S bytes of shared memory per warp; keep a block under ~96 KB
+    // floats_per_sample*4*S bytes of shared memory per warp; keep a block under ~96 KB
     int w = 8;
-    while (w > 1 && (size_t)w * 16 * S > 96 * 1024) w >>= 1;
+    while (w > 1 && (size_t)w * floats_per_sample * 4 * S > 96 * 1024) w >>= 1;
     return w;
 }
+
+// dynamic shared memory above the default 48 KB (minus the kernels' small static arrays) needs an opt-in
+static constexpr size_t SMEM_OPT_IN = 40 * 1024;
 
 int launch_march(const MarchArgs& a, bool sort, cudaStream_t stream)
 {
@@ -335,16 +342,16 @@ int launch_march(const MarchArgs& a, bool sort, cudaStream_t stream)
     NFE_REQUIRE(S >= 2 && S <= MAX_S, "ray march: %d samples per ray unsupported (2..%d)", S, MAX_S);
     NFE_REQUIRE(a.cs <= 32, "ray march: at most 32 semantic channels (got %d)", a.cs);
     if (a.n_rays <= 0) return 0;
-    const int warps = warps_for(S);
-    const size_t smem = (size_t)warps * 16 * S;
+    const int warps = warps_for(S, MARCH_SMEM_FLOATS_PER_SAMPLE);
+    const size_t smem = (size_t)warps * MARCH_SMEM_FLOATS_PER_SAMPLE * 4 * S;
     const int64_t blocks = (a.n_rays + warps - 1) / warps;
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
     if (sort) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > SMEM_OPT_IN) cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         march_kernel<true><<<grid, warps * 32, smem, stream>>>(a);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > SMEM_OPT_IN) cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         march_kernel<false><<<grid, warps * 32, smem, stream>>>(a);
     }
     return check_launch("march_kernel");
@@ -369,16 +376,16 @@ int launch_resample(const ResampleArgs& a, cudaStream_t stream)
     NFE_REQUIRE(a.smooth || (a.ns >= 1 && a.ns < a.S), "sample_pdf: %d weights need at least %d bins (got %d)", a.ns, a.ns + 1, a.S);
     NFE_REQUIRE(a.s_f >= 1, "importance resampling: need at least one importance sample");
     if (a.n_rays <= 0) return 0;
-    const int warps = warps_for(a.S);
+    const int warps = warps_for(a.S, 4);
     const size_t smem = (size_t)warps * 16 * a.S;
     const int64_t blocks = (a.n_rays + warps - 1) / warps;
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
     if (a.smooth) {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(resample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > SMEM_OPT_IN) cudaFuncSetAttribute(resample_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         resample_kernel<true><<<grid, warps * 32, smem, stream>>>(a);
     } else {
-        if (smem > 48 * 1024) cudaFuncSetAttribute(resample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > SMEM_OPT_IN) cudaFuncSetAttribute(resample_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         resample_kernel<false><<<grid, warps * 32, smem, stream>>>(a);
     }
     return check_launch("resample_kernel");
@@ -455,7 +462,7 @@ NFE_EXPORT int nfe_unify_samples(const float* depths1, const float* colors1, con
     a.depths2 = depths2; a.colors2 = colors2; a.segs2 = segs2; a.sigma2 = sigma2; a.s2 = s2;
     a.n_rays = n_rays; a.cc = cc; a.cs = cs;
     int warps = 8;
-    while (warps > 1 && (size_t)warps * 8 * S > 48 * 1024) warps >>= 1;
+    while (warps > 1 && (size_t)warps * 8 * S > SMEM_OPT_IN) warps >>= 1;
     const size_t smem = (size_t)warps * 8 * S;
     const int64_t blocks = (n_rays + warps - 1) / warps;
     const int64_t cap = (int64_t)sm_count() * 8;

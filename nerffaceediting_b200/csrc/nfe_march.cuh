@@ -4,6 +4,7 @@
 
 namespace nfe {
 
+constexpr int MARCH_SMEM_FLOATS_PER_SAMPLE = 5;  // depth, sigma, weight, order, unsorted sigma
 constexpr int MAX_S = 768;  // merged samples per ray (reference configs go up to 192+192)
 
 struct MarchArgs {
