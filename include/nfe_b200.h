@@ -96,9 +96,16 @@ typedef struct {
 
 enum { NFE_DEC_OSG = 0, NFE_DEC_DISENTANGLED = 1, NFE_DEC_SEGMENTATION = 2 };
 
+/* Arithmetic of the decoder MLPs (everything else on the path is fp32 in every mode):
+ *   NFE_PREC_FP32    fp32 FFMA on the CUDA cores;
+ *   NFE_PREC_BF16X3  tcgen05 tensor cores, each product as 3 bf16 MMAs (hi*hi + lo*hi + hi*lo),
+ *                    fp32 accumulation in TMEM: fp32-grade results (meets the 1e-4 tolerance);
+ *   NFE_PREC_BF16    tcgen05 tensor cores, plain bf16 operands (1e-2 tolerance). */
+enum { NFE_PREC_FP32 = 0, NFE_PREC_BF16X3 = 1, NFE_PREC_BF16 = 2 };
+
 /* decoder(sampled_features[n,3,m,C], ray_directions) stand-alone.  feat_norm may be NULL for
  * OSG / Segmentation (which ignore it).  rgb [n,m,color_dim], sigma [n,m], seg [n,m,seg_dim]. */
-int nfe_decoder_fwd(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* feat_norm,
+int nfe_decoder_fwd(int kind, int precision, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* feat_norm,
                     const float* feat_denorm, int n, int64_t m, int channels, float* rgb, float* sigma,
                     float* seg, nfe_stream_t stream);
 
@@ -147,8 +154,6 @@ typedef struct {
     uint64_t seed, offset;   /* Philox stream for stochastic mode / density noise */
     int precision;           /* NFE_PREC_* : arithmetic of the decoder MLPs */
 } nfe_render_cfg;
-
-enum { NFE_PREC_FP32 = 0, NFE_PREC_BF16X3 = 1, NFE_PREC_BF16 = 2 };
 
 /* bytes of device workspace nfe_render_fwd needs for n*n_rays rays with this cfg */
 int64_t nfe_render_workspace_bytes(const nfe_render_cfg* cfg, int n, int64_t n_rays);

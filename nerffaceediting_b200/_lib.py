@@ -52,7 +52,7 @@ SIGNATURES = {
     "nfe_ray_limits_box": (c_int, [c_vp, c_vp, c_i64, c_float, c_vp, c_vp, c_vp]),
     "nfe_sample_stratified": (c_int, [c_i64, c_int, c_int, c_vp, c_double, c_double, c_vp, c_vp, c_vp, c_int, c_u64, c_u64, c_vp, c_vp]),
     "nfe_sample_planes_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_i64, c_float, c_vp, c_vp]),
-    "nfe_decoder_fwd": (c_int, [c_int, _MLP_P, _MLP_P, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
+    "nfe_decoder_fwd": (c_int, [c_int, c_int, _MLP_P, _MLP_P, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp, c_vp, c_vp]),
     "nfe_composite_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "nfe_importance_resample": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_vp, c_int, c_u64, c_u64, c_vp, c_vp, c_vp, c_vp]),
     "nfe_sample_pdf": (c_int, [c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp, c_int, c_u64, c_u64, c_float, c_vp, c_vp]),

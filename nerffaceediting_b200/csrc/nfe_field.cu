@@ -254,9 +254,10 @@ int check_decoder_dims(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, con
     return 0;
 }
 
-int launch_field(int kind, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream)
+int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream)
 {
     if (a.total <= 0) return 0;
+    if (precision != NFE_PREC_FP32) return launch_field_tc(kind, precision, a, net_a, net_b, stream);
     nfe_mlp none = {};
     switch (kind) {
         case NFE_DEC_OSG: return launch_field_kind<NFE_DEC_OSG>(a, *net_a, none, stream);
@@ -307,9 +308,10 @@ static int launch_decoder(const nfe_mlp& a, const nfe_mlp& b, const float* fn, c
     return check_launch("decoder_kernel");
 }
 
-NFE_EXPORT int nfe_decoder_fwd(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* feat_norm, const float* feat_denorm, int n,
-                               int64_t m, int channels, float* rgb, float* sigma, float* seg, nfe_stream_t stream)
+NFE_EXPORT int nfe_decoder_fwd(int kind, int precision, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* feat_norm, const float* feat_denorm,
+                               int n, int64_t m, int channels, float* rgb, float* sigma, float* seg, nfe_stream_t stream)
 {
+    NFE_REQUIRE(precision >= NFE_PREC_FP32 && precision <= NFE_PREC_BF16, "nfe_decoder_fwd: unknown precision mode %d", precision);
     if (int rc = check_decoder_dims(kind, net_a, net_b, "nfe_decoder_fwd")) return rc;
     NFE_REQUIRE(channels == FEAT, "nfe_decoder_fwd: features must have %d channels (got %d)", FEAT, channels);
     if ((int64_t)n * m == 0) return 0;
@@ -317,6 +319,7 @@ NFE_EXPORT int nfe_decoder_fwd(int kind, const nfe_mlp* net_a, const nfe_mlp* ne
     NFE_REQUIRE(kind != NFE_DEC_DISENTANGLED || feat_norm, "nfe_decoder_fwd: the disentangled decoder needs feat_norm");
     NFE_REQUIRE(kind == NFE_DEC_OSG || seg, "nfe_decoder_fwd: seg output missing");
     if ((int64_t)n * m == 0) return 0;
+    if (precision != NFE_PREC_FP32) return launch_decoder_tc(kind, precision, net_a, net_b, feat_norm, feat_denorm, n, m, rgb, sigma, seg, as_stream(stream));
     nfe_mlp none = {};
     switch (kind) {
         case NFE_DEC_OSG: return launch_decoder<NFE_DEC_OSG>(*net_a, none, feat_norm, feat_denorm, n, m, rgb, sigma, seg, as_stream(stream));
@@ -338,7 +341,7 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_run_model_fwd: the disentangled decoder needs the normalised planes");
     NFE_REQUIRE(cfg->kind == NFE_DEC_OSG || seg, "nfe_run_model_fwd: seg output missing");
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_run_model_fwd: plane batch %d does not match point batch %d", plane_batch, n);
-    NFE_REQUIRE(cfg->precision == NFE_PREC_FP32, "nfe_run_model_fwd: precision mode %d not built", cfg->precision);
+    NFE_REQUIRE(cfg->precision >= NFE_PREC_FP32 && cfg->precision <= NFE_PREC_BF16, "nfe_run_model_fwd: unknown precision mode %d", cfg->precision);
     FieldArgs a = {};
     a.set_norm = planes_norm_cl; a.set_denorm = planes_denorm_cl; a.plane_batch = plane_batch; a.H = cfg->height; a.W = cfg->width;
     a.scale = (float)(2.0 / (double)cfg->box_warp);
@@ -346,5 +349,5 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     a.sigma = sigma; a.rgb = rgb; a.seg = seg;
     a.density_noise = cfg->density_noise; a.seed = cfg->seed; a.offset = cfg->offset;
     StageScope t(STAGE_RUN_MODEL, as_stream(stream));
-    return launch_field(cfg->kind, a, net_a, net_b, as_stream(stream));
+    return launch_field(cfg->kind, cfg->precision, a, net_a, net_b, as_stream(stream));
 }

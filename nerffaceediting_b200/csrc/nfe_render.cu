@@ -59,7 +59,7 @@ int check_cfg(const nfe_render_cfg* cfg, const char* who)
     NFE_REQUIRE(cfg->color_dim == 32, "%s: decoder_output_dim must be 32 (got %d)", who, cfg->color_dim);
     NFE_REQUIRE(cfg->seg_dim == (cfg->kind == NFE_DEC_OSG ? 0 : 15), "%s: seg_dim %d unsupported for decoder kind %d", who, cfg->seg_dim, cfg->kind);
     NFE_REQUIRE(cfg->box_warp != 0.0f, "%s: box_warp must be non-zero", who);
-    NFE_REQUIRE(cfg->precision == NFE_PREC_FP32, "%s: precision mode %d not built", who, cfg->precision);
+    NFE_REQUIRE(cfg->precision >= NFE_PREC_FP32 && cfg->precision <= NFE_PREC_BF16, "%s: unknown precision mode %d", who, cfg->precision);
     return 0;
 }
 
@@ -104,7 +104,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
     f.density_noise = cfg->density_noise; f.seed = cfg->seed; f.offset = cfg->offset + 1;
     {
         StageScope t(STAGE_FIELD_COARSE, stream);
-        if (int rc = launch_field(cfg->kind, f, net_a, net_b, stream)) return rc;
+        if (int rc = launch_field(cfg->kind, cfg->precision, f, net_a, net_b, stream)) return rc;
     }
 
     if (int rc = launch_init_minmax(minmax, stream)) return rc;
@@ -131,7 +131,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
         f.sigma = w.sigma_f; f.rgb = w.rgb_f; f.seg = w.seg_f; f.offset = cfg->offset + 3;
         {
             StageScope t(STAGE_FIELD_FINE, stream);
-            if (int rc = launch_field(cfg->kind, f, net_a, net_b, stream)) return rc;
+            if (int rc = launch_field(cfg->kind, cfg->precision, f, net_a, net_b, stream)) return rc;
         }
         // ---- merge + composite (renderer.py:131-135,355-359)
         m.depths2 = df; m.colors2 = w.rgb_f; m.segs2 = w.seg_f; m.sigma2 = w.sigma_f; m.s2 = sf;

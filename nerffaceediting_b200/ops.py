@@ -265,7 +265,7 @@ class MlpRef:
         return ctypes.byref(self.c)
 
 
-def decoder_fwd(kind, seq_a, seq_b, feat_norm, feat_denorm):
+def decoder_fwd(kind, seq_a, seq_b, feat_norm, feat_denorm, precision=_lib.PREC_FP32):
     """decoder(sampled_features [N,3,M,32]...) -> dict(rgb [N,M,32], sigma [N,M,1][, seg [N,M,15]])."""
     fd = _cuda_f32(feat_denorm, "sampled_features")
     fn = _cuda_f32(feat_norm, "sampled_norm_features") if (feat_norm is not None and kind == DEC_DISENTANGLED) else None
@@ -278,7 +278,7 @@ def decoder_fwd(kind, seq_a, seq_b, feat_norm, feat_denorm):
     sigma = torch.empty((n, m, 1), device=fd.device, dtype=torch.float32)
     seg = torch.empty((n, m, 15), device=fd.device, dtype=torch.float32) if kind != DEC_OSG else None
     with _Guard(fd):
-        _lib.check(_lib.load().nfe_decoder_fwd(kind, a.ref(), b.ref() if b else None, _ptr(fn), _ptr(fd), n, m, c, _ptr(rgb), _ptr(sigma),
+        _lib.check(_lib.load().nfe_decoder_fwd(kind, int(precision), a.ref(), b.ref() if b else None, _ptr(fn), _ptr(fd), n, m, c, _ptr(rgb), _ptr(sigma),
                                                _ptr(seg), _stream(fd)), "nfe_decoder_fwd")
     out = {"rgb": rgb, "sigma": sigma}
     if seg is not None:
@@ -363,6 +363,17 @@ def unify_samples(depths1, colors1, sigma1, depths2, colors2, sigma2, segs1=None
 
 
 # ------------------------------------------------------------------------------- fused forward
+PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16x3": _lib.PREC_BF16X3, "bf16": _lib.PREC_BF16}
+
+
+def precision_of(options):
+    """rendering_options['nfe_precision'] -> NFE_PREC_* (decoder MLP arithmetic; default fp32 FFMA)."""
+    name = options.get('nfe_precision', 'fp32') if options is not None else 'fp32'
+    if name not in PRECISIONS:
+        raise RuntimeError(f"nfe_precision must be one of {sorted(PRECISIONS)}, got {name!r}")
+    return PRECISIONS[name]
+
+
 def make_cfg(kind, planes_cl, s_c, s_f, box_warp, white_back=False, density_noise=0.0, stochastic=False, seed=0, offset=0,
              precision=_lib.PREC_FP32):
     _, _, h, w, c = planes_cl.shape

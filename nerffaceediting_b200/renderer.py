@@ -12,6 +12,8 @@ Extra keys read from `rendering_options` (all optional; defaults reproduce the r
                             reference has no such switch (renderer.py:180-190,210-211); its always-on
                             jitter is drawn here from an in-kernel Philox stream seeded from torch's
                             CUDA generator (statistically, not bitwise, equal to torch.rand).
+  nfe_precision      'fp32' arithmetic of the decoder MLPs: 'fp32' (FFMA), 'bf16x3' (tcgen05 tensor cores, three
+                            bf16 MMAs per product, fp32-grade: meets the 1e-4 tolerance) or 'bf16' (tensor cores, 1e-2).
   nfe_cache_planes   False  keep the channel-last staging of the planes between calls (video sweeps).
 
 Instances hold no state of their own beyond the reference's attributes, so objects unpickled from
@@ -142,7 +144,8 @@ class ImportanceRenderer(torch.nn.Module):
         depths_coarse, seed, offset = self._coarse_depths(ray_origins, ray_directions, opts, deterministic)
         s_f = opts['depth_resolution_importance']
         cfg = ops.make_cfg(kind, denorm_cl, opts['depth_resolution'], s_f, opts['box_warp'], opts.get('white_back', False),
-                           opts.get('density_noise', 0) or 0.0, stochastic=not deterministic, seed=seed, offset=offset)
+                           opts.get('density_noise', 0) or 0.0, stochastic=not deterministic, seed=seed, offset=offset,
+                           precision=ops.precision_of(opts))
         u_fine = ops.linspace_table(0, 1, s_f, ray_origins.device) if (s_f > 0 and deterministic) else None
         rgb, seg, depth, wsum, _ = ops.render_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, ray_origins, ray_directions,
                                                   depths_coarse, u_fine)
@@ -192,7 +195,8 @@ class ImportanceRenderer(torch.nn.Module):
             norm_cl = ops.planes_channel_last(norm_planes, cache) if kind == ops.DEC_DISENTANGLED else None
             noise = options.get('density_noise', 0) or 0.0
             seed, offset = ops.philox_state(sample_coordinates.device) if noise > 0 else (0, 0)
-            cfg = ops.make_cfg(kind, denorm_cl, 2, 0, options['box_warp'], density_noise=noise, seed=seed, offset=offset)
+            cfg = ops.make_cfg(kind, denorm_cl, 2, 0, options['box_warp'], density_noise=noise, seed=seed, offset=offset,
+                               precision=ops.precision_of(options))
             return ops.run_model_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, sample_coordinates)
         axes = self.plane_axes
         feats = sample_from_planes(axes, planes, sample_coordinates, padding_mode='zeros', box_warp=options['box_warp'])
