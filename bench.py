@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16x3", "bf16"],
+                    help="decoder MLP arithmetic (rendering_options['nfe_precision'])")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -189,6 +191,9 @@ def main():
     mods = {"sampler": RaySampler(), "normalize_plane": normalize_plane, "renderer": DisentangledImportanceRenderer()}
 
     raw_host, dec, c2w_host, k_host, opts = make_inputs(torch, wl, device, 1000 + rank)
+    opts["nfe_precision"] = args.precision
+    dtype = {"fp32": "f32", "bf16x3": "f32 (gather, compositing) + bf16x3 split tensor-core MLP with f32 accumulate",
+             "bf16": "f32 (gather, compositing) + bf16 tensor-core MLP"}[args.precision]
     dec = dec.to(device)
     raw = raw_host.to(device)
     c2w, k = c2w_host.to(device), k_host.to(device)
@@ -278,7 +283,7 @@ def main():
                 traffic = None
         line = {
             "metric": "rendered rays/sec (48+48 samples)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": wl["desc"], "rays_per_gpu_per_step": rays_per_rank, "sampling": "deterministic (parity mode)",
                        "parallelism": f"batch-sharded x{world}, all-gather of rendered maps" if world > 1 else "single GPU",
                        "cache": "inputs larger than L2 (raw+normalised+staged planes ~0.8 GB per step), no L2 flush needed"},

@@ -257,7 +257,11 @@ int check_decoder_dims(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, con
 int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream)
 {
     if (a.total <= 0) return 0;
-    if (precision != NFE_PREC_FP32) return launch_field_tc(kind, precision, a, net_a, net_b, stream);
+    if (precision != NFE_PREC_FP32) {
+        // NFE_TC_SIMPLE=1 selects the single-role tensor-core kernel (kept as the readable baseline of the pipelined one)
+        static const bool simple = getenv("NFE_TC_SIMPLE") != nullptr;
+        return simple ? launch_field_tc(kind, precision, a, net_a, net_b, stream) : launch_field_pipe(kind, precision, a, net_a, net_b, stream);
+    }
     nfe_mlp none = {};
     switch (kind) {
         case NFE_DEC_OSG: return launch_field_kind<NFE_DEC_OSG>(a, *net_a, none, stream);

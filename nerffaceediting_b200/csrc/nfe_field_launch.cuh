@@ -31,6 +31,8 @@ int check_decoder_dims(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, con
 // precision: NFE_PREC_FP32 -> SIMT fp32 kernel; NFE_PREC_BF16X3 / NFE_PREC_BF16 -> tcgen05 kernels (nfe_field_tc.cu)
 int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream);
 int launch_field_tc(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream);
+// warp-specialised pipelined tensor-core kernel (nfe_field_pipe.cu): the production path for the tensor-core modes
+int launch_field_pipe(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream);
 int launch_decoder_tc(int kind, int precision, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* feat_norm, const float* feat_denorm,
                       int n, int64_t m, float* rgb, float* sigma, float* seg, cudaStream_t stream);
 

@@ -1,0 +1,355 @@
+// Warp-specialised fused gather + decode on the tensor cores: the production field kernel.
+//
+// One persistent CTA per SM, 13 warps with fixed roles, connected by mbarriers:
+//
+//   8 gather warps     tri-plane bilinear gather (L2/L1-bound: 24 texel lines of 128 B per sample) of a
+//                      128-sample tile -> bf16 hi/lo feature tile in a 2-stage shared-memory ring
+//   1 MMA warp         one elected thread issues tcgen05.mma for layer 1 (both nets) and layer 2,
+//                      accumulators in a double-buffered TMEM region; tcgen05.commit signals the
+//                      ring slot free and the accumulators full
+//   4 epilogue warps   thread m owns TMEM lane m = sample m: tcgen05.ld, softplus, bf16 split,
+//                      hidden tile -> shared (A operand of layer 2), then bias + sigmoid + stores
+//
+// While the epilogue warps finish tile i, the gather warps are already two tiles ahead and the
+// tensor core has run layer 1 of tile i+1, so the three resources (LSU/L2, tensor pipe, ALU/SFU)
+// overlap instead of taking turns as in the single-role kernel (nfe_field_tc.cu).
+#include "nfe_field_launch.cuh"
+#include "nfe_mlp_tc.cuh"
+
+namespace nfe {
+
+using namespace tcmlp;
+
+constexpr int GATHER_WARPS = 8;
+constexpr int EPI_WARPS = 4;
+constexpr int MMA_WARP = EPI_WARPS;                         // warp index of the MMA issuer
+constexpr int PIPE_THREADS = (EPI_WARPS + 1 + GATHER_WARPS) * 32;
+constexpr int ROWS_PER_GATHER_WARP = TILE_M / GATHER_WARPS; // 16 -> 4 passes of 4 samples
+constexpr int TMEM_BUF_COLS = 192;                          // D1A 64 | D1B 64 | D2A <=48 | D2B <=32 (OSG: 48+16)
+constexpr int PIPE_TMEM_COLS = 512;
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+template <int KIND, bool SPLIT>
+struct PipeSmem {
+    using T = TcTraits<KIND>;
+    static constexpr int PARTS = SPLIT ? 2 : 1;
+    static constexpr int NETS = T::HAS_B ? 2 : 1;
+    alignas(128) unsigned char a1[2][T::SETS][PARTS][A1_BYTES];   // feature ring
+    alignas(128) unsigned char b1[NETS][PARTS][B1_BYTES];
+    alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
+    alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
+    alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
+    float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
+    float bias2a[T::N_A];
+    float bias2b[T::N_B];
+    alignas(8) uint64_t full[2], empty[2], d1_full[2], d2a_full[2], d2b_full[2], tmem_free[2], a2_full;
+    uint32_t tmem_base;
+};
+
+// softplus in base-2 units: with t = x*log2(e), softplus(x) = ln2 * (max(t,0) + log2(1 + 2^-|t|)).
+// The ln2 factor is folded into the layer-2 weights, log2(e) into the bias (one FFMA makes t).
+__device__ __forceinline__ float softplus_log2(float t)
+{
+    float e, l;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
+    return fmaxf(t, 0.0f) + l;
+}
+
+template <int KIND, bool SPLIT>
+__device__ void pipe_load_params(PipeSmem<KIND, SPLIT>& s, const nfe_mlp& net_a, const nfe_mlp& net_b)
+{
+    using T = TcTraits<KIND>;
+    constexpr int PARTS = SPLIT ? 2 : 1;
+    load_weights<PARTS>(s.b1[0][0], B1_BYTES, net_a.w1, net_a.wgain1, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
+    // layer-2 weights carry the ln2 of softplus_log2: fold it into the gain
+    load_weights<PARTS>(s.b2a[0], sizeof(s.b2a[0]), net_a.w2, net_a.wgain2 * LN2, T::OUT_A, T::N_A, HIDDEN, B2_LBO, B2_SBO);
+    for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s.bias1[0][i] = folded_bias(net_a.b1, net_a.bgain1, i) * LOG2E;
+    for (int i = threadIdx.x; i < T::N_A; i += blockDim.x) s.bias2a[i] = i < T::OUT_A ? folded_bias(net_a.b2, net_a.bgain2, i) : 0.0f;
+    if constexpr (T::HAS_B) {
+        load_weights<PARTS>(s.b1[1][0], B1_BYTES, net_b.w1, net_b.wgain1, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
+        load_weights<PARTS>(s.b2b[0], sizeof(s.b2b[0]), net_b.w2, net_b.wgain2 * LN2, T::OUT_B, T::N_B, HIDDEN, B2_LBO, B2_SBO);
+        for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s.bias1[1][i] = folded_bias(net_b.b1, net_b.bgain1, i) * LOG2E;
+        for (int i = threadIdx.x; i < T::N_B; i += blockDim.x) s.bias2b[i] = i < T::OUT_B ? folded_bias(net_b.b2, net_b.bgain2, i) : 0.0f;
+    }
+}
+
+// hidden = softplus(D1 + b1) of one net for this thread's row, as packed bf16 parts in registers
+template <bool SPLIT>
+__device__ __forceinline__ void hidden_to_regs(uint32_t taddr_row, const float* bias1_log2, uint32_t (&hi)[32], uint32_t (&lo)[32])
+{
+#pragma unroll
+    for (int q = 0; q < HIDDEN / 16; ++q) {
+        float v[16];
+        tc::tmem_ld16(taddr_row + q * 16, v);
+        tc::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float h0 = softplus_log2(fmaf(v[2 * i], LOG2E, bias1_log2[q * 16 + 2 * i]));
+            const float h1 = softplus_log2(fmaf(v[2 * i + 1], LOG2E, bias1_log2[q * 16 + 2 * i + 1]));
+            const __nv_bfloat162 p = __floats2bfloat162_rn(h0, h1);
+            hi[q * 8 + i] = *reinterpret_cast<const uint32_t*>(&p);
+            if (SPLIT) {
+                const float2 back = __bfloat1622float2(p);
+                const __nv_bfloat162 r = __floats2bfloat162_rn(h0 - back.x, h1 - back.y);
+                lo[q * 8 + i] = *reinterpret_cast<const uint32_t*>(&r);
+            }
+        }
+    }
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void hidden_regs_to_smem(unsigned char (*a2)[A2_BYTES], int row, const uint32_t (&hi)[32], const uint32_t (&lo)[32])
+{
+#pragma unroll
+    for (int c8 = 0; c8 < HIDDEN / 8; ++c8) {
+        const uint32_t off = core_offset(row, c8 * 8, A2_LBO, A2_SBO);
+        *reinterpret_cast<uint4*>(a2[0] + off) = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);
+        if (SPLIT) *reinterpret_cast<uint4*>(a2[1] + off) = make_uint4(lo[4 * c8], lo[4 * c8 + 1], lo[4 * c8 + 2], lo[4 * c8 + 3]);
+    }
+}
+
+template <int KIND, bool SPLIT>
+__global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a, nfe_mlp net_a, nfe_mlp net_b)
+{
+    using T = TcTraits<KIND>;
+    constexpr int P = SPLIT ? 1 : 0;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PipeSmem<KIND, SPLIT>& s = *reinterpret_cast<PipeSmem<KIND, SPLIT>*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- setup
+    if (warp == MMA_WARP) tc::tmem_alloc(&s.tmem_base, PIPE_TMEM_COLS);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&s.full[i], GATHER_WARPS);
+            tc::mbar_init(&s.empty[i], 1);
+            tc::mbar_init(&s.d1_full[i], 1);
+            tc::mbar_init(&s.d2a_full[i], 1);
+            tc::mbar_init(&s.d2b_full[i], 1);
+            tc::mbar_init(&s.tmem_free[i], EPI_WARPS);
+        }
+        tc::mbar_init(&s.a2_full, EPI_WARPS);
+        tc::mbar_fence_init();
+    }
+    pipe_load_params(s, net_a, net_b);
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s.tmem_base;
+    const int64_t n_tiles = (a.total + TILE_M - 1) / TILE_M;
+
+    if (warp > MMA_WARP) {
+        // ================================================================ gather warps (producers)
+        const int gw = warp - MMA_WARP - 1;
+        const int g = lane >> 3, c4 = lane & 7;
+        const int64_t set_stride = (int64_t)3 * a.H * a.W * FEAT;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int st = it & 1;
+            tc::mbar_wait(&s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
+            const int64_t base = tile * TILE_M;
+#pragma unroll 2
+            for (int j = 0; j < ROWS_PER_GATHER_WARP / 4; ++j) {
+                const int row = gw * ROWS_PER_GATHER_WARP + 4 * j + g;
+                const int64_t idx = base + row;
+                float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
+                if (idx < a.total) {
+                    float x, y, z;
+                    if (a.coords) {
+                        const float* c = a.coords + idx * 3;
+                        x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
+                    } else {
+                        const int64_t ray = idx / a.s_per_ray;
+                        const float t = __ldg(a.depths + idx);
+                        const float* o = a.origins + ray * 3;
+                        const float* d = a.dirs + ray * 3;
+                        x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
+                    }
+                    const int64_t pbi = a.plane_batch == 1 ? 0 : idx / a.m;
+                    const Taps3 tp = taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W);
+                    if (T::SETS == 2) fa = gather_set(a.set_norm + pbi * set_stride, tp, a.H, a.W, c4);
+                    fb = gather_set(a.set_denorm + pbi * set_stride, tp, a.H, a.W, c4);
+                }
+                if (T::SETS == 2) store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, fa);
+                store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, fb);
+            }
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.full[st]);
+        }
+    } else if (warp == MMA_WARP) {
+        // ================================================================ MMA issuer (one thread)
+        if (lane == 0) {
+            constexpr uint32_t idesc1 = tc::make_idesc_bf16(TILE_M, HIDDEN);
+            constexpr uint32_t idesc2a = tc::make_idesc_bf16(TILE_M, T::N_A);
+            constexpr uint32_t idesc2b = tc::make_idesc_bf16(TILE_M, T::N_B);
+            // layer 1 of tile `it` into ring slot / TMEM buffer it&1
+            auto layer1 = [&](int it) {
+                const int st = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                const uint32_t tb = tmem + st * TMEM_BUF_COLS;
+                tc::mbar_wait(&s.tmem_free[st], ph ^ 1);            // epilogue is done with this TMEM buffer (tile it-2)
+                tc::mbar_wait(&s.full[st], ph);                     // features landed
+                tc::fence_after_sync();
+                issue_gemm<SPLIT>(tb + COL_D1A, s.a1[st][0][0], s.a1[st][0][P], A1_LBO, A1_SBO, s.b1[0][0], s.b1[0][P], B1_LBO, B1_SBO, FEAT, idesc1);
+                if constexpr (T::HAS_B)
+                    issue_gemm<SPLIT>(tb + COL_D1B, s.a1[st][T::SETS - 1][0], s.a1[st][T::SETS - 1][P], A1_LBO, A1_SBO, s.b1[1][0], s.b1[1][P],
+                                      B1_LBO, B1_SBO, FEAT, idesc1);
+                tc::mma_commit(&s.empty[st]);                       // ring slot reusable once these MMAs have read it
+                tc::mma_commit(&s.d1_full[st]);
+            };
+            int it = 0;
+            uint32_t a2_uses = 0;
+            if ((int64_t)blockIdx.x < n_tiles) layer1(0);
+            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+                const uint32_t tb = tmem + (it & 1) * TMEM_BUF_COLS;
+                // layer 2, net A
+                tc::mbar_wait(&s.a2_full, a2_uses++ & 1);
+                tc::fence_after_sync();
+                issue_gemm<SPLIT>(tb + COL_D2A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2a[0], s.b2a[P], B2_LBO, B2_SBO, HIDDEN, idesc2a);
+                tc::mma_commit(&s.d2a_full[it & 1]);
+                // layer 1 of the NEXT tile goes in here, so the epilogue never waits on it
+                if (tile + gridDim.x < n_tiles) layer1(it + 1);
+                if constexpr (T::HAS_B) {
+                    tc::mbar_wait(&s.a2_full, a2_uses++ & 1);
+                    tc::fence_after_sync();
+                    issue_gemm<SPLIT>(tb + COL_D2A + T::N_A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2b[0], s.b2b[P], B2_LBO, B2_SBO, HIDDEN, idesc2b);
+                    tc::mma_commit(&s.d2b_full[it & 1]);
+                }
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================================================================ epilogue warps (TMEM lanes 32*warp ..)
+        const int row = threadIdx.x;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int st = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const uint32_t lane_addr = tmem + st * TMEM_BUF_COLS + ((uint32_t)(warp * 32) << 16);
+            uint32_t hi[32], lo[32];
+            tc::mbar_wait(&s.d1_full[st], ph);
+            tc::fence_after_sync();
+            hidden_to_regs<SPLIT>(lane_addr + COL_D1A, s.bias1[0], hi, lo);
+            // the previous tile's last layer-2 MMA has completed (we waited on its commit), so the hidden tile is free
+            hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.a2_full);
+            if constexpr (T::HAS_B) {
+                hidden_to_regs<SPLIT>(lane_addr + COL_D1B, s.bias1[1], hi, lo);     // overlaps the net-A layer-2 MMA
+                tc::mbar_wait(&s.d2a_full[st], ph);                                // net A consumed the hidden tile
+                tc::fence_after_sync();
+                hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
+                tc::fence_async_smem();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s.a2_full);
+            } else {
+                tc::mbar_wait(&s.d2a_full[st], ph);
+                tc::fence_after_sync();
+            }
+            // ---- outputs
+            const int64_t idx = tile * TILE_M + row;
+            const bool live = idx < a.total;
+            float outa[T::N_A];
+#pragma unroll
+            for (int q = 0; q < T::N_A / 16; ++q) {
+                float v[16];
+                tc::tmem_ld16(lane_addr + COL_D2A + q * 16, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) outa[q * 16 + i] = v[i] + s.bias2a[q * 16 + i];
+            }
+            float sig = outa[0];
+            if (a.density_noise > 0.0f && live) {
+                const uint4 r = philox4x32(a.seed, (uint64_t)idx, a.offset);
+                sig += normal2(r.x, r.y).x * a.density_noise;
+            }
+            if (live) a.sigma[idx] = sig;
+            if constexpr (KIND == NFE_DEC_DISENTANGLED) {
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outa[1 + c];
+                }
+            } else {
+                if (live) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        reinterpret_cast<float4*>(a.rgb + idx * 32)[c] = make_float4(rgb_activation(outa[1 + 4 * c]), rgb_activation(outa[2 + 4 * c]),
+                                                                                      rgb_activation(outa[3 + 4 * c]), rgb_activation(outa[4 + 4 * c]));
+                }
+            }
+            if constexpr (T::HAS_B) {
+                tc::mbar_wait(&s.d2b_full[st], ph);
+                tc::fence_after_sync();
+                float outb[T::N_B];
+#pragma unroll
+                for (int q = 0; q < T::N_B / 16; ++q) {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + COL_D2A + T::N_A + q * 16, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) outb[q * 16 + i] = v[i] + s.bias2b[q * 16 + i];
+                }
+                if (live) {
+                    if constexpr (KIND == NFE_DEC_DISENTANGLED) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            reinterpret_cast<float4*>(a.rgb + idx * 32)[c] = make_float4(rgb_activation(outb[4 * c]), rgb_activation(outb[4 * c + 1]),
+                                                                                          rgb_activation(outb[4 * c + 2]), rgb_activation(outb[4 * c + 3]));
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outb[c];
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.tmem_free[st]);
+        }
+    }
+
+    // ---- teardown
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == MMA_WARP) tc::tmem_dealloc(tmem, PIPE_TMEM_COLS);
+}
+
+template <int KIND, bool SPLIT>
+static int launch_field_pipe_kind(const FieldArgs& a, const nfe_mlp& net_a, const nfe_mlp& net_b, cudaStream_t stream)
+{
+    const size_t smem = sizeof(PipeSmem<KIND, SPLIT>) + 128;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(field_pipe_kernel<KIND, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("field_pipe_kernel: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e)); return 2; }
+        configured = true;
+    }
+    const int64_t n_tiles = (a.total + TILE_M - 1) / TILE_M;
+    const int64_t cap = sm_count();   // persistent: one CTA per SM (it owns all 512 TMEM columns)
+    field_pipe_kernel<KIND, SPLIT><<<(unsigned)(n_tiles < cap ? n_tiles : cap), PIPE_THREADS, smem, stream>>>(a, net_a, net_b);
+    return check_launch("field_pipe_kernel");
+}
+
+int launch_field_pipe(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream)
+{
+    if (a.total <= 0) return 0;
+    nfe_mlp none = {};
+    const bool split = precision == NFE_PREC_BF16X3;
+    switch (kind) {
+        case NFE_DEC_OSG:
+            return split ? launch_field_pipe_kind<NFE_DEC_OSG, true>(a, *net_a, none, stream) : launch_field_pipe_kind<NFE_DEC_OSG, false>(a, *net_a, none, stream);
+        case NFE_DEC_DISENTANGLED:
+            return split ? launch_field_pipe_kind<NFE_DEC_DISENTANGLED, true>(a, *net_a, *net_b, stream)
+                         : launch_field_pipe_kind<NFE_DEC_DISENTANGLED, false>(a, *net_a, *net_b, stream);
+        default:
+            return split ? launch_field_pipe_kind<NFE_DEC_SEGMENTATION, true>(a, *net_a, *net_b, stream)
+                         : launch_field_pipe_kind<NFE_DEC_SEGMENTATION, false>(a, *net_a, *net_b, stream);
+    }
+}
+
+}  // namespace nfe
