@@ -146,9 +146,12 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) field_kernel(FieldArgs a, nf
                     x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
                 }
                 const int64_t pbi = a.plane_batch == 1 ? 0 : idx / a.m;
-                const Taps3 tp = taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W);
-                if (T::SETS == 2) fa = gather_set(a.set_norm + pbi * set_stride, tp, a.H, a.W, c4);
-                fb = gather_set(a.set_denorm + pbi * set_stride, tp, a.H, a.W, c4);
+                const TapSet ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
+                float4 va[12], vb[12];
+                if (T::SETS == 2) gather_load(a.set_norm + pbi * set_stride, ts, c4, va);
+                gather_load(a.set_denorm + pbi * set_stride, ts, c4, vb);
+                if (T::SETS == 2) fa = gather_reduce(va, ts);
+                fb = gather_reduce(vb, ts);
             }
             if (T::SETS == 2) tile[tile_chunk(row, c4)] = fa;
             tile[256 + tile_chunk(row, c4)] = fb;
@@ -257,6 +260,7 @@ int check_decoder_dims(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, con
 int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream)
 {
     if (a.total <= 0) return 0;
+    NFE_REQUIRE((int64_t)a.H * a.W * 3 * FEAT < (1ll << 31), "planes of %dx%d exceed the 32-bit texel offsets of the gather", a.H, a.W);
     if (precision != NFE_PREC_FP32) {
         // NFE_TC_SIMPLE=1 selects the single-role tensor-core kernel (kept as the readable baseline of the pipelined one)
         static const bool simple = getenv("NFE_TC_SIMPLE") != nullptr;

@@ -112,35 +112,65 @@ __device__ __forceinline__ Taps3 taps3(float qx, float qy, float qz, int H, int 
     return r;
 }
 
-// One point's features from one channel-last plane set ([3,H,W,32] floats): the 8 lanes of a
-// group own 4 channels each and walk the 12 taps (3 planes x 4), so a warp-wide LDG.128 fetches
-// 4 whole 128-byte texels (one per lane group).  Returns the plane MEAN ((f0+f1)+f2)/3
-// (decoders' `.mean(1)`, triplane.py:180,211,251-252) for this lane's 4 channels.
-__device__ __forceinline__ float4 gather_set(const float* __restrict__ set, const Taps3& tp, int H, int W, int c4)
+// The 12 taps (3 planes x 4) of one point as branch-free loads: texel offsets in float4 units,
+// clamped into the plane, and weights zeroed for taps that fall outside (padding_mode='zeros').
+// Branch-free matters: a conditional load per tap serialises load -> use -> load and leaves the
+// gather latency-bound (measured: 2-3 loads in flight per warp); unconditional loads can all be
+// issued back to back.
+struct TapSet { int off4[12]; float w[12]; };
+
+__device__ __forceinline__ TapSet make_tapset(const Taps3& tp, int H, int W)
+{
+    TapSet ts;
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int x = tp.t[p].x0 + (k & 1), y = tp.t[p].y0 + (k >> 1);
+            const bool inb = x >= 0 && x < W && y >= 0 && y < H;
+            const int xc = min(max(x, 0), W - 1), yc = min(max(y, 0), H - 1);
+            ts.off4[p * 4 + k] = ((p * H + yc) * W + xc) * (FEAT / 4);
+            ts.w[p * 4 + k] = inb ? tp.t[p].w[k] : 0.0f;
+        }
+    }
+    return ts;
+}
+
+// One point's texels from one channel-last plane set ([3,H,W,32] floats): the 8 lanes of a group
+// own 4 channels each, so a warp-wide LDG.128 fetches 4 whole 128-byte texels (one per lane group).
+__device__ __forceinline__ void gather_load(const float* __restrict__ set, const TapSet& ts, int c4, float4 (&v)[12])
+{
+    const float4* base = reinterpret_cast<const float4*>(set) + c4;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) v[i] = __ldg(base + ts.off4[i]);
+}
+
+// Bilinear blend per plane, then the plane MEAN (decoders' `.mean(1)`, triplane.py:180,211,251-252)
+// for this lane's 4 channels.
+__device__ __forceinline__ float4 gather_reduce(const float4 (&v)[12], const TapSet& ts)
 {
     float4 f[3];
 #pragma unroll
     for (int p = 0; p < 3; ++p) {
-        const float* plane = set + (int64_t)p * H * W * FEAT + 4 * c4;
-        const Taps& t = tp.t[p];
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-            const int x = t.x0 + (k & 1), y = t.y0 + (k >> 1);
-            if (x >= 0 && x < W && y >= 0 && y < H) {
-                const float4 v = __ldg(reinterpret_cast<const float4*>(plane + ((int64_t)y * W + x) * FEAT));
-                acc.x = fmaf(v.x, t.w[k], acc.x); acc.y = fmaf(v.y, t.w[k], acc.y);
-                acc.z = fmaf(v.z, t.w[k], acc.z); acc.w = fmaf(v.w, t.w[k], acc.w);
-            }
+            const float w = ts.w[p * 4 + k];
+            acc.x = fmaf(v[p * 4 + k].x, w, acc.x); acc.y = fmaf(v[p * 4 + k].y, w, acc.y);
+            acc.z = fmaf(v[p * 4 + k].z, w, acc.z); acc.w = fmaf(v[p * 4 + k].w, w, acc.w);
         }
         f[p] = acc;
     }
-    float4 m;
-    m.x = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].x, f[1].x), f[2].x), 3.0f);
-    m.y = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].y, f[1].y), f[2].y), 3.0f);
-    m.z = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].z, f[1].z), f[2].z), 3.0f);
-    m.w = __fdiv_rn(__fadd_rn(__fadd_rn(f[0].w, f[1].w), f[2].w), 3.0f);
-    return m;
+    constexpr float third = 1.0f / 3.0f;
+    return make_float4(((f[0].x + f[1].x) + f[2].x) * third, ((f[0].y + f[1].y) + f[2].y) * third,
+                       ((f[0].z + f[1].z) + f[2].z) * third, ((f[0].w + f[1].w) + f[2].w) * third);
+}
+
+__device__ __forceinline__ float4 gather_set(const float* __restrict__ set, const TapSet& ts, int c4)
+{
+    float4 v[12];
+    gather_load(set, ts, c4, v);
+    return gather_reduce(v, ts);
 }
 
 // Per-warp staging tile: 32 samples x 32 features as float4 chunks, chunk index XOR-swizzled

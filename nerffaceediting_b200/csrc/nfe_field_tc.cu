@@ -170,9 +170,12 @@ __global__ void __launch_bounds__(TILE_M, 1) field_tc_kernel(FieldArgs a, nfe_ml
                     x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
                 }
                 const int64_t pbi = a.plane_batch == 1 ? 0 : idx / a.m;
-                const Taps3 tp = taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W);
-                if (T::SETS == 2) fa = gather_set(a.set_norm + pbi * set_stride, tp, a.H, a.W, c4);
-                fb = gather_set(a.set_denorm + pbi * set_stride, tp, a.H, a.W, c4);
+                const TapSet ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
+                float4 va[12], vb[12];
+                if (T::SETS == 2) gather_load(a.set_norm + pbi * set_stride, ts, c4, va);
+                gather_load(a.set_denorm + pbi * set_stride, ts, c4, vb);
+                if (T::SETS == 2) fa = gather_reduce(va, ts);
+                fb = gather_reduce(vb, ts);
             }
             if (T::SETS == 2) store_features4<SPLIT>(s.a1[0], row, 4 * c4, fa);
             store_features4<SPLIT>(s.a1[T::SETS - 1], row, 4 * c4, fb);
