@@ -1,8 +1,8 @@
 // Warp-specialised fused gather + decode on the tensor cores: the production field kernel.
 //
-// One persistent CTA per SM, 13 warps with fixed roles, connected by mbarriers:
+// One persistent CTA per SM, 16 warps with fixed roles, connected by mbarriers:
 //
-//   8 gather warps     tri-plane bilinear gather (L2/L1-bound: 24 texel lines of 128 B per sample) of a
+//   11 gather warps    tri-plane bilinear gather (L2/L1-bound: 24 texel lines of 128 B per sample) of a
 //                      128-sample tile -> bf16 hi/lo feature tile in a 2-stage shared-memory ring
 //   1 MMA warp         one elected thread issues tcgen05.mma for layer 1 (both nets) and layer 2,
 //                      accumulators in a double-buffered TMEM region; tcgen05.commit signals the
@@ -20,11 +20,11 @@ namespace nfe {
 
 using namespace tcmlp;
 
-constexpr int GATHER_WARPS = 8;
+constexpr int GATHER_WARPS = 11;                           // 16 warps x 128 registers = the whole register file
 constexpr int EPI_WARPS = 4;
 constexpr int MMA_WARP = EPI_WARPS;                         // warp index of the MMA issuer
 constexpr int PIPE_THREADS = (EPI_WARPS + 1 + GATHER_WARPS) * 32;
-constexpr int ROWS_PER_GATHER_WARP = TILE_M / GATHER_WARPS; // 16 -> 4 passes of 4 samples
+constexpr int PASSES_PER_TILE = TILE_M / 4;                 // a pass = 4 samples (8 lanes each); passes are dealt round-robin to the gather warps
 constexpr int TMEM_BUF_COLS = 192;                          // D1A 64 | D1B 64 | D2A <=48 | D2B <=32 (OSG: 48+16)
 constexpr int PIPE_TMEM_COLS = 512;
 
@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             tc::mbar_wait(&s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
             const int64_t base = tile * TILE_M;
 #pragma unroll 2
-            for (int j = 0; j < ROWS_PER_GATHER_WARP / 4; ++j) {
-                const int row = gw * ROWS_PER_GATHER_WARP + 4 * j + g;
+            for (int pass = gw; pass < PASSES_PER_TILE; pass += GATHER_WARPS) {
+                const int row = 4 * pass + g;
                 const int64_t idx = base + row;
                 float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
                 if (idx < a.total) {

@@ -53,15 +53,33 @@ __global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
                 s_raw[e] = first ? a.sigma1[ray * a.s1 + e] : a.sigma2[ray * a.s2 + (e - a.s1)];
             }
             __syncwarp();
-            for (int e = lane; e < S; e += 32) {
-                const float d = s_w[e];
-                int rank = 0;
-#pragma unroll 4
-                for (int j = 0; j < S; ++j) {
-                    const float dj = s_w[j];
-                    rank += (dj < d) || (dj == d && j < e);
+            if (a.inputs_sorted) {
+                // both lists ascending: merge-path ranks by binary search in the other list
+                // (coarse: #fine strictly below; fine: #coarse at or below -> ties keep coarse first)
+                for (int e = lane; e < S; e += 32) {
+                    const float d = s_w[e];
+                    const bool first = e < a.s1;
+                    const float* other = first ? s_w + a.s1 : s_w;
+                    int lo = 0, hi = first ? a.s2 : a.s1;
+                    while (lo < hi) {
+                        const int mid = (lo + hi) >> 1;
+                        const float v = other[mid];
+                        if (first ? (v < d) : (v <= d)) lo = mid + 1; else hi = mid;
+                    }
+                    const int rank = (first ? e : e - a.s1) + lo;
+                    s_depth[rank] = d; s_sigma[rank] = s_raw[e]; s_order[rank] = e;
                 }
-                s_depth[rank] = d; s_sigma[rank] = s_raw[e]; s_order[rank] = e;
+            } else {
+                for (int e = lane; e < S; e += 32) {
+                    const float d = s_w[e];
+                    int rank = 0;
+#pragma unroll 4
+                    for (int j = 0; j < S; ++j) {
+                        const float dj = s_w[j];
+                        rank += (dj < d) || (dj == d && j < e);
+                    }
+                    s_depth[rank] = d; s_sigma[rank] = s_raw[e]; s_order[rank] = e;
+                }
             }
         } else {
             for (int e = lane; e < S; e += 32) {
@@ -81,8 +99,10 @@ __global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
         for (int i = i0; i < i1; ++i) {
             const float delta = __fsub_rn(s_depth[i + 1], s_depth[i]);
             const float sig = __fdiv_rn(__fadd_rn(s_sigma[i], s_sigma[i + 1]), 2.0f);
-            const float dens = softplus_ref(__fsub_rn(sig, 1.0f));
-            const float alpha = __fsub_rn(1.0f, expf(-__fmul_rn(dens, delta)));
+            // SFU exp/log (abs. error ~1e-7): the full-precision versions cost ~80 instructions per interval
+            const float xs = __fsub_rn(sig, 1.0f);
+            const float dens = fmaxf(xs, 0.0f) + __logf(1.0f + __expf(-fabsf(xs)));
+            const float alpha = __fsub_rn(1.0f, __expf(-__fmul_rn(dens, delta)));
             s_w[i] = alpha;  // parked; turned into the weight below
             prod *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
         }
@@ -114,36 +134,42 @@ __global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
 
         // ---- channel sums: lane = channel, sequential over intervals, rows read coalesced
         if (a.cc > 0) {
+            // sum_i w_i (c_i + c_{i+1})/2  ==  sum_k omega_k c_k  with omega_k = (w_{k-1} + w_k)/2 (w_{-1} = w_{S-1} = 0):
+            // one FMA per sample row and no carried "previous row"; omega overwrites the (now dead) densities
+            for (int k = lane; k < S; k += 32) s_sigma[k] = 0.5f * ((k > 0 ? s_w[k - 1] : 0.0f) + (k < n_int ? s_w[k] : 0.0f));
+            __syncwarp();
             for (int c0 = 0; c0 < a.cc; c0 += 32) {
                 const int c = c0 + lane;
                 const bool on = c < a.cc;
                 const bool seg_on = (c0 == 0) && lane < a.cs;
-                float acc = 0.0f, acc_s = 0.0f, prev = 0.0f, prev_s = 0.0f;
+                // row e of the concatenation lives at base1 + e*stride (e < s1) or base2 + e*stride
+                const float* c1 = a.colors1 + ray * a.s1 * a.cc + (on ? c : 0);
+                const float* c2 = a.s2 ? a.colors2 + (ray * a.s2 - a.s1) * a.cc + (on ? c : 0) : c1;
+                const float* g1 = a.cs ? a.segs1 + ray * a.s1 * a.cs + (seg_on ? lane : 0) : nullptr;
+                const float* g2 = (a.cs && a.s2) ? a.segs2 + (ray * a.s2 - a.s1) * a.cs + (seg_on ? lane : 0) : g1;
+                float acc = 0.0f, acc_s = 0.0f;
                 constexpr int UN = 8;  // rows fetched together: the loads are independent, only the sums chain
-                for (int k0 = 0; k0 < S; k0 += UN) {
+                int k0 = 0;
+                for (; k0 + UN <= S; k0 += UN) {
                     float cur[UN], cur_s[UN];
 #pragma unroll
                     for (int u = 0; u < UN; ++u) {
-                        const int k = k0 + u;
-                        cur[u] = 0.0f; cur_s[u] = 0.0f;
-                        if (k < S) {
-                            const int e = s_order[k];
-                            const bool first = e < a.s1;
-                            const int64_t row = first ? ray * a.s1 + e : ray * a.s2 + (e - a.s1);
-                            if (on) cur[u] = __ldg((first ? a.colors1 : a.colors2) + row * a.cc + c);
-                            if (seg_on) cur_s[u] = __ldg((first ? a.segs1 : a.segs2) + row * a.cs + lane);
-                        }
+                        const int e = s_order[k0 + u];
+                        cur[u] = __ldg((e < a.s1 ? c1 : c2) + (int64_t)e * a.cc);
+                        cur_s[u] = a.cs ? __ldg((e < a.s1 ? g1 : g2) + (int64_t)e * a.cs) : 0.0f;
                     }
 #pragma unroll
                     for (int u = 0; u < UN; ++u) {
-                        const int k = k0 + u;
-                        if (k > 0 && k < S) {
-                            const float w = s_w[k - 1];
-                            acc = fmaf(w, (prev + cur[u]) * 0.5f, acc);
-                            acc_s = fmaf(w, (prev_s + cur_s[u]) * 0.5f, acc_s);
-                        }
-                        prev = cur[u]; prev_s = cur_s[u];
+                        const float om = s_sigma[k0 + u];
+                        acc = fmaf(om, cur[u], acc);
+                        acc_s = fmaf(om, cur_s[u], acc_s);
                     }
+                }
+                for (; k0 < S; ++k0) {
+                    const int e = s_order[k0];
+                    const float om = s_sigma[k0];
+                    acc = fmaf(om, __ldg((e < a.s1 ? c1 : c2) + (int64_t)e * a.cc), acc);
+                    if (a.cs) acc_s = fmaf(om, __ldg((e < a.s1 ? g1 : g2) + (int64_t)e * a.cs), acc_s);
                 }
                 if (on) {
                     if (a.white_back) acc = acc + 1.0f - wt;
@@ -253,10 +279,12 @@ __global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int warps_per_block = blockDim.x >> 5;
     const int S = a.S, nw = S - 1, ns = SMOOTH ? S - 3 : a.ns;
-    float* s_z = smem + (size_t)warp * 4 * S;
+    const int per_warp = 4 * S + (a.sort_u ? a.s_f : 0);
+    float* s_z = smem + (size_t)warp * per_warp;
     float* s_om = s_z + S;     // omega_j = weight_j + eps, j in [0, ns)
     float* s_bins = s_om + S;
     float* s_cdf = s_bins + S;
+    float* s_u = s_cdf + S;    // only when sort_u
     for (int64_t ray = (int64_t)blockIdx.x * warps_per_block + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * warps_per_block) {
         if (SMOOTH) {
             for (int e = lane; e < S; e += 32) s_z[e] = a.z_vals[ray * S + e];
@@ -302,10 +330,25 @@ __global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a)
         }
         __syncwarp();
         // inverse CDF
+        const bool sort_u = a.sort_u && !a.u;
+        if (sort_u) {
+            // stochastic draws, emitted in ascending order (the sample is monotone in u), so that the fused
+            // merge can treat the fine list as sorted; the reference sorts everything later anyway
+            for (int k = lane; k < a.s_f; k += 32) s_u[k] = u01(philox4x32(a.seed, (uint64_t)(ray * a.s_f + k), a.offset).x);
+            __syncwarp();
+        }
         for (int k = lane; k < a.s_f; k += 32) {
             float u;
+            int dst = k;
             if (a.u) u = a.u_per_ray ? a.u[ray * a.s_f + k] : a.u[k];
-            else u = u01(philox4x32(a.seed, (uint64_t)(ray * a.s_f + k), a.offset).x);
+            else if (sort_u) {
+                u = s_u[k];
+                dst = 0;
+                for (int j = 0; j < a.s_f; ++j) {
+                    const float uj = s_u[j];
+                    dst += (uj < u) || (uj == u && j < k);
+                }
+            } else u = u01(philox4x32(a.seed, (uint64_t)(ray * a.s_f + k), a.offset).x);
             // searchsorted(right=True): number of cdf entries <= u, over cdf[0..ns]
             int lo = 0, hi = ns + 1;
             while (lo < hi) {
@@ -317,9 +360,9 @@ __global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a)
             if (den < a.eps) den = 1.0f;
             const float frac = __fdiv_rn(__fsub_rn(u, s_cdf[below]), den);
             const float t = __fadd_rn(s_bins[below], __fmul_rn(frac, __fsub_rn(s_bins[above], s_bins[below])));
-            a.out[ray * a.s_f + k] = t;
-            if (a.below) a.below[ray * a.s_f + k] = below;
-            if (a.above) a.above[ray * a.s_f + k] = above;
+            a.out[ray * a.s_f + dst] = t;
+            if (a.below) a.below[ray * a.s_f + dst] = below;
+            if (a.above) a.above[ray * a.s_f + dst] = above;
         }
         __syncwarp();
     }
@@ -376,8 +419,10 @@ int launch_resample(const ResampleArgs& a, cudaStream_t stream)
     NFE_REQUIRE(a.smooth || (a.ns >= 1 && a.ns < a.S), "sample_pdf: %d weights need at least %d bins (got %d)", a.ns, a.ns + 1, a.S);
     NFE_REQUIRE(a.s_f >= 1, "importance resampling: need at least one importance sample");
     if (a.n_rays <= 0) return 0;
-    const int warps = warps_for(a.S, 4);
-    const size_t smem = (size_t)warps * 16 * a.S;
+    const int per_warp = 4 * a.S + (a.sort_u ? a.s_f : 0);
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * per_warp * 4 > 96 * 1024) warps >>= 1;
+    const size_t smem = (size_t)warps * per_warp * 4;
     const int64_t blocks = (a.n_rays + warps - 1) / warps;
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);

@@ -13,6 +13,7 @@ struct MarchArgs {
     const float* depths2; const float* colors2; const float* segs2; const float* sigma2; int s2;
     int64_t n_rays;
     int cc, cs;        // colour / semantic channels (0: weights only)
+    int inputs_sorted; // both sample sets ascending in depth: merge by binary search instead of a full rank sort
     int white_back;
     float* rgb;        // [n_rays,cc]
     float* seg;        // [n_rays,cs]
@@ -25,6 +26,7 @@ struct MarchArgs {
 struct ResampleArgs {
     const float* z_vals; const float* weights;  // smooth: depths [S] + raw coarse weights [S-1]; else bins [S] + pdf weights [ns]
     int smooth; int ns; float eps;
+    int sort_u;        // stochastic draws only: emit the samples in ascending order
     int64_t n_rays; int S, s_f;
     const float* u; int u_per_ray;
     uint64_t seed, offset;

@@ -120,7 +120,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
         }
         float* df = depths_fine_out ? depths_fine_out : w.depths_f;
         ResampleArgs r = {};
-        r.z_vals = depths_coarse; r.weights = wc; r.n_rays = rays; r.S = sc; r.s_f = sf; r.smooth = 1; r.eps = 1e-5f;
+        r.z_vals = depths_coarse; r.weights = wc; r.n_rays = rays; r.S = sc; r.s_f = sf; r.smooth = 1; r.eps = 1e-5f; r.sort_u = 1;
         r.u = cfg->stochastic ? nullptr : u_fine; r.u_per_ray = 0; r.seed = cfg->seed; r.offset = cfg->offset + 2; r.out = df;
         {
             StageScope t(STAGE_RESAMPLE, stream);
@@ -135,6 +135,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
         }
         // ---- merge + composite (renderer.py:131-135,355-359)
         m.depths2 = df; m.colors2 = w.rgb_f; m.segs2 = w.seg_f; m.sigma2 = w.sigma_f; m.s2 = sf;
+        m.inputs_sorted = 1;  // coarse depths ascend by construction; the fine list is emitted sorted (table u, or sort_u)
     }
     m.depths1 = depths_coarse; m.colors1 = w.rgb_c; m.segs1 = w.seg_c; m.sigma1 = w.sigma_c; m.s1 = sc;
     m.cc = 32; m.cs = cfg->seg_dim; m.rgb = rgb; m.seg = seg; m.depth = depth; m.wsum = wsum; m.weights = nullptr; m.minmax = minmax;
