@@ -32,7 +32,8 @@ def _newest_dep():
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link the shared library.  Returns the .so path."""
+    """Compile every .cu for sm_100a and link the shared library.  Returns the .so path.
+    $NFE_NVCC_FLAGS adds flags (e.g. -DNFE_GATHER_WARPS=8) for tuning sweeps on the GPU box."""
     if not force and os.path.exists(LIB) and os.path.getmtime(LIB) >= _newest_dep():
         return LIB
     os.makedirs(OBJ, exist_ok=True)
@@ -44,7 +45,7 @@ def build(force=False, verbose=False):
 
     def compile_one(src):
         obj = os.path.join(OBJ, src.replace(".cu", ".o"))
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("NFE_NVCC_FLAGS", "").split() + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         r = subprocess.run(cmd, capture_output=True, text=True, env=env)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")

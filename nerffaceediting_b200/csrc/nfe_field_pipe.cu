@@ -20,7 +20,13 @@ namespace nfe {
 
 using namespace tcmlp;
 
-constexpr int GATHER_WARPS = 11;                           // 16 warps x 128 registers = the whole register file
+#ifndef NFE_GATHER_WARPS
+#define NFE_GATHER_WARPS 11
+#endif
+#ifndef NFE_PASS_CONTIG
+#define NFE_PASS_CONTIG 1
+#endif
+constexpr int GATHER_WARPS = NFE_GATHER_WARPS;              // 11: 16 warps x 128 registers = the whole register file
 constexpr int EPI_WARPS = 4;
 constexpr int MMA_WARP = EPI_WARPS;                         // warp index of the MMA issuer
 constexpr int PIPE_THREADS = (EPI_WARPS + 1 + GATHER_WARPS) * 32;
@@ -153,7 +159,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             tc::mbar_wait(&s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
             const int64_t base = tile * TILE_M;
 #pragma unroll 2
+#if NFE_PASS_CONTIG
+            // a warp takes consecutive passes = consecutive samples of (mostly) one ray: their XY-plane taps coincide
+            constexpr int PER = (PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS;
+            for (int pass = gw * PER; pass < min(PASSES_PER_TILE, (gw + 1) * PER); ++pass) {
+#else
             for (int pass = gw; pass < PASSES_PER_TILE; pass += GATHER_WARPS) {
+#endif
                 const int row = 4 * pass + g;
                 const int64_t idx = base + row;
                 float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
