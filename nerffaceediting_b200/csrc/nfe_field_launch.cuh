@@ -18,6 +18,12 @@ struct FieldArgs {
     const float* dirs;
     const float* depths;      // [n*R*s_per_ray]
     int s_per_ray;
+    // Locality ordering (ray mode only; 0 = plain order): the rays of one batch item form a quad_stride x
+    // quad_stride image (ray m = row*quad_stride + col).  The pipelined kernel then walks samples as
+    // (4 vertically adjacent rays) x (depth index), so that the four samples of a gather pass share their
+    // (x,z)/(z,x)-plane texels and consecutive passes reuse the (x,y)-plane texels.
+    int quad_stride;
+    int64_t rays_per_item;
     int64_t m;                // samples per batch item
     int64_t total;            // n*m
     float* sigma;             // [total]

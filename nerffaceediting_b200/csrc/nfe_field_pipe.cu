@@ -117,6 +117,31 @@ __device__ __forceinline__ void hidden_regs_to_smem(unsigned char (*a2)[A2_BYTES
     }
 }
 
+// Tile row -> sample.  Plain order: sample L is index L.  Quad order (FieldArgs::quad_stride): L enumerates
+// (quad of 4 vertically adjacent rays) x (depth index s) x (ray in quad); the sample's storage index stays
+// ray*S + s, so every consumer of the outputs is unaffected.  `item` is the batch item (plane set) of the sample.
+struct SampleRef { int64_t idx; int item; };
+
+__device__ __forceinline__ SampleRef sample_of(const FieldArgs& a, int64_t L)
+{
+    SampleRef r;
+    if (a.quad_stride == 0) {
+        r.idx = L;
+        r.item = (int)(L / a.m);
+        return r;
+    }
+    const uint32_t S = (uint32_t)a.s_per_ray, per_quad = 4u * S, res = (uint32_t)a.quad_stride;
+    const uint32_t quad = (uint32_t)(L / per_quad), within = (uint32_t)(L % per_quad);
+    const uint32_t s = within >> 2, ray_in_quad = within & 3u;
+    const uint32_t quads_per_item = (uint32_t)(a.rays_per_item >> 2);
+    const uint32_t item = quad / quads_per_item, q = quad % quads_per_item;
+    const uint32_t qrow = q / res, col = q % res;
+    const int64_t ray = (int64_t)item * a.rays_per_item + (int64_t)(4u * qrow + ray_in_quad) * res + col;
+    r.idx = ray * S + s;
+    r.item = (int)item;
+    return r;
+}
+
 template <int KIND, bool SPLIT>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a, nfe_mlp net_a, nfe_mlp net_b)
 {
@@ -167,9 +192,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             for (int pass = gw; pass < PASSES_PER_TILE; pass += GATHER_WARPS) {
 #endif
                 const int row = 4 * pass + g;
-                const int64_t idx = base + row;
                 float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
-                if (idx < a.total) {
+                if (base + row < a.total) {
+                    const SampleRef sr = sample_of(a, base + row);
+                    const int64_t idx = sr.idx;
                     float x, y, z;
                     if (a.coords) {
                         const float* c = a.coords + idx * 3;
@@ -181,7 +207,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                         const float* d = a.dirs + ray * 3;
                         x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
                     }
-                    const int64_t pbi = a.plane_batch == 1 ? 0 : idx / a.m;
+                    const int64_t pbi = a.plane_batch == 1 ? 0 : sr.item;
                     const TapSet ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
                     // all 24 texel loads of the sample are issued before the first blend
                     float4 va[12], vb[12];
@@ -269,8 +295,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 tc::fence_after_sync();
             }
             // ---- outputs
-            const int64_t idx = tile * TILE_M + row;
-            const bool live = idx < a.total;
+            const bool live = tile * TILE_M + row < a.total;
+            const int64_t idx = live ? sample_of(a, tile * TILE_M + row).idx : 0;
             float outa[T::N_A];
 #pragma unroll
             for (int q = 0; q < T::N_A / 16; ++q) {

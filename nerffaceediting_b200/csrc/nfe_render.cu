@@ -100,6 +100,14 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
     f.scale = (float)(2.0 / (double)cfg->box_warp);
     f.origins = origins; f.dirs = dirs; f.depths = depths_coarse; f.s_per_ray = sc;
     f.m = n_rays * sc; f.total = rays * sc;
+    {   // locality ordering when the rays of an item form a square image whose side is a multiple of 4 (RaySampler's layout)
+        int64_t side = 1;
+        while (side * side < n_rays) ++side;
+        const bool square = side * side == n_rays && side % 4 == 0 && side < (1 << 15) && rays < (1ll << 32);
+        static const bool disabled = getenv("NFE_NO_QUAD_ORDER") != nullptr;
+        f.quad_stride = (square && !disabled) ? (int)side : 0;
+        f.rays_per_item = n_rays;
+    }
     f.sigma = w.sigma_c; f.rgb = w.rgb_c; f.seg = w.seg_c;
     f.density_noise = cfg->density_noise; f.seed = cfg->seed; f.offset = cfg->offset + 1;
     {
