@@ -58,6 +58,13 @@ int nfe_plane_denormalize(const float* norm, const float* mean, const float* std
 int nfe_planes_to_channel_last(const float* planes, int64_t n_img, int channels, int64_t hw, float* out,
                                nfe_stream_t stream);
 
+/* normalize_plane fused with the staging of BOTH plane sets: planes is [n_img, 32, hw] (n_img = batch*3);
+ * one read produces out_norm (same layout), its channel-last copy and the channel-last copy of the
+ * raw planes — what DisentangledImportanceRenderer.forward needs from triplane.py:95,113-119. */
+int nfe_plane_normalize_staged(const float* planes, const float* mean, const float* std_in, int64_t n_img,
+                               int64_t hw, float* out_norm, float* out_norm_cl, float* out_raw_cl,
+                               nfe_stream_t stream);
+
 /* ---- rays: RaySampler.forward, training/volumetric_rendering/ray_sampler.py:24-63 -------- */
 int nfe_generate_rays(const float* cam2world /*[n,4,4]*/, const float* intrinsics /*[n,3,3]*/, int n,
                       int resolution, float* origins /*[n,res*res,3]*/, float* dirs, nfe_stream_t stream);

@@ -47,6 +47,7 @@ SIGNATURES = {
     "nfe_plane_stats": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "nfe_plane_normalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "nfe_plane_denormalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
+    "nfe_plane_normalize_staged": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "nfe_planes_to_channel_last": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "nfe_generate_rays": (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
     "nfe_ray_limits_box": (c_int, [c_vp, c_vp, c_i64, c_float, c_vp, c_vp, c_vp]),

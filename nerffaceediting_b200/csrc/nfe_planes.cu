@@ -139,6 +139,52 @@ __global__ void __launch_bounds__(256) to_channel_last_kernel(const float* __res
     }
 }
 
+// 32-channel fast path of the staging, optionally fused with the normalisation.
+// A warp owns 32 consecutive pixels of one image: lane = pixel.  It reads the 32 channel rows (32
+// independent, fully coalesced 128-byte loads per lane), and each lane then holds its pixel's whole
+// channel vector, i.e. one 128-byte channel-last texel, written as 8 float4 stores.  With NORMALIZE
+// the same registers also produce (x-mean)/(std+1e-8): the NCHW result (coalesced) and its channel-last
+// copy, so normalize_plane + both stagings cost one read of the planes instead of three.
+template <bool NORMALIZE>
+__global__ void __launch_bounds__(256) stage32_kernel(const float* __restrict__ planes, const float* __restrict__ mean,
+                                                      const float* __restrict__ std_in, int64_t hw, int64_t groups_per_img, int64_t n_groups,
+                                                      float* __restrict__ out_norm, float* __restrict__ out_norm_cl, float* __restrict__ out_raw_cl)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t group = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (group >= n_groups) return;
+    const int64_t img = group / groups_per_img;
+    const int64_t px = (group % groups_per_img) * 32 + lane;
+    const bool live = px < hw;
+    const float* src = planes + img * 32 * hw + px;
+    float x[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) x[c] = live ? __ldg(src + (int64_t)c * hw) : 0.0f;
+    if (live) {
+        float4* dst = reinterpret_cast<float4*>(out_raw_cl + (img * hw + px) * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) dst[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    }
+    if constexpr (NORMALIZE) {
+        // lane c carries the statistics of channel c; broadcast by shuffle
+        const float m_l = mean[img * 32 + lane];
+        const float d_l = __fadd_rn(std_in[img * 32 + lane], 1e-8f);
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+            const float m = __shfl_sync(0xffffffffu, m_l, c), d = __shfl_sync(0xffffffffu, d_l, c);
+            x[c] = __fdiv_rn(__fsub_rn(x[c], m), d);
+        }
+        if (live) {
+            float* dn = out_norm + img * 32 * hw + px;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) dn[(int64_t)c * hw] = x[c];
+            float4* dst = reinterpret_cast<float4*>(out_norm_cl + (img * hw + px) * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) dst[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        }
+    }
+}
+
 }  // namespace nfe
 
 using namespace nfe;
@@ -199,11 +245,34 @@ NFE_EXPORT int nfe_planes_to_channel_last(const float* planes, int64_t n_img, in
     NFE_REQUIRE(planes && out, "nfe_planes_to_channel_last: null pointer");
     NFE_REQUIRE(n_img >= 0 && channels >= 1 && channels <= 256 && hw >= 1, "nfe_planes_to_channel_last: bad sizes");
     if (n_img == 0) return 0;
+    if (channels == 32 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        const int64_t groups_per_img = (hw + 31) / 32, n_groups = n_img * groups_per_img;
+        NFE_REQUIRE((n_groups + 7) / 8 < (1ll << 31), "nfe_planes_to_channel_last: grid too large");
+        stage32_kernel<false><<<(unsigned)((n_groups + 7) / 8), 256, 0, as_stream(stream)>>>(planes, nullptr, nullptr, hw, groups_per_img, n_groups,
+                                                                                           nullptr, nullptr, out);
+        NFE_LAUNCH_CHECK("stage32_kernel");
+        return 0;
+    }
     const int64_t tiles = (hw + CL_PIX - 1) / CL_PIX;
     NFE_REQUIRE(n_img * tiles < (1ll << 31), "nfe_planes_to_channel_last: grid too large");
     const size_t smem = (size_t)channels * (CL_PIX + 1) * sizeof(float);
     if (smem > 48 * 1024) cudaFuncSetAttribute(to_channel_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     to_channel_last_kernel<<<(unsigned)(n_img * tiles), 256, smem, as_stream(stream)>>>(planes, channels, hw, tiles, out);
     NFE_LAUNCH_CHECK("to_channel_last_kernel");
+    return 0;
+}
+
+NFE_EXPORT int nfe_plane_normalize_staged(const float* planes, const float* mean, const float* std_in, int64_t n_img, int64_t hw, float* out_norm,
+                                          float* out_norm_cl, float* out_raw_cl, nfe_stream_t stream)
+{
+    if (n_img == 0 || hw == 0) return 0;
+    NFE_REQUIRE(planes && mean && std_in && out_norm && out_norm_cl && out_raw_cl, "nfe_plane_normalize_staged: null pointer");
+    NFE_REQUIRE(((reinterpret_cast<uintptr_t>(out_norm_cl) | reinterpret_cast<uintptr_t>(out_raw_cl)) & 15) == 0,
+                "nfe_plane_normalize_staged: channel-last outputs must be 16-byte aligned");
+    const int64_t groups_per_img = (hw + 31) / 32, n_groups = n_img * groups_per_img;
+    NFE_REQUIRE((n_groups + 7) / 8 < (1ll << 31), "nfe_plane_normalize_staged: grid too large");
+    stage32_kernel<true><<<(unsigned)((n_groups + 7) / 8), 256, 0, as_stream(stream)>>>(planes, mean, std_in, hw, groups_per_img, n_groups, out_norm,
+                                                                                      out_norm_cl, out_raw_cl);
+    NFE_LAUNCH_CHECK("stage32_kernel");
     return 0;
 }

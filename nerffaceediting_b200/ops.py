@@ -111,17 +111,41 @@ def planes_channel_last(planes, cache=False):
     if x.dim() != 5 or x.shape[1] != 3:
         raise RuntimeError(f"planes: expected [N,3,C,H,W], got {tuple(x.shape)}")
     key = (x.data_ptr(), tuple(x.shape), x._version, x.device.index)
-    if cache and key in _CL_CACHE:
+    if key in _CL_CACHE:      # staged by plane_normalize_staged, or kept from an earlier call with cache=True
         return _CL_CACHE[key][1]
     n, p, c, h, w = x.shape
     out = torch.empty((n, p, h, w, c), device=x.device, dtype=torch.float32)
     with _Guard(x):
         _lib.check(_lib.load().nfe_planes_to_channel_last(_ptr(x), n * p, c, h * w, _ptr(out), _stream(x)), "nfe_planes_to_channel_last")
     if cache:
-        while len(_CL_CACHE) >= _CL_CACHE_MAX:
-            _CL_CACHE.pop(next(iter(_CL_CACHE)))
-        _CL_CACHE[key] = (x, out)
+        _cache_put(key, x, out)
     return out
+
+
+def _cache_put(key, src, staged):
+    while len(_CL_CACHE) >= _CL_CACHE_MAX:
+        _CL_CACHE.pop(next(iter(_CL_CACHE)))
+    _CL_CACHE[key] = (src, staged)
+
+
+def plane_normalize_staged(planes, mean, std):
+    """normalize_plane for tri-plane tensors [N, 96, H, W]: one kernel writes the normalised planes AND the
+    channel-last staging of both the normalised and the raw planes, and registers the staged copies so that
+    the renderer called next on views of (norm, planes) (triplane.py:113-119) skips its own staging pass.
+    The registry keeps the two source tensors alive until the next call replaces them."""
+    x = _cuda_f32(planes, "planes")
+    n, c96, h, w = x.shape
+    norm = torch.empty_like(x)
+    norm_cl = torch.empty((n, 3, h, w, 32), device=x.device, dtype=torch.float32)
+    raw_cl = torch.empty_like(norm_cl)
+    with _Guard(x):
+        _lib.check(_lib.load().nfe_plane_normalize_staged(_ptr(x), _ptr(mean), _ptr(std), n * 3, h * w, _ptr(norm), _ptr(norm_cl), _ptr(raw_cl),
+                                                          _stream(x)), "nfe_plane_normalize_staged")
+    _CL_CACHE.clear()
+    shape5 = (n, 3, 32, h, w)
+    _cache_put((norm.data_ptr(), shape5, norm._version, x.device.index), norm, norm_cl)
+    _cache_put((x.data_ptr(), shape5, x._version, x.device.index), x, raw_cl)
+    return norm
 
 
 def clear_plane_cache():

@@ -90,6 +90,9 @@ def normalize_plane(planes):
     """(planes - mean) / (std + 1e-8) -> (norm_planes, mean, std) (triplane.py:61-65)."""
     ops._no_grad_needed(planes)
     mean, std = ops.plane_stats(planes)
+    if planes.dim() == 4 and planes.shape[1] == 96 and planes.is_contiguous() and planes.dtype == torch.float32:
+        # the generator's [N,96,H,W] tri-planes: also stage both plane sets for the renderer in the same pass
+        return ops.plane_normalize_staged(planes, mean, std), mean, std
     return ops.plane_normalize(planes, mean, std), mean, std
 
 
