@@ -124,7 +124,9 @@ class ImportanceRenderer(torch.nn.Module):
                                        stochastic=not deterministic, seed=seed, offset=offset)
         return depths, seed, offset
 
-    def _render(self, norm_planes, planes, decoder, ray_origins, ray_directions, opts):
+    def _render(self, norm_planes, planes, decoder, ray_origins, ray_directions, opts, defer_clamp=False):
+        """Shared forward.  defer_clamp=True (used by sharding.render_sharded) leaves the depth unclamped and also
+        returns the device {min,max} of this call's sample depths, to be all-reduced before nfe_finish_depth."""
         if isinstance(self.plane_axes, torch.Tensor):
             self.plane_axes = self.plane_axes.to(ray_origins.device)       # as renderer.py:89
         if not ray_origins.is_cuda:
@@ -133,6 +135,8 @@ class ImportanceRenderer(torch.nn.Module):
         deterministic = bool(opts.get('nfe_deterministic', False))
         desc = self._fused_decoder(decoder, norm_planes)
         if desc is None:
+            if defer_clamp:
+                raise NotImplementedError("a ray-sharded render needs one of the reference's decoders (fused path)")
             return self._render_staged(norm_planes, planes, decoder, ray_origins, ray_directions, opts, deterministic)
         kind, seq_a, seq_b = desc
         ops._no_grad_needed(norm_planes, planes, ray_origins, ray_directions, *decoder.parameters())
@@ -147,8 +151,10 @@ class ImportanceRenderer(torch.nn.Module):
                            opts.get('density_noise', 0) or 0.0, stochastic=not deterministic, seed=seed, offset=offset,
                            precision=ops.precision_of(opts))
         u_fine = ops.linspace_table(0, 1, s_f, ray_origins.device) if (s_f > 0 and deterministic) else None
-        rgb, seg, depth, wsum, _ = ops.render_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, ray_origins, ray_directions,
-                                                  depths_coarse, u_fine)
+        rgb, seg, depth, wsum, minmax = ops.render_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, ray_origins, ray_directions,
+                                                       depths_coarse, u_fine, finish_depth=not defer_clamp)
+        if defer_clamp:
+            return rgb, seg, depth, wsum, minmax
         return rgb, seg, depth, wsum
 
     def _render_staged(self, norm_planes, planes, decoder, ray_origins, ray_directions, opts, deterministic):
