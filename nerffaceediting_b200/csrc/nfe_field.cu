@@ -261,6 +261,8 @@ int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net
 {
     if (a.total <= 0) return 0;
     NFE_REQUIRE((int64_t)a.H * a.W * 3 * FEAT < (1ll << 31), "planes of %dx%d exceed the 32-bit texel offsets of the gather", a.H, a.W);
+    NFE_REQUIRE((int64_t)a.plane_batch * a.H * a.W * 3 * (FEAT / 4) < (1ll << 31), "%d plane sets of %dx%d exceed the 32-bit texel offsets of the gather",
+                a.plane_batch, a.H, a.W);
     if (precision != NFE_PREC_FP32) {
         // NFE_TC_SIMPLE=1 selects the single-role tensor-core kernel (kept as the readable baseline of the pipelined one)
         static const bool simple = getenv("NFE_TC_SIMPLE") != nullptr;

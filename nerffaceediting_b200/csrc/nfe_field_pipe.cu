@@ -47,6 +47,7 @@ struct PipeSmem {
     alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
+    alignas(16) uint4 taps[GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][6];   // per sample: 12 offsets + 12 weights
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
     float bias2a[T::N_A];
     float bias2b[T::N_B];
@@ -175,49 +176,79 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
 
     if (warp > MMA_WARP) {
         // ================================================================ gather warps (producers)
+        // Each warp owns PER consecutive passes of the tile (a pass = 4 samples x 8 lanes); consecutive samples of
+        // one ray share their (x,y)-plane texels, so they should meet in the same warp back to back.
         const int gw = warp - MMA_WARP - 1;
         const int g = lane >> 3, c4 = lane & 7;
-        const int64_t set_stride = (int64_t)3 * a.H * a.W * FEAT;
+        constexpr int PER = (PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS;
+        const int64_t set_stride4 = (int64_t)3 * a.H * a.W * (FEAT / 4);     // float4 units
+        const float4* set_a = reinterpret_cast<const float4*>(a.set_norm) + c4;
+        const float4* set_b = reinterpret_cast<const float4*>(a.set_denorm) + c4;
+        uint4* my_taps = s.taps[gw][0];
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int st = it & 1;
-            tc::mbar_wait(&s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
             const int64_t base = tile * TILE_M;
-#pragma unroll 2
-#if NFE_PASS_CONTIG
-            // a warp takes consecutive passes = consecutive samples of (mostly) one ray: their XY-plane taps coincide
-            constexpr int PER = (PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS;
-            for (int pass = gw * PER; pass < min(PASSES_PER_TILE, (gw + 1) * PER); ++pass) {
-#else
-            for (int pass = gw; pass < PASSES_PER_TILE; pass += GATHER_WARPS) {
-#endif
-                const int row = 4 * pass + g;
-                float4 fa = make_float4(0.f, 0.f, 0.f, 0.f), fb = fa;
-                if (base + row < a.total) {
+            // ---- tap pre-pass: ONE lane per sample computes position -> 12 clamped texel offsets + 12 weights and
+            //      parks them in shared memory; the 8 lanes of a sample used to recompute them (8x redundant issue)
+            if (lane < PER * 4) {
+                const int row = gw * PER * 4 + lane;
+                TapSet ts;
+#pragma unroll
+                for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
+                if (row < TILE_M && base + row < a.total) {
                     const SampleRef sr = sample_of(a, base + row);
-                    const int64_t idx = sr.idx;
                     float x, y, z;
                     if (a.coords) {
-                        const float* c = a.coords + idx * 3;
+                        const float* c = a.coords + sr.idx * 3;
                         x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
                     } else {
-                        const int64_t ray = idx / a.s_per_ray;
-                        const float t = __ldg(a.depths + idx);
+                        const int64_t ray = sr.idx / a.s_per_ray;
+                        const float t = __ldg(a.depths + sr.idx);
                         const float* o = a.origins + ray * 3;
                         const float* d = a.dirs + ray * 3;
                         x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
                     }
-                    const int64_t pbi = a.plane_batch == 1 ? 0 : sr.item;
-                    const TapSet ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
-                    // all 24 texel loads of the sample are issued before the first blend
-                    float4 va[12], vb[12];
-                    if (T::SETS == 2) gather_load(a.set_norm + pbi * set_stride, ts, c4, va);
-                    gather_load(a.set_denorm + pbi * set_stride, ts, c4, vb);
-                    if (T::SETS == 2) fa = gather_reduce(va, ts);
-                    fb = gather_reduce(vb, ts);
+                    ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
+                    const int item_off = a.plane_batch == 1 ? 0 : (int)(sr.item * set_stride4);
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
                 }
-                if (T::SETS == 2) store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, fa);
-                store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, fb);
+                uint4* dst = my_taps + lane * 6;
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    dst[q] = make_uint4((uint32_t)ts.off4[4 * q], (uint32_t)ts.off4[4 * q + 1], (uint32_t)ts.off4[4 * q + 2], (uint32_t)ts.off4[4 * q + 3]);
+                    dst[3 + q] = make_uint4(__float_as_uint(ts.w[4 * q]), __float_as_uint(ts.w[4 * q + 1]), __float_as_uint(ts.w[4 * q + 2]),
+                                            __float_as_uint(ts.w[4 * q + 3]));
+                }
+            }
+            __syncwarp();
+            tc::mbar_wait(&s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
+#pragma unroll
+            for (int p = 0; p < PER; ++p) {
+                const int pass = gw * PER + p;
+                if (pass < PASSES_PER_TILE) {
+                    const int row = 4 * pass + g;
+                    TapSet ts;
+                    const uint4* src = my_taps + (p * 4 + g) * 6;
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        const uint4 o4 = src[q], w4 = src[3 + q];
+                        ts.off4[4 * q] = (int)o4.x; ts.off4[4 * q + 1] = (int)o4.y; ts.off4[4 * q + 2] = (int)o4.z; ts.off4[4 * q + 3] = (int)o4.w;
+                        ts.w[4 * q] = __uint_as_float(w4.x); ts.w[4 * q + 1] = __uint_as_float(w4.y);
+                        ts.w[4 * q + 2] = __uint_as_float(w4.z); ts.w[4 * q + 3] = __uint_as_float(w4.w);
+                    }
+                    // all 24 texel loads of the sample (two plane sets) are issued before the first blend
+                    float4 va[12], vb[12];
+                    if (T::SETS == 2) {
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) va[i] = __ldg(set_a + ts.off4[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 12; ++i) vb[i] = __ldg(set_b + ts.off4[i]);
+                    if (T::SETS == 2) store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, gather_reduce(va, ts));
+                    store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, gather_reduce(vb, ts));
+                }
             }
             tc::fence_async_smem();
             __syncwarp();
