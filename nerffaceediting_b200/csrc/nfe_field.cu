@@ -215,9 +215,17 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) field_kernel(FieldArgs a, nf
         __syncwarp();
         const int rows = (int)min((int64_t)32, a.total - base);
         if (lane < rows) a.sigma[base + lane] = row[0];
-        for (int e = lane; e < rows * 32; e += 32) a.rgb[base * 32 + e] = tile_f[(e >> 5) * OUT_STRIDE + 17 + (e & 31)];
-        if constexpr (T::HAS_B) {
-            for (int e = lane; e < rows * 15; e += 32) a.seg[base * 15 + e] = tile_f[(e / 15) * OUT_STRIDE + 1 + (e % 15)];
+        if (a.rec) {
+            // packed records {sigma, seg[15], rgb[32]}: 48 floats per sample, the whole step is one contiguous span
+            for (int e = lane; e < rows * 48; e += 32) {
+                const int r = e / 48, c = e % 48;
+                a.rec[base * 48 + e] = (c == 0 || c >= 16 || T::HAS_B) ? tile_f[r * OUT_STRIDE + (c < 16 ? c : c + 1)] : 0.0f;
+            }
+        } else {
+            for (int e = lane; e < rows * 32; e += 32) a.rgb[base * 32 + e] = tile_f[(e >> 5) * OUT_STRIDE + 17 + (e & 31)];
+            if constexpr (T::HAS_B) {
+                for (int e = lane; e < rows * 15; e += 32) a.seg[base * 15 + e] = tile_f[(e / 15) * OUT_STRIDE + 1 + (e % 15)];
+            }
         }
         __syncwarp();
     }

@@ -29,6 +29,9 @@ struct FieldArgs {
     float* sigma;             // [total]
     float* rgb;               // [total,32]
     float* seg;               // [total,15]
+    // Packed per-sample record used between the render passes instead of rgb/seg: rec[idx] = {sigma, seg[15], rgb[32]}
+    // (48 floats = 12 float4, one contiguous 192-byte row per sample).  sigma is still written to `sigma` as well.
+    float* rec;
     float density_noise;
     uint64_t seed, offset;
 };

@@ -343,17 +343,29 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 sig += normal2(r.x, r.y).x * a.density_noise;
             }
             if (live) a.sigma[idx] = sig;
+            float4* rec = a.rec ? reinterpret_cast<float4*>(a.rec + idx * 48) : nullptr;
+            float4* rgb4 = rec ? rec + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
             if constexpr (KIND == NFE_DEC_DISENTANGLED) {
                 if (live) {
+                    if (rec) {
+                        rec[0] = make_float4(sig, outa[1], outa[2], outa[3]);
 #pragma unroll
-                    for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outa[1 + c];
+                        for (int c = 1; c < 4; ++c) rec[c] = make_float4(outa[4 * c], outa[4 * c + 1], outa[4 * c + 2], outa[4 * c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outa[1 + c];
+                    }
                 }
             } else {
                 if (live) {
+                    if (rec && !T::HAS_B) {
+                        rec[0] = make_float4(sig, 0.f, 0.f, 0.f);
+                        rec[1] = rec[2] = rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        reinterpret_cast<float4*>(a.rgb + idx * 32)[c] = make_float4(rgb_activation(outa[1 + 4 * c]), rgb_activation(outa[2 + 4 * c]),
-                                                                                      rgb_activation(outa[3 + 4 * c]), rgb_activation(outa[4 + 4 * c]));
+                        rgb4[c] = make_float4(rgb_activation(outa[1 + 4 * c]), rgb_activation(outa[2 + 4 * c]),
+                                              rgb_activation(outa[3 + 4 * c]), rgb_activation(outa[4 + 4 * c]));
                 }
             }
             if constexpr (T::HAS_B) {
@@ -372,8 +384,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                     if constexpr (KIND == NFE_DEC_DISENTANGLED) {
 #pragma unroll
                         for (int c = 0; c < 8; ++c)
-                            reinterpret_cast<float4*>(a.rgb + idx * 32)[c] = make_float4(rgb_activation(outb[4 * c]), rgb_activation(outb[4 * c + 1]),
-                                                                                          rgb_activation(outb[4 * c + 2]), rgb_activation(outb[4 * c + 3]));
+                            rgb4[c] = make_float4(rgb_activation(outb[4 * c]), rgb_activation(outb[4 * c + 1]),
+                                                  rgb_activation(outb[4 * c + 2]), rgb_activation(outb[4 * c + 3]));
+                    } else if (rec) {
+                        rec[0] = make_float4(sig, outb[0], outb[1], outb[2]);
+#pragma unroll
+                        for (int c = 1; c < 4; ++c) rec[c] = make_float4(outb[4 * c - 1], outb[4 * c], outb[4 * c + 1], outb[4 * c + 2]);
                     } else {
 #pragma unroll
                         for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outb[c];

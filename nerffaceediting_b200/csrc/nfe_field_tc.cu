@@ -189,10 +189,19 @@ __global__ void __launch_bounds__(TILE_M, 1) field_tc_kernel(FieldArgs a, nfe_ml
                 sig += normal2(r.x, r.y).x * a.density_noise;
             }
             a.sigma[idx] = sig;
+            float4* rec = a.rec ? reinterpret_cast<float4*>(a.rec + idx * 48) : nullptr;
+            float4* rgb4 = rec ? rec + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
-                reinterpret_cast<float4*>(a.rgb + idx * 32)[c] = make_float4(col[4 * c], col[4 * c + 1], col[4 * c + 2], col[4 * c + 3]);
-            if constexpr (T::HAS_B) {
+            for (int c = 0; c < 8; ++c) rgb4[c] = make_float4(col[4 * c], col[4 * c + 1], col[4 * c + 2], col[4 * c + 3]);
+            if (rec) {
+                if (!T::HAS_B) {
+#pragma unroll
+                    for (int c = 0; c < 15; ++c) segv[c] = 0.0f;
+                }
+                rec[0] = make_float4(sig, segv[0], segv[1], segv[2]);
+#pragma unroll
+                for (int c = 1; c < 4; ++c) rec[c] = make_float4(segv[4 * c - 1], segv[4 * c], segv[4 * c + 1], segv[4 * c + 2]);
+            } else if constexpr (T::HAS_B) {
 #pragma unroll
                 for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = segv[c];
             }

@@ -132,8 +132,58 @@ __global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
         blk_max = fmaxf(blk_max, dmax);
         __syncwarp();
 
-        // ---- channel sums: lane = channel, sequential over intervals, rows read coalesced
-        if (a.cc > 0) {
+        // ---- channel sums
+        if (a.rec1) {
+            // Packed records (48 floats = 12 float4 per sample): a half-warp reads one whole 192-byte row per load,
+            // lanes 0-11 take row k, lanes 16-27 row k+1; the two halves are added at the end.
+            for (int k = lane; k < S; k += 32) s_sigma[k] = 0.5f * ((k > 0 ? s_w[k - 1] : 0.0f) + (k < n_int ? s_w[k] : 0.0f));
+            __syncwarp();
+            const int half = lane >> 4, q = lane & 15;
+            const bool on = q < 12;
+            const float4* r1 = reinterpret_cast<const float4*>(a.rec1 + ray * a.s1 * 48) + (on ? q : 0);
+            const float4* r2 = a.s2 ? reinterpret_cast<const float4*>(a.rec2 + (ray * a.s2 - a.s1) * 48) + (on ? q : 0) : r1;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            constexpr int UN = 4;                              // 8 rows in flight per warp
+            int k0 = 0;
+            for (; k0 + 2 * UN <= S; k0 += 2 * UN) {
+                float4 v[UN];
+                float om[UN];
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    const int k = k0 + 2 * u + half;
+                    const int e = s_order[k];
+                    v[u] = __ldg((e < a.s1 ? r1 : r2) + e * 12);
+                    om[u] = s_sigma[k];
+                }
+#pragma unroll
+                for (int u = 0; u < UN; ++u) {
+                    acc.x = fmaf(om[u], v[u].x, acc.x); acc.y = fmaf(om[u], v[u].y, acc.y);
+                    acc.z = fmaf(om[u], v[u].z, acc.z); acc.w = fmaf(om[u], v[u].w, acc.w);
+                }
+            }
+            for (; k0 < S; k0 += 2) {
+                const int k = k0 + half;
+                if (k < S) {
+                    const int e = s_order[k];
+                    const float4 v = __ldg((e < a.s1 ? r1 : r2) + e * 12);
+                    const float om = s_sigma[k];
+                    acc.x = fmaf(om, v.x, acc.x); acc.y = fmaf(om, v.y, acc.y); acc.z = fmaf(om, v.z, acc.z); acc.w = fmaf(om, v.w, acc.w);
+                }
+            }
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
+            acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
+            if (half == 0 && on) {
+                if (q >= 4) {                                   // rgb channels 4(q-4) .. +3
+                    if (a.white_back) { const float bg = 1.0f - wt; acc.x += bg; acc.y += bg; acc.z += bg; acc.w += bg; }
+                    reinterpret_cast<float4*>(a.rgb + ray * 32)[q - 4] =
+                        make_float4(acc.x * 2.0f - 1.0f, acc.y * 2.0f - 1.0f, acc.z * 2.0f - 1.0f, acc.w * 2.0f - 1.0f);
+                } else if (a.cs) {                              // record floats 4q..4q+3 = {sigma|seg[4q-1 .. 4q+2]}
+                    float* sg = a.seg + ray * 15;
+                    if (q > 0) sg[4 * q - 1] = acc.x;
+                    sg[4 * q] = acc.y; sg[4 * q + 1] = acc.z; sg[4 * q + 2] = acc.w;
+                }
+            }
+        } else if (a.cc > 0) {
             // sum_i w_i (c_i + c_{i+1})/2  ==  sum_k omega_k c_k  with omega_k = (w_{k-1} + w_k)/2 (w_{-1} = w_{S-1} = 0):
             // one FMA per sample row and no carried "previous row"; omega overwrites the (now dead) densities
             for (int k = lane; k < S; k += 32) s_sigma[k] = 0.5f * ((k > 0 ? s_w[k - 1] : 0.0f) + (k < n_int ? s_w[k] : 0.0f));

@@ -11,6 +11,9 @@ struct MarchArgs {
     // sample set 1 (coarse) and optional set 2 (fine); rows are [n_rays, s, *]
     const float* depths1; const float* colors1; const float* segs1; const float* sigma1; int s1;
     const float* depths2; const float* colors2; const float* segs2; const float* sigma2; int s2;
+    // packed alternative to colors/segs (the fused render's workspace): rec[row] = {sigma, seg[15], rgb[32]}, 48 floats;
+    // implies cc = 32 and cs = 15 or 0
+    const float* rec1; const float* rec2;
     int64_t n_rays;
     int cc, cs;        // colour / semantic channels (0: weights only)
     int inputs_sorted; // both sample sets ascending in depth: merge by binary search instead of a full rank sort

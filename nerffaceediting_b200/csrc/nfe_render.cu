@@ -11,10 +11,10 @@ namespace {
 
 struct Workspace {
     float* minmax;    // 2 floats (+pad)
-    float* sigma_c; float* rgb_c; float* seg_c;
+    float* sigma_c; float* rec_c;   // densities (compact, for the weights / merge) and packed records {sigma,seg[15],rgb[32]}
     float* w_c;       // coarse weights [T, s_c-1]
     float* depths_f;  // [T, s_f]
-    float* sigma_f; float* rgb_f; float* seg_f;
+    float* sigma_f; float* rec_f;
     int64_t bytes;
 };
 
@@ -31,17 +31,14 @@ Workspace carve(const nfe_render_cfg* cfg, int64_t rays, void* base)
         return r;
     };
     const int64_t sc = cfg->s_c, sf = cfg->s_f;
-    const int64_t seg_w = cfg->seg_dim > 0 ? 15 : 0;
     w.minmax = take(64);
     w.sigma_c = take(rays * sc);
-    w.rgb_c = take(rays * sc * 32);
-    w.seg_c = take(rays * sc * seg_w);
+    w.rec_c = take(rays * sc * 48);
     if (sf > 0) {
         w.w_c = take(rays * (sc - 1));
         w.depths_f = take(rays * sf);
         w.sigma_f = take(rays * sf);
-        w.rgb_f = take(rays * sf * 32);
-        w.seg_f = take(rays * sf * seg_w);
+        w.rec_f = take(rays * sf * 48);
     }
     w.bytes = off;
     return w;
@@ -110,7 +107,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
         f.quad_stride = (square && enabled) ? (int)side : 0;
         f.rays_per_item = n_rays;
     }
-    f.sigma = w.sigma_c; f.rgb = w.rgb_c; f.seg = w.seg_c;
+    f.sigma = w.sigma_c; f.rec = w.rec_c;
     f.density_noise = cfg->density_noise; f.seed = cfg->seed; f.offset = cfg->offset + 1;
     {
         StageScope t(STAGE_FIELD_COARSE, stream);
@@ -138,16 +135,16 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
         }
         // ---- fine pass (renderer.py:122-129,344-353)
         f.depths = df; f.s_per_ray = sf; f.m = n_rays * sf; f.total = rays * sf;
-        f.sigma = w.sigma_f; f.rgb = w.rgb_f; f.seg = w.seg_f; f.offset = cfg->offset + 3;
+        f.sigma = w.sigma_f; f.rec = w.rec_f; f.offset = cfg->offset + 3;
         {
             StageScope t(STAGE_FIELD_FINE, stream);
             if (int rc = launch_field(cfg->kind, cfg->precision, f, net_a, net_b, stream)) return rc;
         }
         // ---- merge + composite (renderer.py:131-135,355-359)
-        m.depths2 = df; m.colors2 = w.rgb_f; m.segs2 = w.seg_f; m.sigma2 = w.sigma_f; m.s2 = sf;
+        m.depths2 = df; m.rec2 = w.rec_f; m.sigma2 = w.sigma_f; m.s2 = sf;
         m.inputs_sorted = 1;  // coarse depths ascend by construction; the fine list is emitted sorted (table u, or sort_u)
     }
-    m.depths1 = depths_coarse; m.colors1 = w.rgb_c; m.segs1 = w.seg_c; m.sigma1 = w.sigma_c; m.s1 = sc;
+    m.depths1 = depths_coarse; m.rec1 = w.rec_c; m.sigma1 = w.sigma_c; m.s1 = sc;
     m.cc = 32; m.cs = cfg->seg_dim; m.rgb = rgb; m.seg = seg; m.depth = depth; m.wsum = wsum; m.weights = nullptr; m.minmax = minmax;
     StageScope t(STAGE_MARCH_FINAL, stream);
     if (int rc = launch_march(m, sf > 0, stream)) return rc;
