@@ -60,7 +60,8 @@ int nfe_planes_to_channel_last(const float* planes, int64_t n_img, int channels,
 
 /* normalize_plane fused with the staging of BOTH plane sets: planes is [n_img, 32, hw] (n_img = batch*3);
  * one read produces out_norm (same layout), its channel-last copy and the channel-last copy of the
- * raw planes — what DisentangledImportanceRenderer.forward needs from triplane.py:95,113-119. */
+ * raw planes — what DisentangledImportanceRenderer.forward needs from triplane.py:95,113-119.
+ * out_raw_cl may be NULL (the single-gather identity needs only the normalised staging). */
 int nfe_plane_normalize_staged(const float* planes, const float* mean, const float* std_in, int64_t n_img,
                                int64_t hw, float* out_norm, float* out_norm_cl, float* out_raw_cl,
                                nfe_stream_t stream);
@@ -160,6 +161,13 @@ typedef struct {
     int stochastic;          /* 0: parity mode (u_fine = linspace table); 1: Philox jitter */
     uint64_t seed, offset;   /* Philox stream for stochastic mode / density noise */
     int precision;           /* NFE_PREC_* : arithmetic of the decoder MLPs */
+    /* Single-gather identity (disentangled decoder, tensor-core modes): if affine_scale != NULL the
+     * de-normalised planes are norm*scale + shift per (item, channel) — device [affine_items, 96] floats,
+     * affine_items = n or 1 (e.g. std+1e-8 / mean of normalize_plane, or swapped statistics,
+     * triplane.py:93-107) — and planes_denorm_cl may be NULL: only the normalised planes are gathered. */
+    const float* affine_scale;
+    const float* affine_shift;
+    int affine_items;
 } nfe_render_cfg;
 
 /* bytes of device workspace nfe_render_fwd needs for n*n_rays rays with this cfg */

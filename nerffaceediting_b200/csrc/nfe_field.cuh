@@ -166,6 +166,28 @@ __device__ __forceinline__ float4 gather_reduce(const float4 (&v)[12], const Tap
                        ((f[0].z + f[1].z) + f[2].z) * third, ((f[0].w + f[1].w) + f[2].w) * third);
 }
 
+// Per-plane blends kept apart (no mean), plus each plane's sum of in-bounds tap weights: what the single-gather
+// identity needs.  With zero padding, sampling an affinely transformed plane P' = s*P + m (per channel) gives
+//   sample(P') = s*sample(P) + m*w_in,   w_in = sum of the in-bounds bilinear weights        
+// so the de-normalised features follow from the normalised gather and the statistics alone.
+__device__ __forceinline__ void gather_reduce_planes(const float4 (&v)[12], const TapSet& ts, float4 (&f)[3], float (&w_in)[3])
+{
+#pragma unroll
+    for (int p = 0; p < 3; ++p) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float ws = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float w = ts.w[p * 4 + k];
+            acc.x = fmaf(v[p * 4 + k].x, w, acc.x); acc.y = fmaf(v[p * 4 + k].y, w, acc.y);
+            acc.z = fmaf(v[p * 4 + k].z, w, acc.z); acc.w = fmaf(v[p * 4 + k].w, w, acc.w);
+            ws += w;
+        }
+        f[p] = acc;
+        w_in[p] = ws;
+    }
+}
+
 __device__ __forceinline__ float4 gather_set(const float* __restrict__ set, const TapSet& ts, int c4)
 {
     float4 v[12];

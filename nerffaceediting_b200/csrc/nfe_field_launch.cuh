@@ -10,6 +10,10 @@ constexpr int FIELD_THREADS = 512;
 struct FieldArgs {
     const float* set_norm;    // channel-last [plane_batch,3,H,W,32]; unused unless the decoder is disentangled
     const float* set_denorm;
+    // Single-gather identity (disentangled decoder, pipelined kernel): when non-NULL the de-normalised planes are
+    // norm*scale + shift per (item, plane-major channel) — [affine_items, 96] floats each, affine_items = n or 1 —
+    // and set_denorm is not read at all.
+    const float* affine_scale; const float* affine_shift; int affine_items;
     int plane_batch, H, W;
     float scale;              // 2 / box_warp
     // sample positions: explicit points, or rays + per-sample depths (sample idx = ray*s_per_ray + s)

@@ -47,7 +47,7 @@ struct PipeSmem {
     alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
-    alignas(16) uint4 taps[GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][6];   // per sample: 12 offsets + 12 weights
+    alignas(16) uint4 taps[GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][7];   // per sample: 12 offsets, 12 weights, item
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
     float bias2a[T::N_A];
     float bias2b[T::N_B];
@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             if (lane < PER * 4) {
                 const int row = gw * PER * 4 + lane;
                 TapSet ts;
+                int item_idx = 0;
 #pragma unroll
                 for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
                 if (row < TILE_M && base + row < a.total) {
@@ -210,11 +211,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                         x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
                     }
                     ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
+                    item_idx = sr.item;
                     const int item_off = a.plane_batch == 1 ? 0 : (int)(sr.item * set_stride4);
 #pragma unroll
                     for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
                 }
-                uint4* dst = my_taps + lane * 6;
+                uint4* dst = my_taps + lane * 7;
+                dst[6] = make_uint4((uint32_t)item_idx, 0u, 0u, 0u);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
                     dst[q] = make_uint4((uint32_t)ts.off4[4 * q], (uint32_t)ts.off4[4 * q + 1], (uint32_t)ts.off4[4 * q + 2], (uint32_t)ts.off4[4 * q + 3]);
@@ -230,13 +233,42 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 if (pass < PASSES_PER_TILE) {
                     const int row = 4 * pass + g;
                     TapSet ts;
-                    const uint4* src = my_taps + (p * 4 + g) * 6;
+                    const uint4* src = my_taps + (p * 4 + g) * 7;
 #pragma unroll
                     for (int q = 0; q < 3; ++q) {
                         const uint4 o4 = src[q], w4 = src[3 + q];
                         ts.off4[4 * q] = (int)o4.x; ts.off4[4 * q + 1] = (int)o4.y; ts.off4[4 * q + 2] = (int)o4.z; ts.off4[4 * q + 3] = (int)o4.w;
                         ts.w[4 * q] = __uint_as_float(w4.x); ts.w[4 * q + 1] = __uint_as_float(w4.y);
                         ts.w[4 * q + 2] = __uint_as_float(w4.z); ts.w[4 * q + 3] = __uint_as_float(w4.w);
+                    }
+                    if (T::SETS == 2 && a.affine_scale) {
+                        // single-gather identity: only the normalised planes are read; the de-normalised features are
+                        // s*f_p + m*w_in per plane (statistics: 6 L1-resident float4 loads per lane)
+                        float4 va[12];
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) va[i] = __ldg(set_a + ts.off4[i]);
+                        const int item = a.affine_items == 1 ? 0 : (int)src[6].x;
+                        const float4* sc = reinterpret_cast<const float4*>(a.affine_scale + (int64_t)item * 96) + c4;
+                        const float4* sh = reinterpret_cast<const float4*>(a.affine_shift + (int64_t)item * 96) + c4;
+                        float4 scl[3], shf[3];
+#pragma unroll
+                        for (int pl = 0; pl < 3; ++pl) { scl[pl] = __ldg(sc + pl * 8); shf[pl] = __ldg(sh + pl * 8); }
+                        float4 f[3];
+                        float w_in[3];
+                        gather_reduce_planes(va, ts, f, w_in);
+                        constexpr float third = 1.0f / 3.0f;
+                        const float4 fa = make_float4(((f[0].x + f[1].x) + f[2].x) * third, ((f[0].y + f[1].y) + f[2].y) * third,
+                                                      ((f[0].z + f[1].z) + f[2].z) * third, ((f[0].w + f[1].w) + f[2].w) * third);
+                        float4 d[3];
+#pragma unroll
+                        for (int pl = 0; pl < 3; ++pl)
+                            d[pl] = make_float4(fmaf(scl[pl].x, f[pl].x, shf[pl].x * w_in[pl]), fmaf(scl[pl].y, f[pl].y, shf[pl].y * w_in[pl]),
+                                                fmaf(scl[pl].z, f[pl].z, shf[pl].z * w_in[pl]), fmaf(scl[pl].w, f[pl].w, shf[pl].w * w_in[pl]));
+                        const float4 fb = make_float4(((d[0].x + d[1].x) + d[2].x) * third, ((d[0].y + d[1].y) + d[2].y) * third,
+                                                      ((d[0].z + d[1].z) + d[2].z) * third, ((d[0].w + d[1].w) + d[2].w) * third);
+                        store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, fa);
+                        store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, fb);
+                        continue;
                     }
                     // all 24 texel loads of the sample (two plane sets) are issued before the first blend
                     float4 va[12], vb[12];

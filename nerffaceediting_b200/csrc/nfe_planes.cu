@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(256) stage32_kernel(const float* __restrict__ 
     float x[32];
 #pragma unroll
     for (int c = 0; c < 32; ++c) x[c] = live ? __ldg(src + (int64_t)c * hw) : 0.0f;
-    if (live) {
+    if (live && out_raw_cl) {
         float4* dst = reinterpret_cast<float4*>(out_raw_cl + (img * hw + px) * 32);
 #pragma unroll
         for (int q = 0; q < 8; ++q) dst[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
@@ -266,7 +266,7 @@ NFE_EXPORT int nfe_plane_normalize_staged(const float* planes, const float* mean
                                           float* out_norm_cl, float* out_raw_cl, nfe_stream_t stream)
 {
     if (n_img == 0 || hw == 0) return 0;
-    NFE_REQUIRE(planes && mean && std_in && out_norm && out_norm_cl && out_raw_cl, "nfe_plane_normalize_staged: null pointer");
+    NFE_REQUIRE(planes && mean && std_in && out_norm && out_norm_cl, "nfe_plane_normalize_staged: null pointer");
     NFE_REQUIRE(((reinterpret_cast<uintptr_t>(out_norm_cl) | reinterpret_cast<uintptr_t>(out_raw_cl)) & 15) == 0,
                 "nfe_plane_normalize_staged: channel-last outputs must be 16-byte aligned");
     const int64_t groups_per_img = (hw + 31) / 32, n_groups = n_img * groups_per_img;

@@ -77,7 +77,11 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
     if (int rc = check_cfg(cfg, "nfe_render_fwd")) return rc;
     if (int rc = check_decoder_dims(cfg->kind, net_a, net_b, "nfe_render_fwd")) return rc;
     if ((int64_t)n * n_rays == 0) return 0;  // empty tensors carry null pointers
-    NFE_REQUIRE(planes_denorm_cl && origins && dirs && depths_coarse && rgb && depth && wsum, "nfe_render_fwd: null pointer");
+    static const bool tc_simple = getenv("NFE_TC_SIMPLE") != nullptr;
+    const bool affine = cfg->affine_scale && cfg->affine_shift && cfg->kind == NFE_DEC_DISENTANGLED && cfg->precision != NFE_PREC_FP32 && !tc_simple;
+    NFE_REQUIRE(!cfg->affine_scale || (cfg->affine_items == 1 || cfg->affine_items == n), "nfe_render_fwd: affine statistics for %d items, batch is %d",
+                cfg->affine_items, n);
+    NFE_REQUIRE((planes_denorm_cl || affine) && origins && dirs && depths_coarse && rgb && depth && wsum, "nfe_render_fwd: null pointer");
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_render_fwd: the disentangled decoder needs the normalised planes");
     NFE_REQUIRE(cfg->seg_dim == 0 || seg, "nfe_render_fwd: seg output missing");
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_render_fwd: plane batch %d does not match ray batch %d", plane_batch, n);
@@ -94,6 +98,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
     // ---- coarse pass (renderer.py:104-113,325-336)
     FieldArgs f = {};
     f.set_norm = planes_norm_cl; f.set_denorm = planes_denorm_cl; f.plane_batch = plane_batch; f.H = cfg->height; f.W = cfg->width;
+    if (affine) { f.affine_scale = cfg->affine_scale; f.affine_shift = cfg->affine_shift; f.affine_items = cfg->affine_items; }
     f.scale = (float)(2.0 / (double)cfg->box_warp);
     f.origins = origins; f.dirs = dirs; f.depths = depths_coarse; f.s_per_ray = sc;
     f.m = n_rays * sc; f.total = rays * sc;

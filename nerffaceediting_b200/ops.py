@@ -95,6 +95,10 @@ def plane_denormalize(norm, mean, std):
     with _Guard(x):
         _lib.check(_lib.load().nfe_plane_denormalize(_ptr(x), _ptr(mean), _ptr(std), slabs, stat, hw, _ptr(out), _stream(x)),
                    "nfe_plane_denormalize")
+    if x.dim() in (4, 5) and (x.shape[1] == 96 or (x.dim() == 5 and x.shape[1] == 3 and x.shape[2] == 32)):
+        k = stat // 96 if stat % 96 == 0 else 0
+        if k in (1, x.shape[0]):
+            _provenance_put(out, _key5(x), std.reshape(k, 96), mean.reshape(k, 96))
     return out
 
 
@@ -122,13 +126,44 @@ def planes_channel_last(planes, cache=False):
     return out
 
 
+# Provenance of de-normalised planes: key(denorm tensor) -> (key(norm tensor), scale [K,96], shift [K,96], keep-alive refs).
+# Filled by plane_normalize_staged (raw = norm*(std+1e-8) + mean) and plane_denormalize (out = norm*std' + mean');
+# read by the disentangled renderer to gather the normalised planes only (single-gather identity).
+_PROVENANCE = {}
+_PROVENANCE_MAX = 4
+
+
+def _key5(t):
+    """Identity of a tri-plane tensor, the same for [N,96,H,W] and its [N,3,32,H,W] view."""
+    if t.dim() == 4:
+        n, c, h, w = t.shape
+        shape5 = (n, 3, c // 3, h, w)
+    else:
+        shape5 = tuple(t.shape)
+    return (t.data_ptr(), shape5, t._version, t.device.index)
+
+
+def _provenance_put(denorm, norm_key, scale, shift):
+    while len(_PROVENANCE) >= _PROVENANCE_MAX:
+        _PROVENANCE.pop(next(iter(_PROVENANCE)))
+    _PROVENANCE[_key5(denorm)] = (norm_key, scale.reshape(scale.shape[0], -1).contiguous(), shift.reshape(shift.shape[0], -1).contiguous(), denorm)
+
+
+def provenance(norm_planes, denorm_planes):
+    """(scale, shift) if denorm_planes is known to be norm_planes*scale + shift per (item, channel), else None."""
+    hit = _PROVENANCE.get(_key5(denorm_planes))
+    if hit is None or hit[0] != _key5(norm_planes):
+        return None
+    return hit[1], hit[2]
+
+
 def _cache_put(key, src, staged):
     while len(_CL_CACHE) >= _CL_CACHE_MAX:
         _CL_CACHE.pop(next(iter(_CL_CACHE)))
     _CL_CACHE[key] = (src, staged)
 
 
-def plane_normalize_staged(planes, mean, std):
+def plane_normalize_staged(planes, mean, std, stage_raw=False):
     """normalize_plane for tri-plane tensors [N, 96, H, W]: one kernel writes the normalised planes AND the
     channel-last staging of both the normalised and the raw planes, and registers the staged copies so that
     the renderer called next on views of (norm, planes) (triplane.py:113-119) skips its own staging pass.
@@ -137,14 +172,16 @@ def plane_normalize_staged(planes, mean, std):
     n, c96, h, w = x.shape
     norm = torch.empty_like(x)
     norm_cl = torch.empty((n, 3, h, w, 32), device=x.device, dtype=torch.float32)
-    raw_cl = torch.empty_like(norm_cl)
+    raw_cl = torch.empty_like(norm_cl) if stage_raw else None
     with _Guard(x):
         _lib.check(_lib.load().nfe_plane_normalize_staged(_ptr(x), _ptr(mean), _ptr(std), n * 3, h * w, _ptr(norm), _ptr(norm_cl), _ptr(raw_cl),
                                                           _stream(x)), "nfe_plane_normalize_staged")
     _CL_CACHE.clear()
-    shape5 = (n, 3, 32, h, w)
-    _cache_put((norm.data_ptr(), shape5, norm._version, x.device.index), norm, norm_cl)
-    _cache_put((x.data_ptr(), shape5, x._version, x.device.index), x, raw_cl)
+    _cache_put(_key5(norm), norm, norm_cl)
+    if raw_cl is not None:
+        _cache_put(_key5(x), x, raw_cl)
+    # the raw planes ARE the de-normalisation of `norm` with their own statistics
+    _provenance_put(x, _key5(norm), std.reshape(n, -1) + 1e-8, mean.reshape(n, -1))
     return norm
 
 
@@ -399,10 +436,24 @@ def precision_of(options):
 
 
 def make_cfg(kind, planes_cl, s_c, s_f, box_warp, white_back=False, density_noise=0.0, stochastic=False, seed=0, offset=0,
-             precision=_lib.PREC_FP32):
+             precision=_lib.PREC_FP32, affine=None):
+    """affine = (scale [K,96], shift [K,96]) device tensors (K = batch or 1) enables the single-gather identity."""
     _, _, h, w, c = planes_cl.shape
-    return NfeRenderCfg(kind, c, h, w, int(s_c), int(s_f), 32, 0 if kind == DEC_OSG else 15, int(bool(white_back)),
-                        float(box_warp), float(density_noise), int(bool(stochastic)), seed, offset, precision)
+    cfg = NfeRenderCfg(kind, c, h, w, int(s_c), int(s_f), 32, 0 if kind == DEC_OSG else 15, int(bool(white_back)),
+                       float(box_warp), float(density_noise), int(bool(stochastic)), seed, offset, precision, None, None, 0)
+    if affine is not None:
+        scale, shift = affine
+        cfg.affine_scale, cfg.affine_shift, cfg.affine_items = scale.data_ptr(), shift.data_ptr(), scale.shape[0]
+        cfg._keep = (scale, shift)          # keep the tensors alive as long as the cfg
+    return cfg
+
+
+def workspace_limit_bytes():
+    """Upper bound for one nfe_render_fwd workspace ($NFE_WORKSPACE_MB, default 8192).  Larger renders (the
+    256^2 x 96+96 x batch-64 sweep would need 158 GB) are split into batch-item / ray-block chunks; the depth
+    clamp's global range is combined across the chunks before nfe_finish_depth, so results do not depend on it."""
+    import os
+    return int(os.environ.get("NFE_WORKSPACE_MB", "8192")) << 20
 
 
 def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dirs, depths_coarse, u_fine,
@@ -413,7 +464,7 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
         raise RuntimeError(f"ray_origins / ray_directions: expected matching [N,R,3], got {tuple(o.shape)} and {tuple(d.shape)}")
     n, r, _ = o.shape
     dev = o.device
-    dc = _cuda_f32(depths_coarse, "depths_coarse")
+    dc = _cuda_f32(depths_coarse, "depths_coarse").reshape(n, r, cfg.s_c)
     a = MlpRef(seq_a, dev)
     b = MlpRef(seq_b, dev) if seq_b is not None else None
     rgb = torch.empty((n, r, 32), device=dev, dtype=torch.float32)
@@ -424,16 +475,61 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
     dfine = torch.empty((n, r, max(cfg.s_f, 1), 1), device=dev, dtype=torch.float32) if return_stages and cfg.s_f else None
     wcoarse = torch.empty((n, r, cfg.s_c - 1, 1), device=dev, dtype=torch.float32) if return_stages and cfg.s_f else None
     lib = _lib.load()
-    with _Guard(o):
-        nbytes = lib.nfe_render_workspace_bytes(ctypes.byref(cfg), n, r)
+    any_planes = planes_denorm_cl if planes_denorm_cl is not None else planes_norm_cl     # denorm is absent under the single-gather identity
+    shared_planes = any_planes.shape[0] == 1 and n > 1
+
+    def call(i0, i1, r0, r1, mm, finish):
+        """rays [r0,r1) of items [i0,i1); a ray sub-range is only used with a single item, so every slice is contiguous"""
+        cn, cr = i1 - i0, r1 - r0
+        nbytes = lib.nfe_render_workspace_bytes(ctypes.byref(cfg), cn, cr)
         if nbytes < 0:
             raise RuntimeError("nfe_render_workspace_bytes: bad arguments")
         ws = torch.empty(max(int(nbytes), 1), device=dev, dtype=torch.uint8)
-        rc = lib.nfe_render_fwd(ctypes.byref(cfg), a.ref(), b.ref() if b else None, _ptr(planes_norm_cl), _ptr(planes_denorm_cl),
-                                planes_denorm_cl.shape[0], _ptr(o), _ptr(d), n, r, _ptr(dc), _ptr(u_fine), _ptr(rgb), _ptr(seg),
-                                _ptr(depth), _ptr(wsum), _ptr(minmax), int(bool(finish_depth)), _ptr(dfine), _ptr(wcoarse),
-                                _ptr(ws), int(nbytes), _stream(o))
-    _lib.check(rc, "nfe_render_fwd")
+        sl = (slice(i0, i1), slice(r0, r1))
+        pn = planes_norm_cl if (planes_norm_cl is None or shared_planes) else planes_norm_cl[i0:i1]
+        pd = planes_denorm_cl if (planes_denorm_cl is None or shared_planes) else planes_denorm_cl[i0:i1]
+        ccfg = cfg
+        if cfg.affine_scale and cfg.affine_items == n and (i0, i1) != (0, n):
+            ccfg = NfeRenderCfg.from_buffer_copy(cfg)                  # per-item statistics: shift to this chunk's items
+            ccfg.affine_scale, ccfg.affine_shift, ccfg.affine_items = cfg.affine_scale + i0 * 96 * 4, cfg.affine_shift + i0 * 96 * 4, cn
+        oo, dd, dcc = o[sl].contiguous(), d[sl].contiguous(), dc[sl].contiguous()     # no copies: whole items, or rays of one item
+        outs = [rgb, seg, depth, wsum]
+        views = [None if t is None else t[sl] for t in outs]
+        direct = all(v is None or v.is_contiguous() for v in views)
+        bufs = views if direct else [None if v is None else torch.empty_like(v) for v in views]
+        rc = lib.nfe_render_fwd(ctypes.byref(ccfg), a.ref(), b.ref() if b else None, _ptr(pn), _ptr(pd), (pn if pd is None else pd).shape[0], _ptr(oo), _ptr(dd), cn, cr,
+                                _ptr(dcc), _ptr(u_fine), _ptr(bufs[0]), _ptr(bufs[1]), _ptr(bufs[2]), _ptr(bufs[3]), _ptr(mm), int(bool(finish)),
+                                _ptr(dfine), _ptr(wcoarse), _ptr(ws), int(nbytes), _stream(o))
+        _lib.check(rc, "nfe_render_fwd")
+        if not direct:
+            for v, bf in zip(views, bufs):
+                if v is not None:
+                    v.copy_(bf)
+
+    with _Guard(o):
+        limit = workspace_limit_bytes()
+        per_item = lib.nfe_render_workspace_bytes(ctypes.byref(cfg), 1, r) if n and r else 0
+        if n * per_item <= limit or n * r == 0:
+            call(0, n, 0, r, minmax, finish_depth)
+        else:
+            if return_stages:
+                raise RuntimeError("render_fwd: stage taps are not available for renders split into workspace chunks")
+            parts = []
+            if per_item <= limit:                                   # groups of whole items
+                step = max(1, limit // per_item)
+                chunks = [(i, min(i + step, n), 0, r) for i in range(0, n, step)]
+            else:                                                   # ray blocks inside each item
+                per_ray = max(1, per_item // r)
+                rstep = max(1, limit // per_ray)
+                chunks = [(i, i + 1, q, min(q + rstep, r)) for i in range(n) for q in range(0, r, rstep)]
+            for (i0, i1, r0, r1) in chunks:
+                mm = torch.empty(2, device=dev, dtype=torch.float32)
+                call(i0, i1, r0, r1, mm, False)
+                parts.append(mm)
+            mms = torch.stack(parts)
+            minmax = torch.stack([mms[:, 0].min(), mms[:, 1].max()])
+            if finish_depth:
+                _lib.check(lib.nfe_finish_depth(_ptr(depth), depth.numel(), _ptr(minmax), _stream(o)), "nfe_finish_depth")
     if return_stages:
         return rgb, seg, depth, wsum, minmax, {"depths_fine": dfine, "weights_coarse": wcoarse}
     return rgb, seg, depth, wsum, minmax

@@ -14,6 +14,9 @@ Extra keys read from `rendering_options` (all optional; defaults reproduce the r
                             CUDA generator (statistically, not bitwise, equal to torch.rand).
   nfe_precision      'fp32' arithmetic of the decoder MLPs: 'fp32' (FFMA), 'bf16x3' (tcgen05 tensor cores, three
                             bf16 MMAs per product, fp32-grade: meets the 1e-4 tolerance) or 'bf16' (tensor cores, 1e-2).
+  nfe_single_gather  True   disentangled renderer, tensor-core modes: when the de-normalised planes are known to be
+                            norm*scale+shift per channel (they came from normalize_plane / denormalize_plane of this
+                            package), gather only the normalised planes and rebuild the other features from the statistics.
   nfe_cache_planes   False  keep the channel-last staging of the planes between calls (video sweeps).
 
 Instances hold no state of their own beyond the reference's attributes, so objects unpickled from
@@ -141,15 +144,22 @@ class ImportanceRenderer(torch.nn.Module):
         kind, seq_a, seq_b = desc
         ops._no_grad_needed(norm_planes, planes, ray_origins, ray_directions, *decoder.parameters())
         cache = bool(opts.get('nfe_cache_planes', False))
-        denorm_cl = ops.planes_channel_last(planes, cache)
+        precision = ops.precision_of(opts)
+        affine = None
+        if kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True):
+            # planes known to be norm*scale + shift per channel (normalize_plane / denormalize_plane made them):
+            # gather the normalised planes only and rebuild the de-normalised features from the statistics
+            affine = ops.provenance(norm_planes, planes)
         norm_cl = ops.planes_channel_last(norm_planes, cache) if kind == ops.DEC_DISENTANGLED else None
-        if denorm_cl.shape[0] not in (1, ray_origins.shape[0]):
-            raise RuntimeError(f"planes batch {denorm_cl.shape[0]} does not match ray batch {ray_origins.shape[0]}")
+        denorm_cl = ops.planes_channel_last(planes, cache) if affine is None else None
+        plane_batch = (norm_cl if denorm_cl is None else denorm_cl).shape[0]
+        if plane_batch not in (1, ray_origins.shape[0]):
+            raise RuntimeError(f"planes batch {plane_batch} does not match ray batch {ray_origins.shape[0]}")
         depths_coarse, seed, offset = self._coarse_depths(ray_origins, ray_directions, opts, deterministic)
         s_f = opts['depth_resolution_importance']
-        cfg = ops.make_cfg(kind, denorm_cl, opts['depth_resolution'], s_f, opts['box_warp'], opts.get('white_back', False),
-                           opts.get('density_noise', 0) or 0.0, stochastic=not deterministic, seed=seed, offset=offset,
-                           precision=ops.precision_of(opts))
+        cfg = ops.make_cfg(kind, norm_cl if denorm_cl is None else denorm_cl, opts['depth_resolution'], s_f, opts['box_warp'],
+                           opts.get('white_back', False), opts.get('density_noise', 0) or 0.0, stochastic=not deterministic, seed=seed,
+                           offset=offset, precision=precision, affine=affine)
         u_fine = ops.linspace_table(0, 1, s_f, ray_origins.device) if (s_f > 0 and deterministic) else None
         rgb, seg, depth, wsum, minmax = ops.render_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, ray_origins, ray_directions,
                                                        depths_coarse, u_fine, finish_depth=not defer_clamp)
