@@ -2,14 +2,13 @@
 //
 // One persistent CTA per SM, 16 warps with fixed roles, connected by mbarriers:
 //
-//   7 gather warps     tri-plane bilinear gather (L2/L1-bound: 24 texel lines of 128 B per sample) of a
+//   11 gather warps    tri-plane bilinear gather (L2/L1-bound: 24 texel lines of 128 B per sample) of a
 //                      128-sample tile -> bf16 hi/lo feature tile in a 2-stage shared-memory ring
 //   1 MMA warp         one elected thread issues tcgen05.mma for layer 1 (both nets) and layer 2,
 //                      accumulators in a double-buffered TMEM region; tcgen05.commit signals the
 //                      ring slot free and the accumulators full
-//   8 epilogue warps   two groups of 4 (one per net); a thread owns one TMEM lane = one sample: tcgen05.ld,
-//                      softplus on the SFU, bf16 split, hidden tile -> shared (A operand of layer 2), then
-//                      bias + sigmoid + stores.  The SFU (2 MUFU per hidden unit) bounds this stage.
+//   4 epilogue warps   thread m owns TMEM lane m = sample m: tcgen05.ld, softplus, bf16 split,
+//                      hidden tile -> shared (A operand of layer 2), then bias + sigmoid + stores
 //
 // While the epilogue warps finish tile i, the gather warps are already two tiles ahead and the
 // tensor core has run layer 1 of tile i+1, so the three resources (LSU/L2, tensor pipe, ALU/SFU)
@@ -22,13 +21,13 @@ namespace nfe {
 using namespace tcmlp;
 
 #ifndef NFE_GATHER_WARPS
-#define NFE_GATHER_WARPS 7
+#define NFE_GATHER_WARPS 11
 #endif
 #ifndef NFE_PASS_CONTIG
 #define NFE_PASS_CONTIG 1
 #endif
-constexpr int GATHER_WARPS = NFE_GATHER_WARPS;              // 8 + 1 + 7 = 16 warps x 128 registers = the whole register file
-constexpr int EPI_WARPS = 8;                                // two groups of 4 (TMEM lane quadrants): group A = net A, group B = net B
+constexpr int GATHER_WARPS = NFE_GATHER_WARPS;              // 11: 16 warps x 128 registers = the whole register file
+constexpr int EPI_WARPS = 4;
 constexpr int MMA_WARP = EPI_WARPS;                         // warp index of the MMA issuer
 constexpr int PIPE_THREADS = (EPI_WARPS + 1 + GATHER_WARPS) * 32;
 constexpr int PASSES_PER_TILE = TILE_M / 4;                 // a pass = 4 samples (8 lanes each); passes are dealt round-robin to the gather warps
@@ -45,14 +44,14 @@ struct PipeSmem {
     static constexpr int NETS = T::HAS_B ? 2 : 1;
     alignas(128) unsigned char a1[2][T::SETS][PARTS][A1_BYTES];   // feature ring
     alignas(128) unsigned char b1[NETS][PARTS][B1_BYTES];
-    alignas(128) unsigned char a2[NETS][PARTS][A2_BYTES];         // hidden tiles (layer-2 A operands), one per net
+    alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
     alignas(16) uint4 taps[GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][7];   // per sample: 12 offsets, 12 weights, item
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
     float bias2a[T::N_A];
     float bias2b[T::N_B];
-    alignas(8) uint64_t full[2], empty[2], d1_full[2], d2a_full[2], d2b_full[2], tmem_free[2], a2_full[2];
+    alignas(8) uint64_t full[2], empty[2], d1_full[2], d2a_full[2], d2b_full[2], tmem_free[2], a2_full;
     uint32_t tmem_base;
 };
 
@@ -162,9 +161,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             tc::mbar_init(&s.d1_full[i], 1);
             tc::mbar_init(&s.d2a_full[i], 1);
             tc::mbar_init(&s.d2b_full[i], 1);
-            tc::mbar_init(&s.tmem_free[i], T::HAS_B ? EPI_WARPS : EPI_WARPS / 2);
-            tc::mbar_init(&s.a2_full[i], EPI_WARPS / 2);
+            tc::mbar_init(&s.tmem_free[i], EPI_WARPS);
         }
+        tc::mbar_init(&s.a2_full, EPI_WARPS);
         tc::mbar_fence_init();
     }
     pipe_load_params(s, net_a, net_b);
@@ -309,124 +308,129 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 tc::mma_commit(&s.d1_full[st]);
             };
             int it = 0;
+            uint32_t a2_uses = 0;
             if ((int64_t)blockIdx.x < n_tiles) layer1(0);
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t tb = tmem + (it & 1) * TMEM_BUF_COLS;
-                // layer 2, net A (its hidden tile comes from epilogue group A)
-                tc::mbar_wait(&s.a2_full[0], it & 1);
+                // layer 2, net A
+                tc::mbar_wait(&s.a2_full, a2_uses++ & 1);
                 tc::fence_after_sync();
-                issue_gemm<SPLIT>(tb + COL_D2A, s.a2[0][0], s.a2[0][P], A2_LBO, A2_SBO, s.b2a[0], s.b2a[P], B2_LBO, B2_SBO, HIDDEN, idesc2a);
+                issue_gemm<SPLIT>(tb + COL_D2A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2a[0], s.b2a[P], B2_LBO, B2_SBO, HIDDEN, idesc2a);
                 tc::mma_commit(&s.d2a_full[it & 1]);
                 // layer 1 of the NEXT tile goes in here, so the epilogue never waits on it
                 if (tile + gridDim.x < n_tiles) layer1(it + 1);
                 if constexpr (T::HAS_B) {
-                    tc::mbar_wait(&s.a2_full[1], it & 1);
+                    tc::mbar_wait(&s.a2_full, a2_uses++ & 1);
                     tc::fence_after_sync();
-                    issue_gemm<SPLIT>(tb + COL_D2A + T::N_A, s.a2[1][0], s.a2[1][P], A2_LBO, A2_SBO, s.b2b[0], s.b2b[P], B2_LBO, B2_SBO, HIDDEN, idesc2b);
+                    issue_gemm<SPLIT>(tb + COL_D2A + T::N_A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2b[0], s.b2b[P], B2_LBO, B2_SBO, HIDDEN, idesc2b);
                     tc::mma_commit(&s.d2b_full[it & 1]);
                 }
             }
         }
         __syncwarp();
     } else {
-        // ================================================================ epilogue warps
-        // Two groups of four warps; warp w of either group owns TMEM lanes 32*(w%4).. = tile rows 32*(w%4)..
-        // Group A runs net A's softplus epilogue and outputs, group B net B's, concurrently: the SFU work
-        // (2 MUFU per hidden unit, 2 per colour) is what bounds this stage, so it is spread over 8 warps.
-        const int grp = warp >> 2;
-        const int row = (warp & 3) * 32 + lane;
-        if (grp == 1 && !T::HAS_B) { /* single-net decoder: nothing for group B */ }
-        else {
-            int it = 0;
-            for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-                const int st = it & 1;
-                const uint32_t ph = (it >> 1) & 1;
-                const uint32_t lane_addr = tmem + st * TMEM_BUF_COLS + ((uint32_t)((warp & 3) * 32) << 16);
-                uint32_t hi[32], lo[32];
-                tc::mbar_wait(&s.d1_full[st], ph);
+        // ================================================================ epilogue warps (TMEM lanes 32*warp ..)
+        const int row = threadIdx.x;
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int st = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const uint32_t lane_addr = tmem + st * TMEM_BUF_COLS + ((uint32_t)(warp * 32) << 16);
+            uint32_t hi[32], lo[32];
+            tc::mbar_wait(&s.d1_full[st], ph);
+            tc::fence_after_sync();
+            hidden_to_regs<SPLIT>(lane_addr + COL_D1A, s.bias1[0], hi, lo);
+            // the previous tile's last layer-2 MMA has completed (we waited on its commit), so the hidden tile is free
+            hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.a2_full);
+            if constexpr (T::HAS_B) {
+                hidden_to_regs<SPLIT>(lane_addr + COL_D1B, s.bias1[1], hi, lo);     // overlaps the net-A layer-2 MMA
+                tc::mbar_wait(&s.d2a_full[st], ph);                                // net A consumed the hidden tile
                 tc::fence_after_sync();
-                hidden_to_regs<SPLIT>(lane_addr + (grp ? COL_D1B : COL_D1A), s.bias1[grp], hi, lo);
-                // this net's layer-2 MMA of the previous tile has completed (this group waited on its commit below)
-                hidden_regs_to_smem<SPLIT>(s.a2[grp], row, hi, lo);
+                hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
                 tc::fence_async_smem();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&s.a2_full[grp]);
-
-                const bool live = tile * TILE_M + row < a.total;
-                const int64_t idx = live ? sample_of(a, tile * TILE_M + row).idx : 0;
-                float* rec = a.rec ? a.rec + idx * 48 : nullptr;
-                float4* rec4 = reinterpret_cast<float4*>(rec);
-                float4* rgb4 = rec ? rec4 + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
-                if (grp == 0) {
-                    tc::mbar_wait(&s.d2a_full[st], ph);
-                    tc::fence_after_sync();
-                    float outa[T::N_A];
+                if (lane == 0) tc::mbar_arrive(&s.a2_full);
+            } else {
+                tc::mbar_wait(&s.d2a_full[st], ph);
+                tc::fence_after_sync();
+            }
+            // ---- outputs
+            const bool live = tile * TILE_M + row < a.total;
+            const int64_t idx = live ? sample_of(a, tile * TILE_M + row).idx : 0;
+            float outa[T::N_A];
 #pragma unroll
-                    for (int q = 0; q < T::N_A / 16; ++q) {
-                        float v[16];
-                        tc::tmem_ld16(lane_addr + COL_D2A + q * 16, v);
-                        tc::tmem_ld_wait();
+            for (int q = 0; q < T::N_A / 16; ++q) {
+                float v[16];
+                tc::tmem_ld16(lane_addr + COL_D2A + q * 16, v);
+                tc::tmem_ld_wait();
 #pragma unroll
-                        for (int i = 0; i < 16; ++i) outa[q * 16 + i] = v[i] + s.bias2a[q * 16 + i];
-                    }
-                    float sig = outa[0];
-                    if (a.density_noise > 0.0f && live) {
-                        const uint4 r = philox4x32(a.seed, (uint64_t)idx, a.offset);
-                        sig += normal2(r.x, r.y).x * a.density_noise;
-                    }
-                    if (live) {
-                        a.sigma[idx] = sig;
-                        if constexpr (KIND == NFE_DEC_DISENTANGLED) {          // net A = geo_net: sigma + 15 semantic logits
-                            if (rec) {
-                                rec4[0] = make_float4(sig, outa[1], outa[2], outa[3]);
+                for (int i = 0; i < 16; ++i) outa[q * 16 + i] = v[i] + s.bias2a[q * 16 + i];
+            }
+            float sig = outa[0];
+            if (a.density_noise > 0.0f && live) {
+                const uint4 r = philox4x32(a.seed, (uint64_t)idx, a.offset);
+                sig += normal2(r.x, r.y).x * a.density_noise;
+            }
+            if (live) a.sigma[idx] = sig;
+            float4* rec = a.rec ? reinterpret_cast<float4*>(a.rec + idx * 48) : nullptr;
+            float4* rgb4 = rec ? rec + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
+            if constexpr (KIND == NFE_DEC_DISENTANGLED) {
+                if (live) {
+                    if (rec) {
+                        rec[0] = make_float4(sig, outa[1], outa[2], outa[3]);
 #pragma unroll
-                                for (int c = 1; c < 4; ++c) rec4[c] = make_float4(outa[4 * c], outa[4 * c + 1], outa[4 * c + 2], outa[4 * c + 3]);
-                            } else {
+                        for (int c = 1; c < 4; ++c) rec[c] = make_float4(outa[4 * c], outa[4 * c + 1], outa[4 * c + 2], outa[4 * c + 3]);
+                    } else {
 #pragma unroll
-                                for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outa[1 + c];
-                            }
-                        } else {                                               // net A = net: sigma + 32 colours
-                            if (rec) {
-                                if constexpr (T::HAS_B) rec[0] = sig;          // group B fills the semantic slots 1..15
-                                else { rec4[0] = make_float4(sig, 0.f, 0.f, 0.f); rec4[1] = rec4[2] = rec4[3] = make_float4(0.f, 0.f, 0.f, 0.f); }
-                            }
-#pragma unroll
-                            for (int c = 0; c < 8; ++c)
-                                rgb4[c] = make_float4(rgb_activation(outa[1 + 4 * c]), rgb_activation(outa[2 + 4 * c]),
-                                                      rgb_activation(outa[3 + 4 * c]), rgb_activation(outa[4 + 4 * c]));
-                        }
-                    }
-                } else {
-                    if constexpr (T::HAS_B) {
-                        tc::mbar_wait(&s.d2b_full[st], ph);
-                        tc::fence_after_sync();
-                        float outb[T::N_B];
-#pragma unroll
-                        for (int q = 0; q < T::N_B / 16; ++q) {
-                            float v[16];
-                            tc::tmem_ld16(lane_addr + COL_D2A + T::N_A + q * 16, v);
-                            tc::tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) outb[q * 16 + i] = v[i] + s.bias2b[q * 16 + i];
-                        }
-                        if (live) {
-                            if constexpr (KIND == NFE_DEC_DISENTANGLED) {      // net B = app_net: 32 colours
-#pragma unroll
-                                for (int c = 0; c < 8; ++c)
-                                    rgb4[c] = make_float4(rgb_activation(outb[4 * c]), rgb_activation(outb[4 * c + 1]),
-                                                          rgb_activation(outb[4 * c + 2]), rgb_activation(outb[4 * c + 3]));
-                            } else {                                           // net B = seg_net: 15 semantic logits
-                                float* sg = rec ? rec + 1 : a.seg + idx * 15;
-#pragma unroll
-                                for (int c = 0; c < 15; ++c) sg[c] = outb[c];
-                            }
-                        }
+                        for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outa[1 + c];
                     }
                 }
-                tc::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&s.tmem_free[st]);
+            } else {
+                if (live) {
+                    if (rec && !T::HAS_B) {
+                        rec[0] = make_float4(sig, 0.f, 0.f, 0.f);
+                        rec[1] = rec[2] = rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c)
+                        rgb4[c] = make_float4(rgb_activation(outa[1 + 4 * c]), rgb_activation(outa[2 + 4 * c]),
+                                              rgb_activation(outa[3 + 4 * c]), rgb_activation(outa[4 + 4 * c]));
+                }
             }
+            if constexpr (T::HAS_B) {
+                tc::mbar_wait(&s.d2b_full[st], ph);
+                tc::fence_after_sync();
+                float outb[T::N_B];
+#pragma unroll
+                for (int q = 0; q < T::N_B / 16; ++q) {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + COL_D2A + T::N_A + q * 16, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) outb[q * 16 + i] = v[i] + s.bias2b[q * 16 + i];
+                }
+                if (live) {
+                    if constexpr (KIND == NFE_DEC_DISENTANGLED) {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c)
+                            rgb4[c] = make_float4(rgb_activation(outb[4 * c]), rgb_activation(outb[4 * c + 1]),
+                                                  rgb_activation(outb[4 * c + 2]), rgb_activation(outb[4 * c + 3]));
+                    } else if (rec) {
+                        rec[0] = make_float4(sig, outb[0], outb[1], outb[2]);
+#pragma unroll
+                        for (int c = 1; c < 4; ++c) rec[c] = make_float4(outb[4 * c - 1], outb[4 * c], outb[4 * c + 1], outb[4 * c + 2]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outb[c];
+                    }
+                }
+            }
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&s.tmem_free[st]);
         }
     }
 
