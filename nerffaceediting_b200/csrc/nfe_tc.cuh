@@ -98,12 +98,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity)
         "{\n\t"
         ".reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"   // suspend-time hint: sleep in hardware, do not spin on issue slots
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t"
         "}\n"
-        :: "r"(smem_u32(mbar)), "r"(parity) : "memory");
+        :: "r"(smem_u32(mbar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 
 // ---- bf16 split: x ~= hi + lo with hi = bf16(x), lo = bf16(x - hi) ------------------------------
