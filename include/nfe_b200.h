@@ -168,6 +168,10 @@ typedef struct {
     const float* affine_scale;
     const float* affine_shift;
     int affine_items;
+    /* nfe_run_model_fwd only: compute and write sigma alone (rgb / seg may be NULL).  Shape extraction
+     * (gen_samples.py:184-222), the density regulariser (loss.py:310-331) and cross-sections read nothing
+     * else; with the disentangled decoder the appearance net and the de-normalised gather are skipped. */
+    int sigma_only;
 } nfe_render_cfg;
 
 /* bytes of device workspace nfe_render_fwd needs for n*n_rays rays with this cfg */

@@ -215,7 +215,9 @@ __global__ void __launch_bounds__(FIELD_THREADS, 1) field_kernel(FieldArgs a, nf
         __syncwarp();
         const int rows = (int)min((int64_t)32, a.total - base);
         if (lane < rows) a.sigma[base + lane] = row[0];
-        if (a.rec) {
+        if (a.sigma_only) {
+            // density-only query: nothing else is written
+        } else if (a.rec) {
             // packed records {sigma, seg[15], rgb[32]}: 48 floats per sample, the whole step is one contiguous span
             for (int e = lane; e < rows * 48; e += 32) {
                 const int r = e / 48, c = e % 48;
@@ -355,9 +357,11 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     if (int rc = check_decoder_dims(cfg->kind, net_a, net_b, "nfe_run_model_fwd")) return rc;
     NFE_REQUIRE(cfg->channels == FEAT, "nfe_run_model_fwd: planes must have %d channels (got %d)", FEAT, cfg->channels);
     if ((int64_t)n * m == 0) return 0;
-    NFE_REQUIRE(planes_denorm_cl && coords && rgb && sigma, "nfe_run_model_fwd: null pointer");
+    const bool sigma_only = cfg->sigma_only != 0;
+    const bool geo_only = sigma_only && cfg->kind == NFE_DEC_DISENTANGLED && cfg->precision != NFE_PREC_FP32;
+    NFE_REQUIRE((planes_denorm_cl || geo_only) && coords && sigma && (rgb || sigma_only), "nfe_run_model_fwd: null pointer");
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_run_model_fwd: the disentangled decoder needs the normalised planes");
-    NFE_REQUIRE(cfg->kind == NFE_DEC_OSG || seg, "nfe_run_model_fwd: seg output missing");
+    NFE_REQUIRE(cfg->kind == NFE_DEC_OSG || seg || sigma_only, "nfe_run_model_fwd: seg output missing");
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_run_model_fwd: plane batch %d does not match point batch %d", plane_batch, n);
     NFE_REQUIRE(cfg->precision >= NFE_PREC_FP32 && cfg->precision <= NFE_PREC_BF16, "nfe_run_model_fwd: unknown precision mode %d", cfg->precision);
     FieldArgs a = {};
@@ -366,6 +370,7 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     a.coords = coords; a.m = m; a.total = (int64_t)n * m; a.s_per_ray = 1;
     a.sigma = sigma; a.rgb = rgb; a.seg = seg;
     a.density_noise = cfg->density_noise; a.seed = cfg->seed; a.offset = cfg->offset;
+    a.sigma_only = sigma_only;
     StageScope t(STAGE_RUN_MODEL, as_stream(stream));
     return launch_field(cfg->kind, cfg->precision, a, net_a, net_b, as_stream(stream));
 }

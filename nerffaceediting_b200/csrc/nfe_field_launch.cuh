@@ -38,6 +38,7 @@ struct FieldArgs {
     float* rec;
     float density_noise;
     uint64_t seed, offset;
+    int sigma_only;           // write sigma only (rgb / seg / rec untouched); the pipelined kernel also skips the work behind them
 };
 
 int check_decoder_dims(int kind, const nfe_mlp* net_a, const nfe_mlp* net_b, const char* who);

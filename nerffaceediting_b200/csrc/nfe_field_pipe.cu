@@ -173,6 +173,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
     tc::fence_after_sync();
     const uint32_t tmem = s.tmem_base;
     const int64_t n_tiles = (a.total + TILE_M - 1) / TILE_M;
+    // sigma_only with the disentangled decoder: sigma is output 0 of geo_net on the normalised planes, so the
+    // de-normalised gather and the whole appearance net are skipped (gather + MLP work drops by ~55 %)
+    const bool skip_b = a.sigma_only && KIND == NFE_DEC_DISENTANGLED;
 
     if (warp > MMA_WARP) {
         // ================================================================ gather warps (producers)
@@ -241,6 +244,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                         ts.w[4 * q] = __uint_as_float(w4.x); ts.w[4 * q + 1] = __uint_as_float(w4.y);
                         ts.w[4 * q + 2] = __uint_as_float(w4.z); ts.w[4 * q + 3] = __uint_as_float(w4.w);
                     }
+                    if (skip_b) {
+                        // density-only query (shape extraction, density regulariser): geometry features alone
+                        float4 va[12];
+#pragma unroll
+                        for (int i = 0; i < 12; ++i) va[i] = __ldg(set_a + ts.off4[i]);
+                        store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, gather_reduce(va, ts));
+                        continue;
+                    }
                     if (T::SETS == 2 && a.affine_scale) {
                         // single-gather identity: only the normalised planes are read; the de-normalised features are
                         // s*f_p + m*w_in per plane (statistics: 6 L1-resident float4 loads per lane)
@@ -301,7 +312,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 tc::mbar_wait(&s.full[st], ph);                     // features landed
                 tc::fence_after_sync();
                 issue_gemm<SPLIT>(tb + COL_D1A, s.a1[st][0][0], s.a1[st][0][P], A1_LBO, A1_SBO, s.b1[0][0], s.b1[0][P], B1_LBO, B1_SBO, FEAT, idesc1);
-                if constexpr (T::HAS_B)
+                if (T::HAS_B && !skip_b)
                     issue_gemm<SPLIT>(tb + COL_D1B, s.a1[st][T::SETS - 1][0], s.a1[st][T::SETS - 1][P], A1_LBO, A1_SBO, s.b1[1][0], s.b1[1][P],
                                       B1_LBO, B1_SBO, FEAT, idesc1);
                 tc::mma_commit(&s.empty[st]);                       // ring slot reusable once these MMAs have read it
@@ -319,7 +330,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 tc::mma_commit(&s.d2a_full[it & 1]);
                 // layer 1 of the NEXT tile goes in here, so the epilogue never waits on it
                 if (tile + gridDim.x < n_tiles) layer1(it + 1);
-                if constexpr (T::HAS_B) {
+                if (T::HAS_B && !skip_b) {
                     tc::mbar_wait(&s.a2_full, a2_uses++ & 1);
                     tc::fence_after_sync();
                     issue_gemm<SPLIT>(tb + COL_D2A + T::N_A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2b[0], s.b2b[P], B2_LBO, B2_SBO, HIDDEN, idesc2b);
@@ -345,7 +356,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             tc::fence_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.a2_full);
-            if constexpr (T::HAS_B) {
+            if (T::HAS_B && !skip_b) {
                 hidden_to_regs<SPLIT>(lane_addr + COL_D1B, s.bias1[1], hi, lo);     // overlaps the net-A layer-2 MMA
                 tc::mbar_wait(&s.d2a_full[st], ph);                                // net A consumed the hidden tile
                 tc::fence_after_sync();
@@ -375,6 +386,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 sig += normal2(r.x, r.y).x * a.density_noise;
             }
             if (live) a.sigma[idx] = sig;
+            if (a.sigma_only) {                                       // nothing else is written
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s.tmem_free[st]);
+                continue;
+            }
             float4* rec = a.rec ? reinterpret_cast<float4*>(a.rec + idx * 48) : nullptr;
             float4* rgb4 = rec ? rec + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
             if constexpr (KIND == NFE_DEC_DISENTANGLED) {

@@ -189,6 +189,7 @@ __global__ void __launch_bounds__(TILE_M, 1) field_tc_kernel(FieldArgs a, nfe_ml
                 sig += normal2(r.x, r.y).x * a.density_noise;
             }
             a.sigma[idx] = sig;
+            if (a.sigma_only) goto next_tile;
             float4* rec = a.rec ? reinterpret_cast<float4*>(a.rec + idx * 48) : nullptr;
             float4* rgb4 = rec ? rec + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
 #pragma unroll
@@ -206,6 +207,7 @@ __global__ void __launch_bounds__(TILE_M, 1) field_tc_kernel(FieldArgs a, nfe_ml
                 for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = segv[c];
             }
         }
+    next_tile:
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();

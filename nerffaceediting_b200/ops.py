@@ -541,7 +541,7 @@ def finish_depth(depth, minmax):
     return depth
 
 
-def run_model_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, coords):
+def run_model_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, coords, sigma_only=False):
     co = _cuda_f32(coords, "sample_coordinates")
     if co.dim() != 3 or co.shape[-1] != 3:
         raise RuntimeError(f"sample_coordinates: expected [N,M,3], got {tuple(co.shape)}")
@@ -549,13 +549,17 @@ def run_model_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, coords):
     dev = co.device
     a = MlpRef(seq_a, dev)
     b = MlpRef(seq_b, dev) if seq_b is not None else None
-    rgb = torch.empty((n, m, 32), device=dev, dtype=torch.float32)
+    cfg.sigma_only = int(bool(sigma_only))
+    rgb = torch.empty((n, m, 32), device=dev, dtype=torch.float32) if not sigma_only else None
     sigma = torch.empty((n, m, 1), device=dev, dtype=torch.float32)
-    seg = torch.empty((n, m, 15), device=dev, dtype=torch.float32) if cfg.seg_dim else None
+    seg = torch.empty((n, m, 15), device=dev, dtype=torch.float32) if (cfg.seg_dim and not sigma_only) else None
+    any_planes = planes_denorm_cl if planes_denorm_cl is not None else planes_norm_cl
     with _Guard(co):
         rc = _lib.load().nfe_run_model_fwd(ctypes.byref(cfg), a.ref(), b.ref() if b else None, _ptr(planes_norm_cl), _ptr(planes_denorm_cl),
-                                           planes_denorm_cl.shape[0], _ptr(co), n, m, _ptr(rgb), _ptr(sigma), _ptr(seg), None, 0, _stream(co))
+                                           any_planes.shape[0], _ptr(co), n, m, _ptr(rgb), _ptr(sigma), _ptr(seg), None, 0, _stream(co))
     _lib.check(rc, "nfe_run_model_fwd")
+    if sigma_only:
+        return {"sigma": sigma}
     out = {"rgb": rgb, "sigma": sigma}
     if seg is not None:
         out["seg"] = seg

@@ -17,6 +17,8 @@ Extra keys read from `rendering_options` (all optional; defaults reproduce the r
   nfe_single_gather  True   disentangled renderer, tensor-core modes: when the de-normalised planes are known to be
                             norm*scale+shift per channel (they came from normalize_plane / denormalize_plane of this
                             package), gather only the normalised planes and rebuild the other features from the statistics.
+  nfe_sigma_only     False  run_model only: return {'sigma'} alone (shape extraction gen_samples.py:184-222, density regulariser
+                            loss.py:310-331); with the disentangled decoder the appearance net and its gather are skipped.
   nfe_cache_planes   False  keep the channel-last staging of the planes between calls (video sweeps).
 
 Instances hold no state of their own beyond the reference's attributes, so objects unpickled from
@@ -207,13 +209,17 @@ class ImportanceRenderer(torch.nn.Module):
             kind, seq_a, seq_b = desc
             ops._no_grad_needed(norm_planes, planes, sample_coordinates, *decoder.parameters())
             cache = bool(options.get('nfe_cache_planes', False))
-            denorm_cl = ops.planes_channel_last(planes, cache)
+            precision = ops.precision_of(options)
+            sigma_only = bool(options.get('nfe_sigma_only', False))
+            # density-only queries with the disentangled decoder on the tensor-core path never touch the de-normalised planes
+            geo_only = sigma_only and kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32']
             norm_cl = ops.planes_channel_last(norm_planes, cache) if kind == ops.DEC_DISENTANGLED else None
+            denorm_cl = None if geo_only else ops.planes_channel_last(planes, cache)
             noise = options.get('density_noise', 0) or 0.0
             seed, offset = ops.philox_state(sample_coordinates.device) if noise > 0 else (0, 0)
-            cfg = ops.make_cfg(kind, denorm_cl, 2, 0, options['box_warp'], density_noise=noise, seed=seed, offset=offset,
-                               precision=ops.precision_of(options))
-            return ops.run_model_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, sample_coordinates)
+            cfg = ops.make_cfg(kind, norm_cl if denorm_cl is None else denorm_cl, 2, 0, options['box_warp'], density_noise=noise, seed=seed,
+                               offset=offset, precision=precision)
+            return ops.run_model_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, sample_coordinates, sigma_only=sigma_only)
         axes = self.plane_axes
         feats = sample_from_planes(axes, planes, sample_coordinates, padding_mode='zeros', box_warp=options['box_warp'])
         if self._disentangled:
