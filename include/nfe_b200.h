@@ -172,6 +172,9 @@ typedef struct {
      * (gen_samples.py:184-222), the density regulariser (loss.py:310-331) and cross-sections read nothing
      * else; with the disentangled decoder the appearance net and the de-normalised gather are skipped. */
     int sigma_only;
+    /* nfe_render_fwd only: write rgb / seg as images [n, channel, n_rays] (the feature_image / seg_image
+     * of triplane.py:122-125, i.e. after permute(0,2,1).reshape(N,C,H,W)) instead of [n, n_rays, channel]. */
+    int image_layout;
 } nfe_render_cfg;
 
 /* bytes of device workspace nfe_render_fwd needs for n*n_rays rays with this cfg */

@@ -175,12 +175,21 @@ __global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
             if (half == 0 && on) {
                 if (q >= 4) {                                   // rgb channels 4(q-4) .. +3
                     if (a.white_back) { const float bg = 1.0f - wt; acc.x += bg; acc.y += bg; acc.z += bg; acc.w += bg; }
-                    reinterpret_cast<float4*>(a.rgb + ray * 32)[q - 4] =
-                        make_float4(acc.x * 2.0f - 1.0f, acc.y * 2.0f - 1.0f, acc.z * 2.0f - 1.0f, acc.w * 2.0f - 1.0f);
+                    const float4 o4 = make_float4(acc.x * 2.0f - 1.0f, acc.y * 2.0f - 1.0f, acc.z * 2.0f - 1.0f, acc.w * 2.0f - 1.0f);
+                    if (a.image_rays) {
+                        // image layout [item, channel, pixel] (triplane.py:122-125 without the permute+contiguous pass)
+                        const int64_t item = ray / a.image_rays, px = ray % a.image_rays;
+                        float* im = a.rgb + (item * 32 + 4 * (q - 4)) * a.image_rays + px;
+                        im[0] = o4.x; im[a.image_rays] = o4.y; im[2 * a.image_rays] = o4.z; im[3 * a.image_rays] = o4.w;
+                    } else {
+                        reinterpret_cast<float4*>(a.rgb + ray * 32)[q - 4] = o4;
+                    }
                 } else if (a.cs) {                              // record floats 4q..4q+3 = {sigma|seg[4q-1 .. 4q+2]}
-                    float* sg = a.seg + ray * 15;
-                    if (q > 0) sg[4 * q - 1] = acc.x;
-                    sg[4 * q] = acc.y; sg[4 * q + 1] = acc.z; sg[4 * q + 2] = acc.w;
+                    const int64_t item = a.image_rays ? ray / a.image_rays : 0, px = a.image_rays ? ray % a.image_rays : 0;
+                    float* sg = a.image_rays ? a.seg + item * 15 * a.image_rays + px : a.seg + ray * 15;
+                    const int64_t st = a.image_rays ? a.image_rays : 1;
+                    if (q > 0) sg[(4 * q - 1) * st] = acc.x;
+                    sg[(4 * q) * st] = acc.y; sg[(4 * q + 1) * st] = acc.z; sg[(4 * q + 2) * st] = acc.w;
                 }
             }
         } else if (a.cc > 0) {

@@ -16,6 +16,7 @@ struct MarchArgs {
     const float* rec1; const float* rec2;
     int64_t n_rays;
     int cc, cs;        // colour / semantic channels (0: weights only)
+    int64_t image_rays; // packed path only: > 0 writes rgb / seg as images [item, channel, image_rays] instead of [ray, channel]
     int inputs_sorted; // both sample sets ascending in depth: merge by binary search instead of a full rank sort
     int white_back;
     float* rgb;        // [n_rays,cc]

@@ -151,6 +151,7 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
     }
     m.depths1 = depths_coarse; m.rec1 = w.rec_c; m.sigma1 = w.sigma_c; m.s1 = sc;
     m.cc = 32; m.cs = cfg->seg_dim; m.rgb = rgb; m.seg = seg; m.depth = depth; m.wsum = wsum; m.weights = nullptr; m.minmax = minmax;
+    m.image_rays = cfg->image_layout ? n_rays : 0;
     StageScope t(STAGE_MARCH_FINAL, stream);
     if (int rc = launch_march(m, sf > 0, stream)) return rc;
     if (finish_depth) return launch_finish_depth(depth, rays, minmax, stream);

@@ -467,8 +467,9 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
     dc = _cuda_f32(depths_coarse, "depths_coarse").reshape(n, r, cfg.s_c)
     a = MlpRef(seq_a, dev)
     b = MlpRef(seq_b, dev) if seq_b is not None else None
-    rgb = torch.empty((n, r, 32), device=dev, dtype=torch.float32)
-    seg = torch.empty((n, r, cfg.seg_dim), device=dev, dtype=torch.float32) if cfg.seg_dim else None
+    image = bool(cfg.image_layout)
+    rgb = torch.empty((n, 32, r) if image else (n, r, 32), device=dev, dtype=torch.float32)
+    seg = torch.empty((n, cfg.seg_dim, r) if image else (n, r, cfg.seg_dim), device=dev, dtype=torch.float32) if cfg.seg_dim else None
     depth = torch.empty((n, r, 1), device=dev, dtype=torch.float32)
     wsum = torch.empty((n, r, 1), device=dev, dtype=torch.float32)
     minmax = torch.empty(2, device=dev, dtype=torch.float32)
@@ -494,7 +495,10 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
             ccfg.affine_scale, ccfg.affine_shift, ccfg.affine_items = cfg.affine_scale + i0 * 96 * 4, cfg.affine_shift + i0 * 96 * 4, cn
         oo, dd, dcc = o[sl].contiguous(), d[sl].contiguous(), dc[sl].contiguous()     # no copies: whole items, or rays of one item
         outs = [rgb, seg, depth, wsum]
-        views = [None if t is None else t[sl] for t in outs]
+        if image and cr != r:
+            raise RuntimeError("render_fwd: image-layout outputs cannot be split into ray blocks; raise NFE_WORKSPACE_MB")
+        map_sl = (slice(i0, i1),) if image else sl            # image layout [n, C, r]: only whole items can be sliced
+        views = [rgb[map_sl], None if seg is None else seg[map_sl], depth[sl], wsum[sl]]
         direct = all(v is None or v.is_contiguous() for v in views)
         bufs = views if direct else [None if v is None else torch.empty_like(v) for v in views]
         rc = lib.nfe_render_fwd(ctypes.byref(ccfg), a.ref(), b.ref() if b else None, _ptr(pn), _ptr(pd), (pn if pd is None else pd).shape[0], _ptr(oo), _ptr(dd), cn, cr,

@@ -19,6 +19,9 @@ Extra keys read from `rendering_options` (all optional; defaults reproduce the r
                             package), gather only the normalised planes and rebuild the other features from the statistics.
   nfe_sigma_only     False  run_model only: return {'sigma'} alone (shape extraction gen_samples.py:184-222, density regulariser
                             loss.py:310-331); with the disentangled decoder the appearance net and its gather are skipped.
+  nfe_image_layout   False  return (feature_image [N,32,H,W], seg_image [N,15,H,W], depth_image [N,1,H,W], weights [N,R,1]) —
+                            what triplane.py:122-125 builds with three permute+reshape+contiguous passes — written in that
+                            layout by the compositing kernel itself.
   nfe_cache_planes   False  keep the channel-last staging of the planes between calls (video sweeps).
 
 Instances hold no state of their own beyond the reference's attributes, so objects unpickled from
@@ -162,11 +165,21 @@ class ImportanceRenderer(torch.nn.Module):
         cfg = ops.make_cfg(kind, norm_cl if denorm_cl is None else denorm_cl, opts['depth_resolution'], s_f, opts['box_warp'],
                            opts.get('white_back', False), opts.get('density_noise', 0) or 0.0, stochastic=not deterministic, seed=seed,
                            offset=offset, precision=precision, affine=affine)
+        if opts.get('nfe_image_layout', False) and not defer_clamp:
+            side = int(round(ray_origins.shape[1] ** 0.5))
+            if side * side != ray_origins.shape[1]:
+                raise RuntimeError("nfe_image_layout needs a square ray grid (RaySampler's res*res rays)")
+            cfg.image_layout = 1
         u_fine = ops.linspace_table(0, 1, s_f, ray_origins.device) if (s_f > 0 and deterministic) else None
         rgb, seg, depth, wsum, minmax = ops.render_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, ray_origins, ray_directions,
                                                        depths_coarse, u_fine, finish_depth=not defer_clamp)
         if defer_clamp:
             return rgb, seg, depth, wsum, minmax
+        if cfg.image_layout:
+            side = int(round(ray_origins.shape[1] ** 0.5))
+            n = ray_origins.shape[0]
+            return (rgb.view(n, 32, side, side), None if seg is None else seg.view(n, seg.shape[1], side, side),
+                    depth.view(n, 1, side, side), wsum)
         return rgb, seg, depth, wsum
 
     def _render_staged(self, norm_planes, planes, decoder, ray_origins, ray_directions, opts, deterministic):
