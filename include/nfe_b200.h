@@ -195,6 +195,35 @@ int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, const nfe_ml
                    float* wsum, float* minmax_out, int finish_depth, float* depths_fine_out,
                    float* weights_coarse_out, void* workspace, int64_t workspace_bytes, nfe_stream_t stream);
 
+/* Byte offsets, inside an nfe_render_fwd workspace, of what the backward pass re-reads:
+ * offsets[0..3] = sigma_c [T,s_c], rec_c [T,s_c,48], sigma_f [T,s_f], rec_f [T,s_f,48] (-1 if absent);
+ * a record is {sigma, seg[15], rgb[32]}. */
+int nfe_render_workspace_layout(const nfe_render_cfg* cfg, int n, int64_t n_rays, int64_t* offsets);
+
+/* ---- backward (BASELINE config 4).  Gradients flow to the plane tensors and the decoder parameters only;
+ *      sample positions carry none (depths_fine is detached in the reference, renderer.py:198,211). ----------
+ * nfe_composite_bwd: ray_marcher.py:68-101 differentiated over the merged samples of the final pass.  Inputs are
+ * the forward's depths / sigma / records of the coarse (1) and fine (2) sets and the gradients of the ray outputs
+ * (g_seg, g_depth, g_wsum optional; minmax = the forward depth range for the clamp); outputs are per-sample
+ * gradients in record layout {d sigma, d seg[15], d rgb[32]}. */
+int nfe_composite_bwd(const float* depths1, const float* sigma1, const float* rec1, int s1, const float* depths2,
+                      const float* sigma2, const float* rec2, int s2, int64_t n_rays, int seg_dim, int white_back,
+                      const float* g_rgb, const float* g_seg, const float* g_depth, const float* g_wsum,
+                      const float* minmax, float* g_rec1, float* g_rec2, nfe_stream_t stream);
+/* Decoder inputs recomputed for the backward: plane-MEAN features [n*n_rays*s_per_ray, 32] of one channel-last
+ * plane set at ray samples (sample_from_planes + .mean(1), renderer.py:55-65, triplane.py:251-252) ... */
+int nfe_feature_mean_fwd(const float* planes_cl, int plane_batch, int height, int width, float box_warp,
+                         const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays,
+                         int s_per_ray, float* out, nfe_stream_t stream);
+/* ... and its backward: scatter-add (red.global.add.v4.f32) of the feature gradients into channel-last plane
+ * gradients [plane_batch,3,H,W,32], which the caller zero-initialises. */
+int nfe_feature_mean_bwd(const float* g_feat, int plane_batch, int height, int width, float box_warp,
+                         const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays,
+                         int s_per_ray, float* g_planes_cl, nfe_stream_t stream);
+/* channel-last [n_img, hw, 32] -> reference layout [n_img, 32, hw] (plane gradients back to [N,3,32,H,W]) */
+int nfe_planes_from_channel_last(const float* planes_cl, int64_t n_img, int channels, int64_t hw, float* out,
+                                 nfe_stream_t stream);
+
 /* Depth clamp split out for sharded renders: depth = clamp(nan_to_num(depth, +inf), min, max)
  * with {min,max} read from device memory (ray_marcher.py:49-50,93-94). */
 int nfe_finish_depth(float* depth, int64_t n_rays, const float* minmax_dev, nfe_stream_t stream);

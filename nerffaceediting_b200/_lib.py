@@ -62,6 +62,11 @@ SIGNATURES = {
     "nfe_render_workspace_bytes": (c_i64, [_CFG_P, c_int, c_i64]),
     "nfe_render_fwd": (c_int, [_CFG_P, _MLP_P, _MLP_P, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_i64, c_vp, c_vp,
                                c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "nfe_render_workspace_layout": (c_int, [_CFG_P, c_int, c_i64, ctypes.POINTER(c_i64)]),
+    "nfe_composite_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nfe_feature_mean_fwd": (c_int, [c_vp, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp]),
+    "nfe_feature_mean_bwd": (c_int, [c_vp, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_int, c_i64, c_int, c_vp, c_vp]),
+    "nfe_planes_from_channel_last": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "nfe_finish_depth": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "nfe_run_model_fwd": (c_int, [_CFG_P, _MLP_P, _MLP_P, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
 }

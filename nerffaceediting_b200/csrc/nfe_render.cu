@@ -68,6 +68,15 @@ NFE_EXPORT int64_t nfe_render_workspace_bytes(const nfe_render_cfg* cfg, int n, 
     return carve(cfg, (int64_t)n * n_rays, nullptr).bytes;
 }
 
+NFE_EXPORT int nfe_render_workspace_layout(const nfe_render_cfg* cfg, int n, int64_t n_rays, int64_t* offsets)
+{
+    NFE_REQUIRE(cfg && offsets && n >= 0 && n_rays >= 0, "nfe_render_workspace_layout: bad arguments");
+    const Workspace w = carve(cfg, (int64_t)n * n_rays, nullptr);
+    auto off = [](const float* p) { return p ? (int64_t)(reinterpret_cast<const char*>(p) - static_cast<const char*>(nullptr)) : (int64_t)-1; };
+    offsets[0] = off(w.sigma_c); offsets[1] = off(w.rec_c); offsets[2] = cfg->s_f > 0 ? off(w.sigma_f) : -1; offsets[3] = cfg->s_f > 0 ? off(w.rec_f) : -1;
+    return 0;
+}
+
 NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* planes_norm_cl,
                               const float* planes_denorm_cl, int plane_batch, const float* origins, const float* dirs, int n, int64_t n_rays,
                               const float* depths_coarse, const float* u_fine, float* rgb, float* seg, float* depth, float* wsum,

@@ -457,8 +457,10 @@ def workspace_limit_bytes():
 
 
 def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dirs, depths_coarse, u_fine,
-               finish_depth=True, return_stages=False):
-    """Fused forward.  Returns (rgb [N,R,32], seg [N,R,15]|None, depth [N,R,1], wsum [N,R,1], minmax [2][, stages])."""
+               finish_depth=True, return_stages=False, keep_workspace=False):
+    """Fused forward.  Returns (rgb [N,R,32], seg [N,R,15]|None, depth [N,R,1], wsum [N,R,1], minmax [2][, stages]).
+    keep_workspace (training): the stages dict also carries views of the per-sample densities / records the
+    backward re-reads (sigma_c, rec_c, sigma_f, rec_f) and keeps the workspace alive."""
     o, d = _cuda_f32(origins, "ray_origins"), _cuda_f32(dirs, "ray_directions")
     if o.dim() != 3 or o.shape[-1] != 3 or d.shape != o.shape:
         raise RuntimeError(f"ray_origins / ray_directions: expected matching [N,R,3], got {tuple(o.shape)} and {tuple(d.shape)}")
@@ -476,6 +478,7 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
     dfine = torch.empty((n, r, max(cfg.s_f, 1), 1), device=dev, dtype=torch.float32) if return_stages and cfg.s_f else None
     wcoarse = torch.empty((n, r, cfg.s_c - 1, 1), device=dev, dtype=torch.float32) if return_stages and cfg.s_f else None
     lib = _lib.load()
+    kept = {}
     any_planes = planes_denorm_cl if planes_denorm_cl is not None else planes_norm_cl     # denorm is absent under the single-gather identity
     shared_planes = any_planes.shape[0] == 1 and n > 1
 
@@ -486,6 +489,7 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
         if nbytes < 0:
             raise RuntimeError("nfe_render_workspace_bytes: bad arguments")
         ws = torch.empty(max(int(nbytes), 1), device=dev, dtype=torch.uint8)
+        kept["ws"] = ws
         sl = (slice(i0, i1), slice(r0, r1))
         pn = planes_norm_cl if (planes_norm_cl is None or shared_planes) else planes_norm_cl[i0:i1]
         pd = planes_denorm_cl if (planes_denorm_cl is None or shared_planes) else planes_denorm_cl[i0:i1]
@@ -513,7 +517,7 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
     with _Guard(o):
         limit = workspace_limit_bytes()
         per_item = lib.nfe_render_workspace_bytes(ctypes.byref(cfg), 1, r) if n and r else 0
-        if n * per_item <= limit or n * r == 0:
+        if n * per_item <= limit or n * r == 0 or keep_workspace:
             call(0, n, 0, r, minmax, finish_depth)
         else:
             if return_stages:
@@ -535,7 +539,21 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
             if finish_depth:
                 _lib.check(lib.nfe_finish_depth(_ptr(depth), depth.numel(), _ptr(minmax), _stream(o)), "nfe_finish_depth")
     if return_stages:
-        return rgb, seg, depth, wsum, minmax, {"depths_fine": dfine, "weights_coarse": wcoarse}
+        stages = {"depths_fine": dfine, "weights_coarse": wcoarse}
+        if keep_workspace and n * r:
+            offs = (ctypes.c_int64 * 4)()
+            _lib.check(lib.nfe_render_workspace_layout(ctypes.byref(cfg), n, r, offs), "nfe_render_workspace_layout")
+            ws = kept["ws"]
+
+            def view(off, *shape):
+                count = 1
+                for s_ in shape:
+                    count *= s_
+                return ws[off:off + 4 * count].view(torch.float32).view(*shape)
+            stages.update(workspace=ws, sigma_c=view(offs[0], n * r, cfg.s_c), rec_c=view(offs[1], n * r, cfg.s_c, 48))
+            if cfg.s_f:
+                stages.update(sigma_f=view(offs[2], n * r, cfg.s_f), rec_f=view(offs[3], n * r, cfg.s_f, 48))
+        return rgb, seg, depth, wsum, minmax, stages
     return rgb, seg, depth, wsum, minmax
 
 

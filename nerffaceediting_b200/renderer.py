@@ -147,7 +147,10 @@ class ImportanceRenderer(torch.nn.Module):
                 raise NotImplementedError("a ray-sharded render needs one of the reference's decoders (fused path)")
             return self._render_staged(norm_planes, planes, decoder, ray_origins, ray_directions, opts, deterministic)
         kind, seq_a, seq_b = desc
-        ops._no_grad_needed(norm_planes, planes, ray_origins, ray_directions, *decoder.parameters())
+        if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (norm_planes, planes, *decoder.parameters())):
+            if defer_clamp:
+                raise NotImplementedError("the ray-sharded render is inference-only")
+            return self._render_training(kind, seq_a, seq_b, norm_planes, planes, ray_origins, ray_directions, opts, deterministic)
         cache = bool(opts.get('nfe_cache_planes', False))
         precision = ops.precision_of(opts)
         affine = None
@@ -180,6 +183,30 @@ class ImportanceRenderer(torch.nn.Module):
             n = ray_origins.shape[0]
             return (rgb.view(n, 32, side, side), None if seg is None else seg.view(n, seg.shape[1], side, side),
                     depth.view(n, 1, side, side), wsum)
+        return rgb, seg, depth, wsum
+
+    def _render_training(self, kind, seq_a, seq_b, norm_planes, planes, ray_origins, ray_directions, opts, deterministic):
+        """Differentiable forward (BASELINE config 4): same fused kernels, workspace kept for the backward
+        (autograd.RenderFunction).  Gradients flow to the plane tensors and the decoder parameters."""
+        from .autograd import RenderFunction
+        with torch.no_grad():
+            depths_coarse, seed, offset = self._coarse_depths(ray_origins, ray_directions, opts, deterministic)
+        s_f = opts['depth_resolution_importance']
+        state = {
+            "kind": kind, "seq_a": seq_a, "seq_b": seq_b,
+            "cfg": dict(s_c=opts['depth_resolution'], s_f=s_f, box_warp=opts['box_warp'], white_back=opts.get('white_back', False),
+                        density_noise=opts.get('density_noise', 0) or 0.0, stochastic=not deterministic, seed=seed, offset=offset,
+                        precision=ops.precision_of(opts)),
+            "rays": (ray_origins.detach().float().contiguous(), ray_directions.detach().float().contiguous()),
+            "depths_coarse": depths_coarse,
+            "u_fine": ops.linspace_table(0, 1, s_f, ray_origins.device) if (s_f > 0 and deterministic) else None,
+        }
+        params = [p for seq in (seq_a, seq_b) if seq is not None for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
+        out = RenderFunction.apply(state, norm_planes if kind == ops.DEC_DISENTANGLED else None, planes, *params)
+        if kind == ops.DEC_OSG:
+            rgb, depth, wsum, _ = out
+            return rgb, None, depth, wsum
+        rgb, seg, depth, wsum, _ = out
         return rgb, seg, depth, wsum
 
     def _render_staged(self, norm_planes, planes, decoder, ray_origins, ray_directions, opts, deterministic):

@@ -88,7 +88,9 @@ def compute_mean_var(planes):
 
 def normalize_plane(planes):
     """(planes - mean) / (std + 1e-8) -> (norm_planes, mean, std) (triplane.py:61-65)."""
-    ops._no_grad_needed(planes)
+    if torch.is_grad_enabled() and planes.requires_grad:
+        from .autograd import NormalizeFunction
+        return NormalizeFunction.apply(planes)
     mean, std = ops.plane_stats(planes)
     if planes.dim() == 4 and planes.shape[1] == 96 and planes.is_contiguous() and planes.dtype == torch.float32:
         # the generator's [N,96,H,W] tri-planes: also stage both plane sets for the renderer in the same pass
@@ -99,5 +101,7 @@ def normalize_plane(planes):
 def denormalize_plane(planes, mean, var):
     """planes * std + mean (triplane.py:66-68).  Statistics may belong to another identity (appearance
     swap), or to one batch item broadcast over the batch (triplane.py:98-103)."""
-    ops._no_grad_needed(planes, mean, var)
+    if torch.is_grad_enabled() and any(t.requires_grad for t in (planes, mean, var)):
+        from .autograd import DenormalizeFunction
+        return DenormalizeFunction.apply(planes, mean, var)
     return ops.plane_denormalize(planes, mean, var)

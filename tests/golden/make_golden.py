@@ -292,7 +292,60 @@ def gold_render():
     save("render_full", cam2world=cams1[0], intrinsics=cams1[1], **arrays)
 
 
+# ------------------------------------------------------------------ 9. backward (config 4): reference autograd
+def gold_backward():
+    """Gradients of a weighted sum of ALL outputs w.r.t. both plane tensors and the decoder parameters, taken by
+    the reference's own autograd graph (deterministic sampling; depths_fine is detached in the reference too,
+    renderer.py:198,211)."""
+    base = dict(synth.FFHQ_RENDERING_OPTIONS, depth_resolution=12, depth_resolution_importance=12)
+    cams = synth.camera_sweep(2)
+    arrays = {}
+    for tag, kind, opts in (("dis", 'dis', base), ("osg", 'osg', base), ("dis_wb", 'dis', dict(base, white_back=True))):
+        n, hw, res = 2, 16, 8
+        raw = T(synth.hash_normal(300, (n, 96, hw, hw))) * 1.5 - 0.3
+        o, d = RaySampler()(cams[0], cams[1], res)
+        dec = make_decoder(kind, 1)
+        g = torch.Generator().manual_seed(7)
+        r = o.shape[1]
+        wr, ws_, wd, ww = torch.randn(n, r, 32, generator=g), torch.randn(n, r, 15, generator=g), torch.randn(n, r, 1, generator=g), torch.randn(n, r, 1, generator=g)
+        if kind == 'osg':
+            planes = raw.view(n, 3, 32, hw, hw).clone().requires_grad_(True)
+            rgb, depth, wsum = deterministic(ImportanceRenderer)(planes, dec, o, d, opts)
+            loss = (rgb * wr).sum() + (depth * wd).sum() + (wsum * ww).sum()
+            loss.backward()
+            arrays[f"{tag}.g_planes"] = planes.grad
+        else:
+            mean = torch.mean(raw, dim=(-1, -2), keepdim=True)
+            var = torch.sqrt(torch.var(raw, dim=(-1, -2), keepdim=True))
+            norm = ((raw - mean) / (var + 1e-8)).view(n, 3, 32, hw, hw).clone().requires_grad_(True)
+            planes = raw.view(n, 3, 32, hw, hw).clone().requires_grad_(True)
+            rgb, seg, depth, wsum = deterministic(DisentangledImportanceRenderer)(norm, planes, dec, o, d, opts)
+            loss = (rgb * wr).sum() + (seg * ws_).sum() + (depth * wd).sum() + (wsum * ww).sum()
+            loss.backward()
+            arrays[f"{tag}.g_norm"] = norm.grad
+            arrays[f"{tag}.g_planes"] = planes.grad
+            arrays[f"{tag}.norm"] = norm.detach()
+        arrays[f"{tag}.loss"] = loss.detach()
+        for k_, p_ in dec.named_parameters():
+            arrays[f"{tag}.g_dec.{k_}"] = p_.grad
+        arrays.update(decoder_arrays(f"{tag}.dec", dec))
+        arrays.update({f"{tag}.wr": wr, f"{tag}.ws": ws_, f"{tag}.wd": wd, f"{tag}.ww": ww})
+    # normalize_plane backward (triplane.py:56-65) through autograd
+    x = (T(synth.hash_normal(301, (2, 96, 8, 8))) * 1.5 - 0.3).requires_grad_(True)
+    mean = torch.mean(x, dim=(-1, -2), keepdim=True)
+    var = torch.sqrt(torch.var(x, dim=(-1, -2), keepdim=True))
+    nrm = (x - mean) / (var + 1e-8)
+    gw = torch.randn(2, 96, 8, 8, generator=torch.Generator().manual_seed(8))
+    gm, gs = torch.randn(2, 96, 1, 1, generator=torch.Generator().manual_seed(9)), torch.randn(2, 96, 1, 1, generator=torch.Generator().manual_seed(10))
+    ((nrm * gw).sum() + (mean * gm).sum() + (var * gs).sum()).backward()
+    arrays.update({"norm.gw": gw, "norm.gm": gm, "norm.gs": gs, "norm.g_x": x.grad})
+    save("backward", cam2world=cams[0], intrinsics=cams[1], **arrays)
+
+
 if __name__ == "__main__":
+    if "--only-backward" in sys.argv:
+        gold_backward()
+        sys.exit(0)
     gold_stats()
     gold_rays()
     gold_gather()
@@ -301,6 +354,7 @@ if __name__ == "__main__":
     gold_resample()
     gold_unify()
     gold_render()
+    gold_backward()
     import platform
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from the reference at {REF}\n"
