@@ -34,6 +34,8 @@ WORKLOADS = {
     "c2": dict(batch=8, res=64, s_c=48, s_f=48, desc="configs[1] hot path: batch 8, 64^2 rays, 48+48, DisentangledOSGDecoder, 2 plane sets 3x32x256x256 fp32"),
     "c1": dict(batch=1, res=64, s_c=48, s_f=48, desc="configs[0]-shaped: batch 1, 64^2 rays, 48+48, DisentangledOSGDecoder"),
     "c3": dict(batch=32, res=128, s_c=48, s_f=48, desc="configs[2]-shaped: batch 32, 128^2 rays, 48+48"),
+    "c4": dict(batch=32, res=64, s_c=48, s_f=48, train=True,
+               desc="configs[3]-shaped training step: renderer forward+backward, batch 32/GPU, 64^2 rays, 48+48, gradients to planes + decoders"),
 }
 GATHER_BYTES_PER_SAMPLE_SET = 12 * 32 * 4      # 3 planes x 4 taps x 32 ch x fp32
 MLP_FLOP_PER_SAMPLE = 14336                    # DisentangledOSGDecoder
@@ -206,7 +208,33 @@ def main():
     rays_per_rank = n * res * res
     gathered = torch.empty((world * n, res * res, 49), device=device) if world > 1 else None
 
+    train = bool(wl.get("train"))
+    if train:
+        # training step (configs[3]): forward + backward of a fixed random projection of every output; gradients reach the raw
+        # planes (through normalize_plane and the renderer) and the decoder parameters; data-parallel ranks all-reduce the
+        # decoder gradients (the plane gradients belong to the per-item backbone activations and stay local)
+        opts["nfe_single_gather"] = False
+        sets_gathered = 2
+        raw.requires_grad_(True)
+        gw = torch.Generator(device="cpu").manual_seed(5)
+        proj = [torch.randn(n, res * res, c, generator=gw).to(device) for c in (32, 15, 1, 1)]
+        params = list(dec.parameters())
+
+        def train_step(planes_dev, c2w_dev, k_dev):
+            planes_dev.grad = None
+            for p_ in params:
+                p_.grad = None
+            out = hot_path_step(torch, mods, planes_dev, dec, c2w_dev, k_dev, res, opts)
+            loss = sum((o_ * w_).sum() for o_, w_ in zip(out, proj))
+            loss.backward()
+            if world > 1:
+                flat = torch.cat([p_.grad.reshape(-1) for p_ in params])
+                dist.all_reduce(flat)
+            return loss
+
     def step_resident():
+        if train:
+            return train_step(raw, c2w, k)
         with torch.no_grad():
             rgb, seg, depth, wsum = hot_path_step(torch, mods, raw, dec, c2w, k, res, opts)
             if world > 1:
@@ -233,7 +261,18 @@ def main():
             dev_cam[slot][1].copy_(k_host, non_blocking=True)
             uploaded[slot].record(copy_stream)
 
+    loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
     def step_e2e():
+        if train:
+            # a training step fed from host memory: planes + cameras up, loss scalar back
+            dev_in[0].requires_grad_(False).copy_(raw_host, non_blocking=True)
+            dev_cam[0][0].copy_(c2w_host, non_blocking=True)
+            dev_cam[0][1].copy_(k_host, non_blocking=True)
+            loss = train_step(dev_in[0].requires_grad_(True), dev_cam[0][0], dev_cam[0][1])
+            loss_host.copy_(loss.detach(), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return
         i = e2e_state["i"]
         slot = i & 1
         main = torch.cuda.current_stream()
@@ -312,15 +351,16 @@ def main():
             except Exception:
                 traffic = None
         line = {
-            "metric": "rendered rays/sec (48+48 samples)", "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": "rendered rays/sec (48+48 samples)" + (", forward+backward" if train else ""), "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": wl["desc"], "rays_per_gpu_per_step": rays_per_rank, "sampling": "deterministic (parity mode)",
                        "parallelism": f"batch-sharded x{world}, all-gather of rendered maps" if world > 1 else "single GPU",
                        "cache": "inputs larger than L2 (raw+normalised+staged planes ~0.8 GB per step), no L2 flush needed"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(raw_host.numel() * 4 + c2w_host.numel() * 4 + k_host.numel() * 4),
-                    "d2h_bytes_per_step": int(out_host[0].numel() * 4),
-                    "note": "uploads double-buffered on a copy stream (step i+1's H2D overlaps step i's render); PCIe-bound"},
+                    "d2h_bytes_per_step": 4 if train else int(out_host[0].numel() * 4),
+                    "note": "training step: planes + cameras uploaded, loss scalar read back, every step" if train else
+                            "uploads double-buffered on a copy stream (step i+1's H2D overlaps step i's render); PCIe-bound"},
             "gpu_launches": launches,
             "roofline": {"kernel": "field_kernel<disentangled> (tri-plane gather + decoder MLPs), coarse+fine launches", "bound": "hbm",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
@@ -334,7 +374,7 @@ def main():
             "stages_ms_per_step": {k_: v[0] / steps for k_, v in stages.items() if v[1]},
             "clocks": clocks,
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not train:   # the CPU port is forward-only
             r = cpu_reference_rate(torch, wl, 3, 1)
             line["cpu_baseline"] = {"value": r["rays_per_s_best"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"] + " (best)"}
         print(json.dumps(line))
