@@ -47,7 +47,7 @@ struct PipeSmem {
     alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
-    alignas(16) uint4 taps[GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][7];   // per sample: 12 offsets, 12 weights, item
+    alignas(16) uint4 taps[2][GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][7];   // per sample: 12 offsets, 12 weights, item; one tile ahead
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
     float bias2a[T::N_A];
     float bias2b[T::N_B];
@@ -143,6 +143,15 @@ __device__ __forceinline__ SampleRef sample_of(const FieldArgs& a, int64_t L)
     return r;
 }
 
+// texel load at lane_base + 16*off4: one IMAD.WIDE.U32 + LDG (pointer arithmetic on a per-lane base costs four
+// 64-bit ALU instructions per load otherwise)
+__device__ __forceinline__ float4 ldg_tap(const float4* lane_base, uint32_t off4)
+{
+    uint64_t addr;
+    asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(off4), "l"(lane_base));
+    return __ldg(reinterpret_cast<const float4*>(addr));
+}
+
 template <int KIND, bool SPLIT>
 __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a, nfe_mlp net_a, nfe_mlp net_b)
 {
@@ -150,7 +159,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
     constexpr int P = SPLIT ? 1 : 0;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PipeSmem<KIND, SPLIT>& s = *reinterpret_cast<PipeSmem<KIND, SPLIT>*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // the shuffle tells the compiler the role index is warp-uniform (uniform branches / registers inside the roles)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
     // ---- setup
     if (warp == MMA_WARP) tc::tmem_alloc(&s.tmem_base, PIPE_TMEM_COLS);
@@ -184,17 +194,22 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
         const int gw = warp - MMA_WARP - 1;
         const int g = lane >> 3, c4 = lane & 7;
         constexpr int PER = (PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS;
+        const int n_pass = min(PER, PASSES_PER_TILE - gw * PER);             // passes this warp owns in every tile (may be <= 0)
         const int64_t set_stride4 = (int64_t)3 * a.H * a.W * (FEAT / 4);     // float4 units
         const float4* set_a = reinterpret_cast<const float4*>(a.set_norm) + c4;
         const float4* set_b = reinterpret_cast<const float4*>(a.set_denorm) + c4;
-        uint4* my_taps = s.taps[gw][0];
-        int it = 0;
-        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
-            const int st = it & 1;
-            const int64_t base = tile * TILE_M;
-            // ---- tap pre-pass: ONE lane per sample computes position -> 12 clamped texel offsets + 12 weights and
-            //      parks them in shared memory; the 8 lanes of a sample used to recompute them (8x redundant issue)
+        // one plane set is read per pass in the single-gather, density-only and one-set decoders: those run the
+        // rolling pipeline below; the two-set gather (24 texels per sample) has no registers left for it
+        const bool affine = T::SETS == 2 && a.affine_scale != nullptr;
+        const bool rolling = T::SETS == 1 || affine || skip_b;
+        const float4* set_r = T::SETS == 2 ? set_a : set_b;
+
+        // ---- tap pre-pass: ONE lane per sample computes position -> 12 clamped texel offsets + 12 weights and parks
+        //      them in shared memory (the 8 lanes of a sample used to recompute them: 8x redundant issue).  It runs
+        //      one tile AHEAD (double-buffered), so its dependent global loads overlap the texel loads in flight.
+        auto prepass = [&](int64_t tile, int buf) {
             if (lane < PER * 4) {
+                const int64_t base = tile * TILE_M;
                 const int row = gw * PER * 4 + lane;
                 TapSet ts;
                 int item_idx = 0;
@@ -219,7 +234,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
 #pragma unroll
                     for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
                 }
-                uint4* dst = my_taps + lane * 7;
+                uint4* dst = s.taps[buf][gw][lane];
                 dst[6] = make_uint4((uint32_t)item_idx, 0u, 0u, 0u);
 #pragma unroll
                 for (int q = 0; q < 3; ++q) {
@@ -228,68 +243,105 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                                             __float_as_uint(ts.w[4 * q + 3]));
                 }
             }
+        };
+        auto read_taps = [&](int buf, int p, TapSet& ts) {
+            const uint4* src = s.taps[buf][gw][p * 4 + g];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const uint4 o4 = src[q], w4 = src[3 + q];
+                ts.off4[4 * q] = (int)o4.x; ts.off4[4 * q + 1] = (int)o4.y; ts.off4[4 * q + 2] = (int)o4.z; ts.off4[4 * q + 3] = (int)o4.w;
+                ts.w[4 * q] = __uint_as_float(w4.x); ts.w[4 * q + 1] = __uint_as_float(w4.y);
+                ts.w[4 * q + 2] = __uint_as_float(w4.z); ts.w[4 * q + 3] = __uint_as_float(w4.w);
+            }
+        };
+
+        float4 va[12];                    // rolling pipeline: the texels of the NEXT pass, in flight while this one is blended
+        if (blockIdx.x < n_tiles && n_pass > 0) {
+            prepass(blockIdx.x, 0);
             __syncwarp();
+            if (rolling) {
+                const uint4* src = s.taps[0][gw][g];
+#pragma unroll
+                for (int q = 0; q < 3; ++q) {
+                    const uint4 o4 = src[q];
+                    va[4 * q] = ldg_tap(set_r, o4.x); va[4 * q + 1] = ldg_tap(set_r, o4.y);
+                    va[4 * q + 2] = ldg_tap(set_r, o4.z); va[4 * q + 3] = ldg_tap(set_r, o4.w);
+                }
+            }
+        }
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+            const int st = it & 1;
+            const bool has_next = tile + gridDim.x < n_tiles;
+            if (n_pass > 0) {
+                if (has_next) prepass(tile + gridDim.x, st ^ 1);
+                __syncwarp();
+            }
             tc::mbar_wait(&s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
+            if (rolling) {
+                for (int p = 0; p < n_pass; ++p) {
+                    const int row = 4 * (gw * PER + p) + g;
+                    // weights of this pass; offsets of the next one (this tile's next pass, else the next tile's first)
+                    const uint4* cur = s.taps[st][gw][p * 4 + g];
+                    const bool more = p + 1 < n_pass;
+                    const bool fetch = more || has_next;
+                    const uint4* nxt = more ? s.taps[st][gw][(p + 1) * 4 + g] : s.taps[st ^ 1][gw][g];
+                    float4 f[3];
+                    float w_in[3];
 #pragma unroll
-            for (int p = 0; p < PER; ++p) {
-                const int pass = gw * PER + p;
-                if (pass < PASSES_PER_TILE) {
-                    const int row = 4 * pass + g;
-                    TapSet ts;
-                    const uint4* src = my_taps + (p * 4 + g) * 7;
-#pragma unroll
-                    for (int q = 0; q < 3; ++q) {
-                        const uint4 o4 = src[q], w4 = src[3 + q];
-                        ts.off4[4 * q] = (int)o4.x; ts.off4[4 * q + 1] = (int)o4.y; ts.off4[4 * q + 2] = (int)o4.z; ts.off4[4 * q + 3] = (int)o4.w;
-                        ts.w[4 * q] = __uint_as_float(w4.x); ts.w[4 * q + 1] = __uint_as_float(w4.y);
-                        ts.w[4 * q + 2] = __uint_as_float(w4.z); ts.w[4 * q + 3] = __uint_as_float(w4.w);
+                    for (int pl = 0; pl < 3; ++pl) {
+                        const uint4 w4 = cur[3 + pl];
+                        const float w0 = __uint_as_float(w4.x), w1 = __uint_as_float(w4.y), w2 = __uint_as_float(w4.z), w3 = __uint_as_float(w4.w);
+                        float4 acc;
+                        acc.x = va[4 * pl].x * w0; acc.y = va[4 * pl].y * w0; acc.z = va[4 * pl].z * w0; acc.w = va[4 * pl].w * w0;
+                        acc.x = fmaf(va[4 * pl + 1].x, w1, acc.x); acc.y = fmaf(va[4 * pl + 1].y, w1, acc.y);
+                        acc.z = fmaf(va[4 * pl + 1].z, w1, acc.z); acc.w = fmaf(va[4 * pl + 1].w, w1, acc.w);
+                        acc.x = fmaf(va[4 * pl + 2].x, w2, acc.x); acc.y = fmaf(va[4 * pl + 2].y, w2, acc.y);
+                        acc.z = fmaf(va[4 * pl + 2].z, w2, acc.z); acc.w = fmaf(va[4 * pl + 2].w, w2, acc.w);
+                        acc.x = fmaf(va[4 * pl + 3].x, w3, acc.x); acc.y = fmaf(va[4 * pl + 3].y, w3, acc.y);
+                        acc.z = fmaf(va[4 * pl + 3].z, w3, acc.z); acc.w = fmaf(va[4 * pl + 3].w, w3, acc.w);
+                        f[pl] = acc;
+                        w_in[pl] = ((w0 + w1) + w2) + w3;
+                        if (fetch) {             // refill the four registers just consumed with the next pass's texels
+                            const uint4 o4 = nxt[pl];
+                            va[4 * pl] = ldg_tap(set_r, o4.x); va[4 * pl + 1] = ldg_tap(set_r, o4.y);
+                            va[4 * pl + 2] = ldg_tap(set_r, o4.z); va[4 * pl + 3] = ldg_tap(set_r, o4.w);
+                        }
                     }
-                    if (skip_b) {
-                        // density-only query (shape extraction, density regulariser): geometry features alone
-                        float4 va[12];
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) va[i] = __ldg(set_a + ts.off4[i]);
-                        store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, gather_reduce(va, ts));
-                        continue;
-                    }
-                    if (T::SETS == 2 && a.affine_scale) {
+                    constexpr float third = 1.0f / 3.0f;
+                    const float4 fa = make_float4(((f[0].x + f[1].x) + f[2].x) * third, ((f[0].y + f[1].y) + f[2].y) * third,
+                                                  ((f[0].z + f[1].z) + f[2].z) * third, ((f[0].w + f[1].w) + f[2].w) * third);
+                    store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, fa);
+                    if (affine && !skip_b) {
                         // single-gather identity: only the normalised planes are read; the de-normalised features are
                         // s*f_p + m*w_in per plane (statistics: 6 L1-resident float4 loads per lane)
-                        float4 va[12];
-#pragma unroll
-                        for (int i = 0; i < 12; ++i) va[i] = __ldg(set_a + ts.off4[i]);
-                        const int item = a.affine_items == 1 ? 0 : (int)src[6].x;
+                        const int item = a.affine_items == 1 ? 0 : (int)cur[6].x;
                         const float4* sc = reinterpret_cast<const float4*>(a.affine_scale + (int64_t)item * 96) + c4;
                         const float4* sh = reinterpret_cast<const float4*>(a.affine_shift + (int64_t)item * 96) + c4;
-                        float4 scl[3], shf[3];
-#pragma unroll
-                        for (int pl = 0; pl < 3; ++pl) { scl[pl] = __ldg(sc + pl * 8); shf[pl] = __ldg(sh + pl * 8); }
-                        float4 f[3];
-                        float w_in[3];
-                        gather_reduce_planes(va, ts, f, w_in);
-                        constexpr float third = 1.0f / 3.0f;
-                        const float4 fa = make_float4(((f[0].x + f[1].x) + f[2].x) * third, ((f[0].y + f[1].y) + f[2].y) * third,
-                                                      ((f[0].z + f[1].z) + f[2].z) * third, ((f[0].w + f[1].w) + f[2].w) * third);
                         float4 d[3];
 #pragma unroll
-                        for (int pl = 0; pl < 3; ++pl)
-                            d[pl] = make_float4(fmaf(scl[pl].x, f[pl].x, shf[pl].x * w_in[pl]), fmaf(scl[pl].y, f[pl].y, shf[pl].y * w_in[pl]),
-                                                fmaf(scl[pl].z, f[pl].z, shf[pl].z * w_in[pl]), fmaf(scl[pl].w, f[pl].w, shf[pl].w * w_in[pl]));
+                        for (int pl = 0; pl < 3; ++pl) {
+                            const float4 scl = __ldg(sc + pl * 8), shf = __ldg(sh + pl * 8);
+                            d[pl] = make_float4(fmaf(scl.x, f[pl].x, shf.x * w_in[pl]), fmaf(scl.y, f[pl].y, shf.y * w_in[pl]),
+                                                fmaf(scl.z, f[pl].z, shf.z * w_in[pl]), fmaf(scl.w, f[pl].w, shf.w * w_in[pl]));
+                        }
                         const float4 fb = make_float4(((d[0].x + d[1].x) + d[2].x) * third, ((d[0].y + d[1].y) + d[2].y) * third,
                                                       ((d[0].z + d[1].z) + d[2].z) * third, ((d[0].w + d[1].w) + d[2].w) * third);
-                        store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, fa);
                         store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, fb);
-                        continue;
                     }
+                }
+            } else {
+                for (int p = 0; p < n_pass; ++p) {
+                    const int row = 4 * (gw * PER + p) + g;
+                    TapSet ts;
+                    read_taps(st, p, ts);
                     // all 24 texel loads of the sample (two plane sets) are issued before the first blend
-                    float4 va[12], vb[12];
-                    if (T::SETS == 2) {
+                    float4 vb[12];
 #pragma unroll
-                        for (int i = 0; i < 12; ++i) va[i] = __ldg(set_a + ts.off4[i]);
-                    }
+                    for (int i = 0; i < 12; ++i) va[i] = ldg_tap(set_a, (uint32_t)ts.off4[i]);
 #pragma unroll
-                    for (int i = 0; i < 12; ++i) vb[i] = __ldg(set_b + ts.off4[i]);
-                    if (T::SETS == 2) store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, gather_reduce(va, ts));
+                    for (int i = 0; i < 12; ++i) vb[i] = ldg_tap(set_b, (uint32_t)ts.off4[i]);
+                    store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, gather_reduce(va, ts));
                     store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, gather_reduce(vb, ts));
                 }
             }
