@@ -2,7 +2,7 @@
 //
 // One persistent CTA per SM, 16 warps with fixed roles, connected by mbarriers:
 //
-//   11 gather warps    tri-plane bilinear gather (L2/L1-bound: 24 texel lines of 128 B per sample) of a
+//   8 gather warps     tri-plane bilinear gather (L2/L1-bound: 24 texel lines of 128 B per sample) of a
 //                      128-sample tile -> bf16 hi/lo feature tile in a 2-stage shared-memory ring
 //   1 MMA warp         one elected thread issues tcgen05.mma for layer 1 (both nets) and layer 2,
 //                      accumulators in a double-buffered TMEM region; tcgen05.commit signals the
@@ -21,12 +21,12 @@ namespace nfe {
 using namespace tcmlp;
 
 #ifndef NFE_GATHER_WARPS
-#define NFE_GATHER_WARPS 11
+#define NFE_GATHER_WARPS 8
 #endif
 #ifndef NFE_PASS_CONTIG
 #define NFE_PASS_CONTIG 1
 #endif
-constexpr int GATHER_WARPS = NFE_GATHER_WARPS;              // 11: 16 warps x 128 registers = the whole register file
+constexpr int GATHER_WARPS = NFE_GATHER_WARPS;              // 8 measured best (4: 0.57, 6: 0.50, 8: 0.455, 11: 0.47 ms per pass at c2)
 constexpr int EPI_WARPS = 4;
 constexpr int MMA_WARP = EPI_WARPS;                         // warp index of the MMA issuer
 constexpr int PIPE_THREADS = (EPI_WARPS + 1 + GATHER_WARPS) * 32;
@@ -143,6 +143,14 @@ __device__ __forceinline__ SampleRef sample_of(const FieldArgs& a, int64_t L)
     return r;
 }
 
+#ifdef NFE_PIPE_PROFILE
+// Debug build only: cycles each role spends blocked on each barrier (slot k) and in total (slot 15), summed over CTAs.
+__device__ unsigned long long g_pipe_prof[3][16];
+#define PIPE_WAIT(slot, bar, par) do { const long long t0_ = clock64(); tc::mbar_wait(bar, par); prof_[slot] += clock64() - t0_; } while (0)
+#else
+#define PIPE_WAIT(slot, bar, par) tc::mbar_wait(bar, par)
+#endif
+
 // texel load at lane_base + 16*off4: one IMAD.WIDE.U32 + LDG (pointer arithmetic on a per-lane base costs four
 // 64-bit ALU instructions per load otherwise)
 __device__ __forceinline__ float4 ldg_tap(const float4* lane_base, uint32_t off4)
@@ -186,6 +194,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
     // sigma_only with the disentangled decoder: sigma is output 0 of geo_net on the normalised planes, so the
     // de-normalised gather and the whole appearance net are skipped (gather + MLP work drops by ~55 %)
     const bool skip_b = a.sigma_only && KIND == NFE_DEC_DISENTANGLED;
+#ifdef NFE_PIPE_PROFILE
+    long long prof_[16] = {};
+    const long long prof_t0_ = clock64();
+#endif
 
     if (warp > MMA_WARP) {
         // ================================================================ gather warps (producers)
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 if (has_next) prepass(tile + gridDim.x, st ^ 1);
                 __syncwarp();
             }
-            tc::mbar_wait(&s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
+            PIPE_WAIT(0, &s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
             if (rolling) {
                 for (int p = 0; p < n_pass; ++p) {
                     const int row = 4 * (gw * PER + p) + g;
@@ -360,8 +372,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 const int st = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
                 const uint32_t tb = tmem + st * TMEM_BUF_COLS;
-                tc::mbar_wait(&s.tmem_free[st], ph ^ 1);            // epilogue is done with this TMEM buffer (tile it-2)
-                tc::mbar_wait(&s.full[st], ph);                     // features landed
+                PIPE_WAIT(1, &s.tmem_free[st], ph ^ 1);            // epilogue is done with this TMEM buffer (tile it-2)
+                PIPE_WAIT(2, &s.full[st], ph);                     // features landed
                 tc::fence_after_sync();
                 issue_gemm<SPLIT>(tb + COL_D1A, s.a1[st][0][0], s.a1[st][0][P], A1_LBO, A1_SBO, s.b1[0][0], s.b1[0][P], B1_LBO, B1_SBO, FEAT, idesc1);
                 if (T::HAS_B && !skip_b)
@@ -376,14 +388,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
                 const uint32_t tb = tmem + (it & 1) * TMEM_BUF_COLS;
                 // layer 2, net A
-                tc::mbar_wait(&s.a2_full, a2_uses++ & 1);
+                PIPE_WAIT(3, &s.a2_full, a2_uses++ & 1);
                 tc::fence_after_sync();
                 issue_gemm<SPLIT>(tb + COL_D2A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2a[0], s.b2a[P], B2_LBO, B2_SBO, HIDDEN, idesc2a);
                 tc::mma_commit(&s.d2a_full[it & 1]);
                 // layer 1 of the NEXT tile goes in here, so the epilogue never waits on it
                 if (tile + gridDim.x < n_tiles) layer1(it + 1);
                 if (T::HAS_B && !skip_b) {
-                    tc::mbar_wait(&s.a2_full, a2_uses++ & 1);
+                    PIPE_WAIT(3, &s.a2_full, a2_uses++ & 1);
                     tc::fence_after_sync();
                     issue_gemm<SPLIT>(tb + COL_D2A + T::N_A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2b[0], s.b2b[P], B2_LBO, B2_SBO, HIDDEN, idesc2b);
                     tc::mma_commit(&s.d2b_full[it & 1]);
@@ -400,7 +412,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             const uint32_t ph = (it >> 1) & 1;
             const uint32_t lane_addr = tmem + st * TMEM_BUF_COLS + ((uint32_t)(warp * 32) << 16);
             uint32_t hi[32], lo[32];
-            tc::mbar_wait(&s.d1_full[st], ph);
+            PIPE_WAIT(4, &s.d1_full[st], ph);
             tc::fence_after_sync();
             hidden_to_regs<SPLIT>(lane_addr + COL_D1A, s.bias1[0], hi, lo);
             // the previous tile's last layer-2 MMA has completed (we waited on its commit), so the hidden tile is free
@@ -410,14 +422,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             if (lane == 0) tc::mbar_arrive(&s.a2_full);
             if (T::HAS_B && !skip_b) {
                 hidden_to_regs<SPLIT>(lane_addr + COL_D1B, s.bias1[1], hi, lo);     // overlaps the net-A layer-2 MMA
-                tc::mbar_wait(&s.d2a_full[st], ph);                                // net A consumed the hidden tile
+                PIPE_WAIT(5, &s.d2a_full[st], ph);                                // net A consumed the hidden tile
                 tc::fence_after_sync();
                 hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
                 tc::fence_async_smem();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&s.a2_full);
             } else {
-                tc::mbar_wait(&s.d2a_full[st], ph);
+                PIPE_WAIT(5, &s.d2a_full[st], ph);
                 tc::fence_after_sync();
             }
             // ---- outputs
@@ -470,7 +482,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 }
             }
             if constexpr (T::HAS_B) {
-                tc::mbar_wait(&s.d2b_full[st], ph);
+                PIPE_WAIT(6, &s.d2b_full[st], ph);
                 tc::fence_after_sync();
                 float outb[T::N_B];
 #pragma unroll
@@ -503,6 +515,13 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
         }
     }
 
+#ifdef NFE_PIPE_PROFILE
+    if (lane == 0) {
+        const int role = warp > MMA_WARP ? 0 : (warp == MMA_WARP ? 1 : 2);
+        prof_[15] = clock64() - prof_t0_;
+        for (int i = 0; i < 16; ++i) atomicAdd(&g_pipe_prof[role][i], (unsigned long long)prof_[i]);
+    }
+#endif
     // ---- teardown
     tc::fence_before_sync();
     __syncthreads();
@@ -543,3 +562,13 @@ int launch_field_pipe(int kind, int precision, const FieldArgs& a, const nfe_mlp
 }
 
 }  // namespace nfe
+
+#ifdef NFE_PIPE_PROFILE
+NFE_EXPORT int nfe_debug_pipe_profile(unsigned long long* out48, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out48, nfe::g_pipe_prof, sizeof(unsigned long long) * 48);
+    if (reset) { unsigned long long z[48] = {}; cudaMemcpyToSymbol(nfe::g_pipe_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif

@@ -91,11 +91,15 @@ __device__ void load_params(Smem<KIND, SPLIT>& s, const nfe_mlp& net_a, const nf
 template <bool SPLIT>
 __device__ __forceinline__ void store_features4(unsigned char (*a1)[A1_BYTES], int row, int k0, float4 f)
 {
-    __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-    tc::split_bf16(f.x, h0, l0); tc::split_bf16(f.y, h1, l1); tc::split_bf16(f.z, h2, l2); tc::split_bf16(f.w, h3, l3);
+    // packed conversions (F2FP, two values per instruction); the scalar form goes through the XU pipe the softplus needs
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(f.x, f.y), h23 = __floats2bfloat162_rn(f.z, f.w);
     const uint32_t off = core_offset(row, k0, A1_LBO, A1_SBO);
-    *reinterpret_cast<uint2*>(a1[0] + off) = make_uint2(tc::pack_bf16(h0, h1), tc::pack_bf16(h2, h3));
-    if (SPLIT) *reinterpret_cast<uint2*>(a1[1] + off) = make_uint2(tc::pack_bf16(l0, l1), tc::pack_bf16(l2, l3));
+    *reinterpret_cast<uint2*>(a1[0] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+    if (SPLIT) {
+        const float2 b01 = __bfloat1622float2(h01), b23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(f.x - b01.x, f.y - b01.y), l23 = __floats2bfloat162_rn(f.z - b23.x, f.w - b23.y);
+        *reinterpret_cast<uint2*>(a1[1] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+    }
 }
 
 // One thread issues a whole GEMM: D (+)= A * B^T over K (multiple of 16), with the three split terms.
