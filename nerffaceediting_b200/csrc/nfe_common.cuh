@@ -176,4 +176,26 @@ __device__ __forceinline__ void atomic_max_float(float* addr, float v)
     else atomicMin(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2): one issue slot for two lanes of arithmetic; each half
+//      rounds exactly like the scalar instruction
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d)
+        : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)), "l"(*reinterpret_cast<unsigned long long*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    unsigned long long d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
 }  // namespace nfe

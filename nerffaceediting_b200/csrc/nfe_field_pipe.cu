@@ -47,7 +47,7 @@ struct PipeSmem {
     alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
-    alignas(16) uint4 taps[2][GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][7];   // per sample: 12 offsets, 12 weights, item; one tile ahead
+    alignas(16) uint4 taps[2][GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][10];   // per sample: 12 offsets, 12 weights as (w,w) pairs, item; one tile ahead
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
     float bias2a[T::N_A];
     float bias2b[T::N_B];
@@ -59,6 +59,9 @@ struct PipeSmem {
 // The ln2 factor is folded into the layer-2 weights, log2(e) into the bias (one FFMA makes t).
 __device__ __forceinline__ float softplus_log2(float t)
 {
+#ifdef NFE_ABLATE_SOFTPLUS
+    return t;      // timing experiment only (wrong results): how much of the kernel is the epilogue's SFU chain
+#endif
     float e, l;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-fabsf(t)));
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + e));
@@ -83,10 +86,25 @@ __device__ void pipe_load_params(PipeSmem<KIND, SPLIT>& s, const nfe_mlp& net_a,
     }
 }
 
-// hidden = softplus(D1 + b1) of one net for this thread's row, as packed bf16 parts in registers
+// sigmoid(x) * 1.002 - 0.001 (triplane.py:188,219,269) for two colours at once
+__device__ __forceinline__ float2 rgb_activation2(float2 x)
+{
+    const float2 n = fmul2(x, make_float2(-LOG2E, -LOG2E));
+    float e0, e1, r0, r1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(n.x));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(n.y));
+    const float2 d = fadd2(make_float2(e0, e1), make_float2(1.0f, 1.0f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(d.x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(d.y));
+    return ffma2(make_float2(r0, r1), make_float2(1.002f, 1.002f), make_float2(-0.001f, -0.001f));
+}
+
+// hidden = softplus(D1 + b1) of one net for this thread's row, as packed bf16 parts in registers.  Pairs of
+// hidden units go through packed fp32 instructions (the epilogue warps are issue-bound).
 template <bool SPLIT>
 __device__ __forceinline__ void hidden_to_regs(uint32_t taddr_row, const float* bias1_log2, uint32_t (&hi)[32], uint32_t (&lo)[32])
 {
+    const float2 k2 = make_float2(LOG2E, LOG2E), one2 = make_float2(1.0f, 1.0f), neg2 = make_float2(-1.0f, -1.0f);
 #pragma unroll
     for (int q = 0; q < HIDDEN / 16; ++q) {
         float v[16];
@@ -94,13 +112,19 @@ __device__ __forceinline__ void hidden_to_regs(uint32_t taddr_row, const float* 
         tc::tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const float h0 = softplus_log2(fmaf(v[2 * i], LOG2E, bias1_log2[q * 16 + 2 * i]));
-            const float h1 = softplus_log2(fmaf(v[2 * i + 1], LOG2E, bias1_log2[q * 16 + 2 * i + 1]));
-            const __nv_bfloat162 p = __floats2bfloat162_rn(h0, h1);
+            const float2 t = ffma2(make_float2(v[2 * i], v[2 * i + 1]), k2, *reinterpret_cast<const float2*>(bias1_log2 + q * 16 + 2 * i));
+            float e0, e1, l0, l1;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-fabsf(t.x)));
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-fabsf(t.y)));
+            const float2 s1 = fadd2(make_float2(e0, e1), one2);
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(s1.x));
+            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(s1.y));
+            const float2 h = fadd2(make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f)), make_float2(l0, l1));
+            const __nv_bfloat162 p = __floats2bfloat162_rn(h.x, h.y);
             hi[q * 8 + i] = *reinterpret_cast<const uint32_t*>(&p);
             if (SPLIT) {
-                const float2 back = __bfloat1622float2(p);
-                const __nv_bfloat162 r = __floats2bfloat162_rn(h0 - back.x, h1 - back.y);
+                const float2 d = ffma2(__bfloat1622float2(p), neg2, h);      // h - bf16(h), exact
+                const __nv_bfloat162 r = __floats2bfloat162_rn(d.x, d.y);
                 lo[q * 8 + i] = *reinterpret_cast<const uint32_t*>(&r);
             }
         }
@@ -155,6 +179,9 @@ __device__ unsigned long long g_pipe_prof[3][16];
 // 64-bit ALU instructions per load otherwise)
 __device__ __forceinline__ float4 ldg_tap(const float4* lane_base, uint32_t off4)
 {
+#ifdef NFE_ABLATE_GATHER
+    return make_float4(__uint_as_float(off4), 0.f, 0.f, 0.f);      // timing experiment only (wrong results): no texel loads
+#endif
     uint64_t addr;
     asm("mad.wide.u32 %0, %1, 16, %2;" : "=l"(addr) : "r"(off4), "l"(lane_base));
     return __ldg(reinterpret_cast<const float4*>(addr));
@@ -247,12 +274,14 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                     for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
                 }
                 uint4* dst = s.taps[buf][gw][lane];
-                dst[6] = make_uint4((uint32_t)item_idx, 0u, 0u, 0u);
+                dst[9] = make_uint4((uint32_t)item_idx, 0u, 0u, 0u);
 #pragma unroll
-                for (int q = 0; q < 3; ++q) {
+                for (int q = 0; q < 3; ++q)
                     dst[q] = make_uint4((uint32_t)ts.off4[4 * q], (uint32_t)ts.off4[4 * q + 1], (uint32_t)ts.off4[4 * q + 2], (uint32_t)ts.off4[4 * q + 3]);
-                    dst[3 + q] = make_uint4(__float_as_uint(ts.w[4 * q]), __float_as_uint(ts.w[4 * q + 1]), __float_as_uint(ts.w[4 * q + 2]),
-                                            __float_as_uint(ts.w[4 * q + 3]));
+#pragma unroll
+                for (int q = 0; q < 6; ++q) {
+                    const uint32_t w0 = __float_as_uint(ts.w[2 * q]), w1 = __float_as_uint(ts.w[2 * q + 1]);
+                    dst[3 + q] = make_uint4(w0, w0, w1, w1);
                 }
             }
         };
@@ -260,10 +289,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             const uint4* src = s.taps[buf][gw][p * 4 + g];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                const uint4 o4 = src[q], w4 = src[3 + q];
+                const uint4 o4 = src[q], wa = src[3 + 2 * q], wb = src[4 + 2 * q];
                 ts.off4[4 * q] = (int)o4.x; ts.off4[4 * q + 1] = (int)o4.y; ts.off4[4 * q + 2] = (int)o4.z; ts.off4[4 * q + 3] = (int)o4.w;
-                ts.w[4 * q] = __uint_as_float(w4.x); ts.w[4 * q + 1] = __uint_as_float(w4.y);
-                ts.w[4 * q + 2] = __uint_as_float(w4.z); ts.w[4 * q + 3] = __uint_as_float(w4.w);
+                ts.w[4 * q] = __uint_as_float(wa.x); ts.w[4 * q + 1] = __uint_as_float(wa.z);
+                ts.w[4 * q + 2] = __uint_as_float(wb.x); ts.w[4 * q + 3] = __uint_as_float(wb.z);
             }
         };
 
@@ -298,48 +327,43 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                     const bool more = p + 1 < n_pass;
                     const bool fetch = more || has_next;
                     const uint4* nxt = more ? s.taps[st][gw][(p + 1) * 4 + g] : s.taps[st ^ 1][gw][g];
-                    float4 f[3];
-                    float w_in[3];
+                    // packed fp32 pairs: channels (x,y) and (z,w) of the lane's float4; the tap weights sit in shared
+                    // memory duplicated as (w,w) so they are FFMA2 operands as loaded
+                    float2 f01[3], f23[3], w_in[3];
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl) {
-                        const uint4 w4 = cur[3 + pl];
-                        const float w0 = __uint_as_float(w4.x), w1 = __uint_as_float(w4.y), w2 = __uint_as_float(w4.z), w3 = __uint_as_float(w4.w);
-                        float4 acc;
-                        acc.x = va[4 * pl].x * w0; acc.y = va[4 * pl].y * w0; acc.z = va[4 * pl].z * w0; acc.w = va[4 * pl].w * w0;
-                        acc.x = fmaf(va[4 * pl + 1].x, w1, acc.x); acc.y = fmaf(va[4 * pl + 1].y, w1, acc.y);
-                        acc.z = fmaf(va[4 * pl + 1].z, w1, acc.z); acc.w = fmaf(va[4 * pl + 1].w, w1, acc.w);
-                        acc.x = fmaf(va[4 * pl + 2].x, w2, acc.x); acc.y = fmaf(va[4 * pl + 2].y, w2, acc.y);
-                        acc.z = fmaf(va[4 * pl + 2].z, w2, acc.z); acc.w = fmaf(va[4 * pl + 2].w, w2, acc.w);
-                        acc.x = fmaf(va[4 * pl + 3].x, w3, acc.x); acc.y = fmaf(va[4 * pl + 3].y, w3, acc.y);
-                        acc.z = fmaf(va[4 * pl + 3].z, w3, acc.z); acc.w = fmaf(va[4 * pl + 3].w, w3, acc.w);
-                        f[pl] = acc;
-                        w_in[pl] = ((w0 + w1) + w2) + w3;
+                        const float4 wa = *reinterpret_cast<const float4*>(&cur[3 + 2 * pl]), wb = *reinterpret_cast<const float4*>(&cur[4 + 2 * pl]);
+                        const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+                        float2 a01 = fmul2(make_float2(va[4 * pl].x, va[4 * pl].y), w0), a23 = fmul2(make_float2(va[4 * pl].z, va[4 * pl].w), w0);
+                        a01 = ffma2(make_float2(va[4 * pl + 1].x, va[4 * pl + 1].y), w1, a01); a23 = ffma2(make_float2(va[4 * pl + 1].z, va[4 * pl + 1].w), w1, a23);
+                        a01 = ffma2(make_float2(va[4 * pl + 2].x, va[4 * pl + 2].y), w2, a01); a23 = ffma2(make_float2(va[4 * pl + 2].z, va[4 * pl + 2].w), w2, a23);
+                        a01 = ffma2(make_float2(va[4 * pl + 3].x, va[4 * pl + 3].y), w3, a01); a23 = ffma2(make_float2(va[4 * pl + 3].z, va[4 * pl + 3].w), w3, a23);
+                        f01[pl] = a01; f23[pl] = a23;
+                        w_in[pl] = fadd2(fadd2(fadd2(w0, w1), w2), w3);
                         if (fetch) {             // refill the four registers just consumed with the next pass's texels
                             const uint4 o4 = nxt[pl];
                             va[4 * pl] = ldg_tap(set_r, o4.x); va[4 * pl + 1] = ldg_tap(set_r, o4.y);
                             va[4 * pl + 2] = ldg_tap(set_r, o4.z); va[4 * pl + 3] = ldg_tap(set_r, o4.w);
                         }
                     }
-                    constexpr float third = 1.0f / 3.0f;
-                    const float4 fa = make_float4(((f[0].x + f[1].x) + f[2].x) * third, ((f[0].y + f[1].y) + f[2].y) * third,
-                                                  ((f[0].z + f[1].z) + f[2].z) * third, ((f[0].w + f[1].w) + f[2].w) * third);
-                    store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, fa);
+                    const float2 third2 = make_float2(1.0f / 3.0f, 1.0f / 3.0f);
+                    const float2 fa01 = fmul2(fadd2(fadd2(f01[0], f01[1]), f01[2]), third2), fa23 = fmul2(fadd2(fadd2(f23[0], f23[1]), f23[2]), third2);
+                    store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, make_float4(fa01.x, fa01.y, fa23.x, fa23.y));
                     if (affine && !skip_b) {
                         // single-gather identity: only the normalised planes are read; the de-normalised features are
                         // s*f_p + m*w_in per plane (statistics: 6 L1-resident float4 loads per lane)
-                        const int item = a.affine_items == 1 ? 0 : (int)cur[6].x;
+                        const int item = a.affine_items == 1 ? 0 : (int)cur[9].x;
                         const float4* sc = reinterpret_cast<const float4*>(a.affine_scale + (int64_t)item * 96) + c4;
                         const float4* sh = reinterpret_cast<const float4*>(a.affine_shift + (int64_t)item * 96) + c4;
-                        float4 d[3];
+                        float2 d01[3], d23[3];
 #pragma unroll
                         for (int pl = 0; pl < 3; ++pl) {
                             const float4 scl = __ldg(sc + pl * 8), shf = __ldg(sh + pl * 8);
-                            d[pl] = make_float4(fmaf(scl.x, f[pl].x, shf.x * w_in[pl]), fmaf(scl.y, f[pl].y, shf.y * w_in[pl]),
-                                                fmaf(scl.z, f[pl].z, shf.z * w_in[pl]), fmaf(scl.w, f[pl].w, shf.w * w_in[pl]));
+                            d01[pl] = ffma2(make_float2(scl.x, scl.y), f01[pl], fmul2(make_float2(shf.x, shf.y), w_in[pl]));
+                            d23[pl] = ffma2(make_float2(scl.z, scl.w), f23[pl], fmul2(make_float2(shf.z, shf.w), w_in[pl]));
                         }
-                        const float4 fb = make_float4(((d[0].x + d[1].x) + d[2].x) * third, ((d[0].y + d[1].y) + d[2].y) * third,
-                                                      ((d[0].z + d[1].z) + d[2].z) * third, ((d[0].w + d[1].w) + d[2].w) * third);
-                        store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, fb);
+                        const float2 fb01 = fmul2(fadd2(fadd2(d01[0], d01[1]), d01[2]), third2), fb23 = fmul2(fadd2(fadd2(d23[0], d23[1]), d23[2]), third2);
+                        store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, make_float4(fb01.x, fb01.y, fb23.x, fb23.y));
                     }
                 }
             } else {
@@ -442,7 +466,10 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 tc::tmem_ld16(lane_addr + COL_D2A + q * 16, v);
                 tc::tmem_ld_wait();
 #pragma unroll
-                for (int i = 0; i < 16; ++i) outa[q * 16 + i] = v[i] + s.bias2a[q * 16 + i];
+                for (int i = 0; i < 8; ++i) {
+                    const float2 o2 = fadd2(make_float2(v[2 * i], v[2 * i + 1]), *reinterpret_cast<const float2*>(&s.bias2a[q * 16 + 2 * i]));
+                    outa[q * 16 + 2 * i] = o2.x; outa[q * 16 + 2 * i + 1] = o2.y;
+                }
             }
             float sig = outa[0];
             if (a.density_noise > 0.0f && live) {
@@ -491,14 +518,19 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                     tc::tmem_ld16(lane_addr + COL_D2A + T::N_A + q * 16, v);
                     tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) outb[q * 16 + i] = v[i] + s.bias2b[q * 16 + i];
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 o2 = fadd2(make_float2(v[2 * i], v[2 * i + 1]), *reinterpret_cast<const float2*>(&s.bias2b[q * 16 + 2 * i]));
+                        outb[q * 16 + 2 * i] = o2.x; outb[q * 16 + 2 * i + 1] = o2.y;
+                    }
                 }
                 if (live) {
                     if constexpr (KIND == NFE_DEC_DISENTANGLED) {
 #pragma unroll
-                        for (int c = 0; c < 8; ++c)
-                            rgb4[c] = make_float4(rgb_activation(outb[4 * c]), rgb_activation(outb[4 * c + 1]),
-                                                  rgb_activation(outb[4 * c + 2]), rgb_activation(outb[4 * c + 3]));
+                        for (int c = 0; c < 8; ++c) {
+                            const float2 lo2 = rgb_activation2(make_float2(outb[4 * c], outb[4 * c + 1]));
+                            const float2 hi2 = rgb_activation2(make_float2(outb[4 * c + 2], outb[4 * c + 3]));
+                            rgb4[c] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                        }
                     } else if (rec) {
                         rec[0] = make_float4(sig, outb[0], outb[1], outb[2]);
 #pragma unroll

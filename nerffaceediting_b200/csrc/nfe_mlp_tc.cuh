@@ -96,8 +96,9 @@ __device__ __forceinline__ void store_features4(unsigned char (*a1)[A1_BYTES], i
     const uint32_t off = core_offset(row, k0, A1_LBO, A1_SBO);
     *reinterpret_cast<uint2*>(a1[0] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
     if (SPLIT) {
-        const float2 b01 = __bfloat1622float2(h01), b23 = __bfloat1622float2(h23);
-        const __nv_bfloat162 l01 = __floats2bfloat162_rn(f.x - b01.x, f.y - b01.y), l23 = __floats2bfloat162_rn(f.z - b23.x, f.w - b23.y);
+        const float2 neg2 = make_float2(-1.0f, -1.0f);
+        const float2 d01 = ffma2(__bfloat1622float2(h01), neg2, make_float2(f.x, f.y)), d23 = ffma2(__bfloat1622float2(h23), neg2, make_float2(f.z, f.w));
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(d01.x, d01.y), l23 = __floats2bfloat162_rn(d23.x, d23.y);
         *reinterpret_cast<uint2*>(a1[1] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
     }
 }
