@@ -220,6 +220,18 @@ int nfe_feature_mean_fwd(const float* planes_cl, int plane_batch, int height, in
 int nfe_feature_mean_bwd(const float* g_feat, int plane_batch, int height, int width, float box_warp,
                          const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays,
                          int s_per_ray, float* g_planes_cl, nfe_stream_t stream);
+/* Fused backward of gather + DisentangledOSGDecoder (triplane.py:249-270 and renderer.py:55-65 differentiated) for one
+ * pass of samples (sample idx = ray*s_per_ray + s at depth depths[idx]), on the tensor cores:
+ * recomputes the plane-mean features and hidden activations, back-propagates the per-sample record gradients
+ * g_rec [total,48] = d/d{sigma, seg[15], rgb[32]} (rec = the forward's records, for the colour sigmoid), scatter-adds
+ * the feature gradients into the two channel-last plane gradients and ACCUMULATES the raw-parameter gradients
+ * (shapes of the parameters; FullyConnectedLayer gains applied) — all gradient buffers are zero-initialised /
+ * carried by the caller.  kind must be NFE_DEC_DISENTANGLED. */
+int nfe_field_bwd(int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width,
+                  float box_warp, const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays,
+                  int s_per_ray, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec, const float* g_rec,
+                  float* g_planes_norm_cl, float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a, float* g_b2_a,
+                  float* g_w1_b, float* g_b1_b, float* g_w2_b, float* g_b2_b, nfe_stream_t stream);
 /* channel-last [n_img, hw, 32] -> reference layout [n_img, 32, hw] (plane gradients back to [N,3,32,H,W]) */
 int nfe_planes_from_channel_last(const float* planes_cl, int64_t n_img, int channels, int64_t hw, float* out,
                                  nfe_stream_t stream);

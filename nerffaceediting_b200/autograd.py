@@ -16,6 +16,7 @@ Gradients reach the two plane tensors and the decoder parameters; sample positio
 are data and depths_fine is detached in the reference, renderer.py:198,211).
 """
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -100,8 +101,20 @@ class RenderFunction(torch.autograd.Function):
             pb, _, h, w, _ = any_cl.shape
             g_denorm_cl = torch.zeros_like(denorm_cl)
             g_norm_cl = torch.zeros_like(norm_cl) if norm_cl is not None else None
+            fused = kind == ops.DEC_DISENTANGLED and os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1"
+            if fused:
+                # 2-4 fused: one tcgen05 kernel per pass recomputes features and activations, back-propagates both
+                # decoder nets, scatter-adds into the plane gradients and accumulates the parameter gradients
+                mlp_a, mlp_b = ops.MlpRef(seq_a, dev), ops.MlpRef(seq_b, dev)
+                full = [g if g is not None else torch.zeros_like(p) for g, p in zip(g_params, params)]
+                for depths, s, rec, g_rec in ((dc, s_c, st["rec_c"], g_rec_c), (df, s_f, st.get("rec_f"), g_rec_f)):
+                    if not s:
+                        continue
+                    _lib.check(lib.nfe_field_bwd(kind, P(norm_cl), P(denorm_cl), pb, h, w, ctypes.c_float(cfg.box_warp), P(o), P(d), P(depths), n, r, s,
+                                                 mlp_a.ref(), mlp_b.ref(), P(rec), P(g_rec), P(g_norm_cl), P(g_denorm_cl),
+                                                 *[P(t) for t in full], stream), "nfe_field_bwd")
             for depths, s, g_rec in ((dc, s_c, g_rec_c), (df, s_f, g_rec_f)):
-                if not s:
+                if not s or fused:
                     continue
                 total = n * r * s
                 geom = (pb, h, w, ctypes.c_float(cfg.box_warp), P(o), P(d), P(depths), n, r, s)

@@ -1,0 +1,441 @@
+// Fused backward of gather + DisentangledOSGDecoder on the tensor cores (BASELINE config 4).
+//
+// Per 128-sample tile, one CTA (256 threads) does what the reference's autograd graph does in ~40 kernels
+// (grid_sampler backward, two addmm/softplus/addmm/sigmoid chains, triplane.py:249-270):
+//
+//   gather        X = [mean features of the normalised planes | of the raw planes | 1]      (128 x 80, bf16 hi/lo)
+//   G1            pre_n = X_n W1_n^T                                                          (tcgen05, TMEM)
+//   epilogue 1    H_n = softplus(pre_n + b1_n) -> smem;  dY_n from the per-sample record gradients
+//                 (geo: d sigma, d seg; app: d rgb * 1.002 * s(1-s), s recovered from the saved rgb)
+//   G2            dH_n = dY_n W2_n                              G4   dW2 += H^T dY   (operands read MN-major)
+//   epilogue 2    dpre_n = dH_n * sigmoid(pre_n + b1_n) -> smem (over H)
+//   G3            dX_n = dpre_n W1_n                            G5   dW1 | db1 += dpre^T [X | 1]
+//   epilogue 3    dX -> smem (fp32) -> red.global.add.v4.f32 of w_tap/3 * dX into the channel-last plane gradients
+//
+// dW1/db1/dW2 accumulate in TMEM over all tiles of the CTA and are added to the global gradients once at the end
+// (db2 in registers).  Every product runs as three bf16 MMAs (hi*hi + lo*hi + hi*lo, fp32 accumulate), like the
+// forward's bf16x3 mode.  The two weight-gradient GEMMs contract over the tile's ROWS: their operands are the same
+// shared-memory tiles the other GEMMs read K-major, described MN-major (transposed) to the tensor core, so nothing
+// is transposed in software.
+#include "nfe_field.cuh"
+#include "nfe_mlp_tc.cuh"
+
+namespace nfe {
+
+using namespace tcmlp;
+
+namespace fb {
+
+constexpr int THREADS = 256;
+constexpr int XA_COLS = 80, XA_LBO = 160, XA_SBO = (XA_COLS / 8) * XA_LBO, XA_BYTES = 16 * XA_SBO;   // [X_norm | X_raw | 1 0..0]
+constexpr int HC_COLS = 128, HC_LBO = 128, HC_SBO = (HC_COLS / 8) * HC_LBO, HC_BYTES = 16 * HC_SBO;  // [H_geo | H_app], later dpre
+constexpr int DY_COLS = 48, DY_LBO = 128, DY_SBO = (DY_COLS / 8) * DY_LBO, DY_BYTES = 16 * DY_SBO;   // [dY_geo(16) | dY_app(32)]
+constexpr int W2T_LBO = 128, W2T_SBO = 512, W2T_BYTES = 8 * W2T_SBO;     // B of G2: [N=64 x K<=32], element (j,o) = W2[o][j]
+constexpr int W1T_LBO = 128, W1T_SBO = 1024, W1T_BYTES = 4 * W1T_SBO;    // B of G3: [N=32 x K=64], element (i,j) = W1[j][i]
+constexpr int GX_STRIDE = 68;                                            // fp32 dX staging row stride (floats), aliases hc
+// TMEM columns
+constexpr int C_PRE = 0, C_DH = 128, C_DX = 256, C_DW1 = 320, C_DW2 = 400, TMEM_ALLOC = 512;
+
+struct Smem {
+    alignas(128) unsigned char xa[2][XA_BYTES];
+    alignas(128) unsigned char hc[2][HC_BYTES];
+    alignas(128) unsigned char dy[2][DY_BYTES];
+    alignas(128) unsigned char w1[2][2][B1_BYTES];
+    alignas(128) unsigned char w2t[2][2][W2T_BYTES];
+    alignas(128) unsigned char w1t[2][2][W1T_BYTES];
+    alignas(16) int tap_off[TILE_M][12];
+    alignas(16) float tap_w[TILE_M][12];
+    float bias1[2][HIDDEN];
+    alignas(8) uint64_t bar;
+    uint32_t tmem_base;
+};
+static_assert(GX_STRIDE * 4 * TILE_M <= 2 * HC_BYTES, "dX staging must fit in the hidden tile it aliases");
+
+struct Args {
+    const float* set_norm; const float* set_raw;      // channel-last plane sets
+    float* g_norm; float* g_raw;                      // channel-last plane gradients (zero-initialised by the caller)
+    int plane_batch, H, W; float scale;
+    const float* origins; const float* dirs; const float* depths;
+    int s_per_ray; int64_t m, total;
+    const float* rec;                                 // forward records [total,48] (rgb for the sigmoid derivative)
+    const float* g_rec;                               // d loss / d record [total,48]
+    float* gw1[2]; float* gb1[2]; float* gw2[2]; float* gb2[2];    // raw-parameter gradients (accumulated atomically)
+};
+
+// instruction descriptor with both operands MN-major (bits 15/16)
+__host__ __device__ constexpr uint32_t idesc_mn(int M, int N) { return tc::make_idesc_bf16(M, N) | (1u << 15) | (1u << 16); }
+
+// D (+)= A^T-view * B^T-view contracting over the 128 tile rows; both tiles are stored K-major [rows x cols] with
+// (lbo,sbo); read MN-major the roles swap: stride between 8-row K blocks = sbo, between 8-column MN blocks = lbo
+__device__ __forceinline__ void issue_gemm_rows(uint32_t tmem_d, const unsigned char* a_hi, const unsigned char* a_lo, int a_lbo, int a_sbo,
+                                                const unsigned char* b_hi, const unsigned char* b_lo, int b_lbo, int b_sbo, uint32_t idesc, bool accumulate)
+{
+    bool acc = accumulate;
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const unsigned char* a = (t == 1) ? a_lo : a_hi;
+        const unsigned char* b = (t == 2) ? b_lo : b_hi;
+        for (int ks = 0; ks < TILE_M / 16; ++ks) {
+            const uint64_t da = tc::make_desc(tc::smem_u32(a) + ks * 2 * a_sbo, a_sbo, a_lbo);
+            const uint64_t db = tc::make_desc(tc::smem_u32(b) + ks * 2 * b_sbo, b_sbo, b_lbo);
+            tc::mma_bf16_ss(tmem_d, da, db, idesc, acc);
+            acc = true;
+        }
+    }
+}
+
+// transposed, gain-folded weight operand: dst element (n, k) = w[k * ld + n] * gain for n < N, k < K (zero elsewhere)
+__device__ void load_weights_t(unsigned char* dst, size_t part_stride, const float* w, float gain, int N, int K, int K_pad, int ld, int lbo, int sbo)
+{
+    for (int i = threadIdx.x; i < N * K_pad; i += blockDim.x) {
+        const int n = i / K_pad, k = i % K_pad;
+        const float v = k < K ? __fmul_rn(__ldg(w + k * ld + n), gain) : 0.0f;
+        __nv_bfloat16 hi, lo;
+        tc::split_bf16(v, hi, lo);
+        const uint32_t off = core_offset(n, k, lbo, sbo);
+        *reinterpret_cast<__nv_bfloat16*>(dst + off) = hi;
+        *reinterpret_cast<__nv_bfloat16*>(dst + part_stride + off) = lo;
+    }
+}
+
+// 8 consecutive columns of one row as bf16 hi / lo parts (two 16-byte stores)
+__device__ __forceinline__ void store8(unsigned char* hi_tile, unsigned char* lo_tile, uint32_t off, const float (&v)[8])
+{
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162 p = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        const float2 back = __bfloat1622float2(p);
+        const __nv_bfloat162 r = __floats2bfloat162_rn(v[2 * i] - back.x, v[2 * i + 1] - back.y);
+        h[i] = *reinterpret_cast<const uint32_t*>(&p);
+        l[i] = *reinterpret_cast<const uint32_t*>(&r);
+    }
+    *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v)
+{
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp geo, nfe_mlp app)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int net = warp >> 2;                       // epilogue role: warps 0-3 geo_net, 4-7 app_net
+    const int row = (warp & 3) * 32 + lane;          // TMEM lane = tile row
+    const nfe_mlp& mine = net ? app : geo;
+
+    // ---- setup: TMEM, barrier, weights (three layouts), the constant [1 0 .. 0] block of X
+    if (warp == 0) tc::tmem_alloc(&s.tmem_base, TMEM_ALLOC);
+    if (threadIdx.x == 0) { tc::mbar_init(&s.bar, 1); tc::mbar_fence_init(); }
+    for (int n = 0; n < 2; ++n) {
+        const nfe_mlp& p = n ? app : geo;
+        load_weights<2>(s.w1[n][0], B1_BYTES, p.w1, p.wgain1, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
+        load_weights_t(s.w2t[n][0], W2T_BYTES, p.w2, p.wgain2, HIDDEN, p.out_dim, n ? 32 : 16, HIDDEN, W2T_LBO, W2T_SBO);
+        load_weights_t(s.w1t[n][0], W1T_BYTES, p.w1, p.wgain1, FEAT, HIDDEN, HIDDEN, FEAT, W1T_LBO, W1T_SBO);
+        for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s.bias1[n][i] = folded_bias(p.b1, p.bgain1, i);
+    }
+    for (int i = threadIdx.x; i < TILE_M * 16; i += blockDim.x) {
+        const int r = i >> 4, c = 64 + (i & 15);
+        const uint32_t off = core_offset(r, c, XA_LBO, XA_SBO);
+        *reinterpret_cast<__nv_bfloat16*>(s.xa[0] + off) = __float2bfloat16_rn(c == 64 ? 1.0f : 0.0f);
+        *reinterpret_cast<__nv_bfloat16*>(s.xa[1] + off) = __float2bfloat16_rn(0.0f);
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s.tmem_base;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    uint32_t phase = 0;
+    float db2[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) db2[i] = 0.0f;
+
+    const int64_t n_tiles = (a.total + TILE_M - 1) / TILE_M;
+    const int64_t set_stride4 = (int64_t)3 * a.H * a.W * (FEAT / 4);
+    const int c4 = threadIdx.x & 7;
+    bool first = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t base = tile * TILE_M;
+        // ---- gather both plane sets (8 lanes per sample, 32 samples per step)
+#pragma unroll 1
+        for (int p = 0; p < TILE_M / 32; ++p) {
+            const int r = p * 32 + (threadIdx.x >> 3);
+            const int64_t idx = base + r;
+            TapSet ts;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
+            if (idx < a.total) {
+                const int64_t ray = idx / a.s_per_ray;
+                const float t = __ldg(a.depths + idx);
+                const float* o = a.origins + ray * 3;
+                const float* d = a.dirs + ray * 3;
+                const float x = ray_point(__ldg(o), t, __ldg(d)), y = ray_point(__ldg(o + 1), t, __ldg(d + 1)), z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
+                ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
+                const int item_off = a.plane_batch == 1 ? 0 : (int)((idx / a.m) * set_stride4);
+#pragma unroll
+                for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
+            }
+            if (c4 < 3) {                              // taps kept for the scatter at the end of the tile
+                *reinterpret_cast<int4*>(&s.tap_off[r][4 * c4]) = make_int4(ts.off4[4 * c4], ts.off4[4 * c4 + 1], ts.off4[4 * c4 + 2], ts.off4[4 * c4 + 3]);
+                *reinterpret_cast<float4*>(&s.tap_w[r][4 * c4]) = make_float4(ts.w[4 * c4], ts.w[4 * c4 + 1], ts.w[4 * c4 + 2], ts.w[4 * c4 + 3]);
+            }
+            float4 va[12], vb[12];
+            gather_load(a.set_norm, ts, c4, va);
+            gather_load(a.set_raw, ts, c4, vb);
+            const float4 fa = gather_reduce(va, ts), fb = gather_reduce(vb, ts);
+#pragma unroll
+            for (int set = 0; set < 2; ++set) {
+                const float4 f = set ? fb : fa;
+                const __nv_bfloat162 h01 = __floats2bfloat162_rn(f.x, f.y), h23 = __floats2bfloat162_rn(f.z, f.w);
+                const float2 b01 = __bfloat1622float2(h01), b23 = __bfloat1622float2(h23);
+                const __nv_bfloat162 l01 = __floats2bfloat162_rn(f.x - b01.x, f.y - b01.y), l23 = __floats2bfloat162_rn(f.z - b23.x, f.w - b23.y);
+                const uint32_t off = core_offset(r, set * 32 + 4 * c4, XA_LBO, XA_SBO);
+                *reinterpret_cast<uint2*>(s.xa[0] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+                *reinterpret_cast<uint2*>(s.xa[1] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
+            }
+        }
+        tc::fence_async_smem();
+        __syncthreads();
+
+        // ---- G1: pre = X W1^T for both nets
+        if (threadIdx.x == 0) {
+            tc::fence_after_sync();
+            constexpr uint32_t id1 = tc::make_idesc_bf16(TILE_M, HIDDEN);
+            for (int n = 0; n < 2; ++n)
+                issue_gemm<true>(tmem + C_PRE + 64 * n, s.xa[0] + 4 * n * XA_LBO, s.xa[1] + 4 * n * XA_LBO, XA_LBO, XA_SBO, s.w1[n][0], s.w1[n][1],
+                                 B1_LBO, B1_SBO, FEAT, id1);
+            tc::mma_commit(&s.bar);
+        }
+        tc::mbar_wait(&s.bar, phase); phase ^= 1;
+        tc::fence_after_sync();
+
+        // ---- epilogue 1: hidden activations and output-layer gradients of this thread's (row, net)
+        const bool live = base + row < a.total;
+        {
+#pragma unroll 1
+            for (int q = 0; q < HIDDEN / 16; ++q) {
+                float v[16];
+                tc::tmem_ld16(lane_addr + C_PRE + 64 * net + q * 16, v);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = softplus_fast(v[i] + s.bias1[net][q * 16 + i]);
+                float h8[8];
+#pragma unroll
+                for (int c8 = 0; c8 < 2; ++c8) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) h8[i] = v[c8 * 8 + i];
+                    store8(s.hc[0], s.hc[1], core_offset(row, 64 * net + q * 16 + c8 * 8, HC_LBO, HC_SBO), h8);
+                }
+            }
+            const float4* g4 = reinterpret_cast<const float4*>(a.g_rec + (base + row) * 48);
+            const float4* r4 = reinterpret_cast<const float4*>(a.rec + (base + row) * 48);
+            if (net == 0) {
+#pragma unroll
+                for (int c8 = 0; c8 < 2; ++c8) {
+                    float d8[8];
+                    const float4 g0 = live ? __ldg(g4 + 2 * c8) : make_float4(0.f, 0.f, 0.f, 0.f), g1 = live ? __ldg(g4 + 2 * c8 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    d8[0] = g0.x; d8[1] = g0.y; d8[2] = g0.z; d8[3] = g0.w; d8[4] = g1.x; d8[5] = g1.y; d8[6] = g1.z; d8[7] = g1.w;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) db2[c8 * 8 + i] += d8[i];
+                    store8(s.dy[0], s.dy[1], core_offset(row, c8 * 8, DY_LBO, DY_SBO), d8);
+                }
+            } else {
+#pragma unroll
+                for (int c8 = 0; c8 < 4; ++c8) {
+                    float d8[8];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 g = live ? __ldg(g4 + 4 + 2 * c8 + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 y = live ? __ldg(r4 + 4 + 2 * c8 + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        // rgb = s*1.002 - 0.001 with s = sigmoid(out)  =>  d rgb / d out = 1.002 * s * (1 - s)
+                        const float gs[4] = {g.x, g.y, g.z, g.w}, ys[4] = {y.x, y.y, y.z, y.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float sg = (ys[i] + 0.001f) * (1.0f / 1.002f);
+                            d8[4 * h + i] = gs[i] * 1.002f * sg * (1.0f - sg);
+                        }
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) db2[c8 * 8 + i] += d8[i];
+                    store8(s.dy[0], s.dy[1], core_offset(row, 16 + c8 * 8, DY_LBO, DY_SBO), d8);
+                }
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+
+        // ---- G2: dH = dY W2;  G4: dW2^T += H^T dY (contraction over the tile rows)
+        if (threadIdx.x == 0) {
+            tc::fence_after_sync();
+            constexpr uint32_t id2 = tc::make_idesc_bf16(TILE_M, HIDDEN);
+            issue_gemm<true>(tmem + C_DH, s.dy[0], s.dy[1], DY_LBO, DY_SBO, s.w2t[0][0], s.w2t[0][1], W2T_LBO, W2T_SBO, 16, id2);
+            issue_gemm<true>(tmem + C_DH + 64, s.dy[0] + 2 * DY_LBO, s.dy[1] + 2 * DY_LBO, DY_LBO, DY_SBO, s.w2t[1][0], s.w2t[1][1], W2T_LBO, W2T_SBO, 32, id2);
+            issue_gemm_rows(tmem + C_DW2, s.hc[0], s.hc[1], HC_LBO, HC_SBO, s.dy[0], s.dy[1], DY_LBO, DY_SBO, idesc_mn(TILE_M, DY_COLS), !first);
+            tc::mma_commit(&s.bar);
+        }
+        tc::mbar_wait(&s.bar, phase); phase ^= 1;
+        tc::fence_after_sync();
+
+        // ---- epilogue 2: dpre = dH * sigmoid(pre + b1), over the hidden tile
+#pragma unroll 1
+        for (int q = 0; q < HIDDEN / 16; ++q) {
+            float pre[16], dh[16];
+            tc::tmem_ld16(lane_addr + C_PRE + 64 * net + q * 16, pre);
+            tc::tmem_ld16(lane_addr + C_DH + 64 * net + q * 16, dh);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) dh[i] *= sigmoid_fast(pre[i] + s.bias1[net][q * 16 + i]);
+            float d8[8];
+#pragma unroll
+            for (int c8 = 0; c8 < 2; ++c8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) d8[i] = dh[c8 * 8 + i];
+                store8(s.hc[0], s.hc[1], core_offset(row, 64 * net + q * 16 + c8 * 8, HC_LBO, HC_SBO), d8);
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+
+        // ---- G3: dX = dpre W1;  G5: [dW1 | db1] += dpre^T [X | 1]
+        if (threadIdx.x == 0) {
+            tc::fence_after_sync();
+            constexpr uint32_t id3 = tc::make_idesc_bf16(TILE_M, FEAT);
+            for (int n = 0; n < 2; ++n)
+                issue_gemm<true>(tmem + C_DX + 32 * n, s.hc[0] + 8 * n * HC_LBO, s.hc[1] + 8 * n * HC_LBO, HC_LBO, HC_SBO, s.w1t[n][0], s.w1t[n][1],
+                                 W1T_LBO, W1T_SBO, HIDDEN, id3);
+            issue_gemm_rows(tmem + C_DW1, s.hc[0], s.hc[1], HC_LBO, HC_SBO, s.xa[0], s.xa[1], XA_LBO, XA_SBO, idesc_mn(TILE_M, XA_COLS), !first);
+            tc::mma_commit(&s.bar);
+        }
+        tc::mbar_wait(&s.bar, phase); phase ^= 1;
+        tc::fence_after_sync();
+        first = false;
+
+        // ---- epilogue 3: dX of this (row, set) -> fp32 staging (over the hidden tile, which G5 has finished reading)
+        float* gx = reinterpret_cast<float*>(s.hc[0]);
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float v[16];
+            tc::tmem_ld16(lane_addr + C_DX + 32 * net + q * 16, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<float4*>(gx + row * GX_STRIDE + 32 * net + 16 * q + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        // ---- gather backward: w_tap/3 * dX into the channel-last plane gradients
+        constexpr float third = 1.0f / 3.0f;
+#pragma unroll 1
+        for (int p = 0; p < TILE_M / 32; ++p) {
+            const int r = p * 32 + (threadIdx.x >> 3);
+            if (base + r >= a.total) continue;
+            float4 gn = *reinterpret_cast<const float4*>(gx + r * GX_STRIDE + 4 * c4), gr = *reinterpret_cast<const float4*>(gx + r * GX_STRIDE + 32 + 4 * c4);
+            gn = make_float4(gn.x * third, gn.y * third, gn.z * third, gn.w * third);
+            gr = make_float4(gr.x * third, gr.y * third, gr.z * third, gr.w * third);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                const float w = s.tap_w[r][i];
+                if (w != 0.0f) {
+                    const int64_t off = (int64_t)s.tap_off[r][i] * 4 + 4 * c4;
+                    red_add_v4(a.g_norm + off, make_float4(gn.x * w, gn.y * w, gn.z * w, gn.w * w));
+                    red_add_v4(a.g_raw + off, make_float4(gr.x * w, gr.y * w, gr.z * w, gr.w * w));
+                }
+            }
+        }
+        __syncthreads();      // the staging tile and the taps are reused by the next tile
+    }
+
+    // ---- parameter gradients of this CTA -> global (chain rule through the FullyConnectedLayer gains)
+    if (!first) {
+        tc::fence_after_sync();
+        if (warp < 4) {
+            const int n = row >> 6, j = row & 63;               // accumulator row = hidden unit j of net n
+            const nfe_mlp& p = n ? app : geo;
+            const uint32_t la = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll 1
+            for (int q = 0; q < XA_COLS / 16; ++q) {
+                float v[16];
+                tc::tmem_ld16(la + C_DW1 + q * 16, v);
+                tc::tmem_ld_wait();
+                if (q == 4) atomicAdd(a.gb1[n] + j, v[0] * p.bgain1);
+                else if ((q >> 1) == n) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(a.gw1[n] + j * FEAT + (q & 1) * 16 + i, v[i] * p.wgain1);
+                }
+            }
+#pragma unroll 1
+            for (int q = 0; q < DY_COLS / 16; ++q) {
+                float v[16];
+                tc::tmem_ld16(la + C_DW2 + q * 16, v);
+                tc::tmem_ld_wait();
+                const bool mine_q = n == 0 ? q == 0 : q >= 1;
+                if (mine_q) {
+                    const int o0 = n == 0 ? 0 : (q - 1) * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) atomicAdd(a.gw2[n] + (o0 + i) * HIDDEN + j, v[i] * p.wgain2);
+                }
+            }
+        }
+        // db2: column sums over the rows this thread handled, reduced over the warp
+        const int n_out = net ? 32 : 16;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            float v = db2[i];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0 && i < n_out) atomicAdd(a.gb2[net] + i, v * mine.bgain2);
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, TMEM_ALLOC);
+}
+
+}  // namespace fb
+}  // namespace nfe
+
+using namespace nfe;
+
+NFE_EXPORT int nfe_field_bwd(int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width, float box_warp,
+                             const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays, int s_per_ray,
+                             const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec, const float* g_rec, float* g_planes_norm_cl,
+                             float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a, float* g_b2_a, float* g_w1_b, float* g_b1_b,
+                             float* g_w2_b, float* g_b2_b, nfe_stream_t stream)
+{
+    const int64_t total = (int64_t)n * n_rays * s_per_ray;
+    if (total == 0) return 0;
+    NFE_REQUIRE(kind == NFE_DEC_DISENTANGLED, "nfe_field_bwd: only the DisentangledOSGDecoder has a fused backward (kind %d)", kind);
+    NFE_REQUIRE(planes_norm_cl && planes_cl && origins && dirs && depths && net_a && net_b && rec && g_rec && g_planes_norm_cl && g_planes_cl,
+                "nfe_field_bwd: null pointer");
+    NFE_REQUIRE(g_w1_a && g_b1_a && g_w2_a && g_b2_a && g_w1_b && g_b1_b && g_w2_b && g_b2_b, "nfe_field_bwd: null parameter-gradient pointer");
+    NFE_REQUIRE(net_a->in_dim == FEAT && net_a->hidden == HIDDEN && net_a->out_dim == 16 && net_b->in_dim == FEAT && net_b->hidden == HIDDEN &&
+                net_b->out_dim == 32, "nfe_field_bwd: decoder widths must be 32-64-16 / 32-64-32");
+    NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_field_bwd: plane batch %d does not match ray batch %d", plane_batch, n);
+    NFE_REQUIRE((int64_t)plane_batch * height * width * 3 * (FEAT / 4) < (1ll << 31), "nfe_field_bwd: planes exceed the 32-bit texel offsets");
+    fb::Args a = {};
+    a.set_norm = planes_norm_cl; a.set_raw = planes_cl; a.g_norm = g_planes_norm_cl; a.g_raw = g_planes_cl;
+    a.plane_batch = plane_batch; a.H = height; a.W = width; a.scale = (float)(2.0 / (double)box_warp);
+    a.origins = origins; a.dirs = dirs; a.depths = depths; a.s_per_ray = s_per_ray; a.m = n_rays * s_per_ray; a.total = total;
+    a.rec = rec; a.g_rec = g_rec;
+    a.gw1[0] = g_w1_a; a.gb1[0] = g_b1_a; a.gw2[0] = g_w2_a; a.gb2[0] = g_b2_a;
+    a.gw1[1] = g_w1_b; a.gb1[1] = g_b1_b; a.gw2[1] = g_w2_b; a.gb2[1] = g_b2_b;
+    const size_t smem = sizeof(fb::Smem) + 128;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(fb::field_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NFE_REQUIRE(e == cudaSuccess, "nfe_field_bwd: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        configured = true;
+    }
+    const int64_t n_tiles = (total + TILE_M - 1) / TILE_M;
+    const int64_t cap = sm_count();
+    fb::field_bwd_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, *net_b);
+    NFE_LAUNCH_CHECK("field_bwd_kernel");
+    return 0;
+}

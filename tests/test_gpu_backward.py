@@ -154,3 +154,68 @@ def test_denormalize_plane_backward(dev):
         for a, b in zip(ours, ref):
             assert a.grad.shape == b.grad.shape
             assert rel_err(N(a.grad), b.grad.float().numpy()) < 1e-5
+
+
+def test_fused_decoder_backward_matches_library_gemm_path(dev, monkeypatch):
+    """The fused tcgen05 decoder backward (nfe_field_bwd) against the same backward run on library GEMMs
+    (NFE_BWD_LIBRARY_GEMM=1, itself pinned to the reference's autograd above), at a size where every CTA walks several
+    tiles, so the TMEM-resident parameter-gradient accumulators are exercised across tiles."""
+    from nerffaceediting_b200 import triplane
+    from nerffaceediting_b200.ray_sampler import RaySampler
+    from nerffaceediting_b200.renderer import DisentangledImportanceRenderer
+    g = golden("backward")
+    n, hw, res = 2, 32, 40
+    c2w, k = synth.camera_sweep(n)
+    with torch.no_grad():
+        o, d = RaySampler()(T(c2w.numpy(), dev), T(k.numpy(), dev), res)
+    opts = dict(synth.FFHQ_RENDERING_OPTIONS, depth_resolution=24, depth_resolution_importance=24, nfe_deterministic=True, nfe_precision="fp32")
+    gen = torch.Generator().manual_seed(11)
+    proj = [torch.randn(n, res * res, c, generator=gen).to(dev) for c in (32, 15, 1, 1)]
+    grads = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("NFE_BWD_LIBRARY_GEMM", mode)
+        raw = T(synth.hash_normal(77, (n, 96, hw, hw)) * np.float32(1.5) - np.float32(0.3), dev).requires_grad_(True)
+        dec = torch_decoder(g, "dis.dec", "dis", 1.0, dev)
+        norm, _, _ = triplane.normalize_plane(raw)
+        out = DisentangledImportanceRenderer()(norm.view(n, 3, 32, hw, hw), raw.view(n, 3, 32, hw, hw), dec, o, d, opts)
+        sum((a * b).sum() for a, b in zip(out, proj)).backward()
+        grads[mode] = [raw.grad] + [p.grad for p in dec.parameters()]
+    names = ["raw planes"] + [nm for nm, _ in dec.named_parameters()]
+    for nm, a, b in zip(names, grads["0"], grads["1"]):
+        assert rel_err(N(a), N(b)) < TOL, nm
+
+
+def test_fused_decoder_backward_lr_multiplier_and_frozen_parameters(dev):
+    """FullyConnectedLayer gains (decoder_lr_mul != 1) go through the chain rule; frozen parameters get no gradient."""
+    from nerffaceediting_b200.ray_sampler import RaySampler
+    from nerffaceediting_b200.renderer import DisentangledImportanceRenderer
+    from nerffaceediting_b200.triplane import DisentangledOSGDecoder
+    g = golden("backward")
+    with torch.no_grad():
+        o, d = RaySampler()(T(g["cam2world"], dev), T(g["intrinsics"], dev), 8)
+    torch.manual_seed(5)
+    dec = DisentangledOSGDecoder(32, {'decoder_lr_mul': 0.5, 'decoder_output_dim': 32, 'decoder_seg_dim': 15}).to(dev)
+    with torch.no_grad():
+        for p in dec.parameters():
+            p.add_(0.3 * torch.randn_like(p))
+    dec.geo_net[0].bias.requires_grad_(False)
+    planes = torch.randn(2, 3, 32, 16, 16, device=dev)
+    norm = torch.randn(2, 3, 32, 16, 16, device=dev)
+    opts = dict(BASE, nfe_deterministic=True, nfe_precision="fp32")
+    res = {}
+    import os
+    for mode in ("1", "0"):
+        os.environ["NFE_BWD_LIBRARY_GEMM"] = mode
+        try:
+            for p in dec.parameters():
+                p.grad = None
+            a, b = norm.clone().requires_grad_(True), planes.clone().requires_grad_(True)
+            out = DisentangledImportanceRenderer()(a, b, dec, o, d, opts)
+            (out[0].sum() + (out[1] ** 2).sum() + out[2].sum()).backward()
+            res[mode] = [a.grad, b.grad] + [p.grad for p in dec.parameters()]
+        finally:
+            os.environ.pop("NFE_BWD_LIBRARY_GEMM", None)
+    assert res["0"][2 + 1] is None and res["1"][2 + 1] is None            # geo_net[0].bias is frozen
+    for x, y in zip(res["0"], res["1"]):
+        if x is not None:
+            assert rel_err(N(x), N(y)) < TOL
