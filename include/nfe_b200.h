@@ -53,6 +53,12 @@ int nfe_plane_normalize(const float* planes, const float* mean, const float* std
                         int64_t hw, float* out, nfe_stream_t stream);
 int nfe_plane_denormalize(const float* norm, const float* mean, const float* std_in, int64_t n_slabs,
                           int64_t stat_slabs, int64_t hw, float* out, nfe_stream_t stream);
+/* Backward of normalize_plane (the autograd of triplane.py:56-65): upstream gradients g_norm [n_slabs,hw] (may be NULL),
+ * g_mean / g_std [n_slabs] (may be NULL) -> g_planes [n_slabs,hw]; norm and std_in are the forward's outputs.
+ * sums_ws is a [n_slabs,2] DOUBLE scratch (per-slab sum(g), sum(g*norm)). */
+int nfe_plane_normalize_bwd(const float* g_norm, const float* norm, const float* std_in, const float* g_mean,
+                            const float* g_std, int64_t n_slabs, int64_t hw, double* sums_ws, float* g_planes,
+                            nfe_stream_t stream);
 /* Layout staging for the gather: [n_img, C, hw] (reference NCHW, triplane.py:114-115) ->
  * channel-last [n_img, hw, C] so that one bilinear tap is one contiguous C*4-byte line. */
 int nfe_planes_to_channel_last(const float* planes, int64_t n_img, int channels, int64_t hw, float* out,
@@ -226,12 +232,19 @@ int nfe_feature_mean_bwd(const float* g_feat, int plane_batch, int height, int w
  * g_rec [total,48] = d/d{sigma, seg[15], rgb[32]} (rec = the forward's records, for the colour sigmoid), scatter-adds
  * the feature gradients into the two channel-last plane gradients and ACCUMULATES the raw-parameter gradients
  * (shapes of the parameters; FullyConnectedLayer gains applied) — all gradient buffers are zero-initialised /
- * carried by the caller.  kind must be NFE_DEC_DISENTANGLED. */
+ * carried by the caller.  kind must be NFE_DEC_DISENTANGLED.
+ * Single-gather backward: when affine_scale is non-NULL the raw planes are norm*scale + shift per (item, plane-major
+ * channel) ([affine_items,96] floats each, affine_items = n or 1; what normalize_plane / denormalize_plane made,
+ * triplane.py:61-68).  planes_cl / g_planes_cl are then unused (may be NULL): only the normalised planes are gathered,
+ * their gradient carries both branches, and the gradients w.r.t. scale and shift are ACCUMULATED into
+ * g_affine_scale / g_affine_shift [affine_items,96] (zero-initialised by the caller). */
 int nfe_field_bwd(int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width,
                   float box_warp, const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays,
                   int s_per_ray, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec, const float* g_rec,
                   float* g_planes_norm_cl, float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a, float* g_b2_a,
-                  float* g_w1_b, float* g_b1_b, float* g_w2_b, float* g_b2_b, nfe_stream_t stream);
+                  float* g_w1_b, float* g_b1_b, float* g_w2_b, float* g_b2_b, const float* affine_scale,
+                  const float* affine_shift, int affine_items, float* g_affine_scale, float* g_affine_shift,
+                  nfe_stream_t stream);
 /* channel-last [n_img, hw, 32] -> reference layout [n_img, 32, hw] (plane gradients back to [N,3,32,H,W]) */
 int nfe_planes_from_channel_last(const float* planes_cl, int64_t n_img, int channels, int64_t hw, float* out,
                                  nfe_stream_t stream);

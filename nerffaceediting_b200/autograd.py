@@ -45,17 +45,25 @@ def _decode(kind, seq_a, seq_b, fn, fd):
 
 class RenderFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, state, norm_planes, planes, *params):
-        """state: dict(kind, seq_a, seq_b, cfg kwargs, rays, depths_coarse, u_fine).  params are the decoder parameters,
-        passed only so that autograd tracks them; the kernels read them from the modules."""
+    def forward(ctx, state, norm_planes, planes, scale_src, shift_src, *params):
+        """state: dict(kind, seq_a, seq_b, cfg kwargs, rays, depths_coarse, u_fine[, affine_eps]).  params are the decoder
+        parameters, passed only so that autograd tracks them; the kernels read them from the modules.
+        scale_src / shift_src (or None): statistics with planes == norm_planes*(scale_src + affine_eps) + shift_src per
+        (item, channel) — the single-gather identity: `planes` is then never read and its gradient flows through them."""
         kind = state["kind"]
-        denorm_cl = ops.planes_channel_last(planes)
+        affine = None
+        if scale_src is not None:
+            k = scale_src.numel() // 96
+            affine = ((scale_src.detach().reshape(k, 96).float() + state["affine_eps"]).contiguous(), shift_src.detach().reshape(k, 96).float().contiguous())
+        denorm_cl = ops.planes_channel_last(planes) if affine is None else None
         norm_cl = ops.planes_channel_last(norm_planes) if kind == ops.DEC_DISENTANGLED else None
-        cfg = ops.make_cfg(kind, denorm_cl, **state["cfg"])
+        cfg = ops.make_cfg(kind, norm_cl if denorm_cl is None else denorm_cl, affine=affine, **state["cfg"])
         o, d = state["rays"]
         rgb, seg, depth, wsum, minmax, st = ops.render_fwd(cfg, state["seq_a"], state["seq_b"], norm_cl, denorm_cl, o, d, state["depths_coarse"],
                                                           state["u_fine"], return_stages=True, keep_workspace=True)
         ctx.state, ctx.cfg = state, cfg
+        ctx.affine = affine
+        ctx.stat_shapes = None if scale_src is None else (scale_src.shape, shift_src.shape)
         ctx.saved = (norm_cl, denorm_cl, st, minmax)
         ctx.plane_shapes = (None if norm_planes is None else norm_planes.shape, planes.shape)
         ctx.mark_non_differentiable(minmax)
@@ -95,13 +103,17 @@ class RenderFunction(torch.autograd.Function):
                                              n * r, cfg.seg_dim, cfg.white_back, P(g_rgb), P(g_seg), P(g_depth), P(g_wsum), P(minmax),
                                              P(g_rec_c), P(g_rec_f), stream), "nfe_composite_bwd")
             params = [p for seq in (seq_a, seq_b) if seq is not None for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
-            live = [i for i, p in enumerate(params) if ctx.needs_input_grad[3 + i]]
+            live = [i for i, p in enumerate(params) if ctx.needs_input_grad[5 + i]]
             g_params = [torch.zeros_like(p) if i in live else None for i, p in enumerate(params)]
-            any_cl = denorm_cl
+            affine = ctx.affine
+            any_cl = denorm_cl if denorm_cl is not None else norm_cl
             pb, _, h, w, _ = any_cl.shape
-            g_denorm_cl = torch.zeros_like(denorm_cl)
+            g_denorm_cl = torch.zeros_like(denorm_cl) if denorm_cl is not None else None
             g_norm_cl = torch.zeros_like(norm_cl) if norm_cl is not None else None
-            fused = kind == ops.DEC_DISENTANGLED and os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1"
+            g_scale = g_shift = None
+            if affine is not None:
+                g_scale, g_shift = torch.zeros_like(affine[0]), torch.zeros_like(affine[1])
+            fused = kind == ops.DEC_DISENTANGLED and (affine is not None or os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1")
             if fused:
                 # 2-4 fused: one tcgen05 kernel per pass recomputes features and activations, back-propagates both
                 # decoder nets, scatter-adds into the plane gradients and accumulates the parameter gradients
@@ -112,7 +124,8 @@ class RenderFunction(torch.autograd.Function):
                         continue
                     _lib.check(lib.nfe_field_bwd(kind, P(norm_cl), P(denorm_cl), pb, h, w, ctypes.c_float(cfg.box_warp), P(o), P(d), P(depths), n, r, s,
                                                  mlp_a.ref(), mlp_b.ref(), P(rec), P(g_rec), P(g_norm_cl), P(g_denorm_cl),
-                                                 *[P(t) for t in full], stream), "nfe_field_bwd")
+                                                 *[P(t) for t in full], P(affine[0]) if affine else None, P(affine[1]) if affine else None,
+                                                 affine[0].shape[0] if affine else 0, P(g_scale), P(g_shift), stream), "nfe_field_bwd")
             for depths, s, g_rec in ((dc, s_c, g_rec_c), (df, s_f, g_rec_f)):
                 if not s or fused:
                     continue
@@ -160,9 +173,12 @@ class RenderFunction(torch.autograd.Function):
                 _lib.check(lib.nfe_planes_from_channel_last(P(g_cl), g_cl.shape[0] * 3, 32, h * w, P(out), stream), "nfe_planes_from_channel_last")
                 return out
             norm_shape, plane_shape = ctx.plane_shapes
-            g_planes = to_ref(g_denorm_cl, plane_shape) if ctx.needs_input_grad[2] else None
+            g_planes = to_ref(g_denorm_cl, plane_shape) if (g_denorm_cl is not None and ctx.needs_input_grad[2]) else None
             g_norm = to_ref(g_norm_cl, norm_shape) if (g_norm_cl is not None and ctx.needs_input_grad[1]) else None
-        return (None, g_norm, g_planes) + tuple(g_params)
+            if affine is not None:
+                g_scale = g_scale.reshape(ctx.stat_shapes[0]) if ctx.needs_input_grad[3] else None
+                g_shift = g_shift.reshape(ctx.stat_shapes[1]) if ctx.needs_input_grad[4] else None
+        return (None, g_norm, g_planes, g_scale, g_shift) + tuple(g_params)
 
 
 class NormalizeFunction(torch.autograd.Function):
@@ -172,7 +188,7 @@ class NormalizeFunction(torch.autograd.Function):
     def forward(ctx, planes):
         mean, std = ops.plane_stats(planes)
         if planes.dim() == 4 and planes.shape[1] == 96 and planes.is_contiguous() and planes.dtype == torch.float32:
-            norm = ops.plane_normalize_staged(planes.detach(), mean, std, stage_raw=True)
+            norm = ops.plane_normalize_staged(planes.detach(), mean, std)      # the raw set is staged on demand (single-gather identity: never)
         else:
             norm = ops.plane_normalize(planes, mean, std)
         ctx.save_for_backward(norm, std)
@@ -182,15 +198,19 @@ class NormalizeFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_norm, g_mean, g_std):
         norm, std = ctx.saved_tensors
-        n = ctx.hw
-        d = std + 1e-8
-        g = torch.zeros_like(norm) if g_norm is None else g_norm
-        # d n_j / d x_i = (delta_ij - 1/N)/d - n_j * n_i * d / ((N-1) * std * d)   (std is the unbiased one)
-        gx = (g - g.mean(dim=(-1, -2), keepdim=True)) / d - norm * (g * norm).sum(dim=(-1, -2), keepdim=True) / ((n - 1) * std)
-        if g_mean is not None:
-            gx = gx + g_mean / n
-        if g_std is not None:
-            gx = gx + g_std * norm * d / ((n - 1) * std)
+        # d n_j / d x_i = (delta_ij - 1/N)/d - n_j * n_i * d / ((N-1) * std * d)   (std is the unbiased one), i.e.
+        #   gx = (g - mean(g))/d - norm*sum(g*norm)/((N-1)*std) + g_mean/N + g_std*norm*d/((N-1)*std)
+        # in two streaming CUDA passes (csrc/nfe_planes.cu)
+        def f32(t):
+            return None if t is None else t.contiguous().float()
+        g, gm, gs = f32(g_norm), f32(g_mean), f32(g_std)
+        slabs = norm.numel() // ctx.hw
+        gx = torch.empty_like(norm)
+        sums = torch.empty((slabs, 2), device=norm.device, dtype=torch.float64) if g is not None else None
+        with torch.cuda.device(norm.device):
+            _lib.check(_lib.load().nfe_plane_normalize_bwd(ops._ptr(g), ops._ptr(norm), ops._ptr(std), ops._ptr(gm), ops._ptr(gs), slabs, ctx.hw,
+                                                           ops._ptr(sums), ops._ptr(gx), torch.cuda.current_stream(norm.device).cuda_stream),
+                       "nfe_plane_normalize_bwd")
         return gx
 
 

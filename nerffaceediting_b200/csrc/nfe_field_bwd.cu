@@ -17,6 +17,15 @@
 // forward's bf16x3 mode.  The two weight-gradient GEMMs contract over the tile's ROWS: their operands are the same
 // shared-memory tiles the other GEMMs read K-major, described MN-major (transposed) to the tensor core, so nothing
 // is transposed in software.
+//
+// AFFINE = true is the backward of the forward's single-gather identity: the raw planes are known to be
+// norm*scale + shift per (item, plane, channel), so only the normalised set is gathered and only its gradient is
+// scattered.  With f_p the per-plane blend of the normalised planes and w_p the in-bounds tap-weight sum,
+//   X_raw = mean_p(scale_p f_p + shift_p w_p)   =>   d f_p = (dX_norm + scale_p dX_raw)/3,
+//   d scale_p = sum_samples f_p dX_raw / 3,      d shift_p = sum_samples w_p dX_raw / 3
+// (the two statistics gradients accumulate in registers per batch item and leave as a handful of atomics).  Gather and
+// scatter traffic — the two phases that dominate the kernel — halve.
+#include <cuda_fp16.h>
 #include "nfe_field.cuh"
 #include "nfe_mlp_tc.cuh"
 
@@ -36,6 +45,7 @@ constexpr int GX_STRIDE = 68;                                            // fp32
 // TMEM columns
 constexpr int C_PRE = 0, C_DH = 128, C_DX = 256, C_DW1 = 320, C_DW2 = 400, TMEM_ALLOC = 512;
 
+template <bool AFFINE>
 struct Smem {
     alignas(128) unsigned char xa[2][XA_BYTES];
     alignas(128) unsigned char hc[2][HC_BYTES];
@@ -45,6 +55,8 @@ struct Smem {
     alignas(128) unsigned char w1t[2][2][W1T_BYTES];
     alignas(16) int tap_off[TILE_M][12];
     alignas(16) float tap_w[TILE_M][12];
+    int tap_item[TILE_M];
+    alignas(16) __half fp[AFFINE ? TILE_M : 1][96];      // per-plane blends of the normalised planes, kept for d scale
     float bias1[2][HIDDEN];
     alignas(8) uint64_t bar;
     uint32_t tmem_base;
@@ -60,6 +72,9 @@ struct Args {
     const float* rec;                                 // forward records [total,48] (rgb for the sigmoid derivative)
     const float* g_rec;                               // d loss / d record [total,48]
     float* gw1[2]; float* gb1[2]; float* gw2[2]; float* gb2[2];    // raw-parameter gradients (accumulated atomically)
+    // AFFINE: raw = norm*scale + shift, [affine_items, 96] each (affine_items = batch or 1), and their gradients
+    const float* affine_scale; const float* affine_shift; int affine_items;
+    float* g_scale; float* g_shift;
 };
 
 // instruction descriptor with both operands MN-major (bits 15/16)
@@ -119,10 +134,19 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v)
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+#ifdef NFE_BWD_PROFILE
+// Debug build only: cycles thread 0 of every CTA spends in each phase of the tile loop, summed over CTAs.
+__device__ unsigned long long g_bwd_prof[16];
+#define BWD_MARK(slot) do { if (threadIdx.x == 0) { const long long t_ = clock64(); prof_[slot] += t_ - prof_t_; prof_t_ = t_; } } while (0)
+#else
+#define BWD_MARK(slot) do { } while (0)
+#endif
+
+template <bool AFFINE>
 __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp geo, nfe_mlp app)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem& s = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    Smem<AFFINE>& s = *reinterpret_cast<Smem<AFFINE>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int net = warp >> 2;                       // epilogue role: warps 0-3 geo_net, 4-7 app_net
     const int row = (warp & 3) * 32 + lane;          // TMEM lane = tile row
@@ -159,16 +183,55 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
     const int64_t set_stride4 = (int64_t)3 * a.H * a.W * (FEAT / 4);
     const int c4 = threadIdx.x & 7;
     bool first = true;
+    // AFFINE: statistics gradients of this thread's 4 channels x 3 planes for batch item `cur_item`
+    float4 ds[3], dm[3];
+#pragma unroll
+    for (int p = 0; p < 3; ++p) ds[p] = dm[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cur_item = -1;
+    auto flush_stats = [&]() {
+        if (!AFFINE || cur_item < 0) return;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+            float vs[8] = {ds[p].x, ds[p].y, ds[p].z, ds[p].w, dm[p].x, dm[p].y, dm[p].z, dm[p].w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {       // the 4 sample groups of the warp hold the same channels
+                vs[i] += __shfl_xor_sync(0xffffffffu, vs[i], 8);
+                vs[i] += __shfl_xor_sync(0xffffffffu, vs[i], 16);
+            }
+            if (lane < 8) {
+                float* gs = a.g_scale + (int64_t)cur_item * 96 + p * 32 + 4 * c4;
+                float* gm = a.g_shift + (int64_t)cur_item * 96 + p * 32 + 4 * c4;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { atomicAdd(gs + i, vs[i]); atomicAdd(gm + i, vs[4 + i]); }
+            }
+            ds[p] = dm[p] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+#ifdef NFE_BWD_PROFILE
+    long long prof_[16] = {};
+    long long prof_t_ = clock64();
+#endif
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * TILE_M;
-        // ---- gather both plane sets (8 lanes per sample, 32 samples per step)
-#pragma unroll 1
-        for (int p = 0; p < TILE_M / 32; ++p) {
-            const int r = p * 32 + (threadIdx.x >> 3);
+        BWD_MARK(9);
+        // AFFINE: which item's statistics this tile feeds (a tile straddling two items goes sample by sample)
+        bool straddle = false;
+        if (AFFINE) {
+            const int64_t last = (base + TILE_M < a.total ? base + TILE_M : a.total) - 1;
+            const int it_first = a.affine_items == 1 ? 0 : (int)(base / a.m), it_last = a.affine_items == 1 ? 0 : (int)(last / a.m);
+            straddle = it_first != it_last;
+            if (!straddle && it_first != cur_item) { flush_stats(); cur_item = it_first; }
+        }
+        // ---- tap pre-pass: ONE thread per sample turns (ray, depth) into 12 clamped texel offsets + 12 weights in shared
+        //      memory (kept for the scatter at the end of the tile); the 8 lanes of a sample used to recompute them, with
+        //      the dependent depth / ray loads on every lane's critical path
+        if (threadIdx.x < TILE_M) {
+            const int r = threadIdx.x;
             const int64_t idx = base + r;
             TapSet ts;
 #pragma unroll
             for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
+            int item = 0;
             if (idx < a.total) {
                 const int64_t ray = idx / a.s_per_ray;
                 const float t = __ldg(a.depths + idx);
@@ -176,18 +239,30 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                 const float* d = a.dirs + ray * 3;
                 const float x = ray_point(__ldg(o), t, __ldg(d)), y = ray_point(__ldg(o + 1), t, __ldg(d + 1)), z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
                 ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
-                const int item_off = a.plane_batch == 1 ? 0 : (int)((idx / a.m) * set_stride4);
+                item = (int)(idx / a.m);
+                const int item_off = a.plane_batch == 1 ? 0 : (int)(item * set_stride4);
 #pragma unroll
                 for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
             }
-            if (c4 < 3) {                              // taps kept for the scatter at the end of the tile
-                *reinterpret_cast<int4*>(&s.tap_off[r][4 * c4]) = make_int4(ts.off4[4 * c4], ts.off4[4 * c4 + 1], ts.off4[4 * c4 + 2], ts.off4[4 * c4 + 3]);
-                *reinterpret_cast<float4*>(&s.tap_w[r][4 * c4]) = make_float4(ts.w[4 * c4], ts.w[4 * c4 + 1], ts.w[4 * c4 + 2], ts.w[4 * c4 + 3]);
+            s.tap_item[r] = item;
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                *reinterpret_cast<int4*>(&s.tap_off[r][4 * q]) = make_int4(ts.off4[4 * q], ts.off4[4 * q + 1], ts.off4[4 * q + 2], ts.off4[4 * q + 3]);
+                *reinterpret_cast<float4*>(&s.tap_w[r][4 * q]) = make_float4(ts.w[4 * q], ts.w[4 * q + 1], ts.w[4 * q + 2], ts.w[4 * q + 3]);
             }
-            float4 va[12], vb[12];
-            gather_load(a.set_norm, ts, c4, va);
-            gather_load(a.set_raw, ts, c4, vb);
-            const float4 fa = gather_reduce(va, ts), fb = gather_reduce(vb, ts);
+        }
+        __syncthreads();
+        // ---- gather (8 lanes per sample, 32 samples per step; AFFINE: two steps' texel loads in flight together)
+        auto read_taps = [&](int r, TapSet& ts) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int4 o4 = *reinterpret_cast<const int4*>(&s.tap_off[r][4 * q]);
+                const float4 w4 = *reinterpret_cast<const float4*>(&s.tap_w[r][4 * q]);
+                ts.off4[4 * q] = o4.x; ts.off4[4 * q + 1] = o4.y; ts.off4[4 * q + 2] = o4.z; ts.off4[4 * q + 3] = o4.w;
+                ts.w[4 * q] = w4.x; ts.w[4 * q + 1] = w4.y; ts.w[4 * q + 2] = w4.z; ts.w[4 * q + 3] = w4.w;
+            }
+        };
+        auto store_x = [&](int r, const float4& fa, const float4& fb) {
 #pragma unroll
             for (int set = 0; set < 2; ++set) {
                 const float4 f = set ? fb : fa;
@@ -198,9 +273,59 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                 *reinterpret_cast<uint2*>(s.xa[0] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
                 *reinterpret_cast<uint2*>(s.xa[1] + off) = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
             }
+        };
+        if constexpr (AFFINE) {
+#pragma unroll 1
+            for (int p = 0; p < TILE_M / 32; p += 2) {
+                const int r0 = p * 32 + (threadIdx.x >> 3), r1 = r0 + 32;
+                TapSet t0, t1;
+                float4 v0[12], v1[12];
+                read_taps(r0, t0);
+                read_taps(r1, t1);
+                gather_load(a.set_norm, t0, c4, v0);
+                gather_load(a.set_norm, t1, c4, v1);
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int r = h ? r1 : r0;
+                    float4 f[3];
+                    float w_in[3];
+                    gather_reduce_planes(h ? v1 : v0, h ? t1 : t0, f, w_in);
+                    constexpr float third = 1.0f / 3.0f;
+                    const float4 fa = make_float4(((f[0].x + f[1].x) + f[2].x) * third, ((f[0].y + f[1].y) + f[2].y) * third,
+                                                  ((f[0].z + f[1].z) + f[2].z) * third, ((f[0].w + f[1].w) + f[2].w) * third);
+                    const int64_t item = a.affine_items == 1 ? 0 : s.tap_item[r];
+                    const float4* sc = reinterpret_cast<const float4*>(a.affine_scale + item * 96) + c4;
+                    const float4* sh = reinterpret_cast<const float4*>(a.affine_shift + item * 96) + c4;
+                    float4 dn[3];
+#pragma unroll
+                    for (int pl = 0; pl < 3; ++pl) {
+                        const float4 scl = __ldg(sc + pl * 8), shf = __ldg(sh + pl * 8);
+                        dn[pl] = make_float4(fmaf(scl.x, f[pl].x, shf.x * w_in[pl]), fmaf(scl.y, f[pl].y, shf.y * w_in[pl]),
+                                             fmaf(scl.z, f[pl].z, shf.z * w_in[pl]), fmaf(scl.w, f[pl].w, shf.w * w_in[pl]));
+                        __half2* dst = reinterpret_cast<__half2*>(&s.fp[r][pl * 32 + 4 * c4]);
+                        dst[0] = __floats2half2_rn(f[pl].x, f[pl].y);
+                        dst[1] = __floats2half2_rn(f[pl].z, f[pl].w);
+                    }
+                    const float4 fb = make_float4(((dn[0].x + dn[1].x) + dn[2].x) * third, ((dn[0].y + dn[1].y) + dn[2].y) * third,
+                                                  ((dn[0].z + dn[1].z) + dn[2].z) * third, ((dn[0].w + dn[1].w) + dn[2].w) * third);
+                    store_x(r, fa, fb);
+                }
+            }
+        } else {
+#pragma unroll 1
+            for (int p = 0; p < TILE_M / 32; ++p) {
+                const int r = p * 32 + (threadIdx.x >> 3);
+                TapSet ts;
+                float4 va[12], vb[12];
+                read_taps(r, ts);
+                gather_load(a.set_norm, ts, c4, va);
+                gather_load(a.set_raw, ts, c4, vb);
+                store_x(r, gather_reduce(va, ts), gather_reduce(vb, ts));
+            }
         }
         tc::fence_async_smem();
         __syncthreads();
+        BWD_MARK(0);
 
         // ---- G1: pre = X W1^T for both nets
         if (threadIdx.x == 0) {
@@ -211,11 +336,26 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                                  B1_LBO, B1_SBO, FEAT, id1);
             tc::mma_commit(&s.bar);
         }
+        // record gradients (and the saved colours) of this thread's row: requested now, consumed after the softplus loop
+        const bool live = base + row < a.total;
+        float4 pg[8], py[8];
+        {
+            const float4* g4 = reinterpret_cast<const float4*>(a.g_rec + (base + row) * 48);
+            const float4* r4 = reinterpret_cast<const float4*>(a.rec + (base + row) * 48);
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (net == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) pg[i] = live ? __ldg(g4 + i) : z4;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { pg[i] = live ? __ldg(g4 + 4 + i) : z4; py[i] = live ? __ldg(r4 + 4 + i) : z4; }
+            }
+        }
         tc::mbar_wait(&s.bar, phase); phase ^= 1;
         tc::fence_after_sync();
+        BWD_MARK(1);
 
         // ---- epilogue 1: hidden activations and output-layer gradients of this thread's (row, net)
-        const bool live = base + row < a.total;
         {
 #pragma unroll 1
             for (int q = 0; q < HIDDEN / 16; ++q) {
@@ -232,13 +372,11 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                     store8(s.hc[0], s.hc[1], core_offset(row, 64 * net + q * 16 + c8 * 8, HC_LBO, HC_SBO), h8);
                 }
             }
-            const float4* g4 = reinterpret_cast<const float4*>(a.g_rec + (base + row) * 48);
-            const float4* r4 = reinterpret_cast<const float4*>(a.rec + (base + row) * 48);
             if (net == 0) {
 #pragma unroll
                 for (int c8 = 0; c8 < 2; ++c8) {
                     float d8[8];
-                    const float4 g0 = live ? __ldg(g4 + 2 * c8) : make_float4(0.f, 0.f, 0.f, 0.f), g1 = live ? __ldg(g4 + 2 * c8 + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float4 g0 = pg[2 * c8], g1 = pg[2 * c8 + 1];
                     d8[0] = g0.x; d8[1] = g0.y; d8[2] = g0.z; d8[3] = g0.w; d8[4] = g1.x; d8[5] = g1.y; d8[6] = g1.z; d8[7] = g1.w;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) db2[c8 * 8 + i] += d8[i];
@@ -250,8 +388,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                     float d8[8];
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const float4 g = live ? __ldg(g4 + 4 + 2 * c8 + h) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        const float4 y = live ? __ldg(r4 + 4 + 2 * c8 + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        const float4 g = pg[2 * c8 + h], y = py[2 * c8 + h];
                         // rgb = s*1.002 - 0.001 with s = sigmoid(out)  =>  d rgb / d out = 1.002 * s * (1 - s)
                         const float gs[4] = {g.x, g.y, g.z, g.w}, ys[4] = {y.x, y.y, y.z, y.w};
 #pragma unroll
@@ -269,6 +406,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
+        BWD_MARK(2);
 
         // ---- G2: dH = dY W2;  G4: dW2^T += H^T dY (contraction over the tile rows)
         if (threadIdx.x == 0) {
@@ -281,6 +419,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         }
         tc::mbar_wait(&s.bar, phase); phase ^= 1;
         tc::fence_after_sync();
+        BWD_MARK(3);
 
         // ---- epilogue 2: dpre = dH * sigmoid(pre + b1), over the hidden tile
 #pragma unroll 1
@@ -302,6 +441,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
+        BWD_MARK(4);
 
         // ---- G3: dX = dpre W1;  G5: [dW1 | db1] += dpre^T [X | 1]
         if (threadIdx.x == 0) {
@@ -316,6 +456,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         tc::mbar_wait(&s.bar, phase); phase ^= 1;
         tc::fence_after_sync();
         first = false;
+        BWD_MARK(5);
 
         // ---- epilogue 3: dX of this (row, set) -> fp32 staging (over the hidden tile, which G5 has finished reading)
         float* gx = reinterpret_cast<float*>(s.hc[0]);
@@ -330,6 +471,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         }
         tc::fence_before_sync();
         __syncthreads();
+        BWD_MARK(6);
         // ---- gather backward: w_tap/3 * dX into the channel-last plane gradients
         constexpr float third = 1.0f / 3.0f;
 #pragma unroll 1
@@ -339,6 +481,37 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
             float4 gn = *reinterpret_cast<const float4*>(gx + r * GX_STRIDE + 4 * c4), gr = *reinterpret_cast<const float4*>(gx + r * GX_STRIDE + 32 + 4 * c4);
             gn = make_float4(gn.x * third, gn.y * third, gn.z * third, gn.w * third);
             gr = make_float4(gr.x * third, gr.y * third, gr.z * third, gr.w * third);
+            if constexpr (AFFINE) {
+                const int64_t item = a.affine_items == 1 ? 0 : s.tap_item[r];
+                const float4* sc = reinterpret_cast<const float4*>(a.affine_scale + item * 96) + c4;
+#pragma unroll
+                for (int p = 0; p < 3; ++p) {
+                    const float4 scl = __ldg(sc + p * 8);
+                    const float4 gf = make_float4(fmaf(scl.x, gr.x, gn.x), fmaf(scl.y, gr.y, gn.y), fmaf(scl.z, gr.z, gn.z), fmaf(scl.w, gr.w, gn.w));
+                    float w_in = 0.0f;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float w = s.tap_w[r][4 * p + k];
+                        w_in += w;
+                        if (w != 0.0f)
+                            red_add_v4(a.g_norm + (int64_t)s.tap_off[r][4 * p + k] * 4 + 4 * c4, make_float4(gf.x * w, gf.y * w, gf.z * w, gf.w * w));
+                    }
+                    const __half2* src = reinterpret_cast<const __half2*>(&s.fp[r][p * 32 + 4 * c4]);
+                    const float2 f01 = __half22float2(src[0]), f23 = __half22float2(src[1]);
+                    const float4 dsv = make_float4(f01.x * gr.x, f01.y * gr.y, f23.x * gr.z, f23.y * gr.w);
+                    const float4 dmv = make_float4(w_in * gr.x, w_in * gr.y, w_in * gr.z, w_in * gr.w);
+                    if (!straddle) {
+                        ds[p].x += dsv.x; ds[p].y += dsv.y; ds[p].z += dsv.z; ds[p].w += dsv.w;
+                        dm[p].x += dmv.x; dm[p].y += dmv.y; dm[p].z += dmv.z; dm[p].w += dmv.w;
+                    } else {
+                        float* gs = a.g_scale + item * 96 + p * 32 + 4 * c4;
+                        float* gm = a.g_shift + item * 96 + p * 32 + 4 * c4;
+                        atomicAdd(gs, dsv.x); atomicAdd(gs + 1, dsv.y); atomicAdd(gs + 2, dsv.z); atomicAdd(gs + 3, dsv.w);
+                        atomicAdd(gm, dmv.x); atomicAdd(gm + 1, dmv.y); atomicAdd(gm + 2, dmv.z); atomicAdd(gm + 3, dmv.w);
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
                 const float w = s.tap_w[r][i];
@@ -350,8 +523,14 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
             }
         }
         __syncthreads();      // the staging tile and the taps are reused by the next tile
+        BWD_MARK(7);
     }
+#ifdef NFE_BWD_PROFILE
+    if (threadIdx.x == 0)
+        for (int i = 0; i < 16; ++i) atomicAdd(&g_bwd_prof[i], (unsigned long long)prof_[i]);
+#endif
 
+    flush_stats();
     // ---- parameter gradients of this CTA -> global (chain rule through the FullyConnectedLayer gains)
     if (!first) {
         tc::fence_after_sync();
@@ -407,13 +586,20 @@ NFE_EXPORT int nfe_field_bwd(int kind, const float* planes_norm_cl, const float*
                              const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays, int s_per_ray,
                              const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec, const float* g_rec, float* g_planes_norm_cl,
                              float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a, float* g_b2_a, float* g_w1_b, float* g_b1_b,
-                             float* g_w2_b, float* g_b2_b, nfe_stream_t stream)
+                             float* g_w2_b, float* g_b2_b, const float* affine_scale, const float* affine_shift, int affine_items,
+                             float* g_affine_scale, float* g_affine_shift, nfe_stream_t stream)
 {
     const int64_t total = (int64_t)n * n_rays * s_per_ray;
     if (total == 0) return 0;
+    const bool affine = affine_scale != nullptr;
     NFE_REQUIRE(kind == NFE_DEC_DISENTANGLED, "nfe_field_bwd: only the DisentangledOSGDecoder has a fused backward (kind %d)", kind);
-    NFE_REQUIRE(planes_norm_cl && planes_cl && origins && dirs && depths && net_a && net_b && rec && g_rec && g_planes_norm_cl && g_planes_cl,
-                "nfe_field_bwd: null pointer");
+    NFE_REQUIRE(planes_norm_cl && origins && dirs && depths && net_a && net_b && rec && g_rec && g_planes_norm_cl, "nfe_field_bwd: null pointer");
+    if (affine) {
+        NFE_REQUIRE(affine_shift && g_affine_scale && g_affine_shift, "nfe_field_bwd: the single-gather backward needs shift and both statistics gradients");
+        NFE_REQUIRE(affine_items == n || affine_items == 1, "nfe_field_bwd: %d statistics rows for a batch of %d", affine_items, n);
+    } else {
+        NFE_REQUIRE(planes_cl && g_planes_cl, "nfe_field_bwd: null raw-plane pointer (and no affine statistics)");
+    }
     NFE_REQUIRE(g_w1_a && g_b1_a && g_w2_a && g_b2_a && g_w1_b && g_b1_b && g_w2_b && g_b2_b, "nfe_field_bwd: null parameter-gradient pointer");
     NFE_REQUIRE(net_a->in_dim == FEAT && net_a->hidden == HIDDEN && net_a->out_dim == 16 && net_b->in_dim == FEAT && net_b->hidden == HIDDEN &&
                 net_b->out_dim == 32, "nfe_field_bwd: decoder widths must be 32-64-16 / 32-64-32");
@@ -426,16 +612,31 @@ NFE_EXPORT int nfe_field_bwd(int kind, const float* planes_norm_cl, const float*
     a.rec = rec; a.g_rec = g_rec;
     a.gw1[0] = g_w1_a; a.gb1[0] = g_b1_a; a.gw2[0] = g_w2_a; a.gb2[0] = g_b2_a;
     a.gw1[1] = g_w1_b; a.gb1[1] = g_b1_b; a.gw2[1] = g_w2_b; a.gb2[1] = g_b2_b;
-    const size_t smem = sizeof(fb::Smem) + 128;
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(fb::field_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    a.affine_scale = affine_scale; a.affine_shift = affine_shift; a.affine_items = affine_items;
+    a.g_scale = g_affine_scale; a.g_shift = g_affine_shift;
+    const size_t smem = (affine ? sizeof(fb::Smem<true>) : sizeof(fb::Smem<false>)) + 128;
+    static bool configured[2] = {false, false};
+    if (!configured[affine]) {
+        cudaError_t e = affine ? cudaFuncSetAttribute(fb::field_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                               : cudaFuncSetAttribute(fb::field_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         NFE_REQUIRE(e == cudaSuccess, "nfe_field_bwd: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
-        configured = true;
+        configured[affine] = true;
     }
     const int64_t n_tiles = (total + TILE_M - 1) / TILE_M;
     const int64_t cap = sm_count();
-    fb::field_bwd_kernel<<<(unsigned)(n_tiles < cap ? n_tiles : cap), fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, *net_b);
+    const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
+    if (affine) fb::field_bwd_kernel<true><<<grid, fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, *net_b);
+    else fb::field_bwd_kernel<false><<<grid, fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, *net_b);
     NFE_LAUNCH_CHECK("field_bwd_kernel");
     return 0;
 }
+
+#ifdef NFE_BWD_PROFILE
+NFE_EXPORT int nfe_debug_bwd_profile(unsigned long long* out16, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, nfe::fb::g_bwd_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(nfe::fb::g_bwd_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif

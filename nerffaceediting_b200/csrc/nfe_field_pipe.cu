@@ -33,6 +33,15 @@ constexpr int PIPE_THREADS = (EPI_WARPS + 1 + GATHER_WARPS) * 32;
 constexpr int PASSES_PER_TILE = TILE_M / 4;                 // a pass = 4 samples (8 lanes each); passes are dealt round-robin to the gather warps
 constexpr int TMEM_BUF_COLS = 192;                          // D1A 64 | D1B 64 | D2A <=48 | D2B <=32 (OSG: 48+16)
 constexpr int PIPE_TMEM_COLS = 512;
+// Record staging: thread m parks its 192-byte record in shared memory and the warp writes its 32 records (6 KB,
+// contiguous in the plain sample order) back out with fully coalesced 16-byte stores.  A direct STG.128 of 32 records
+// touches 32 different lines per instruction (32 L1 wavefronts each; the record stores were a quarter of the kernel's
+// L1 data-pipe load, as much as all the texel gathers); staged it is 4 + 4 + 4 (STS, LDS, STG).
+// Row stride 208 B: a quarter-warp's 16-byte stores fall into 8 different bank groups.
+#ifndef NFE_REC_STAGE
+#define NFE_REC_STAGE 1
+#endif
+constexpr int REC_STAGE_STRIDE = 208;
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
@@ -48,6 +57,7 @@ struct PipeSmem {
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
     alignas(16) uint4 taps[2][GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][10];   // per sample: 12 offsets, 12 weights as (w,w) pairs, item; one tile ahead
+    alignas(16) unsigned char recbuf[NFE_REC_STAGE ? TILE_M : 1][REC_STAGE_STRIDE];   // record staging (each warp owns its 32 rows)
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
     float bias2a[T::N_A];
     float bias2b[T::N_B];
@@ -483,7 +493,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 if (lane == 0) tc::mbar_arrive(&s.tmem_free[st]);
                 continue;
             }
-            float4* rec = a.rec ? reinterpret_cast<float4*>(a.rec + idx * 48) : nullptr;
+            // staged records need the tile's rows to be consecutive samples (plain order)
+            const bool staged = NFE_REC_STAGE && a.rec && a.quad_stride == 0;
+            float4* rec = a.rec ? (staged ? reinterpret_cast<float4*>(s.recbuf[row]) : reinterpret_cast<float4*>(a.rec + idx * 48)) : nullptr;
             float4* rgb4 = rec ? rec + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
             if constexpr (KIND == NFE_DEC_DISENTANGLED) {
                 if (live) {
@@ -544,6 +556,22 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.tmem_free[st]);
+            if (staged) {
+                // 16-byte chunk g of the warp's 32 records sits at row g/12, chunk g%12 of the staging rows
+                const int64_t row0 = tile * TILE_M + warp * 32;
+                const int n_chunks = (int)min((int64_t)32, a.total - row0) * 12;
+                float4* gdst = reinterpret_cast<float4*>(a.rec + row0 * 48);
+                int r = lane / 12, c = lane % 12;
+#pragma unroll
+                for (int k = 0; k < 12; ++k) {
+                    const int g = k * 32 + lane;
+                    const float4 v = *reinterpret_cast<const float4*>(s.recbuf[warp * 32 + r] + c * 16);
+                    if (g < n_chunks) gdst[g] = v;
+                    r += 2; c += 8;
+                    if (c >= 12) { c -= 12; r += 1; }
+                }
+                __syncwarp();          // the rows are rewritten by the next tile
+            }
         }
     }
 

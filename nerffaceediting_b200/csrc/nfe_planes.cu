@@ -185,6 +185,78 @@ __global__ void __launch_bounds__(256) stage32_kernel(const float* __restrict__ 
     }
 }
 
+
+// ---- backward of normalize_plane (triplane.py:56-65): norm = (x - mean)/(std + 1e-8), mean/std over H,W (std unbiased).
+// With d = std + 1e-8, n = H*W and the upstream gradients (g, g_mean, g_std):
+//   gx = g/d - mean(g)/d + g_mean/n + norm * (g_std*d - sum(g*norm)) / ((n-1)*std)
+// Pass 1: per slab sum(g) and sum(g*norm) (double accumulation, like the forward statistics); pass 2: the elementwise
+// combination.  Two streaming passes (reads g, norm twice; writes gx once) replace ~25 ATen kernels.
+__global__ void __launch_bounds__(512) plane_normalize_bwd_sums_kernel(const float* __restrict__ g, const float* __restrict__ norm, int64_t hw,
+                                                                       double* __restrict__ sums)
+{
+    const float* gp = g + (int64_t)blockIdx.x * hw;
+    const float* np_ = norm + (int64_t)blockIdx.x * hw;
+    double s = 0.0, sn = 0.0;
+    const bool vec = (hw % 4 == 0) && (((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(np_)) & 15) == 0);
+    if (vec) {
+        const float4* g4 = reinterpret_cast<const float4*>(gp);
+        const float4* n4 = reinterpret_cast<const float4*>(np_);
+        for (int64_t i = threadIdx.x; i < hw / 4; i += blockDim.x) {
+            const float4 a = __ldg(g4 + i), b = __ldg(n4 + i);
+            s += ((double)a.x + (double)a.y) + ((double)a.z + (double)a.w);
+            sn += ((double)a.x * (double)b.x + (double)a.y * (double)b.y) + ((double)a.z * (double)b.z + (double)a.w * (double)b.w);
+        }
+    } else {
+        for (int64_t i = threadIdx.x; i < hw; i += blockDim.x) { s += (double)gp[i]; sn += (double)gp[i] * (double)np_[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); sn += __shfl_xor_sync(0xffffffffu, sn, o); }
+    __shared__ double sh_s[16], sh_n[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh_s[warp] = s; sh_n[warp] = sn; }
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        s = lane < nw ? sh_s[lane] : 0.0;
+        sn = lane < nw ? sh_n[lane] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); sn += __shfl_xor_sync(0xffffffffu, sn, o); }
+        if (lane == 0) { sums[2 * blockIdx.x] = s; sums[2 * blockIdx.x + 1] = sn; }
+    }
+}
+
+__global__ void __launch_bounds__(256) plane_normalize_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ norm,
+                                                                        const float* __restrict__ std_in, const float* __restrict__ g_mean,
+                                                                        const float* __restrict__ g_std, const double* __restrict__ sums,
+                                                                        int64_t hw, int chunks_per_slab, float* __restrict__ out)
+{
+    const int64_t slab = blockIdx.x / chunks_per_slab;
+    const int chunk = blockIdx.x % chunks_per_slab;
+    const double n = (double)hw, sd = (double)std_in[slab], d = sd + 1e-8;
+    const double sum_g = g ? sums[2 * slab] : 0.0, sum_gn = g ? sums[2 * slab + 1] : 0.0;
+    const float A = (float)(1.0 / d);
+    const float B = (float)(-(sum_g / n) / d + (g_mean ? (double)g_mean[slab] / n : 0.0));
+    const float C = (float)(((g_std ? (double)g_std[slab] * d : 0.0) - sum_gn) / ((n - 1.0) * sd));
+    const int64_t per = (hw + chunks_per_slab - 1) / chunks_per_slab;
+    const int64_t lo = chunk * per, hi = min(hw, lo + per);
+    const float* gp = g ? g + slab * hw : nullptr;
+    const float* np_ = norm + slab * hw;
+    float* y = out + slab * hw;
+    const bool vec = (hw % 4 == 0) && (per % 4 == 0) &&
+                     (((reinterpret_cast<uintptr_t>(gp) | reinterpret_cast<uintptr_t>(np_) | reinterpret_cast<uintptr_t>(y)) & 15) == 0);
+    if (vec) {
+        const float4* g4 = reinterpret_cast<const float4*>(gp);
+        const float4* n4 = reinterpret_cast<const float4*>(np_);
+        float4* y4 = reinterpret_cast<float4*>(y);
+        for (int64_t i = lo / 4 + threadIdx.x; i < hi / 4; i += blockDim.x) {
+            const float4 a = gp ? __ldg(g4 + i) : make_float4(0.f, 0.f, 0.f, 0.f), b = __ldg(n4 + i);
+            y4[i] = make_float4(fmaf(C, b.x, fmaf(A, a.x, B)), fmaf(C, b.y, fmaf(A, a.y, B)), fmaf(C, b.z, fmaf(A, a.z, B)), fmaf(C, b.w, fmaf(A, a.w, B)));
+        }
+    } else {
+        for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) y[i] = fmaf(C, np_[i], fmaf(A, gp ? gp[i] : 0.0f, B));
+    }
+}
+
 }  // namespace nfe
 
 using namespace nfe;
@@ -274,5 +346,25 @@ NFE_EXPORT int nfe_plane_normalize_staged(const float* planes, const float* mean
     stage32_kernel<true><<<(unsigned)((n_groups + 7) / 8), 256, 0, as_stream(stream)>>>(planes, mean, std_in, hw, groups_per_img, n_groups, out_norm,
                                                                                       out_norm_cl, out_raw_cl);
     NFE_LAUNCH_CHECK("stage32_kernel");
+    return 0;
+}
+
+NFE_EXPORT int nfe_plane_normalize_bwd(const float* g_norm, const float* norm, const float* std_in, const float* g_mean, const float* g_std,
+                                       int64_t n_slabs, int64_t hw, double* sums_ws, float* g_planes, nfe_stream_t stream)
+{
+    if (n_slabs == 0 || hw == 0) return 0;
+    NFE_REQUIRE(norm && std_in && g_planes, "nfe_plane_normalize_bwd: null pointer");
+    NFE_REQUIRE(!g_norm || sums_ws, "nfe_plane_normalize_bwd: the reduction workspace ([n_slabs,2] doubles) is missing");
+    NFE_REQUIRE(n_slabs >= 0 && hw >= 2, "nfe_plane_normalize_bwd: bad sizes");
+    NFE_REQUIRE(n_slabs < (1ll << 31), "nfe_plane_normalize_bwd: grid too large");
+    if (g_norm) {
+        plane_normalize_bwd_sums_kernel<<<(unsigned)n_slabs, 512, 0, as_stream(stream)>>>(g_norm, norm, hw, sums_ws);
+        NFE_LAUNCH_CHECK("plane_normalize_bwd_sums_kernel");
+    }
+    const int chunks = chunks_for(n_slabs, hw);
+    NFE_REQUIRE(n_slabs * chunks < (1ll << 31), "nfe_plane_normalize_bwd: grid too large");
+    plane_normalize_bwd_apply_kernel<<<(unsigned)(n_slabs * chunks), 256, 0, as_stream(stream)>>>(g_norm, norm, std_in, g_mean, g_std, sums_ws, hw,
+                                                                                               chunks, g_planes);
+    NFE_LAUNCH_CHECK("plane_normalize_bwd_apply_kernel");
     return 0;
 }

@@ -157,6 +157,27 @@ def provenance(norm_planes, denorm_planes):
     return hit[1], hit[2]
 
 
+# Autograd sources of a provenance entry: the (possibly grad-tracked) statistics tensors the scale and shift came from,
+# scale = scale_src + eps.  Attached by triplane.normalize_plane / denormalize_plane on their differentiable paths so that
+# the training-step renderer can use the single-gather identity and send the statistics gradients back (autograd.py).
+_PROVENANCE_SRC = {}
+
+
+def provenance_attach(denorm, scale_src, eps, shift_src):
+    key = _key5(denorm)
+    if key in _PROVENANCE:
+        for k in [k for k in _PROVENANCE_SRC if k not in _PROVENANCE]:
+            _PROVENANCE_SRC.pop(k)
+        _PROVENANCE_SRC[key] = (scale_src, float(eps), shift_src)
+
+
+def provenance_sources(norm_planes, denorm_planes):
+    """(scale_src, eps, shift_src) for a (norm, denorm) pair with known provenance and attached sources, else None."""
+    if provenance(norm_planes, denorm_planes) is None:
+        return None
+    return _PROVENANCE_SRC.get(_key5(denorm_planes))
+
+
 def _cache_put(key, src, staged):
     while len(_CL_CACHE) >= _CL_CACHE_MAX:
         _CL_CACHE.pop(next(iter(_CL_CACHE)))

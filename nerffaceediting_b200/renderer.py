@@ -27,6 +27,8 @@ Extra keys read from `rendering_options` (all optional; defaults reproduce the r
 Instances hold no state of their own beyond the reference's attributes, so objects unpickled from
 reference checkpoints (which skip __init__) work.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -202,7 +204,15 @@ class ImportanceRenderer(torch.nn.Module):
             "u_fine": ops.linspace_table(0, 1, s_f, ray_origins.device) if (s_f > 0 and deterministic) else None,
         }
         params = [p for seq in (seq_a, seq_b) if seq is not None for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
-        out = RenderFunction.apply(state, norm_planes if kind == ops.DEC_DISENTANGLED else None, planes, *params)
+        # single-gather identity in training: planes known to be norm*scale + shift are never read; their gradient goes
+        # through the statistics instead (autograd.RenderFunction, csrc/nfe_field_bwd.cu AFFINE)
+        scale_src = shift_src = None
+        if (kind == ops.DEC_DISENTANGLED and state["cfg"]["precision"] != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True)
+                and os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1"):
+            src = ops.provenance_sources(norm_planes, planes)
+            if src is not None and src[0].numel() == src[2].numel() and src[0].numel() in (96, 96 * ray_origins.shape[0]):
+                scale_src, state["affine_eps"], shift_src = src
+        out = RenderFunction.apply(state, norm_planes if kind == ops.DEC_DISENTANGLED else None, planes, scale_src, shift_src, *params)
         if kind == ops.DEC_OSG:
             rgb, depth, wsum, _ = out
             return rgb, None, depth, wsum

@@ -90,7 +90,9 @@ def normalize_plane(planes):
     """(planes - mean) / (std + 1e-8) -> (norm_planes, mean, std) (triplane.py:61-65)."""
     if torch.is_grad_enabled() and planes.requires_grad:
         from .autograd import NormalizeFunction
-        return NormalizeFunction.apply(planes)
+        norm, mean, std = NormalizeFunction.apply(planes)
+        ops.provenance_attach(planes, std, 1e-8, mean)       # planes == norm*(std+1e-8) + mean: lets the renderer gather one set
+        return norm, mean, std
     mean, std = ops.plane_stats(planes)
     if planes.dim() == 4 and planes.shape[1] == 96 and planes.is_contiguous() and planes.dtype == torch.float32:
         # the generator's [N,96,H,W] tri-planes: also stage both plane sets for the renderer in the same pass
@@ -103,5 +105,8 @@ def denormalize_plane(planes, mean, var):
     swap), or to one batch item broadcast over the batch (triplane.py:98-103)."""
     if torch.is_grad_enabled() and any(t.requires_grad for t in (planes, mean, var)):
         from .autograd import DenormalizeFunction
-        return DenormalizeFunction.apply(planes, mean, var)
+        out = DenormalizeFunction.apply(planes, mean, var)
+        if torch.is_tensor(mean) and torch.is_tensor(var):
+            ops.provenance_attach(out, var, 0.0, mean)
+        return out
     return ops.plane_denormalize(planes, mean, var)

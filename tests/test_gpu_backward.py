@@ -219,3 +219,71 @@ def test_fused_decoder_backward_lr_multiplier_and_frozen_parameters(dev):
     for x, y in zip(res["0"], res["1"]):
         if x is not None:
             assert rel_err(N(x), N(y)) < TOL
+
+
+def _chain(dev, g, single_gather, swap, n=2, hw=32, res=23, s=16, seed=21):     # 529*16 samples per item: one tile straddles the two items
+    """raw -> normalize_plane [-> denormalize_plane with other statistics] -> disentangled renderer (bf16x3) -> loss;
+    returns the gradients w.r.t. the raw planes, the swapped statistics and the decoder parameters."""
+    from nerffaceediting_b200 import triplane
+    from nerffaceediting_b200.ray_sampler import RaySampler
+    from nerffaceediting_b200.renderer import DisentangledImportanceRenderer
+    c2w, k = synth.camera_sweep(n)
+    with torch.no_grad():
+        o, d = RaySampler()(T(c2w.numpy(), dev), T(k.numpy(), dev), res)
+    opts = dict(synth.FFHQ_RENDERING_OPTIONS, depth_resolution=s, depth_resolution_importance=s, nfe_deterministic=True,
+                nfe_precision="bf16x3", nfe_single_gather=single_gather)
+    gen = torch.Generator().manual_seed(seed)
+    proj = [torch.randn(n, res * res, c, generator=gen).to(dev) for c in (32, 15, 1, 1)]
+    raw = T(synth.hash_normal(78, (n, 96, hw, hw)) * np.float32(1.5) - np.float32(0.3), dev).requires_grad_(True)
+    dec = torch_decoder(g, "dis.dec", "dis", 1.0, dev)
+    norm, mean, std = triplane.normalize_plane(raw)
+    stats = []
+    if swap:
+        k_items = 1 if swap == "one" else n
+        stats = [(torch.randn(k_items, 96, 1, 1, generator=gen) * 0.5).to(dev).requires_grad_(True),
+                 (torch.rand(k_items, 96, 1, 1, generator=gen) + 0.5).to(dev).requires_grad_(True)]
+        planes = triplane.denormalize_plane(norm, stats[0], stats[1])
+    else:
+        planes = raw
+    out = DisentangledImportanceRenderer()(norm.view(n, 3, 32, hw, hw), planes.view(n, 3, 32, hw, hw), dec, o, d, opts)
+    sum((a * b).sum() for a, b in zip(out, proj)).backward()
+    return [raw.grad] + [t.grad for t in stats] + [p.grad for p in dec.parameters()], [float(x.detach().abs().max()) for x in out]
+
+
+@pytest.mark.parametrize("swap", [None, "all", "one"])
+def test_single_gather_backward_matches_two_gather_backward(dev, swap):
+    """The AFFINE backward (planes = norm*scale + shift never read; gradient through the statistics) against the
+    two-gather backward on the same chain: raw-plane, swapped-statistics and decoder gradients agree."""
+    g = golden("backward")
+    one, _ = _chain(dev, g, True, swap)
+    two, _ = _chain(dev, g, False, swap)
+    names = ["raw planes"] + (["mean'", "std'"] if swap else []) + ["geo.w1", "geo.b1", "geo.w2", "geo.b2", "app.w1", "app.b1", "app.w2", "app.b2"]
+    for nm, a, b in zip(names, one, two):
+        assert a is not None and b is not None and a.shape == b.shape, nm
+        assert rel_err(N(a), N(b)) < 2 * TOL, nm
+
+
+def test_single_gather_training_chain_vs_reference_autograd(dev):
+    """normalize_plane -> renderer chain with the tensor-core forward and the single-gather backward, against the golden
+    gradients of the reference's autograd pushed through the analytic normalisation backward."""
+    from nerffaceediting_b200 import triplane
+    from nerffaceediting_b200.ray_sampler import RaySampler
+    from nerffaceediting_b200.renderer import DisentangledImportanceRenderer
+    g = golden("backward")
+    n, hw, res = 2, 16, 8
+    raw = T(synth.hash_normal(300, (n, 96, hw, hw)) * np.float32(1.5) - np.float32(0.3), dev).requires_grad_(True)
+    with torch.no_grad():
+        o, d = RaySampler()(T(g["cam2world"], dev), T(g["intrinsics"], dev), res)
+    dec = torch_decoder(g, "dis.dec", "dis", 1.0, dev)
+    norm, _, _ = triplane.normalize_plane(raw)
+    out = DisentangledImportanceRenderer()(norm.view(n, 3, 32, hw, hw), raw.view(n, 3, 32, hw, hw), dec, o, d,
+                                           dict(BASE, nfe_deterministic=True, nfe_precision="bf16x3"))
+    _loss(g, "dis", out, dev).backward()
+    x = raw.detach().cpu().double().requires_grad_(True)
+    mean = x.mean(dim=(-1, -2), keepdim=True)
+    std = x.var(dim=(-1, -2), keepdim=True).sqrt()
+    ((x - mean) / (std + 1e-8)).backward(torch.from_numpy(g["dis.g_norm"]).double().view(n, 96, hw, hw))
+    want = x.grad.float().numpy() + g["dis.g_planes"].reshape(n, 96, hw, hw)
+    assert rel_err(N(raw.grad), want) < 2 * TOL
+    for name, p in dec.named_parameters():
+        assert rel_err(N(p.grad), g[f"dis.g_dec.{name}"]) < 2 * TOL, name
