@@ -68,17 +68,6 @@ __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence
 // make generic-proxy shared-memory writes visible to the async proxy (the tensor core's operand reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-// ---- bulk async copy shared -> global (TMA engine, no tensor map): size and both addresses multiples of 16 bytes.
-// The issuing thread owns the bulk-group; wait_read<N> returns once all but the N most recent groups have finished
-// READING their shared-memory source (the buffer may be rewritten), wait_all once they have completed.
-__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
-{
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-
 // ---- TMEM -> registers: 16 consecutive fp32 columns of this thread's lane ---------------------
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
 {

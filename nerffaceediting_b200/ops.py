@@ -5,6 +5,8 @@ wrong device / dtype raises RuntimeError; there is no CPU path.
 """
 import ctypes
 
+import os
+
 import torch
 
 from . import _lib
@@ -449,8 +451,10 @@ PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16x3": _lib.PREC_BF16X3, "bf16": _lib.P
 
 
 def precision_of(options):
-    """rendering_options['nfe_precision'] -> NFE_PREC_* (decoder MLP arithmetic; default fp32 FFMA)."""
-    name = options.get('nfe_precision', 'fp32') if options is not None else 'fp32'
+    """rendering_options['nfe_precision'] -> NFE_PREC_* (decoder MLP arithmetic).  Default: $NFE_DEFAULT_PRECISION, else 'bf16x3'
+    — the tensor-core path whose results stay within the path's fp32 tolerance (1e-4) of the reference."""
+    default = os.environ.get("NFE_DEFAULT_PRECISION", "bf16x3")
+    name = options.get('nfe_precision', default) if options is not None else default
     if name not in PRECISIONS:
         raise RuntimeError(f"nfe_precision must be one of {sorted(PRECISIONS)}, got {name!r}")
     return PRECISIONS[name]

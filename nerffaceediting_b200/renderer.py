@@ -12,8 +12,9 @@ Extra keys read from `rendering_options` (all optional; defaults reproduce the r
                             reference has no such switch (renderer.py:180-190,210-211); its always-on
                             jitter is drawn here from an in-kernel Philox stream seeded from torch's
                             CUDA generator (statistically, not bitwise, equal to torch.rand).
-  nfe_precision      'fp32' arithmetic of the decoder MLPs: 'fp32' (FFMA), 'bf16x3' (tcgen05 tensor cores, three
-                            bf16 MMAs per product, fp32-grade: meets the 1e-4 tolerance) or 'bf16' (tensor cores, 1e-2).
+  nfe_precision    'bf16x3' arithmetic of the decoder MLPs: 'bf16x3' (tcgen05 tensor cores, three bf16 MMAs per product with
+                            fp32 accumulation, fp32-grade: meets the path's 1e-4 tolerance; the default, overridable with
+                            $NFE_DEFAULT_PRECISION), 'fp32' (FFMA on the CUDA cores) or 'bf16' (tensor cores, 1e-2).
   nfe_single_gather  True   disentangled renderer, tensor-core modes: when the de-normalised planes are known to be
                             norm*scale+shift per channel (they came from normalize_plane / denormalize_plane of this
                             package), gather only the normalised planes and rebuild the other features from the statistics.
