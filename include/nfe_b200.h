@@ -59,6 +59,11 @@ int nfe_plane_denormalize(const float* norm, const float* mean, const float* std
 int nfe_plane_normalize_bwd(const float* g_norm, const float* norm, const float* std_in, const float* g_mean,
                             const float* g_std, int64_t n_slabs, int64_t hw, double* sums_ws, float* g_planes,
                             nfe_stream_t stream);
+/* SR pre-resize of the rendered feature image: torch.nn.functional.interpolate(x, size=(out_h,out_w),
+ * mode='bilinear', align_corners=False, antialias=antialias) as called at training/superresolution.py:48-52,80-84,282-286.
+ * in [n_img, in_h, in_w] (n_img = batch*channels) -> out [n_img, out_h, out_w]. */
+int nfe_resize_bilinear(const float* in, int64_t n_img, int in_h, int in_w, int out_h, int out_w, int antialias,
+                        float* out, nfe_stream_t stream);
 /* Layout staging for the gather: [n_img, C, hw] (reference NCHW, triplane.py:114-115) ->
  * channel-last [n_img, hw, C] so that one bilinear tap is one contiguous C*4-byte line. */
 int nfe_planes_to_channel_last(const float* planes, int64_t n_img, int channels, int64_t hw, float* out,

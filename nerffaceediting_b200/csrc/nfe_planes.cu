@@ -257,6 +257,70 @@ __global__ void __launch_bounds__(256) plane_normalize_bwd_apply_kernel(const fl
     }
 }
 
+
+// ---- SR pre-resize: F.interpolate(x, size, mode='bilinear', align_corners=False, antialias=...)
+// of the rendered feature image (superresolution.py:48-52,80-84,282-286).  One thread per output pixel; the separable
+// tap weights are recomputed per thread (<= 2*max(scale,1)+2 taps per axis; 2-3 for the shipped 64^2 -> 128^2 case) and
+// the horizontal sums are formed first, like ATen's two passes.  The image (4 MB at c2) was just written by the
+// compositing kernel and is read from L2.
+struct AxisTaps { int first, n; float scale, support, inv, center; };
+
+__device__ __forceinline__ AxisTaps axis_taps(int o, int in, int out, int antialias)
+{
+    AxisTaps t;
+    t.scale = (float)in / (float)out;
+    if (!antialias) {
+        float src = fmaxf(t.scale * ((float)o + 0.5f) - 0.5f, 0.0f);
+        int i0 = min((int)src, in - 1);
+        t.first = i0; t.n = i0 < in - 1 ? 2 : 1; t.center = src - (float)i0;      // center holds the fraction
+        t.support = t.inv = 0.0f;
+        return t;
+    }
+    t.support = t.scale >= 1.0f ? t.scale : 1.0f;
+    t.inv = t.scale >= 1.0f ? __fdiv_rn(1.0f, t.scale) : 1.0f;
+    t.center = t.scale * ((float)o + 0.5f);
+    t.first = max((int)(t.center - t.support + 0.5f), 0);
+    t.n = min((int)(t.center + t.support + 0.5f), in) - t.first;
+    return t;
+}
+
+__device__ __forceinline__ float axis_weight(const AxisTaps& t, int j, int antialias)
+{
+    if (!antialias) return t.n == 1 ? 1.0f : (j == 0 ? 1.0f - t.center : t.center);
+    const float x = fabsf(((float)(j + t.first) - t.center + 0.5f) * t.inv);
+    return x < 1.0f ? 1.0f - x : 0.0f;
+}
+
+constexpr int RESIZE_ROWS = 8;      // output rows per block: the per-column tap set is computed once and reused for all of them
+
+__global__ void __launch_bounds__(128) resize_bilinear_kernel(const float* __restrict__ in, int row_groups, int ih, int iw, int oh, int ow,
+                                                              int antialias, float* __restrict__ out)
+{
+    const int img = blockIdx.x / row_groups, oy0 = (blockIdx.x % row_groups) * RESIZE_ROWS;
+    const float* src = in + (int64_t)img * ih * iw;
+    float* dst = out + (int64_t)img * oh * ow;
+    for (int ox = threadIdx.x; ox < ow; ox += blockDim.x) {
+        const AxisTaps tx = axis_taps(ox, iw, ow, antialias);
+        float sx = 0.0f;
+        for (int j = 0; j < tx.n; ++j) sx += axis_weight(tx, j, antialias);
+        const float rx = sx != 0.0f ? __fdiv_rn(1.0f, sx) : 0.0f;            // plain bilinear: the two weights already sum to 1
+        for (int r = 0; r < RESIZE_ROWS && oy0 + r < oh; ++r) {
+            const AxisTaps ty = axis_taps(oy0 + r, ih, oh, antialias);
+            float sy = 0.0f;
+            for (int j = 0; j < ty.n; ++j) sy += axis_weight(ty, j, antialias);
+            const float ry = sy != 0.0f ? __fdiv_rn(1.0f, sy) : 0.0f;
+            float acc = 0.0f;
+            for (int jy = 0; jy < ty.n; ++jy) {
+                const float* row = src + (int64_t)(ty.first + jy) * iw + tx.first;
+                float h = 0.0f;
+                for (int jx = 0; jx < tx.n; ++jx) h = fmaf(axis_weight(tx, jx, antialias) * rx, __ldg(row + jx), h);
+                acc = fmaf(axis_weight(ty, jy, antialias) * ry, h, acc);
+            }
+            dst[(int64_t)(oy0 + r) * ow + ox] = acc;
+        }
+    }
+}
+
 }  // namespace nfe
 
 using namespace nfe;
@@ -366,5 +430,18 @@ NFE_EXPORT int nfe_plane_normalize_bwd(const float* g_norm, const float* norm, c
     plane_normalize_bwd_apply_kernel<<<(unsigned)(n_slabs * chunks), 256, 0, as_stream(stream)>>>(g_norm, norm, std_in, g_mean, g_std, sums_ws, hw,
                                                                                                chunks, g_planes);
     NFE_LAUNCH_CHECK("plane_normalize_bwd_apply_kernel");
+    return 0;
+}
+
+NFE_EXPORT int nfe_resize_bilinear(const float* in, int64_t n_img, int in_h, int in_w, int out_h, int out_w, int antialias, float* out,
+                                   nfe_stream_t stream)
+{
+    if (n_img == 0) return 0;
+    NFE_REQUIRE(in && out, "nfe_resize_bilinear: null pointer");
+    NFE_REQUIRE(n_img > 0 && in_h >= 1 && in_w >= 1 && out_h >= 1 && out_w >= 1, "nfe_resize_bilinear: bad sizes");
+    const int row_groups = (out_h + RESIZE_ROWS - 1) / RESIZE_ROWS;
+    NFE_REQUIRE(n_img * row_groups < (1ll << 31), "nfe_resize_bilinear: grid too large");
+    resize_bilinear_kernel<<<(unsigned)(n_img * row_groups), 128, 0, as_stream(stream)>>>(in, row_groups, in_h, in_w, out_h, out_w, antialias, out);
+    NFE_LAUNCH_CHECK("resize_bilinear_kernel");
     return 0;
 }

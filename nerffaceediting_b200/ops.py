@@ -104,6 +104,21 @@ def plane_denormalize(norm, mean, std):
     return out
 
 
+def resize_bilinear(x, size, antialias=True):
+    """torch.nn.functional.interpolate(x, size=(size, size), mode='bilinear', align_corners=False, antialias=antialias)
+    for the super-resolution module's input (superresolution.py:48-52,80-84,282-286).  x [N,C,H,W]."""
+    x = _cuda_f32(x, "x")
+    if x.dim() != 4:
+        raise RuntimeError(f"resize_bilinear: expected [N,C,H,W], got {tuple(x.shape)}")
+    _no_grad_needed(x)
+    n, c, h, w = x.shape
+    oh, ow = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+    out = torch.empty((n, c, oh, ow), device=x.device, dtype=torch.float32)
+    with _Guard(x):
+        _lib.check(_lib.load().nfe_resize_bilinear(_ptr(x), n * c, h, w, oh, ow, int(bool(antialias)), _ptr(out), _stream(x)), "nfe_resize_bilinear")
+    return out
+
+
 _CL_CACHE = {}
 _CL_CACHE_MAX = 2
 

@@ -716,3 +716,84 @@ NFO_API int nfo_run_model(const nfo_render_cfg* cfg, const nfo_mlp* net_a, const
 }
 
 NFO_API int nfo_version(void) { return 1; }
+
+
+/* ------------------------------------------------------------------------------------------
+ * SR pre-resize: torch.nn.functional.interpolate(x, size, mode='bilinear',
+ * align_corners=False, antialias=sr_antialias) as called on the rendered feature image and its first three
+ * channels at training/superresolution.py:48-52,80-84,282-286.  The arithmetic lives in ATen (not under
+ * /root/reference); restated from its published definition:
+ *   scale = in/out per axis;
+ *   antialias: triangle filter of half-width support = max(scale, 1) around center = scale*(o + 0.5), taps
+ *     [max(int(center - support + 0.5), 0), min(int(center + support + 0.5), in)), weight
+ *     max(0, 1 - |(j - center + 0.5) / max(scale, 1)|), normalised to sum 1; horizontal pass, then vertical;
+ *   plain: src = max(scale*(o + 0.5) - 0.5, 0), i0 = floor(src), i1 = min(i0 + 1, in - 1), weights (1 - t, t).
+ * in [n_img, ih, iw] -> out [n_img, oh, ow]. */
+static int nfo_aa_weights(int o, int in, int out, int antialias, int* first, float* w /* >= 2*ceil(max(scale,1)) + 2 */)
+{
+    const float scale = (float)in / (float)out;
+    if (!antialias) {
+        float src = scale * ((float)o + 0.5f) - 0.5f;
+        if (src < 0.0f) src = 0.0f;
+        int i0 = (int)src;
+        if (i0 > in - 1) i0 = in - 1;
+        const int has1 = i0 < in - 1;
+        const float t = src - (float)i0;
+        *first = i0;
+        w[0] = 1.0f - t;
+        w[1] = t;
+        if (!has1) { w[0] = 1.0f; return 1; }      /* i1 == i0: both weights land on the same texel */
+        return 2;
+    }
+    const float support = scale >= 1.0f ? scale : 1.0f;
+    const float inv = scale >= 1.0f ? 1.0f / scale : 1.0f;
+    const float center = scale * ((float)o + 0.5f);
+    int lo = (int)(center - support + 0.5f);
+    if (lo < 0) lo = 0;
+    int hi = (int)(center + support + 0.5f);
+    if (hi > in) hi = in;
+    const int n = hi - lo;
+    float total = 0.0f;
+    for (int j = 0; j < n; ++j) {
+        float x = ((float)(j + lo) - center + 0.5f) * inv;
+        if (x < 0.0f) x = -x;
+        w[j] = x < 1.0f ? 1.0f - x : 0.0f;
+        total += w[j];
+    }
+    for (int j = 0; j < n; ++j) w[j] = total != 0.0f ? w[j] / total : 0.0f;
+    *first = lo;
+    return n;
+}
+
+NFO_API void nfo_resize_bilinear(const float* in, int64_t n_img, int ih, int iw, int oh, int ow, int antialias, float* out)
+{
+    const int max_taps_x = 2 * (int)ceilf((float)iw / (float)ow > 1.0f ? (float)iw / (float)ow : 1.0f) + 3;
+    const int max_taps_y = 2 * (int)ceilf((float)ih / (float)oh > 1.0f ? (float)ih / (float)oh : 1.0f) + 3;
+#pragma omp parallel
+    {
+        float* wx = (float*)malloc(sizeof(float) * (size_t)max_taps_x);
+        float* wy = (float*)malloc(sizeof(float) * (size_t)max_taps_y);
+        float* row = (float*)malloc(sizeof(float) * (size_t)ih * (size_t)ow);     /* horizontal pass of one image */
+#pragma omp for schedule(static)
+        for (int64_t img = 0; img < n_img; ++img) {
+            const float* src = in + img * ih * iw;
+            for (int x = 0; x < ow; ++x) {
+                int x0; const int nx = nfo_aa_weights(x, iw, ow, antialias, &x0, wx);
+                for (int y = 0; y < ih; ++y) {
+                    float acc = 0.0f;
+                    for (int j = 0; j < nx; ++j) acc += wx[j] * src[y * iw + x0 + j];
+                    row[y * ow + x] = acc;
+                }
+            }
+            for (int y = 0; y < oh; ++y) {
+                int y0; const int ny = nfo_aa_weights(y, ih, oh, antialias, &y0, wy);
+                for (int x = 0; x < ow; ++x) {
+                    float acc = 0.0f;
+                    for (int j = 0; j < ny; ++j) acc += wy[j] * row[(y0 + j) * ow + x];
+                    out[img * oh * ow + y * ow + x] = acc;
+                }
+            }
+        }
+        free(wx); free(wy); free(row);
+    }
+}

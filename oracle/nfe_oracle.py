@@ -138,6 +138,17 @@ def denormalize_plane(norm, mean, std):
     return out
 
 
+def resize_bilinear(x, size, antialias=True):
+    """F.interpolate(x, size=(size, size), mode='bilinear', align_corners=False, antialias=...) on [N,C,H,W]
+    (superresolution.py:282-286)."""
+    x = _f(x)
+    n, c, h, w = x.shape
+    oh, ow = (size, size) if isinstance(size, int) else size
+    out = np.empty((n, c, oh, ow), np.float32)
+    lib().nfo_resize_bilinear(_p(x), ctypes.c_int64(n * c), int(h), int(w), int(oh), int(ow), int(bool(antialias)), _p(out))
+    return out
+
+
 # --------------------------------------------------------------------------- rays
 def generate_rays(cam2world, intrinsics, resolution):
     c, k = _f(cam2world).reshape(-1, 16), _f(intrinsics).reshape(-1, 9)

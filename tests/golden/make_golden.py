@@ -342,7 +342,28 @@ def gold_backward():
     save("backward", cam2world=cams[0], intrinsics=cams[1], **arrays)
 
 
+# ------------------------------------------------------------------ 10. SR pre-resize (superresolution.py:282-286)
+def gold_resize():
+    """The super-resolution module's own call on the rendered feature image: F.interpolate(..., mode='bilinear',
+    align_corners=False, antialias=sr_antialias).  Cases: the shipped 64^2 -> 128^2 (both antialias settings), a 256^2
+    render taken DOWN to 128^2 (config 5), and odd sizes."""
+    import torch.nn.functional as F
+    arrays = {}
+    for tag, (n, c, h, w, oh, ow, aa) in {"up64_aa": (2, 5, 64, 64, 128, 128, True), "up64": (2, 5, 64, 64, 128, 128, False),
+                                         "down256_aa": (1, 3, 256, 256, 128, 128, True), "down256": (1, 3, 256, 256, 128, 128, False),
+                                         "odd_aa": (1, 2, 45, 37, 128, 128, True), "odd_down_aa": (1, 2, 301, 173, 128, 96, True),
+                                         "odd_down": (1, 2, 301, 173, 128, 96, False)}.items():
+        x = T(synth.hash_normal(500 + h + oh + int(aa), (n, c, h, w)))
+        y = F.interpolate(x, size=(oh, ow), mode='bilinear', align_corners=False, antialias=aa)
+        arrays[f"{tag}.cfg"] = np.array([n, c, h, w, oh, ow, int(aa), 500 + h + oh + int(aa)])
+        arrays[f"{tag}.out"] = y[:, :, ::3, ::5].contiguous()          # a strided subset keeps the fixture small
+    save("resize", **arrays)
+
+
 if __name__ == "__main__":
+    if "--only-resize" in sys.argv:
+        gold_resize()
+        sys.exit(0)
     if "--only-backward" in sys.argv:
         gold_backward()
         sys.exit(0)
@@ -355,6 +376,7 @@ if __name__ == "__main__":
     gold_unify()
     gold_render()
     gold_backward()
+    gold_resize()
     import platform
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from the reference at {REF}\n"
