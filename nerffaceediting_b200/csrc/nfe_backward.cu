@@ -140,17 +140,26 @@ __global__ void __launch_bounds__(256) march_bwd_kernel(MarchBwdArgs a)
         g_rgb_sum = warp_sum(g_rgb_sum);
         const float4* r1 = reinterpret_cast<const float4*>(a.rec1 + ray * a.s1 * 48) + (on ? q : 0);
         const float4* r2 = a.s2 ? reinterpret_cast<const float4*>(a.rec2 + (ray * a.s2 - a.s1) * 48) + (on ? q : 0) : r1;
-        for (int k0 = 0; k0 < S; k0 += 2) {
-            const int k = k0 + half;
-            float part = 0.0f;
-            if (k < S && on) {
-                const int e = s_order[k];
-                const float4 v = __ldg((e < a.s1 ? r1 : r2) + e * 12);
-                part = gv.x * v.x + gv.y * v.y + gv.z * v.z + gv.w * v.w;
+        constexpr int UN = 4;                              // 8 record rows in flight per warp (one load per row used to be waited for in turn)
+        for (int k0 = 0; k0 < S; k0 += 2 * UN) {
+            float4 v[UN];
+#pragma unroll
+            for (int u = 0; u < UN; ++u) {
+                const int k = k0 + 2 * u + half;
+                v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (k < S && on) {
+                    const int e = s_order[k];
+                    v[u] = __ldg((e < a.s1 ? r1 : r2) + e * 12);
+                }
             }
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-            if (q == 0 && k < S) s_dot[k] = part;
+            for (int u = 0; u < UN; ++u) {
+                const int k = k0 + 2 * u + half;
+                float part = gv.x * v[u].x + gv.y * v[u].y + gv.z * v[u].z + gv.w * v[u].w;
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+                if (q == 0 && k < S) s_dot[k] = part;
+            }
         }
         __syncwarp();
 
