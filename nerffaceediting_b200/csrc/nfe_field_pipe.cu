@@ -56,7 +56,6 @@ struct PipeSmem {
     alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
-    alignas(16) float aff[GATHER_WARPS][2][96];      // single-gather identity: (scale, shift) of the batch item each gather warp is on
     alignas(16) uint4 taps[2][GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][10];   // per sample: 12 offsets, 12 weights as (w,w) pairs, item; one tile ahead
     alignas(16) unsigned char recbuf[NFE_REC_STAGE ? TILE_M : 1][REC_STAGE_STRIDE];   // record staging (each warp owns its 32 rows)
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
@@ -116,15 +115,11 @@ template <bool SPLIT>
 __device__ __forceinline__ void hidden_to_regs(uint32_t taddr_row, const float* bias1_log2, uint32_t (&hi)[32], uint32_t (&lo)[32])
 {
     const float2 k2 = make_float2(LOG2E, LOG2E), one2 = make_float2(1.0f, 1.0f), neg2 = make_float2(-1.0f, -1.0f);
-    // the TMEM load of the next 16 columns is in flight while these 16 go through the softplus
-    float vv[2][16];
-    tc::tmem_ld16(taddr_row, vv[0]);
 #pragma unroll
     for (int q = 0; q < HIDDEN / 16; ++q) {
+        float v[16];
+        tc::tmem_ld16(taddr_row + q * 16, v);
         tc::tmem_ld_wait();
-        tc::tmem_ld_fence(vv[q & 1]);
-        if (q + 1 < HIDDEN / 16) tc::tmem_ld16(taddr_row + (q + 1) * 16, vv[(q + 1) & 1]);
-        const float (&v)[16] = vv[q & 1];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const float2 t = ffma2(make_float2(v[2 * i], v[2 * i + 1]), k2, *reinterpret_cast<const float2*>(bias1_log2 + q * 16 + 2 * i));
@@ -261,31 +256,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
         // ---- tap pre-pass: ONE lane per sample computes position -> 12 clamped texel offsets + 12 weights and parks
         //      them in shared memory (the 8 lanes of a sample used to recompute them: 8x redundant issue).  It runs
         //      one tile AHEAD (double-buffered), so its dependent global loads overlap the texel loads in flight.
-        //      Its global loads (depth, ray origin / direction, or the explicit point) are issued TWO tiles ahead into
-        //      registers (prepass_load) and consumed one tile ahead (prepass_compute): they were the largest exposed
-        //      latency in the gather warps (12 % of the kernel's stall samples on the first use of the loaded position).
-        float raw_t = 0.0f, raw_o[3] = {0.f, 0.f, 0.f}, raw_d[3] = {0.f, 0.f, 0.f};      // raw_o doubles as the explicit point
-        auto prepass_load = [&](int64_t tile) {
-            if (lane < PER * 4) {
-                const int64_t base = tile * TILE_M;
-                const int row = gw * PER * 4 + lane;
-                if (row < TILE_M && base + row < a.total) {
-                    const SampleRef sr = sample_of(a, base + row);
-                    if (a.coords) {
-                        const float* c = a.coords + sr.idx * 3;
-                        raw_o[0] = __ldg(c); raw_o[1] = __ldg(c + 1); raw_o[2] = __ldg(c + 2);
-                    } else {
-                        const int64_t ray = sr.idx / a.s_per_ray;
-                        raw_t = __ldg(a.depths + sr.idx);
-                        const float* o = a.origins + ray * 3;
-                        const float* d = a.dirs + ray * 3;
-                        raw_o[0] = __ldg(o); raw_o[1] = __ldg(o + 1); raw_o[2] = __ldg(o + 2);
-                        raw_d[0] = __ldg(d); raw_d[1] = __ldg(d + 1); raw_d[2] = __ldg(d + 2);
-                    }
-                }
-            }
-        };
-        auto prepass_compute = [&](int64_t tile, int buf) {
+        auto prepass = [&](int64_t tile, int buf) {
             if (lane < PER * 4) {
                 const int64_t base = tile * TILE_M;
                 const int row = gw * PER * 4 + lane;
@@ -295,8 +266,17 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
                 if (row < TILE_M && base + row < a.total) {
                     const SampleRef sr = sample_of(a, base + row);
-                    float x = raw_o[0], y = raw_o[1], z = raw_o[2];
-                    if (!a.coords) { x = ray_point(raw_o[0], raw_t, raw_d[0]); y = ray_point(raw_o[1], raw_t, raw_d[1]); z = ray_point(raw_o[2], raw_t, raw_d[2]); }
+                    float x, y, z;
+                    if (a.coords) {
+                        const float* c = a.coords + sr.idx * 3;
+                        x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
+                    } else {
+                        const int64_t ray = sr.idx / a.s_per_ray;
+                        const float t = __ldg(a.depths + sr.idx);
+                        const float* o = a.origins + ray * 3;
+                        const float* d = a.dirs + ray * 3;
+                        x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
+                    }
                     ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
                     item_idx = sr.item;
                     const int item_off = a.plane_batch == 1 ? 0 : (int)(sr.item * set_stride4);
@@ -326,22 +306,9 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             }
         };
 
-        // single-gather identity: the statistics of the item this warp is working on live in its shared-memory slot (they
-        // were 6 global loads per pass, evicted from L1 by the texel traffic: 12 % of the kernel's stall samples)
-        int warp_item = -1;
-        auto load_stats = [&](int item) {
-            __syncwarp();
-            for (int i = lane; i < 192; i += 32)
-                s.aff[gw][i / 96][i % 96] = __ldg((i < 96 ? a.affine_scale : a.affine_shift) + (int64_t)item * 96 + i % 96);
-            __syncwarp();
-            warp_item = item;
-        };
-        if (affine && a.affine_items == 1) load_stats(0);
         float4 va[12];                    // rolling pipeline: the texels of the NEXT pass, in flight while this one is blended
         if (blockIdx.x < n_tiles && n_pass > 0) {
-            prepass_load(blockIdx.x);
-            prepass_compute(blockIdx.x, 0);
-            if ((int64_t)blockIdx.x + gridDim.x < n_tiles) prepass_load((int64_t)blockIdx.x + gridDim.x);
+            prepass(blockIdx.x, 0);
             __syncwarp();
             if (rolling) {
                 const uint4* src = s.taps[0][gw][g];
@@ -358,8 +325,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             const int st = it & 1;
             const bool has_next = tile + gridDim.x < n_tiles;
             if (n_pass > 0) {
-                if (has_next) prepass_compute(tile + gridDim.x, st ^ 1);                       // from the registers loaded one tile ago
-                if (tile + 2 * (int64_t)gridDim.x < n_tiles) prepass_load(tile + 2 * (int64_t)gridDim.x);
+                if (has_next) prepass(tile + gridDim.x, st ^ 1);
                 __syncwarp();
             }
             PIPE_WAIT(0, &s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
@@ -397,19 +363,12 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                         // single-gather identity: only the normalised planes are read; the de-normalised features are
                         // s*f_p + m*w_in per plane (statistics: 6 L1-resident float4 loads per lane)
                         const int item = a.affine_items == 1 ? 0 : (int)cur[9].x;
-                        if (!__all_sync(0xffffffffu, item == warp_item)) {
-                            // a new item starts: reload the slot once the whole pass is inside it (a pass straddling two
-                            // items reads the statistics from global memory below)
-                            const int first = __shfl_sync(0xffffffffu, item, 0);
-                            if (__all_sync(0xffffffffu, item == first)) load_stats(first);
-                        }
-                        const bool cached = item == warp_item;
-                        const float4* sc = cached ? reinterpret_cast<const float4*>(s.aff[gw][0]) + c4 : reinterpret_cast<const float4*>(a.affine_scale + (int64_t)item * 96) + c4;
-                        const float4* sh = cached ? reinterpret_cast<const float4*>(s.aff[gw][1]) + c4 : reinterpret_cast<const float4*>(a.affine_shift + (int64_t)item * 96) + c4;
+                        const float4* sc = reinterpret_cast<const float4*>(a.affine_scale + (int64_t)item * 96) + c4;
+                        const float4* sh = reinterpret_cast<const float4*>(a.affine_shift + (int64_t)item * 96) + c4;
                         float2 d01[3], d23[3];
 #pragma unroll
                         for (int pl = 0; pl < 3; ++pl) {
-                            const float4 scl = sc[pl * 8], shf = sh[pl * 8];
+                            const float4 scl = __ldg(sc + pl * 8), shf = __ldg(sh + pl * 8);
                             d01[pl] = ffma2(make_float2(scl.x, scl.y), f01[pl], fmul2(make_float2(shf.x, shf.y), w_in[pl]));
                             d23[pl] = ffma2(make_float2(scl.z, scl.w), f23[pl], fmul2(make_float2(shf.z, shf.w), w_in[pl]));
                         }

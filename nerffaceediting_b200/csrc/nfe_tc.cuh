@@ -81,14 +81,6 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16])
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-// tcgen05.ld fills its destination registers asynchronously, until the wait.  When other work sits between a load and its
-// wait (software-pipelined epilogues), pin the order for the compiler: the values pass through a volatile asm placed after
-// the wait, so no use can be hoisted above it.
-__device__ __forceinline__ void tmem_ld_fence(float (&v)[16])
-{
-#pragma unroll
-    for (int i = 0; i < 16; ++i) asm volatile("" : "+f"(v[i]));
-}
 
 // ---- mbarrier ----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count)
