@@ -117,6 +117,7 @@ def cpu_reference_rate(torch, wl, steps, warmup, threads=None):
     from oracle import nfe_oracle as orc
     threads = threads or os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(threads)
+    orc.set_num_threads(threads)        # torchrun exports OMP_NUM_THREADS=1 and libgomp has already read it
     raw_host, dec, c2w, k, opts = make_inputs(torch, dict(wl, batch=1), torch.device("cpu"), 0)
     raw = raw_host.numpy()
     kind, a, b, cd, sd = orc.decoder_nets(dec)
@@ -190,6 +191,8 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
     mods = {"sampler": RaySampler(), "normalize_plane": normalize_plane, "renderer": DisentangledImportanceRenderer()}

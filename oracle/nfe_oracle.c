@@ -797,3 +797,21 @@ NFO_API void nfo_resize_bilinear(const float* in, int64_t n_img, int ih, int iw,
         free(wx); free(wy); free(row);
     }
 }
+
+
+/* Thread control for the timing legs of bench.py: launchers such as torchrun export OMP_NUM_THREADS=1, which libgomp
+ * reads once at load time; this sets the team size explicitly.  Returns the previous maximum. */
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+NFO_API int nfo_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    const int prev = omp_get_max_threads();
+    if (n > 0) omp_set_num_threads(n);
+    return prev;
+#else
+    (void)n;
+    return 1;
+#endif
+}

@@ -138,6 +138,11 @@ def denormalize_plane(norm, mean, std):
     return out
 
 
+def set_num_threads(n):
+    """OpenMP team size of the oracle (libgomp reads OMP_NUM_THREADS only once, and torchrun exports it as 1)."""
+    return int(lib().nfo_set_num_threads(int(n)))
+
+
 def resize_bilinear(x, size, antialias=True):
     """F.interpolate(x, size=(size, size), mode='bilinear', align_corners=False, antialias=...) on [N,C,H,W]
     (superresolution.py:282-286)."""
