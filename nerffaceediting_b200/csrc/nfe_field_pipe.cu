@@ -56,7 +56,9 @@ struct PipeSmem {
     alignas(128) unsigned char a2[PARTS][A2_BYTES];               // hidden tile, used by net A then net B
     alignas(128) unsigned char b2a[PARTS][(T::N_A / 8) * B2_SBO];
     alignas(128) unsigned char b2b[PARTS][(T::N_B / 8) * B2_SBO];
-    alignas(16) uint4 taps[2][GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][10];   // per sample: 12 offsets, 12 weights as (w,w) pairs, item; one tile ahead
+    // per sample: 12 offsets, 12 weights, item; one tile ahead.  The weights used to be parked as (w,w) pairs, FFMA2 operands
+    // as loaded: 3 more LDS.128 per pass — shared-memory wavefronts are what bounds this kernel (0.422 -> 0.389 ms per pass)
+    alignas(16) uint4 taps[2][GATHER_WARPS][((PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS) * 4][7];
     alignas(16) unsigned char recbuf[NFE_REC_STAGE ? TILE_M : 1][REC_STAGE_STRIDE];   // record staging (each warp owns its 32 rows)
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
     float bias2a[T::N_A];
@@ -291,25 +293,24 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                     for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
                 }
                 uint4* dst = s.taps[buf][gw][lane];
-                dst[9] = make_uint4((uint32_t)item_idx, 0u, 0u, 0u);
+                dst[6] = make_uint4((uint32_t)item_idx, 0u, 0u, 0u);
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     dst[q] = make_uint4((uint32_t)ts.off4[4 * q], (uint32_t)ts.off4[4 * q + 1], (uint32_t)ts.off4[4 * q + 2], (uint32_t)ts.off4[4 * q + 3]);
 #pragma unroll
-                for (int q = 0; q < 6; ++q) {
-                    const uint32_t w0 = __float_as_uint(ts.w[2 * q]), w1 = __float_as_uint(ts.w[2 * q + 1]);
-                    dst[3 + q] = make_uint4(w0, w0, w1, w1);
-                }
+                for (int q = 0; q < 3; ++q)
+                    dst[3 + q] = make_uint4(__float_as_uint(ts.w[4 * q]), __float_as_uint(ts.w[4 * q + 1]), __float_as_uint(ts.w[4 * q + 2]), __float_as_uint(ts.w[4 * q + 3]));
             }
         };
         auto read_taps = [&](int buf, int p, TapSet& ts) {
             const uint4* src = s.taps[buf][gw][p * 4 + g];
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
-                const uint4 o4 = src[q], wa = src[3 + 2 * q], wb = src[4 + 2 * q];
+                const uint4 o4 = src[q];
                 ts.off4[4 * q] = (int)o4.x; ts.off4[4 * q + 1] = (int)o4.y; ts.off4[4 * q + 2] = (int)o4.z; ts.off4[4 * q + 3] = (int)o4.w;
-                ts.w[4 * q] = __uint_as_float(wa.x); ts.w[4 * q + 1] = __uint_as_float(wa.z);
-                ts.w[4 * q + 2] = __uint_as_float(wb.x); ts.w[4 * q + 3] = __uint_as_float(wb.z);
+                const uint4 w4 = src[3 + q];
+                ts.w[4 * q] = __uint_as_float(w4.x); ts.w[4 * q + 1] = __uint_as_float(w4.y);
+                ts.w[4 * q + 2] = __uint_as_float(w4.z); ts.w[4 * q + 3] = __uint_as_float(w4.w);
             }
         };
 
@@ -349,8 +350,8 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                     float2 f01[3], f23[3], w_in[3];
 #pragma unroll
                     for (int pl = 0; pl < 3; ++pl) {
-                        const float4 wa = *reinterpret_cast<const float4*>(&cur[3 + 2 * pl]), wb = *reinterpret_cast<const float4*>(&cur[4 + 2 * pl]);
-                        const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+                        const float4 w4 = *reinterpret_cast<const float4*>(&cur[3 + pl]);
+                        const float2 w0 = make_float2(w4.x, w4.x), w1 = make_float2(w4.y, w4.y), w2 = make_float2(w4.z, w4.z), w3 = make_float2(w4.w, w4.w);
                         float2 a01 = fmul2(make_float2(va[4 * pl].x, va[4 * pl].y), w0), a23 = fmul2(make_float2(va[4 * pl].z, va[4 * pl].w), w0);
                         a01 = ffma2(make_float2(va[4 * pl + 1].x, va[4 * pl + 1].y), w1, a01); a23 = ffma2(make_float2(va[4 * pl + 1].z, va[4 * pl + 1].w), w1, a23);
                         a01 = ffma2(make_float2(va[4 * pl + 2].x, va[4 * pl + 2].y), w2, a01); a23 = ffma2(make_float2(va[4 * pl + 2].z, va[4 * pl + 2].w), w2, a23);
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                     if (affine && !skip_b) {
                         // single-gather identity: only the normalised planes are read; the de-normalised features are
                         // s*f_p + m*w_in per plane (statistics: 6 L1-resident float4 loads per lane)
-                        const int item = a.affine_items == 1 ? 0 : (int)cur[9].x;
+                        const int item = a.affine_items == 1 ? 0 : (int)cur[6].x;
                         const float4* sc = reinterpret_cast<const float4*>(a.affine_scale + (int64_t)item * 96) + c4;
                         const float4* sh = reinterpret_cast<const float4*>(a.affine_shift + (int64_t)item * 96) + c4;
                         float2 d01[3], d23[3];
