@@ -33,6 +33,13 @@ constexpr int PIPE_THREADS = (EPI_WARPS + 1 + GATHER_WARPS) * 32;
 constexpr int PASSES_PER_TILE = TILE_M / 4;                 // a pass = 4 samples (8 lanes each); passes are dealt round-robin to the gather warps
 constexpr int TMEM_BUF_COLS = 192;                          // D1A 64 | D1B 64 | D2A <=48 | D2B <=32 (OSG: 48+16)
 constexpr int PIPE_TMEM_COLS = 512;
+// NFE_TMEM_A: the hidden activations (A operand of layer 2) go to tensor memory with tcgen05.st instead of shared memory:
+// columns 384.. hold [H_A hi | H_A lo | H_B hi | H_B lo], 32 columns each (64 bf16 per row).  No 32 STS.128 + proxy fence per
+// row and tile, and net B's hidden tile no longer waits for net A's layer-2 MMA to release a shared buffer.
+#ifndef NFE_TMEM_A
+#define NFE_TMEM_A 0
+#endif
+constexpr int COL_HID = 2 * TMEM_BUF_COLS;                  // 384
 // Record staging: thread m parks its 192-byte record in shared memory and the warp writes its 32 records (6 KB,
 // contiguous in the plain sample order) back out with fully coalesced 16-byte stores.  A direct STG.128 of 32 records
 // touches 32 different lines per instruction (32 L1 wavefronts each; the record stores were a quarter of the kernel's
@@ -152,6 +159,38 @@ __device__ __forceinline__ void hidden_regs_to_smem(unsigned char (*a2)[A2_BYTES
         *reinterpret_cast<uint4*>(a2[0] + off) = make_uint4(hi[4 * c8], hi[4 * c8 + 1], hi[4 * c8 + 2], hi[4 * c8 + 3]);
         if (SPLIT) *reinterpret_cast<uint4*>(a2[1] + off) = make_uint4(lo[4 * c8], lo[4 * c8 + 1], lo[4 * c8 + 2], lo[4 * c8 + 3]);
     }
+}
+
+// One thread issues D (+)= A * B^T with A in tensor memory (K/2 columns from tmem_a_*), B in shared memory, three split terms
+template <bool SPLIT>
+__device__ __forceinline__ void issue_gemm_ts(uint32_t tmem_d, uint32_t tmem_a_hi, uint32_t tmem_a_lo, const unsigned char* b_hi, const unsigned char* b_lo,
+                                              int b_lbo, int b_sbo, int K, uint32_t idesc)
+{
+    bool acc = false;
+    constexpr int TERMS = SPLIT ? 3 : 1;
+#pragma unroll
+    for (int t = 0; t < TERMS; ++t) {
+        const uint32_t ta = (t == 1) ? tmem_a_lo : tmem_a_hi;       // hi*hi, lo*hi, hi*lo
+        const unsigned char* b = (t == 2) ? b_lo : b_hi;
+        for (int k = 0; k < K; k += 16) {
+            const uint64_t db = tc::make_desc(tc::smem_u32(b) + (k >> 3) * b_lbo, b_lbo, b_sbo);
+            tc::mma_bf16_ts(tmem_d, ta + (k >> 1), db, idesc, acc);
+            acc = true;
+        }
+    }
+}
+
+// hidden tile of one net -> tensor memory: 32 columns of hi parts at taddr, 32 of lo parts at taddr + 32
+template <bool SPLIT>
+__device__ __forceinline__ void hidden_regs_to_tmem(uint32_t taddr, const uint32_t (&hi)[32], const uint32_t (&lo)[32])
+{
+    tc::tmem_st16(taddr, hi);
+    tc::tmem_st16(taddr + 16, hi + 16);
+    if (SPLIT) {
+        tc::tmem_st16(taddr + 32, lo);
+        tc::tmem_st16(taddr + 48, lo + 16);
+    }
+    tc::tmem_st_wait();
 }
 
 // Tile row -> sample.  Plain order: sample L is index L.  Quad order (FieldArgs::quad_stride): L enumerates
@@ -432,14 +471,22 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
                 // layer 2, net A
                 PIPE_WAIT(3, &s.a2_full, a2_uses++ & 1);
                 tc::fence_after_sync();
+#if NFE_TMEM_A
+                issue_gemm_ts<SPLIT>(tb + COL_D2A, tmem + COL_HID, tmem + COL_HID + 32, s.b2a[0], s.b2a[P], B2_LBO, B2_SBO, HIDDEN, idesc2a);
+#else
                 issue_gemm<SPLIT>(tb + COL_D2A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2a[0], s.b2a[P], B2_LBO, B2_SBO, HIDDEN, idesc2a);
+#endif
                 tc::mma_commit(&s.d2a_full[it & 1]);
                 // layer 1 of the NEXT tile goes in here, so the epilogue never waits on it
                 if (tile + gridDim.x < n_tiles) layer1(it + 1);
                 if (T::HAS_B && !skip_b) {
                     PIPE_WAIT(3, &s.a2_full, a2_uses++ & 1);
                     tc::fence_after_sync();
+#if NFE_TMEM_A
+                    issue_gemm_ts<SPLIT>(tb + COL_D2A + T::N_A, tmem + COL_HID + 64, tmem + COL_HID + 96, s.b2b[0], s.b2b[P], B2_LBO, B2_SBO, HIDDEN, idesc2b);
+#else
                     issue_gemm<SPLIT>(tb + COL_D2A + T::N_A, s.a2[0], s.a2[P], A2_LBO, A2_SBO, s.b2b[0], s.b2b[P], B2_LBO, B2_SBO, HIDDEN, idesc2b);
+#endif
                     tc::mma_commit(&s.d2b_full[it & 1]);
                 }
             }
@@ -458,18 +505,33 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             tc::fence_after_sync();
             hidden_to_regs<SPLIT>(lane_addr + COL_D1A, s.bias1[0], hi, lo);
             // the previous tile's last layer-2 MMA has completed (we waited on its commit), so the hidden tile is free
+#if NFE_TMEM_A
+            const uint32_t hid_addr = tmem + COL_HID + ((uint32_t)(warp * 32) << 16);
+            hidden_regs_to_tmem<SPLIT>(hid_addr, hi, lo);
+            tc::fence_before_sync();
+#else
             hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
             tc::fence_async_smem();
+#endif
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.a2_full);
             if (T::HAS_B && !skip_b) {
                 hidden_to_regs<SPLIT>(lane_addr + COL_D1B, s.bias1[1], hi, lo);     // overlaps the net-A layer-2 MMA
+#if NFE_TMEM_A
+                hidden_regs_to_tmem<SPLIT>(hid_addr + 64, hi, lo);                // its own columns: no wait for net A's MMA
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s.a2_full);
+                PIPE_WAIT(5, &s.d2a_full[st], ph);
+                tc::fence_after_sync();
+#else
                 PIPE_WAIT(5, &s.d2a_full[st], ph);                                // net A consumed the hidden tile
                 tc::fence_after_sync();
                 hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
                 tc::fence_async_smem();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&s.a2_full);
+#endif
             } else {
                 PIPE_WAIT(5, &s.d2a_full[st], ph);
                 tc::fence_after_sync();
