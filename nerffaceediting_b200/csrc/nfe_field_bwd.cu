@@ -489,12 +489,16 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                     const float4 scl = __ldg(sc + p * 8);
                     const float4 gf = make_float4(fmaf(scl.x, gr.x, gn.x), fmaf(scl.y, gr.y, gn.y), fmaf(scl.z, gr.z, gn.z), fmaf(scl.w, gr.w, gn.w));
                     float w_in = 0.0f;
+                    const float4 w4 = *reinterpret_cast<const float4*>(&s.tap_w[r][4 * p]);      // one LDS.128 each for the plane's 4 taps
+                    const int4 o4 = *reinterpret_cast<const int4*>(&s.tap_off[r][4 * p]);
+                    const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+                    const int os[4] = {o4.x, o4.y, o4.z, o4.w};
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const float w = s.tap_w[r][4 * p + k];
+                        const float w = ws[k];
                         w_in += w;
                         if (w != 0.0f)
-                            red_add_v4(a.g_norm + (int64_t)s.tap_off[r][4 * p + k] * 4 + 4 * c4, make_float4(gf.x * w, gf.y * w, gf.z * w, gf.w * w));
+                            red_add_v4(a.g_norm + (int64_t)os[k] * 4 + 4 * c4, make_float4(gf.x * w, gf.y * w, gf.z * w, gf.w * w));
                     }
                     const __half2* src = reinterpret_cast<const __half2*>(&s.fp[r][p * 32 + 4 * c4]);
                     const float2 f01 = __half22float2(src[0]), f23 = __half22float2(src[1]);
