@@ -129,6 +129,16 @@ __device__ __forceinline__ void store8(unsigned char* hi_tile, unsigned char* lo
     *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
+// texel loads with the streaming planes (1 and 2: no reuse between the samples a warp walks) bypassing L1 allocation
+__device__ __forceinline__ void gather_load_streaming(const float* __restrict__ set, const TapSet& ts, int c4, float4 (&v)[12])
+{
+    const float4* base = reinterpret_cast<const float4*>(set) + c4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __ldg(base + ts.off4[i]);
+#pragma unroll
+    for (int i = 4; i < 12; ++i) v[i] = __ldcg(base + ts.off4[i]);
+}
+
 __device__ __forceinline__ void red_add_v4(float* addr, float4 v)
 {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
@@ -282,8 +292,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                 float4 v0[12], v1[12];
                 read_taps(r0, t0);
                 read_taps(r1, t1);
-                gather_load(a.set_norm, t0, c4, v0);
-                gather_load(a.set_norm, t1, c4, v1);
+                gather_load_streaming(a.set_norm, t0, c4, v0);
+                gather_load_streaming(a.set_norm, t1, c4, v1);
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const int r = h ? r1 : r0;
