@@ -27,7 +27,10 @@ __device__ __forceinline__ double shfl_xor_double(double v, int mask)
 //   shared slice per warp: depth[S] sigma[S] weight[S] order[S]
 // ------------------------------------------------------------------------------------------
 template <bool SORT>
-__global__ void __launch_bounds__(256) march_kernel(MarchArgs a)
+#ifndef NFE_MARCH_MIN_BLOCKS
+#define NFE_MARCH_MIN_BLOCKS 4      // 64 registers: 4 blocks per SM keep more record rows in flight (merge+composite at c2: 0.157 -> 0.142 ms; 5 is slower)
+#endif
+__global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchArgs a)
 {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -337,7 +340,10 @@ __global__ void __launch_bounds__(256) unify_kernel(MarchArgs a, float* __restri
 //                 ns = S-3 pdf entries, bins = the S-1 mid-depths.
 // SMOOTH = false: sample_pdf stand-alone — inputs are bins [S] and weights [ns] as given.
 template <bool SMOOTH>
-__global__ void __launch_bounds__(256) resample_kernel(ResampleArgs a)
+#ifndef NFE_RESAMPLE_MIN_BLOCKS
+#define NFE_RESAMPLE_MIN_BLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, NFE_RESAMPLE_MIN_BLOCKS) resample_kernel(ResampleArgs a)
 {
     extern __shared__ __align__(16) float smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
