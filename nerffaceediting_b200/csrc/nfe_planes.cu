@@ -145,8 +145,11 @@ __global__ void __launch_bounds__(256) to_channel_last_kernel(const float* __res
 // channel vector, i.e. one 128-byte channel-last texel, written as 8 float4 stores.  With NORMALIZE
 // the same registers also produce (x-mean)/(std+1e-8): the NCHW result (coalesced) and its channel-last
 // copy, so normalize_plane + both stagings cost one read of the planes instead of three.
+#ifndef NFE_STAGE_MIN_BLOCKS
+#define NFE_STAGE_MIN_BLOCKS 4
+#endif
 template <bool NORMALIZE>
-__global__ void __launch_bounds__(256) stage32_kernel(const float* __restrict__ planes, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256, NFE_STAGE_MIN_BLOCKS) stage32_kernel(const float* __restrict__ planes, const float* __restrict__ mean,
                                                       const float* __restrict__ std_in, int64_t hw, int64_t groups_per_img, int64_t n_groups,
                                                       float* __restrict__ out_norm, float* __restrict__ out_norm_cl, float* __restrict__ out_raw_cl)
 {
