@@ -36,6 +36,9 @@ WORKLOADS = {
     "c3": dict(batch=32, res=128, s_c=48, s_f=48, desc="configs[2]-shaped: batch 32, 128^2 rays, 48+48"),
     "c4": dict(batch=32, res=64, s_c=48, s_f=48, train=True,
                desc="configs[3]-shaped training step: renderer forward+backward, batch 32/GPU, 64^2 rays, 48+48, gradients to planes + decoders"),
+    # configs[4]: one identity (ONE plane set, batch-broadcast) under 64 poses per GPU, 256^2 rays, 96+96 samples
+    "c5": dict(batch=64, plane_batch=1, res=256, s_c=96, s_f=96,
+               desc="configs[4]-shaped video sweep: 64 poses/GPU of one identity (plane batch 1, broadcast), 256^2 rays, 96+96"),
 }
 GATHER_BYTES_PER_SAMPLE_SET = 12 * 32 * 4      # 3 planes x 4 taps x 32 ch x fp32
 MLP_FLOP_PER_SAMPLE = 14336                    # DisentangledOSGDecoder
@@ -93,7 +96,8 @@ def make_inputs(torch, wl, device, seed):
     from nerffaceediting_b200.triplane import DisentangledOSGDecoder
     g = torch.Generator(device="cpu").manual_seed(seed)
     n = wl["batch"]
-    raw_host = torch.randn(n, 96, 256, 256, generator=g).pin_memory() if device.type == "cuda" else torch.randn(n, 96, 256, 256, generator=g)
+    pb = wl.get("plane_batch", n)
+    raw_host = torch.randn(pb, 96, 256, 256, generator=g).pin_memory() if device.type == "cuda" else torch.randn(pb, 96, 256, 256, generator=g)
     torch.manual_seed(seed)
     dec = DisentangledOSGDecoder(32, {'decoder_lr_mul': 1, 'decoder_output_dim': 32, 'decoder_seg_dim': 15})
     c2w, k = synth.camera_sweep(n)
@@ -118,7 +122,7 @@ def cpu_reference_rate(torch, wl, steps, warmup, threads=None):
     threads = threads or os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(threads)
     orc.set_num_threads(threads)        # torchrun exports OMP_NUM_THREADS=1 and libgomp has already read it
-    raw_host, dec, c2w, k, opts = make_inputs(torch, dict(wl, batch=1), torch.device("cpu"), 0)
+    raw_host, dec, c2w, k, opts = make_inputs(torch, dict(wl, batch=1, plane_batch=1), torch.device("cpu"), 0)
     raw = raw_host.numpy()
     kind, a, b, cd, sd = orc.decoder_nets(dec)
     rays = wl["res"] ** 2
@@ -140,7 +144,7 @@ def cpu_reference_rate(torch, wl, steps, warmup, threads=None):
         times.append(time.perf_counter() - t0)
     best, mean = min(times), sum(times) / len(times)
     return {"rays_per_s_best": rays / best, "rays_per_s_mean": rays / mean, "ms_per_step": mean * 1e3, "cores": threads,
-            "sample": f"1 of {wl['batch']} batch items per step ({rays} rays, {wl['s_c']}+{wl['s_f']} samples, 2 plane sets, stats+normalise included), "
+            "sample": f"1 of {wl['batch']} batch items (poses) per step ({rays} rays, {wl['s_c']}+{wl['s_f']} samples, 2 plane sets, stats+normalise included), "
                       f"{steps} steps after {warmup} warm-up"}
 
 
@@ -150,7 +154,7 @@ def run_reference(args, wl):
     if rank != 0:
         return
     r = cpu_reference_rate(torch, wl, max(args.steps, 1), max(args.warmup, 1))
-    line = {"impl": "reference", "metric": "rendered rays/sec (48+48 samples)", "value": r["rays_per_s_mean"], "unit": "rays/s",
+    line = {"impl": "reference", "metric": f"rendered rays/sec ({wl['s_c']}+{wl['s_f']} samples)", "value": r["rays_per_s_mean"], "unit": "rays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": wl["desc"], "note": "CPU restatement (oracle port) of the reference renderer on the box's host cores"},
@@ -172,6 +176,9 @@ def main():
                     help="disable the single-gather identity (gather both plane sets, as the reference does)")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="decoder MLP arithmetic (rendering_options['nfe_precision'])")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="replay the step as ONE CUDA graph (nerffaceediting_b200.graphs; single-GPU inference workloads; "
+                         "pays off where the step is launch-bound, i.e. c1)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -254,9 +261,17 @@ def main():
                 dist.all_reduce(flat)
             return loss
 
+    graphed = None
+    if args.cuda_graph:
+        if train or world > 1:
+            raise SystemExit("--cuda-graph covers the single-GPU inference workloads (the training step and the NCCL ring stay eager)")
+        from nerffaceediting_b200 import graphs
+
     def step_resident():
         if train:
             return train_step(raw, c2w, k)
+        if graphed is not None:
+            return graphed["resident"]()
         with torch.no_grad():
             rgb, seg, depth, wsum = hot_path_step(torch, mods, raw, dec, c2w, k, res, opts)
             if world > 1:
@@ -304,7 +319,10 @@ def main():
                 upload(0)
             upload(slot ^ 1)                                            # next step's inputs, overlapping this step's render
             main.wait_event(uploaded[slot])
-            rgb, seg, depth, wsum = hot_path_step(torch, mods, dev_in[slot], dec, dev_cam[slot][0], dev_cam[slot][1], res, opts)
+            if graphed is not None:
+                rgb, seg, depth, wsum = graphed["slot"][slot]()
+            else:
+                rgb, seg, depth, wsum = hot_path_step(torch, mods, dev_in[slot], dec, dev_cam[slot][0], dev_cam[slot][1], res, opts)
             packed = pack_and_gather(rgb, seg, depth, wsum)
             consumed[slot].record(main)
             out_host[slot].copy_(packed, non_blocking=True)
@@ -348,6 +366,18 @@ def main():
 
     sampler = ClockSampler(local) if rank == 0 else None
     ms_total, launches, stages = timed(step_resident, True)
+    ms_eager = ms_total
+    if args.cuda_graph:
+        # the eager pass above supplies the per-stage events (they cannot be recorded inside a replay); the value is the replayed step
+        for buf in dev_in:
+            buf.copy_(raw)                                              # capture runs the step on the ring slots: give them real planes
+        for cam in dev_cam:
+            cam[0].copy_(c2w); cam[1].copy_(k)
+        graphed = {"resident": graphs.capture(lambda: hot_path_step(torch, mods, raw, dec, c2w, k, res, opts)),
+                   "slot": [graphs.capture(lambda s_=s_: hot_path_step(torch, mods, dev_in[s_], dec, dev_cam[s_][0], dev_cam[s_][1], res, opts))
+                            for s_ in (0, 1)]}
+        ms_total, _, _ = timed(step_resident, False)
+        launches = graphed["resident"].kernels * steps
     clocks = sampler.stop() if sampler else None
     ms_e2e, _, _ = timed(step_e2e, False)
 
@@ -359,7 +389,9 @@ def main():
         # dominant kernel: the fused gather+decode field kernel (coarse + fine launches)
         f_ms = stages["field_coarse"][0] + stages["field_fine"][0]
         f_n = stages["field_coarse"][1] + stages["field_fine"][1]
-        samples_per_launch = rays_per_rank * (wl["s_c"] + wl["s_f"]) / 2
+        # the host splits a call whose workspace would exceed NFE_WORKSPACE_MB into item chunks (c3, c5): count the launches that
+        # actually ran, every sample of the timed steps being gathered + decoded exactly once
+        samples_per_launch = rays_per_rank * (wl["s_c"] + wl["s_f"]) * steps / max(f_n, 1)
         alg_bytes = samples_per_launch * sets_gathered * GATHER_BYTES_PER_SAMPLE_SET
         avg_ms = f_ms / max(f_n, 1)
         achieved = alg_bytes / (avg_ms * 1e-3) / 1e9
@@ -372,11 +404,13 @@ def main():
             except Exception:
                 traffic = None
         line = {
-            "metric": "rendered rays/sec (48+48 samples)" + (", forward+backward" if train else ""), "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+            "metric": f"rendered rays/sec ({wl['s_c']}+{wl['s_f']} samples)" + (", forward+backward" if train else ""), "value": value, "unit": "rays/s", "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
             "config": {"workload": wl["desc"], "rays_per_gpu_per_step": rays_per_rank, "sampling": "deterministic (parity mode)",
                        "parallelism": f"batch-sharded x{world}, NCCL all-gather of rendered maps overlapped on a comm stream" if world > 1 else "single GPU",
-                       "cache": "inputs larger than L2 (raw+normalised+staged planes ~0.8 GB per step), no L2 flush needed"},
+                       "cache": ("one 25 MB plane set stays L2-resident by design (one identity, many poses); the per-step stream of per-sample records "
+                                 "(chunked workspace, GBs) and the 822 MB of output maps pass through L2 between steps, no separate flush") if wl.get("plane_batch") == 1 else
+                                "inputs larger than L2 (raw+normalised+staged planes ~0.8 GB per step), no L2 flush needed"},
             "e2e": {"value": e2e_value, "unit": "rays/s", "ms_per_step": ms_e2e / steps,
                     "h2d_bytes_per_step": int(raw_host.numel() * 4 + c2w_host.numel() * 4 + k_host.numel() * 4),
                     "d2h_bytes_per_step": 4 if train else int(out_host[0].numel() * 4),
@@ -387,7 +421,7 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "mlp_tflops": samples_per_launch * MLP_FLOP_PER_SAMPLE / (avg_ms * 1e-3) / 1e12,
-                         "share_of_step": f_ms / ms_total,
+                         "share_of_step": f_ms / ms_eager,
                          "plane_sets_gathered": sets_gathered,
                          "note": "gather bytes actually requested (1536 B per sample per plane set gathered) / kernel time; with the single-gather "
                                  "identity only the normalised set is gathered (the reference's two-set figure would be 2x this); the planes are "
@@ -395,9 +429,17 @@ def main():
             "stages_ms_per_step": {k_: v[0] / steps for k_, v in stages.items() if v[1]},
             "clocks": clocks,
         }
+        if args.cuda_graph:
+            line["cuda_graph"] = {"kernels_per_replay": graphed["resident"].kernels, "eager_ms_per_step": ms_eager / steps,
+                                  "note": "value and e2e replay the step as one CUDA graph; roofline and stages come from the eager pass of the "
+                                          "same steps run just before (stage events cannot be recorded inside a replay)"}
+            line["config"]["cuda_graph"] = True
         if world == 1 and not args.no_cpu_baseline and not train:   # the CPU port is forward-only
             r = cpu_reference_rate(torch, wl, 3, 1)
             line["cpu_baseline"] = {"value": r["rays_per_s_best"], "unit": "rays/s", "cores": r["cores"], "kind": "port", "sample": r["sample"] + " (best)"}
+            if wl["res"] <= 64:                                        # the scalar figure SURVEY.md §8d also asks for (one more bounded step)
+                r1 = cpu_reference_rate(torch, wl, 1, 0, threads=1)
+                line["cpu_baseline"]["one_thread_value"] = r1["rays_per_s_best"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -267,9 +267,19 @@ def linspace_table(start, end, steps, device):
     return t
 
 
+_PHILOX_DRAWS = [0]
+
+
+def philox_draws():
+    """How many times a call asked for a Philox (seed, offset) so far; graphs.capture uses it to refuse calls whose random
+    state would be frozen into a CUDA graph."""
+    return _PHILOX_DRAWS[0]
+
+
 def philox_state(device, n_streams=4):
     """(seed, offset) from torch's CUDA generator, advanced so successive calls differ and
     torch.manual_seed makes stochastic renders reproducible."""
+    _PHILOX_DRAWS[0] += 1
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     seed, offset = gen.initial_seed(), gen.get_offset()
     gen.set_offset(offset + 4 * n_streams)

@@ -57,12 +57,12 @@ def fake_finish(depth, minmax):
     return torch.clamp(d, minmax[0], minmax[1])
 
 
-def _worker(rank, world, port, n, r, results):
+def _worker(rank, world, port, n, r, results, shared=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.manual_seed(0)
-        planes = torch.randn(n, 3, 32, 4, 4)
+        planes = torch.randn(1 if shared else n, 3, 32, 4, 4)      # shared: one identity under n poses (BASELINE configs[4])
         o, d = torch.randn(n, r, 3), torch.randn(n, r, 3)
         out = sharding.render_sharded(None, None, planes, None, o, d, {}, render_local=fake_render, finish=fake_finish)
         ref = fake_render(None, planes, o, d)
@@ -86,4 +86,15 @@ def test_render_sharded_matches_single_rank_gloo(n, r):
     mgr = mp.Manager()
     results = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), n, r, results), nprocs=world, join=True)
+    assert dict(results) == {0: True, 1: True}
+
+
+@pytest.mark.parametrize("n,r", [(4, 37), (5, 16), (1, 64)])
+def test_render_sharded_shared_plane_set_gloo(n, r):
+    """BASELINE configs[4]: ONE plane set (plane batch 1) under n poses.  Poses are split across ranks (batch-first) with the
+    plane set replicated, ragged pose counts included; with a single pose the rays are split instead."""
+    world = 2
+    mgr = mp.Manager()
+    results = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), n, r, results, True), nprocs=world, join=True)
     assert dict(results) == {0: True, 1: True}
