@@ -68,6 +68,25 @@ def test_no_cpu_fallback():
         ImportanceRenderer()(torch.randn(1, 3, 32, 8, 8), dec, torch.zeros(1, 2, 3), torch.ones(1, 2, 3), synth.FFHQ_RENDERING_OPTIONS)
 
 
+def test_graph_capture_needs_cuda():
+    from nerffaceediting_b200 import graphs
+    if torch.cuda.is_available():
+        pytest.skip("CPU-container check")
+    with pytest.raises(RuntimeError, match="CUDA"):
+        graphs.capture(lambda: None)
+
+
+def test_bench_workloads_cover_every_baseline_config():
+    """bench.py names one workload per BASELINE.json config (c1..c5) and the reference arm runs the oracle port on them."""
+    import json
+    import bench
+    configs = json.load(open(os.path.join(ROOT, "BASELINE.json")))["configs"]
+    assert sorted(bench.WORKLOADS) == [f"c{i + 1}" for i in range(len(configs))]
+    assert bench.WORKLOADS["c5"]["plane_batch"] == 1 and bench.WORKLOADS["c5"]["res"] == 256 and bench.WORKLOADS["c5"]["s_c"] == 96
+    raw, dec, c2w, k, opts = bench.make_inputs(torch, dict(bench.WORKLOADS["c5"], batch=2), torch.device("cpu"), 0)
+    assert raw.shape == (1, 96, 256, 256) and c2w.shape == (2, 4, 4) and opts["depth_resolution_importance"] == 96
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libnfe_b200.so")
