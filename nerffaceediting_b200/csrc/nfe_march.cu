@@ -3,6 +3,7 @@
 // and inverse-CDF importance resampling (sample_importance/sample_pdf, renderer.py:194-253).
 // Everything a ray needs between samples stays in the warp's shared-memory slice; cross-lane
 // work is shuffle scans.
+#include <cstdlib>
 #include "nfe_march.cuh"
 
 namespace nfe {
@@ -22,10 +23,24 @@ __device__ __forceinline__ double shfl_xor_double(double v, int mask)
     return __hiloint2double(hi, lo);
 }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ------------------------------------------------------------------------------------------
 // march_kernel: optional merge-sort of [set1 | set2] by depth, then mid-point compositing.
 //   shared slice per warp: depth[S] sigma[S] weight[S] order[S]
 // ------------------------------------------------------------------------------------------
+#ifndef NFE_MARCH_RING_DEFAULT
+#define NFE_MARCH_RING_DEFAULT 1    // merge+composite on B200: c2 0.142 -> 0.128 ms, c3 1.89 -> 1.72 ms, c5 28.7 -> 25.9 ms (4 / 12 / 16 groups: 0.135 / 0.130 / 0.143); $NFE_MARCH_RING=0 restores the register-staged loads
+#endif
+#ifndef NFE_MARCH_RING_GROUPS
+#define NFE_MARCH_RING_GROUPS 8            // groups (of two rows) in a warp's record ring: 3 KB per warp
+#endif
 template <bool SORT>
 #ifndef NFE_MARCH_MIN_BLOCKS
 #define NFE_MARCH_MIN_BLOCKS 4      // 64 registers: 4 blocks per SM keep more record rows in flight (merge+composite at c2: 0.157 -> 0.142 ms; 5 is slower)
@@ -49,6 +64,26 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
         // instead of register-staged loads was tried and is slower (0.27 ms: one 8-warp block per SM, each ray's load,
         // weights and sums in series), so the loads below stay as they are.
         const int64_t ray = a.n_rays - 1 - ray_it;
+        // ---- record ring (packed path, a.ring groups): the rows of a ray are summed in MEMORY order (sum_k omega_k c_order[k] ==
+        //      sum_e omega'_e c_e with omega' scattered by entry), so their addresses are known before the merge: the first
+        //      a.ring groups (two rows each) are requested here with cp.async and land while the merge and the scans run
+        const int rg_half = lane >> 4, rg_q = lane & 15;
+        const bool rg_on = rg_q < 12;
+        const float4* rg_r1 = nullptr;
+        const float4* rg_r2 = nullptr;
+        uint32_t rg_slot0 = 0;
+        if (a.ring) {
+            rg_r1 = reinterpret_cast<const float4*>(a.rec1 + ray * a.s1 * 48) + rg_q;
+            rg_r2 = a.s2 ? reinterpret_cast<const float4*>(a.rec2 + (ray * a.s2 - a.s1) * 48) + rg_q : rg_r1;
+            char* ring_base = reinterpret_cast<char*>(smem) + (((size_t)warps_per_block * MARCH_SMEM_FLOATS_PER_SAMPLE * S * 4 + 15) & ~(size_t)15)
+                              + (size_t)warp * a.ring * MARCH_RING_GROUP_BYTES;
+            rg_slot0 = (uint32_t)__cvta_generic_to_shared(ring_base) + (uint32_t)(rg_half * 192 + rg_q * 16);
+            for (int g = 0; g < a.ring; ++g) {
+                const int e = 2 * g + rg_half;
+                if (rg_on && e < S) cp_async16(rg_slot0 + g * MARCH_RING_GROUP_BYTES, (e < a.s1 ? rg_r1 : rg_r2) + e * 12);
+                cp_async_commit();
+            }
+        }
         // ---- load (and merge) depths / densities
         if (SORT) {
             // stage the concatenation in s_w (depth) / s_raw (sigma), then rank-sort (stable: ties keep
@@ -153,6 +188,30 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             constexpr int UN = 4;                              // 8 rows in flight per warp
             int k0 = 0;
+            if (a.ring) {
+                // omega by entry (s_raw is free after the merge), then walk the ring: group g holds rows 2g, 2g+1 in memory order;
+                // every lane reads back exactly the 16 bytes it requested itself, so cp.async.wait_group is all the ordering needed
+                for (int k = lane; k < S; k += 32) s_raw[s_order[k]] = s_sigma[k];
+                __syncwarp();
+                const int n_groups = (S + 1) >> 1;
+                int slot = 0;
+                for (int g = 0; g < n_groups; ++g) {
+                    cp_async_wait<NFE_MARCH_RING_GROUPS - 1>();       // a.ring == NFE_MARCH_RING_GROUPS groups were committed after group g-1: g has landed
+                    const int e = 2 * g + rg_half;
+                    if (rg_on && e < S) {
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                     : "r"(rg_slot0 + slot * MARCH_RING_GROUP_BYTES) : "memory");
+                        const float om = s_raw[e];
+                        acc.x = fmaf(om, v.x, acc.x); acc.y = fmaf(om, v.y, acc.y); acc.z = fmaf(om, v.z, acc.z); acc.w = fmaf(om, v.w, acc.w);
+                    }
+                    const int e2 = 2 * (g + a.ring) + rg_half;      // refill the slot just consumed
+                    if (rg_on && e2 < S) cp_async16(rg_slot0 + slot * MARCH_RING_GROUP_BYTES, (e2 < a.s1 ? rg_r1 : rg_r2) + e2 * 12);
+                    cp_async_commit();
+                    slot = slot + 1 == a.ring ? 0 : slot + 1;
+                }
+                k0 = S;                                        // the register-staged loops below are skipped
+            }
             for (; k0 + 2 * UN <= S; k0 += 2 * UN) {
                 float4 v[UN];
                 float om[UN];
@@ -456,16 +515,22 @@ int launch_march(const MarchArgs& a, bool sort, cudaStream_t stream)
     NFE_REQUIRE(a.cs <= 32, "ray march: at most 32 semantic channels (got %d)", a.cs);
     if (a.n_rays <= 0) return 0;
     const int warps = warps_for(S, MARCH_SMEM_FLOATS_PER_SAMPLE);
-    const size_t smem = (size_t)warps * MARCH_SMEM_FLOATS_PER_SAMPLE * 4 * S;
+    size_t smem = (size_t)warps * MARCH_SMEM_FLOATS_PER_SAMPLE * 4 * S;
+    MarchArgs args = a;
+    // packed records: cp.async ring of NFE_MARCH_RING_GROUPS groups per warp behind the scan arrays ($NFE_MARCH_RING=0 keeps the
+    // register-staged loads)
+    static const bool ring_on = [] { const char* e = getenv("NFE_MARCH_RING"); return e ? atoi(e) != 0 : NFE_MARCH_RING_DEFAULT != 0; }();
+    args.ring = (a.rec1 && ring_on) ? NFE_MARCH_RING_GROUPS : 0;
+    if (args.ring) smem = ((smem + 15) & ~(size_t)15) + (size_t)warps * args.ring * MARCH_RING_GROUP_BYTES;
     const int64_t blocks = (a.n_rays + warps - 1) / warps;
     const int64_t cap = (int64_t)sm_count() * 8;
     const unsigned grid = (unsigned)(blocks < cap ? blocks : cap);
     if (sort) {
         if (smem > SMEM_OPT_IN) cudaFuncSetAttribute(march_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        march_kernel<true><<<grid, warps * 32, smem, stream>>>(a);
+        march_kernel<true><<<grid, warps * 32, smem, stream>>>(args);
     } else {
         if (smem > SMEM_OPT_IN) cudaFuncSetAttribute(march_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        march_kernel<false><<<grid, warps * 32, smem, stream>>>(a);
+        march_kernel<false><<<grid, warps * 32, smem, stream>>>(args);
     }
     return check_launch("march_kernel");
 }

@@ -5,6 +5,7 @@
 namespace nfe {
 
 constexpr int MARCH_SMEM_FLOATS_PER_SAMPLE = 5;  // depth, sigma, weight, order, unsorted sigma
+constexpr int MARCH_RING_GROUP_BYTES = 2 * 192;  // one ring group = two 192-byte record rows (one per half-warp)
 constexpr int MAX_S = 768;  // merged samples per ray (reference configs go up to 192+192)
 
 struct MarchArgs {
@@ -19,6 +20,7 @@ struct MarchArgs {
     int64_t image_rays; // packed path only: > 0 writes rgb / seg as images [item, channel, image_rays] instead of [ray, channel]
     int inputs_sorted; // both sample sets ascending in depth: merge by binary search instead of a full rank sort
     int white_back;
+    int ring;          // packed path only (set by launch_march): groups of the per-warp cp.async record ring, 0 = register-staged loads
     float* rgb;        // [n_rays,cc]
     float* seg;        // [n_rays,cs]
     float* depth;      // [n_rays], UNCLAMPED (finish_depth applies the global clamp)
