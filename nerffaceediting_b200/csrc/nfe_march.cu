@@ -23,6 +23,44 @@ __device__ __forceinline__ double shfl_xor_double(double v, int mask)
     return __hiloint2double(hi, lo);
 }
 
+// Weights of the S-1 intervals of one ray (ray_marcher.py:37-47,80-90): s_w[i] = alpha_i * prod_{j<i} (1 - alpha_j + 1e-10).
+// Each lane owns a contiguous chunk of intervals; transmittance by a multiplicative warp scan of the chunk products.
+// wd / wt return this lane's share of sum w_i * mid-depth_i and sum w_i.  Shared by march_kernel and the fused
+// coarse-weights + resample kernel, so both see bit-identical weights.
+__device__ __forceinline__ void ray_interval_weights(const float* s_depth, const float* s_sigma, float* s_w, int S, int lane, float& wd, float& wt)
+{
+    const int n_int = S - 1;
+    const int chunk = (n_int + 31) / 32;
+    const int i0 = lane * chunk, i1 = min(n_int, i0 + chunk);
+    float prod = 1.0f;
+    for (int i = i0; i < i1; ++i) {
+        const float delta = __fsub_rn(s_depth[i + 1], s_depth[i]);
+        const float sig = __fdiv_rn(__fadd_rn(s_sigma[i], s_sigma[i + 1]), 2.0f);
+        // SFU exp/log (abs. error ~1e-7): the full-precision versions cost ~80 instructions per interval
+        const float xs = __fsub_rn(sig, 1.0f);
+        const float dens = fmaxf(xs, 0.0f) + __logf(1.0f + __expf(-fabsf(xs)));
+        const float alpha = __fsub_rn(1.0f, __expf(-__fmul_rn(dens, delta)));
+        s_w[i] = alpha;  // parked; turned into the weight below
+        prod *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+    }
+    float incl = prod;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl *= up;
+    }
+    float T = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) T = 1.0f;
+    for (int i = i0; i < i1; ++i) {
+        const float alpha = s_w[i];
+        const float w = __fmul_rn(alpha, T);
+        T *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
+        s_w[i] = w;
+        wd = fmaf(w, __fdiv_rn(__fadd_rn(s_depth[i], s_depth[i + 1]), 2.0f), wd);
+        wt = __fadd_rn(wt, w);
+    }
+}
+
 __device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void* src)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
@@ -133,40 +171,12 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
         }
         __syncwarp();
 
-        // ---- weights: each lane owns a contiguous chunk of intervals; transmittance by a
-        //      multiplicative warp scan of the chunk products
+        // ---- weights (ray_interval_weights above); the depth range of the ray for the clamp
         const int n_int = S - 1;
-        const int chunk = (n_int + 31) / 32;
-        const int i0 = lane * chunk, i1 = min(n_int, i0 + chunk);
-        float prod = 1.0f, dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
-        for (int i = i0; i < i1; ++i) {
-            const float delta = __fsub_rn(s_depth[i + 1], s_depth[i]);
-            const float sig = __fdiv_rn(__fadd_rn(s_sigma[i], s_sigma[i + 1]), 2.0f);
-            // SFU exp/log (abs. error ~1e-7): the full-precision versions cost ~80 instructions per interval
-            const float xs = __fsub_rn(sig, 1.0f);
-            const float dens = fmaxf(xs, 0.0f) + __logf(1.0f + __expf(-fabsf(xs)));
-            const float alpha = __fsub_rn(1.0f, __expf(-__fmul_rn(dens, delta)));
-            s_w[i] = alpha;  // parked; turned into the weight below
-            prod *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-        }
+        float dmin = __int_as_float(0x7f800000), dmax = __int_as_float(0xff800000);
         for (int e = lane; e < S; e += 32) { dmin = fminf(dmin, s_depth[e]); dmax = fmaxf(dmax, s_depth[e]); }
-        float incl = prod;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const float up = __shfl_up_sync(0xffffffffu, incl, o);
-            if (lane >= o) incl *= up;
-        }
-        float T = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) T = 1.0f;
         float wd = 0.0f, wt = 0.0f;
-        for (int i = i0; i < i1; ++i) {
-            const float alpha = s_w[i];
-            const float w = alpha * T;
-            T *= __fadd_rn(__fsub_rn(1.0f, alpha), 1e-10f);
-            s_w[i] = w;
-            wd = fmaf(w, __fdiv_rn(__fadd_rn(s_depth[i], s_depth[i + 1]), 2.0f), wd);
-            wt += w;
-        }
+        ray_interval_weights(s_depth, s_sigma, s_w, S, lane, wd, wt);
         wd = warp_sum(wd);
         wt = warp_sum(wt);
         dmin = warp_min(dmin);
@@ -417,7 +427,18 @@ __global__ void __launch_bounds__(256, NFE_RESAMPLE_MIN_BLOCKS) resample_kernel(
     for (int64_t ray = (int64_t)blockIdx.x * warps_per_block + warp; ray < a.n_rays; ray += (int64_t)gridDim.x * warps_per_block) {
         if (SMOOTH) {
             for (int e = lane; e < S; e += 32) s_z[e] = a.z_vals[ray * S + e];
-            for (int e = lane; e < nw; e += 32) s_cdf[e] = a.weights[ray * nw + e];  // raw weights parked in s_cdf
+            if (a.sigma) {
+                // fused coarse pass (renderer.py:118,340): the compositing weights of the coarse samples are formed here from
+                // the densities instead of being written by march_kernel<false> and read back (one launch and a round trip less)
+                for (int e = lane; e < S; e += 32) s_om[e] = a.sigma[ray * S + e];
+                __syncwarp();
+                float wd = 0.0f, wt = 0.0f;
+                ray_interval_weights(s_z, s_om, s_cdf, S, lane, wd, wt);
+                __syncwarp();
+                if (a.weights_out) for (int e = lane; e < nw; e += 32) a.weights_out[ray * nw + e] = s_cdf[e];
+            } else {
+                for (int e = lane; e < nw; e += 32) s_cdf[e] = a.weights[ray * nw + e];  // raw weights parked in s_cdf
+            }
             __syncwarp();
             // max_pool1d(k=2,s=1,pad=1) then avg_pool1d(k=2,s=1), + 0.01 (renderer.py:205-207); bins = mid-depths;
             // only smoothed[1:-1] enters the pdf (renderer.py:210)

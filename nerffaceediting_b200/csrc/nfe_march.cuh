@@ -31,6 +31,8 @@ struct MarchArgs {
 
 struct ResampleArgs {
     const float* z_vals; const float* weights;  // smooth: depths [S] + raw coarse weights [S-1]; else bins [S] + pdf weights [ns]
+    const float* sigma; float* weights_out;     // smooth only: densities [S] instead of `weights` (the kernel forms the compositing weights itself,
+                                                // ray_marcher.py:37-47) and, optionally, where to export them [S-1]
     int smooth; int ns; float eps;
     int sort_u;        // stochastic draws only: emit the samples in ascending order
     int64_t n_rays; int S, s_f;

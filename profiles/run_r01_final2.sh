@@ -10,9 +10,12 @@ timeout 120 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu-baseline
 timeout 240 python bench.py --workload c5 --steps 3 --warmup 3 > gpurun_out/bench_c5.json 2> gpurun_out/bench_c5.err; python profiles/summarize_bench.py < gpurun_out/bench_c5.json; tail -3 gpurun_out/bench_c5.err
 echo "t=$(( $(date +%s)-S ))s"
 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_c2.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/b_c2.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"field_pipe|march_kernel" -s 10 -c 4 -o gpurun_out/prof_c2 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/p_c2.log 2>&1
+timeout 200 ncu --set full --clock-control none --import-source on -k regex:"field_pipe|march_kernel|resample" -s 12 -c 4 -o gpurun_out/prof_c2 -f python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/p_c2.log 2>&1
 echo "t=$(( $(date +%s)-S ))s"
 timeout 120 python bench.py --workload c3 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err
-timeout 60 python bench.py --workload c1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err
+timeout 60 python bench.py --workload c1 --steps 50 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c1.json 2> gpurun_out/bench_c1.err
+for v in "--precision bf16:bf16" "--precision fp32:fp32" "--two-gather:two_gather"; do
+  timeout 60 python bench.py ${v%%:*} --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/bench_c2_${v##*:}.json 2>/dev/null
+done
 timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_c4.csv python bench.py --workload c4 --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/b_c4.log 2>&1
 echo "total t=$(( $(date +%s)-S ))s"
