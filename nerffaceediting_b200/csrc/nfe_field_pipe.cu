@@ -36,6 +36,9 @@ constexpr int PIPE_TMEM_COLS = 512;
 // NFE_TMEM_A: the hidden activations (A operand of layer 2) go to tensor memory with tcgen05.st instead of shared memory:
 // columns 384.. hold [H_A hi | H_A lo | H_B hi | H_B lo], 32 columns each (64 bf16 per row).  No 32 STS.128 + proxy fence per
 // row and tile, and net B's hidden tile no longer waits for net A's layer-2 MMA to release a shared buffer.
+#ifndef NFE_EPI_HALVES
+#define NFE_EPI_HALVES 1  // hidden activations leave for tensor memory in halves of 32 units: 128 -> 117 registers, coarse pass 0.3788 -> 0.3764 ms at c2
+#endif
 #ifndef NFE_TMEM_A
 #define NFE_TMEM_A 1      // measured at c2: 0.389 -> 0.381 ms per pass, and 32 KB of shared memory less
 #endif
@@ -148,6 +151,45 @@ __device__ __forceinline__ void hidden_to_regs(uint32_t taddr_row, const float* 
             }
         }
     }
+}
+
+// hidden_to_regs + hidden_regs_to_tmem in halves of 32 hidden units: each half's packed parts leave for tensor memory as soon
+// as they exist, so 16 + 16 registers are live instead of 32 + 32 (NFE_EPI_HALVES)
+template <bool SPLIT>
+__device__ __forceinline__ void hidden_to_tmem_halves(uint32_t taddr_row, const float* bias1_log2, uint32_t hid_addr)
+{
+    const float2 k2 = make_float2(LOG2E, LOG2E), one2 = make_float2(1.0f, 1.0f), neg2 = make_float2(-1.0f, -1.0f);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            float v[16];
+            tc::tmem_ld16(taddr_row + (h * 2 + q) * 16, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float2 t = ffma2(make_float2(v[2 * i], v[2 * i + 1]), k2, *reinterpret_cast<const float2*>(bias1_log2 + (h * 2 + q) * 16 + 2 * i));
+                float e0, e1, l0, l1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-fabsf(t.x)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-fabsf(t.y)));
+                const float2 s1 = fadd2(make_float2(e0, e1), one2);
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(s1.x));
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(s1.y));
+                const float2 hh = fadd2(make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f)), make_float2(l0, l1));
+                const __nv_bfloat162 p = __floats2bfloat162_rn(hh.x, hh.y);
+                hi[q * 8 + i] = *reinterpret_cast<const uint32_t*>(&p);
+                if (SPLIT) {
+                    const float2 d = ffma2(__bfloat1622float2(p), neg2, hh);      // h - bf16(h), exact
+                    const __nv_bfloat162 r = __floats2bfloat162_rn(d.x, d.y);
+                    lo[q * 8 + i] = *reinterpret_cast<const uint32_t*>(&r);
+                }
+            }
+        }
+        tc::tmem_st16(hid_addr + h * 16, hi);
+        if (SPLIT) tc::tmem_st16(hid_addr + 32 + h * 16, lo);
+    }
+    tc::tmem_st_wait();
 }
 
 template <bool SPLIT>
@@ -503,21 +545,37 @@ __global__ void __launch_bounds__(PIPE_THREADS, 1) field_pipe_kernel(FieldArgs a
             uint32_t hi[32], lo[32];
             PIPE_WAIT(4, &s.d1_full[st], ph);
             tc::fence_after_sync();
+#if NFE_TMEM_A && NFE_EPI_HALVES
+            // the previous tile's last layer-2 MMA has completed (we waited on its commit), so the hidden tile is free
+            const uint32_t hid_addr = tmem + COL_HID + ((uint32_t)(warp * 32) << 16);
+            hidden_to_tmem_halves<SPLIT>(lane_addr + COL_D1A, s.bias1[0], hid_addr);
+            tc::fence_before_sync();
+#elif NFE_TMEM_A
             hidden_to_regs<SPLIT>(lane_addr + COL_D1A, s.bias1[0], hi, lo);
             // the previous tile's last layer-2 MMA has completed (we waited on its commit), so the hidden tile is free
-#if NFE_TMEM_A
             const uint32_t hid_addr = tmem + COL_HID + ((uint32_t)(warp * 32) << 16);
             hidden_regs_to_tmem<SPLIT>(hid_addr, hi, lo);
             tc::fence_before_sync();
 #else
+            hidden_to_regs<SPLIT>(lane_addr + COL_D1A, s.bias1[0], hi, lo);
             hidden_regs_to_smem<SPLIT>(s.a2, row, hi, lo);
             tc::fence_async_smem();
 #endif
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.a2_full);
             if (T::HAS_B && !skip_b) {
+#if NFE_TMEM_A && NFE_EPI_HALVES
+                hidden_to_tmem_halves<SPLIT>(lane_addr + COL_D1B, s.bias1[1], hid_addr + 64);   // overlaps the net-A layer-2 MMA; its own columns
+#else
                 hidden_to_regs<SPLIT>(lane_addr + COL_D1B, s.bias1[1], hi, lo);     // overlaps the net-A layer-2 MMA
-#if NFE_TMEM_A
+#endif
+#if NFE_TMEM_A && NFE_EPI_HALVES
+                tc::fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s.a2_full);
+                PIPE_WAIT(5, &s.d2a_full[st], ph);
+                tc::fence_after_sync();
+#elif NFE_TMEM_A
                 hidden_regs_to_tmem<SPLIT>(hid_addr + 64, hi, lo);                // its own columns: no wait for net A's MMA
                 tc::fence_before_sync();
                 __syncwarp();
