@@ -77,7 +77,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #define NFE_MARCH_RING_DEFAULT 1    // merge+composite on B200: c2 0.142 -> 0.128 ms, c3 1.89 -> 1.72 ms, c5 28.7 -> 25.9 ms (4 / 12 / 16 groups: 0.135 / 0.130 / 0.143); $NFE_MARCH_RING=0 restores the register-staged loads
 #endif
 #ifndef NFE_MARCH_RING_GROUPS
-#define NFE_MARCH_RING_GROUPS 8            // groups (of two rows) in a warp's record ring: 3 KB per warp
+#define NFE_MARCH_RING_GROUPS 4            // groups (of 2*NFE_MARCH_GROUP_PAIRS rows) in a warp's record ring: 16 rows = 3 KB per warp (6 groups: no better)
 #endif
 template <bool SORT>
 #ifndef NFE_MARCH_MIN_BLOCKS
@@ -117,8 +117,11 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
                               + (size_t)warp * a.ring * MARCH_RING_GROUP_BYTES;
             rg_slot0 = (uint32_t)__cvta_generic_to_shared(ring_base) + (uint32_t)(rg_half * 192 + rg_q * 16);
             for (int g = 0; g < a.ring; ++g) {
-                const int e = 2 * g + rg_half;
-                if (rg_on && e < S) cp_async16(rg_slot0 + g * MARCH_RING_GROUP_BYTES, (e < a.s1 ? rg_r1 : rg_r2) + e * 12);
+#pragma unroll
+                for (int j = 0; j < NFE_MARCH_GROUP_PAIRS; ++j) {
+                    const int e = 2 * (NFE_MARCH_GROUP_PAIRS * g + j) + rg_half;
+                    if (rg_on && e < S) cp_async16(rg_slot0 + g * MARCH_RING_GROUP_BYTES + j * 384, (e < a.s1 ? rg_r1 : rg_r2) + e * 12);
+                }
                 cp_async_commit();
             }
         }
@@ -199,24 +202,30 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
             constexpr int UN = 4;                              // 8 rows in flight per warp
             int k0 = 0;
             if (a.ring) {
-                // omega by entry (s_raw is free after the merge), then walk the ring: group g holds rows 2g, 2g+1 in memory order;
+                // omega by entry (s_raw is free after the merge), then walk the ring: group g holds 2*NFE_MARCH_GROUP_PAIRS consecutive rows in memory order;
                 // every lane reads back exactly the 16 bytes it requested itself, so cp.async.wait_group is all the ordering needed
                 for (int k = lane; k < S; k += 32) s_raw[s_order[k]] = s_sigma[k];
                 __syncwarp();
-                const int n_groups = (S + 1) >> 1;
+                const int n_groups = (S + 2 * NFE_MARCH_GROUP_PAIRS - 1) / (2 * NFE_MARCH_GROUP_PAIRS);
                 int slot = 0;
                 for (int g = 0; g < n_groups; ++g) {
                     cp_async_wait<NFE_MARCH_RING_GROUPS - 1>();       // a.ring == NFE_MARCH_RING_GROUPS groups were committed after group g-1: g has landed
-                    const int e = 2 * g + rg_half;
-                    if (rg_on && e < S) {
-                        float4 v;
-                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                                     : "r"(rg_slot0 + slot * MARCH_RING_GROUP_BYTES) : "memory");
-                        const float om = s_raw[e];
-                        acc.x = fmaf(om, v.x, acc.x); acc.y = fmaf(om, v.y, acc.y); acc.z = fmaf(om, v.z, acc.z); acc.w = fmaf(om, v.w, acc.w);
+#pragma unroll
+                    for (int j = 0; j < NFE_MARCH_GROUP_PAIRS; ++j) {
+                        const int e = 2 * (NFE_MARCH_GROUP_PAIRS * g + j) + rg_half;
+                        if (rg_on && e < S) {
+                            float4 v;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                         : "r"(rg_slot0 + slot * MARCH_RING_GROUP_BYTES + j * 384) : "memory");
+                            const float om = s_raw[e];
+                            acc.x = fmaf(om, v.x, acc.x); acc.y = fmaf(om, v.y, acc.y); acc.z = fmaf(om, v.z, acc.z); acc.w = fmaf(om, v.w, acc.w);
+                        }
                     }
-                    const int e2 = 2 * (g + a.ring) + rg_half;      // refill the slot just consumed
-                    if (rg_on && e2 < S) cp_async16(rg_slot0 + slot * MARCH_RING_GROUP_BYTES, (e2 < a.s1 ? rg_r1 : rg_r2) + e2 * 12);
+#pragma unroll
+                    for (int j = 0; j < NFE_MARCH_GROUP_PAIRS; ++j) {   // refill the slot just consumed
+                        const int e2 = 2 * (NFE_MARCH_GROUP_PAIRS * (g + a.ring) + j) + rg_half;
+                        if (rg_on && e2 < S) cp_async16(rg_slot0 + slot * MARCH_RING_GROUP_BYTES + j * 384, (e2 < a.s1 ? rg_r1 : rg_r2) + e2 * 12);
+                    }
                     cp_async_commit();
                     slot = slot + 1 == a.ring ? 0 : slot + 1;
                 }
