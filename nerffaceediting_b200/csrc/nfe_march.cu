@@ -419,7 +419,7 @@ __global__ void __launch_bounds__(256) unify_kernel(MarchArgs a, float* __restri
 // SMOOTH = false: sample_pdf stand-alone — inputs are bins [S] and weights [ns] as given.
 template <bool SMOOTH>
 #ifndef NFE_RESAMPLE_MIN_BLOCKS
-#define NFE_RESAMPLE_MIN_BLOCKS 4
+#define NFE_RESAMPLE_MIN_BLOCKS 4   // with the coarse weights fused in (c2): 3 blocks 0.060 ms, 4 blocks 0.049 ms (16 bytes of spill), 6 blocks 0.053 ms
 #endif
 __global__ void __launch_bounds__(256, NFE_RESAMPLE_MIN_BLOCKS) resample_kernel(ResampleArgs a)
 {
