@@ -232,9 +232,14 @@ def gold_unify():
 
 
 # ------------------------------------------------------------------ 8. full forward (renderer.py:88-148,301-363)
-def run_forward(kind, planes_seed, plane_shape, cams, res, opts, ray_stride=1, lr=1):
+def run_forward(kind, planes_seed, plane_shape, cams, res, opts, ray_stride=1, lr=1, poses=None):
     n = plane_shape[0]
     raw = T(synth.hash_normal(planes_seed, plane_shape)) * 1.5 - 0.3        # [N,96,H,W] "backbone output"
+    if poses is not None:
+        # one identity under several poses (utils.py:78-80): the reference needs the plane batch to match the ray batch
+        assert n == 1
+        n = poses
+        raw = raw.expand(n, -1, -1, -1).contiguous()
     c2w, k = cams
     o, d = RaySampler()(c2w, k, res)
     o, d = o[:, ::ray_stride].contiguous(), d[:, ::ray_stride].contiguous()
@@ -290,6 +295,17 @@ def gold_render():
         arrays.update({f"{tag}.{k}": v for k, v in out.items()})
         arrays[f"{tag}.seed"] = seed
     save("render_full", cam2world=cams1[0], intrinsics=cams1[1], **arrays)
+
+
+def gold_video_sweep():
+    """BASELINE configs[4] shape: ONE identity (3x32x256x256 planes) under 3 poses, 256^2 rays of which every 1021st is kept
+    (65 per pose), 96+96 samples.  The fixture stores the rays and the reference outputs; planes come back from the seed."""
+    cams = synth.camera_sweep(3)
+    opts = dict(synth.FFHQ_RENDERING_OPTIONS, depth_resolution=96, depth_resolution_importance=96)
+    out = run_forward('dis', 203, (1, 96, 256, 256), cams, 256, opts, ray_stride=1021, poses=3)
+    arrays = {f"c5_dis.{k}": v for k, v in out.items()}
+    arrays["c5_dis.seed"] = 203
+    save("render_video_sweep", cam2world=cams[0], intrinsics=cams[1], **arrays)
 
 
 # ------------------------------------------------------------------ 9. backward (config 4): reference autograd
@@ -364,6 +380,9 @@ if __name__ == "__main__":
     if "--only-resize" in sys.argv:
         gold_resize()
         sys.exit(0)
+    if "--only-video-sweep" in sys.argv:
+        gold_video_sweep()
+        sys.exit(0)
     if "--only-backward" in sys.argv:
         gold_backward()
         sys.exit(0)
@@ -375,6 +394,7 @@ if __name__ == "__main__":
     gold_resample()
     gold_unify()
     gold_render()
+    gold_video_sweep()
     gold_backward()
     gold_resize()
     import platform
