@@ -115,7 +115,11 @@ def hot_path_step(torch, mods, raw, dec, c2w, k, res, opts):
     o, d = mods["sampler"](c2w, k, res)
     norm, mean, std = mods["normalize_plane"](raw)
     n, _, h, w = raw.shape
-    return mods["renderer"](norm.view(n, 3, 32, h, w), raw.view(n, 3, 32, h, w), dec, o, d, opts)
+    planes = raw
+    if mods.get("swap"):
+        # appearance swap (BASELINE configs[2], triplane.py:93-107): every item is de-normalised with its neighbour's statistics
+        planes = mods["denormalize_plane"](norm, mean.roll(1, 0), std.roll(1, 0))
+    return mods["renderer"](norm.view(n, 3, 32, h, w), planes.view(n, 3, 32, h, w), dec, o, d, opts)
 
 
 def cpu_reference_rate(torch, wl, steps, warmup, threads=None):
@@ -180,6 +184,9 @@ def main():
                     help="disable the single-gather identity (gather both plane sets, as the reference does)")
     ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"],
                     help="decoder MLP arithmetic (rendering_options['nfe_precision'])")
+    ap.add_argument("--swap-statistics", action="store_true",
+                    help="appearance swap inside the step (BASELINE configs[2]): denormalize_plane with the neighbouring item's mean/std "
+                         "before the render (one more 3-pass-equivalent kernel over the planes; the single-gather identity still applies)")
     ap.add_argument("--cuda-graph", action="store_true",
                     help="replay the step as ONE CUDA graph (nerffaceediting_b200.graphs; single-GPU inference workloads; "
                          "pays off where the step is launch-bound, i.e. c1)")
@@ -193,7 +200,7 @@ def main():
     from nerffaceediting_b200 import _lib
     from nerffaceediting_b200.ray_sampler import RaySampler
     from nerffaceediting_b200.renderer import DisentangledImportanceRenderer
-    from nerffaceediting_b200.triplane import normalize_plane
+    from nerffaceediting_b200.triplane import denormalize_plane, normalize_plane
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -206,7 +213,10 @@ def main():
             os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=device)
     steps, warmup = max(args.steps, 1), max(args.warmup, 3)
-    mods = {"sampler": RaySampler(), "normalize_plane": normalize_plane, "renderer": DisentangledImportanceRenderer()}
+    mods = {"sampler": RaySampler(), "normalize_plane": normalize_plane, "denormalize_plane": denormalize_plane,
+            "renderer": DisentangledImportanceRenderer(), "swap": bool(args.swap_statistics)}
+    if args.swap_statistics and (wl.get("train") or wl["batch"] < 2):
+        raise SystemExit("--swap-statistics needs an inference workload with at least two batch items")
 
     raw_host, dec, c2w_host, k_host, opts = make_inputs(torch, wl, device, 1000 + rank)
     opts["nfe_precision"] = args.precision
@@ -444,6 +454,8 @@ def main():
             "stages_ms_per_step": {k_: v[0] / steps for k_, v in stages.items() if v[1]},
             "clocks": clocks,
         }
+        if args.swap_statistics:
+            line["config"]["statistics_swap"] = "denormalize_plane(norm, roll(mean), roll(std)) inside the step"
         if graph_extra is not None:
             line["cuda_graph"] = graph_extra
         if args.cuda_graph:
