@@ -59,6 +59,18 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", {}
 
 
+def tensor_frac(mlp_tflops, precision, peaks):
+    """Tensor-pipe share of the decoder MLPs: the MMA work actually issued (bf16x3 runs every product as three bf16 MMAs) over the
+    measured dense bf16 peak of MEASURED_PEAKS.json; None for the FFMA mode or when no measured peak is available."""
+    try:
+        peak = float(peaks.get("bf16_tflops") or 0.0)
+    except (TypeError, ValueError, AttributeError):
+        return None
+    if precision == "fp32" or peak <= 0.0:
+        return None
+    return mlp_tflops * (3.0 if precision == "bf16x3" else 1.0) / peak
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -446,6 +458,7 @@ def main():
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "peak_source": peak_src, "avg_launch_ms": avg_ms, "algorithmic_bytes_per_launch": alg_bytes,
                          "mlp_tflops": samples_per_launch * MLP_FLOP_PER_SAMPLE / (avg_ms * 1e-3) / 1e12,
+                         "mlp_tensor_frac": tensor_frac(samples_per_launch * MLP_FLOP_PER_SAMPLE / (avg_ms * 1e-3) / 1e12, args.precision, peaks),
                          "share_of_step": f_ms / ms_eager,
                          "plane_sets_gathered": sets_gathered,
                          "note": "gather bytes actually requested (1536 B per sample per plane set gathered) / kernel time; with the single-gather "
