@@ -76,6 +76,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 #ifndef NFE_MARCH_RING_DEFAULT
 #define NFE_MARCH_RING_DEFAULT 1    // merge+composite on B200: c2 0.142 -> 0.128 ms, c3 1.89 -> 1.72 ms, c5 28.7 -> 25.9 ms (4 / 12 / 16 groups: 0.135 / 0.130 / 0.143); $NFE_MARCH_RING=0 restores the register-staged loads
 #endif
+#if NFE_MARCH_FULL_WARP && !defined(NFE_MARCH_RING_GROUPS)
+#define NFE_MARCH_RING_GROUPS 3            // full-warp variant: 3 groups of 8 rows = 4.5 KB per warp
+#endif
 #ifndef NFE_MARCH_RING_GROUPS
 #define NFE_MARCH_RING_GROUPS 4            // groups (of 2*NFE_MARCH_GROUP_PAIRS rows) in a warp's record ring: 16 rows = 3 KB per warp (6 groups: no better)
 #endif
@@ -115,6 +118,19 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
             rg_r2 = a.s2 ? reinterpret_cast<const float4*>(a.rec2 + (ray * a.s2 - a.s1) * 48) + rg_q : rg_r1;
             char* ring_base = reinterpret_cast<char*>(smem) + (((size_t)warps_per_block * MARCH_SMEM_FLOATS_PER_SAMPLE * S * 4 + 15) & ~(size_t)15)
                               + (size_t)warp * a.ring * MARCH_RING_GROUP_BYTES;
+#if NFE_MARCH_FULL_WARP
+            // chunk c = lane + 32 j (j = 0..2) of a group's 96 chunks: row c / 12 of the group, 16-byte piece c % 12 of that row
+            rg_r1 -= rg_q; rg_r2 -= rg_q;
+            rg_slot0 = (uint32_t)__cvta_generic_to_shared(ring_base) + (uint32_t)(lane * 16);
+            for (int g = 0; g < a.ring; ++g) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int c = lane + 32 * j, e = 8 * g + c / 12;
+                    if (e < S) cp_async16(rg_slot0 + g * MARCH_RING_GROUP_BYTES + j * 512, (e < a.s1 ? rg_r1 : rg_r2) + e * 12 + c % 12);
+                }
+                cp_async_commit();
+            }
+#else
             rg_slot0 = (uint32_t)__cvta_generic_to_shared(ring_base) + (uint32_t)(rg_half * 192 + rg_q * 16);
             for (int g = 0; g < a.ring; ++g) {
 #pragma unroll
@@ -124,6 +140,7 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
                 }
                 cp_async_commit();
             }
+#endif
         }
         // ---- load (and merge) depths / densities
         if (SORT) {
@@ -206,6 +223,52 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
                 // every lane reads back exactly the 16 bytes it requested itself, so cp.async.wait_group is all the ordering needed
                 for (int k = lane; k < S; k += 32) s_raw[s_order[k]] = s_sigma[k];
                 __syncwarp();
+#if NFE_MARCH_FULL_WARP
+                float4 part[3];
+#pragma unroll
+                for (int j = 0; j < 3; ++j) part[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int n_groups8 = (S + 7) >> 3;
+                int slot8 = 0;
+                for (int g = 0; g < n_groups8; ++g) {
+                    cp_async_wait<NFE_MARCH_RING_GROUPS - 1>();
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int c = lane + 32 * j, e = 8 * g + c / 12;
+                        if (e < S) {
+                            float4 v;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                         : "r"(rg_slot0 + slot8 * MARCH_RING_GROUP_BYTES + j * 512) : "memory");
+                            const float om = s_raw[e];
+                            part[j].x = fmaf(om, v.x, part[j].x); part[j].y = fmaf(om, v.y, part[j].y);
+                            part[j].z = fmaf(om, v.z, part[j].z); part[j].w = fmaf(om, v.w, part[j].w);
+                        }
+                    }
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {   // refill the slot just consumed
+                        const int c = lane + 32 * j, e2 = 8 * (g + a.ring) + c / 12;
+                        if (e2 < S) cp_async16(rg_slot0 + slot8 * MARCH_RING_GROUP_BYTES + j * 512, (e2 < a.s1 ? rg_r1 : rg_r2) + e2 * 12 + c % 12);
+                    }
+                    cp_async_commit();
+                    slot8 = slot8 + 1 == a.ring ? 0 : slot8 + 1;
+                }
+                // (lane, j) holds the partial sums of piece (lane + 32 j) % 12: fold the 96 partials through the (now idle) first ring slot;
+                // lanes 0-11 end up with the totals of piece q = lane, which is what the output code below expects of the lower half-warp
+                cp_async_wait<0>();
+#pragma unroll
+                for (int j = 0; j < 3; ++j)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rg_slot0 + j * 512), "f"(part[j].x), "f"(part[j].y), "f"(part[j].z), "f"(part[j].w) : "memory");
+                __syncwarp();
+                if (lane < 12) {
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        float4 v;
+                        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                                     : "r"(rg_slot0 + r * 192) : "memory");
+                        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+                    }
+                }
+                __syncwarp();
+#else
                 const int n_groups = (S + 2 * NFE_MARCH_GROUP_PAIRS - 1) / (2 * NFE_MARCH_GROUP_PAIRS);
                 int slot = 0;
                 for (int g = 0; g < n_groups; ++g) {
@@ -229,6 +292,7 @@ __global__ void __launch_bounds__(256, NFE_MARCH_MIN_BLOCKS) march_kernel(MarchA
                     cp_async_commit();
                     slot = slot + 1 == a.ring ? 0 : slot + 1;
                 }
+#endif
                 k0 = S;                                        // the register-staged loops below are skipped
             }
             for (; k0 + 2 * UN <= S; k0 += 2 * UN) {
