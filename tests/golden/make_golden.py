@@ -376,7 +376,34 @@ def gold_resize():
     save("resize", **arrays)
 
 
+def gold_losses():
+    """SURVEY.md §8f row f4 — the training-side consumers of the rendered maps, from the reference's own training/loss.py:
+    remap_seg, the segmentation cross-entropy (loss.py:276-277), RGBuvHistBlock and the per-label / whole-image histogram
+    distances (loss.py:57-157).  Inputs come back from the seeds; outputs are stored (the histograms as a strided subset)."""
+    from training.loss import RGBuvHistBlock, compute_seg_hist_dist, compute_whole_hist_dist, remap_seg
+    b, res = 3, 32
+    img = torch.tanh(T(synth.hash_normal(701, (b, 3, res, res))))                  # image_raw in (-1, 1)
+    seg = T(synth.hash_normal(702, (b, 15, res, res))) * 2.0                        # image_seg logits
+    seg[:, 13] += 0.8 * torch.linspace(-1, 1, res)[None, :, None]                   # hair at the top, skin in the middle: uneven masks,
+    seg[:, 1] += 1.5
+    seg[1, 2] -= 100.0                                                              # label 2 is empty in item 1 (zero histogram)
+    seg[0, 8] -= 100.0                                                              # label 8 is empty in the target item
+    labels19 = (T(synth.hash_normal(703, (b, 1, res, res))).abs() * 6.5).long().clamp(0, 18)
+    hist = RGBuvHistBlock()
+    with torch.no_grad():
+        h_whole = hist(img.reshape(b, 3, -1))
+        ce = torch.nn.CrossEntropyLoss()(seg, remap_seg(labels19.clone()).squeeze(1))
+        save("losses", cfg=np.array([b, res, 701, 702, 703]), labels19=labels19.numpy().astype(np.int8),
+             remapped=remap_seg(labels19.clone()).numpy().astype(np.int8), cross_entropy=ce,
+             hist_whole=h_whole[:, :, ::2, ::2].contiguous(), hist_whole_sums=h_whole.sum(dim=(2, 3)),
+             whole_hist_dist=compute_whole_hist_dist(hist, img), seg_hist_dist=compute_seg_hist_dist(hist, img, seg),
+             argmax_counts=torch.stack([(seg.argmax(1) == i).sum(dim=(1, 2)) for i in range(15)], dim=1))
+
+
 if __name__ == "__main__":
+    if "--only-losses" in sys.argv:
+        gold_losses()
+        sys.exit(0)
     if "--only-resize" in sys.argv:
         gold_resize()
         sys.exit(0)
@@ -397,6 +424,7 @@ if __name__ == "__main__":
     gold_video_sweep()
     gold_backward()
     gold_resize()
+    gold_losses()
     import platform
     with open(os.path.join(HERE, "PROVENANCE.txt"), "w") as f:
         f.write(f"generated by tests/golden/make_golden.py from the reference at {REF}\n"
