@@ -123,6 +123,16 @@ _CL_CACHE = {}
 _CL_CACHE_MAX = 2
 
 
+def _version_of(t):
+    """Version counter of a tensor, the staleness check of the registries below.  Tensors created under torch.inference_mode()
+    do not track one (RuntimeError): they get a fresh object, which never compares equal, so every lookup misses and nothing is
+    registered for them — the renderer then stages and gathers both plane sets itself (correct, just not the fast path)."""
+    try:
+        return t._version
+    except RuntimeError:
+        return object()
+
+
 def planes_channel_last(planes, cache=False):
     """[N,3,C,H,W] (reference layout) -> channel-last [N,3,H,W,C] staging buffer for the gather.
     With cache=True (rendering_options['nfe_cache_planes']) the staged copy is kept, keyed on
@@ -131,7 +141,7 @@ def planes_channel_last(planes, cache=False):
     x = _cuda_f32(planes, "planes")
     if x.dim() != 5 or x.shape[1] != 3:
         raise RuntimeError(f"planes: expected [N,3,C,H,W], got {tuple(x.shape)}")
-    key = (x.data_ptr(), tuple(x.shape), x._version, x.device.index)
+    key = (x.data_ptr(), tuple(x.shape), _version_of(x), x.device.index)
     if key in _CL_CACHE:      # staged by plane_normalize_staged, or kept from an earlier call with cache=True
         return _CL_CACHE[key][1]
     n, p, c, h, w = x.shape
@@ -157,10 +167,12 @@ def _key5(t):
         shape5 = (n, 3, c // 3, h, w)
     else:
         shape5 = tuple(t.shape)
-    return (t.data_ptr(), shape5, t._version, t.device.index)
+    return (t.data_ptr(), shape5, _version_of(t), t.device.index)
 
 
 def _provenance_put(denorm, norm_key, scale, shift):
+    if not isinstance(norm_key[2], int) or not isinstance(_version_of(denorm), int):
+        return                                  # inference tensors: no version counter, nothing to key on
     while len(_PROVENANCE) >= _PROVENANCE_MAX:
         _PROVENANCE.pop(next(iter(_PROVENANCE)))
     _PROVENANCE[_key5(denorm)] = (norm_key, scale.reshape(scale.shape[0], -1).contiguous(), shift.reshape(shift.shape[0], -1).contiguous(), denorm)
@@ -196,6 +208,8 @@ def provenance_sources(norm_planes, denorm_planes):
 
 
 def _cache_put(key, src, staged):
+    if not isinstance(key[2], int):
+        return
     while len(_CL_CACHE) >= _CL_CACHE_MAX:
         _CL_CACHE.pop(next(iter(_CL_CACHE)))
     _CL_CACHE[key] = (src, staged)

@@ -109,6 +109,27 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert r.returncode == 0 and r.stdout.strip() == ""
 
 
+def test_plane_registries_key_on_version_and_tolerate_inference_tensors():
+    """The staging / provenance registries key on (address, shape, version): a 4-D tensor and its 5-D view share a key, an
+    in-place write invalidates it, and tensors made under torch.inference_mode() (no version counter) simply never hit."""
+    from nerffaceediting_b200 import ops
+    norm, raw = torch.randn(2, 96, 4, 4), torch.randn(2, 96, 4, 4)
+    assert ops._key5(norm) == ops._key5(norm.view(2, 3, 32, 4, 4))
+    ops._provenance_put(raw, ops._key5(norm), torch.ones(2, 96), torch.zeros(2, 96))
+    hit = ops.provenance(norm.view(2, 3, 32, 4, 4), raw.view(2, 3, 32, 4, 4))
+    assert hit is not None and hit[0].shape == (2, 96)
+    raw.add_(1.0)                                               # stale: the version moved on
+    assert ops.provenance(norm, raw) is None
+    with torch.inference_mode():
+        n2, r2 = torch.randn(1, 96, 4, 4), torch.randn(1, 96, 4, 4)
+        before = len(ops._PROVENANCE)
+        ops._provenance_put(r2, ops._key5(n2), torch.ones(1, 96), torch.zeros(1, 96))
+        assert len(ops._PROVENANCE) == before and ops.provenance(n2, r2) is None
+        ops._cache_put(ops._key5(n2), n2, n2)
+        assert ops._key5(n2) not in ops._CL_CACHE
+    ops._PROVENANCE.clear()
+
+
 def test_missing_library_fails_loudly(monkeypatch):
     monkeypatch.setattr(_lib, "_lib", None)
     monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libnfe_b200.so")
