@@ -108,7 +108,7 @@ class ClockSampler:
 
 
 def make_inputs(torch, wl, device, seed):
-    from nerffaceediting_b200 import synth
+    import synth_inputs as synth
     from nerffaceediting_b200.triplane import DisentangledOSGDecoder
     g = torch.Generator(device="cpu").manual_seed(seed)
     n = wl["batch"]
@@ -137,7 +137,7 @@ def hot_path_step(torch, mods, raw, dec, c2w, k, res, opts):
 def cpu_reference_rate(torch, wl, steps, warmup, threads=None):
     """rays/s of the CPU restatement of the reference path (oracle/), one batch item per step."""
     import numpy as np
-    from nerffaceediting_b200 import synth
+    import synth_inputs as synth
     from oracle import nfe_oracle as orc
     threads = threads or os.cpu_count() or 1
     os.environ["OMP_NUM_THREADS"] = str(threads)

@@ -251,6 +251,16 @@ int nfe_field_bwd(int kind, const float* planes_norm_cl, const float* planes_cl,
                   float* g_w1_b, float* g_b1_b, float* g_w2_b, float* g_b2_b, const float* affine_scale,
                   const float* affine_shift, int affine_items, float* g_affine_scale, float* g_affine_shift,
                   nfe_stream_t stream);
+/* Backward of run_model (renderer.py:259-287 differentiated; the density regulariser of training/loss.py:310-331 back-propagates
+ * through G.sample_mixed -> run_model): nfe_field_bwd at explicit points.  coords [n,m,3]; rec / g_rec [n*m,48] are the forward's
+ * outputs and their gradients packed as records {sigma, seg[15], rgb[32]} (only rec's rgb part is read; absent gradients are
+ * zeros).  Everything else as nfe_field_bwd.  Sample coordinates carry no gradient. */
+int nfe_run_model_bwd(int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width,
+                      float box_warp, const float* coords, int n, int64_t m, const nfe_mlp* net_a, const nfe_mlp* net_b,
+                      const float* rec, const float* g_rec, float* g_planes_norm_cl, float* g_planes_cl, float* g_w1_a,
+                      float* g_b1_a, float* g_w2_a, float* g_b2_a, float* g_w1_b, float* g_b1_b, float* g_w2_b, float* g_b2_b,
+                      const float* affine_scale, const float* affine_shift, int affine_items, float* g_affine_scale,
+                      float* g_affine_shift, nfe_stream_t stream);
 /* channel-last [n_img, hw, 32] -> reference layout [n_img, 32, hw] (plane gradients back to [N,3,32,H,W]) */
 int nfe_planes_from_channel_last(const float* planes_cl, int64_t n_img, int channels, int64_t hw, float* out,
                                  nfe_stream_t stream);

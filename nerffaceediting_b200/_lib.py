@@ -69,6 +69,8 @@ SIGNATURES = {
     "nfe_planes_from_channel_last": (c_int, [c_vp, c_i64, c_int, c_i64, c_vp, c_vp]),
     "nfe_field_bwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_float, c_vp, c_vp, c_vp, c_int, c_i64, c_int, _MLP_P, _MLP_P, c_vp, c_vp,
                               c_vp, c_vp] + [c_vp] * 8 + [c_vp, c_vp, c_int, c_vp, c_vp] + [c_vp]),
+    "nfe_run_model_bwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_float, c_vp, c_int, c_i64, _MLP_P, _MLP_P, c_vp, c_vp,
+                                  c_vp, c_vp] + [c_vp] * 8 + [c_vp, c_vp, c_int, c_vp, c_vp] + [c_vp]),
     "nfe_plane_normalize_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "nfe_resize_bilinear": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "nfe_finish_depth": (c_int, [c_vp, c_i64, c_vp, c_vp]),

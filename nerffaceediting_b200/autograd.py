@@ -43,6 +43,125 @@ def _decode(kind, seq_a, seq_b, fn, fd):
     return x[:, :1], (_mlp(fd, seq_b) if kind == ops.DEC_SEGMENTATION else None), rgb
 
 
+def _decoder_params(seq_a, seq_b):
+    return [p for seq in (seq_a, seq_b) if seq is not None for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
+
+
+class _FieldBackward:
+    """Backward of gather + decoder for one or more passes of samples, accumulated into one set of gradient buffers:
+    channel-last plane gradients, decoder-parameter gradients and (single-gather identity) the statistics gradients.
+    Samples are either rays x depths (renderer forward) or explicit points (run_model)."""
+
+    def __init__(self, kind, seq_a, seq_b, norm_cl, denorm_cl, affine, box_warp, needs_param_grad, dev):
+        self.kind, self.seq_a, self.seq_b = kind, seq_a, seq_b
+        self.norm_cl, self.denorm_cl, self.affine, self.box_warp, self.dev = norm_cl, denorm_cl, affine, box_warp, dev
+        self.params = _decoder_params(seq_a, seq_b)
+        self.live = [i for i, need in enumerate(needs_param_grad) if need]
+        self.g_params = [torch.zeros_like(p) if i in self.live else None for i, p in enumerate(self.params)]
+        any_cl = denorm_cl if denorm_cl is not None else norm_cl
+        self.pb, _, self.h, self.w, _ = any_cl.shape
+        self.g_denorm_cl = torch.zeros_like(denorm_cl) if denorm_cl is not None else None
+        self.g_norm_cl = torch.zeros_like(norm_cl) if norm_cl is not None else None
+        self.g_scale = self.g_shift = None
+        if affine is not None:
+            self.g_scale, self.g_shift = torch.zeros_like(affine[0]), torch.zeros_like(affine[1])
+        # one tcgen05 kernel per pass (csrc/nfe_field_bwd.cu) for the disentangled decoder; the other two decoders (and
+        # NFE_BWD_LIBRARY_GEMM=1 as a cross-check) run the MLP backward on library GEMMs between two gather kernels
+        self.fused = kind == ops.DEC_DISENTANGLED and (affine is not None or os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1")
+        if self.fused:
+            self.full = [g if g is not None else torch.zeros_like(p) for g, p in zip(self.g_params, self.params)]
+
+    def run_pass(self, n, rec, g_rec, rays=None, coords=None):
+        """rays = (origins [n,r,3], dirs [n,r,3], depths [n,r,s]) or coords [n,m,3]; rec / g_rec [n*m, 48]."""
+        lib, P = _lib.load(), ops._ptr
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        kind, affine = self.kind, self.affine
+        if self.fused:
+            mlp_a, mlp_b = ops.MlpRef(self.seq_a, self.dev), ops.MlpRef(self.seq_b, self.dev)
+            tail = (mlp_a.ref(), mlp_b.ref(), P(rec), P(g_rec), P(self.g_norm_cl), P(self.g_denorm_cl), *[P(t) for t in self.full],
+                    P(affine[0]) if affine else None, P(affine[1]) if affine else None, affine[0].shape[0] if affine else 0,
+                    P(self.g_scale), P(self.g_shift), stream)
+            if coords is not None:
+                _lib.check(lib.nfe_run_model_bwd(kind, P(self.norm_cl), P(self.denorm_cl), self.pb, self.h, self.w, ctypes.c_float(self.box_warp),
+                                                 P(coords), n, coords.shape[1], *tail), "nfe_run_model_bwd")
+            else:
+                o, d, depths = rays
+                _lib.check(lib.nfe_field_bwd(kind, P(self.norm_cl), P(self.denorm_cl), self.pb, self.h, self.w, ctypes.c_float(self.box_warp),
+                                             P(o), P(d), P(depths), n, o.shape[1], depths.shape[2], *tail), "nfe_field_bwd")
+            return
+        if coords is not None:
+            # explicit points as degenerate rays: origin = point, direction = 0, depth = 0 (o + 0*0 = o exactly)
+            o = coords
+            d = torch.zeros_like(coords)
+            depths = torch.zeros(coords.shape[:2] + (1,), device=self.dev)
+        else:
+            o, d, depths = rays
+        r, s_ = o.shape[1], depths.shape[2]
+        total = n * r * s_
+        geom = (self.pb, self.h, self.w, ctypes.c_float(self.box_warp), P(o), P(d), P(depths), n, r, s_)
+        # decoder inputs
+        fd = torch.empty((total, 32), device=self.dev)
+        _lib.check(lib.nfe_feature_mean_fwd(P(self.denorm_cl), *geom, P(fd), stream), "nfe_feature_mean_fwd")
+        fn = None
+        if self.norm_cl is not None:
+            fn = torch.empty((total, 32), device=self.dev)
+            _lib.check(lib.nfe_feature_mean_fwd(P(self.norm_cl), *geom, P(fn), stream), "nfe_feature_mean_fwd")
+        g_flat = g_rec.reshape(total, 48)
+        g_fd = torch.empty_like(fd)
+        g_fn = torch.empty_like(fn) if fn is not None else None
+        # decoder backward on library GEMMs, in row chunks
+        for lo in range(0, total, MAX_ROWS):
+            hi = min(total, lo + MAX_ROWS)
+            with torch.enable_grad():
+                xd = fd[lo:hi].detach().requires_grad_(True)
+                xn = fn[lo:hi].detach().requires_grad_(True) if fn is not None else None
+                sigma, seg, rgb = _decode(kind, self.seq_a, self.seq_b, xn, xd)
+                outs, gouts = [sigma, rgb], [g_flat[lo:hi, :1], g_flat[lo:hi, 16:48]]
+                if seg is not None:
+                    outs.append(seg)
+                    gouts.append(g_flat[lo:hi, 1:16])
+                inputs = [xd] + ([xn] if xn is not None else []) + [self.params[i] for i in self.live]
+                res = torch.autograd.grad(outs, inputs, gouts, allow_unused=True)
+            g_fd[lo:hi] = res[0]
+            k = 1
+            if xn is not None:
+                g_fn[lo:hi] = res[1] if res[1] is not None else 0
+                k = 2
+            for i, g in zip(self.live, res[k:]):
+                if g is not None:
+                    self.g_params[i] += g
+        # gather backward
+        _lib.check(lib.nfe_feature_mean_bwd(P(g_fd), *geom, P(self.g_denorm_cl), stream), "nfe_feature_mean_bwd")
+        if g_fn is not None:
+            _lib.check(lib.nfe_feature_mean_bwd(P(g_fn), *geom, P(self.g_norm_cl), stream), "nfe_feature_mean_bwd")
+
+    def finish(self, norm_shape, plane_shape, need_norm, need_planes, stat_shapes, need_scale, need_shift):
+        """(g_norm, g_planes, g_scale, g_shift, g_params) in the reference layouts."""
+        lib, P = _lib.load(), ops._ptr
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        if self.fused:
+            self.g_params = [self.full[i] if i in self.live else None for i in range(len(self.params))]
+
+        def to_ref(g_cl, shape):
+            out = torch.empty(shape, device=self.dev)
+            _lib.check(lib.nfe_planes_from_channel_last(P(g_cl), g_cl.shape[0] * 3, 32, self.h * self.w, P(out), stream), "nfe_planes_from_channel_last")
+            return out
+        g_planes = to_ref(self.g_denorm_cl, plane_shape) if (self.g_denorm_cl is not None and need_planes) else None
+        g_norm = to_ref(self.g_norm_cl, norm_shape) if (self.g_norm_cl is not None and need_norm) else None
+        g_scale = g_shift = None
+        if self.affine is not None:
+            g_scale = self.g_scale.reshape(stat_shapes[0]) if need_scale else None
+            g_shift = self.g_shift.reshape(stat_shapes[1]) if need_shift else None
+        return g_norm, g_planes, g_scale, g_shift, self.g_params
+
+
+def _affine_of(scale_src, shift_src, eps):
+    if scale_src is None:
+        return None
+    k = scale_src.numel() // 96
+    return ((scale_src.detach().reshape(k, 96).float() + eps).contiguous(), shift_src.detach().reshape(k, 96).float().contiguous())
+
+
 class RenderFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, state, norm_planes, planes, scale_src, shift_src, *params):
@@ -51,10 +170,7 @@ class RenderFunction(torch.autograd.Function):
         scale_src / shift_src (or None): statistics with planes == norm_planes*(scale_src + affine_eps) + shift_src per
         (item, channel) — the single-gather identity: `planes` is then never read and its gradient flows through them."""
         kind = state["kind"]
-        affine = None
-        if scale_src is not None:
-            k = scale_src.numel() // 96
-            affine = ((scale_src.detach().reshape(k, 96).float() + state["affine_eps"]).contiguous(), shift_src.detach().reshape(k, 96).float().contiguous())
+        affine = _affine_of(scale_src, shift_src, state.get("affine_eps", 0.0))
         denorm_cl = ops.planes_channel_last(planes) if affine is None else None
         norm_cl = ops.planes_channel_last(norm_planes) if kind == ops.DEC_DISENTANGLED else None
         cfg = ops.make_cfg(kind, norm_cl if denorm_cl is None else denorm_cl, affine=affine, **state["cfg"])
@@ -102,101 +218,94 @@ class RenderFunction(torch.autograd.Function):
             _lib.check(lib.nfe_composite_bwd(P(dc), P(st["sigma_c"]), P(st["rec_c"]), s_c, P(df), P(st.get("sigma_f")), P(st.get("rec_f")), s_f,
                                              n * r, cfg.seg_dim, cfg.white_back, P(g_rgb), P(g_seg), P(g_depth), P(g_wsum), P(minmax),
                                              P(g_rec_c), P(g_rec_f), stream), "nfe_composite_bwd")
-            params = [p for seq in (seq_a, seq_b) if seq is not None for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
-            live = [i for i, p in enumerate(params) if ctx.needs_input_grad[5 + i]]
-            g_params = [torch.zeros_like(p) if i in live else None for i, p in enumerate(params)]
-            affine = ctx.affine
-            any_cl = denorm_cl if denorm_cl is not None else norm_cl
-            pb, _, h, w, _ = any_cl.shape
-            g_denorm_cl = torch.zeros_like(denorm_cl) if denorm_cl is not None else None
-            g_norm_cl = torch.zeros_like(norm_cl) if norm_cl is not None else None
-            g_scale = g_shift = None
-            if affine is not None:
-                g_scale, g_shift = torch.zeros_like(affine[0]), torch.zeros_like(affine[1])
-            fused = kind == ops.DEC_DISENTANGLED and (affine is not None or os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1")
-            if fused:
-                # 2-4 fused: one tcgen05 kernel per pass recomputes features and activations, back-propagates both
-                # decoder nets, scatter-adds into the plane gradients and accumulates the parameter gradients
-                mlp_a, mlp_b = ops.MlpRef(seq_a, dev), ops.MlpRef(seq_b, dev)
-                full = [g if g is not None else torch.zeros_like(p) for g, p in zip(g_params, params)]
-                for depths, s, rec, g_rec in ((dc, s_c, st["rec_c"], g_rec_c), (df, s_f, st.get("rec_f"), g_rec_f)):
-                    if not s:
-                        continue
-                    _lib.check(lib.nfe_field_bwd(kind, P(norm_cl), P(denorm_cl), pb, h, w, ctypes.c_float(cfg.box_warp), P(o), P(d), P(depths), n, r, s,
-                                                 mlp_a.ref(), mlp_b.ref(), P(rec), P(g_rec), P(g_norm_cl), P(g_denorm_cl),
-                                                 *[P(t) for t in full], P(affine[0]) if affine else None, P(affine[1]) if affine else None,
-                                                 affine[0].shape[0] if affine else 0, P(g_scale), P(g_shift), stream), "nfe_field_bwd")
-            for depths, s, g_rec in ((dc, s_c, g_rec_c), (df, s_f, g_rec_f)):
-                if not s or fused:
-                    continue
-                total = n * r * s
-                geom = (pb, h, w, ctypes.c_float(cfg.box_warp), P(o), P(d), P(depths), n, r, s)
-                # 2. decoder inputs
-                fd = torch.empty((total, 32), device=dev)
-                _lib.check(lib.nfe_feature_mean_fwd(P(denorm_cl), *geom, P(fd), stream), "nfe_feature_mean_fwd")
-                fn = None
-                if norm_cl is not None:
-                    fn = torch.empty((total, 32), device=dev)
-                    _lib.check(lib.nfe_feature_mean_fwd(P(norm_cl), *geom, P(fn), stream), "nfe_feature_mean_fwd")
-                g_flat = g_rec.reshape(total, 48)
-                g_fd = torch.empty_like(fd)
-                g_fn = torch.empty_like(fn) if fn is not None else None
-                # 3. decoder backward on library GEMMs, in row chunks
-                for lo in range(0, total, MAX_ROWS):
-                    hi = min(total, lo + MAX_ROWS)
-                    with torch.enable_grad():
-                        xd = fd[lo:hi].detach().requires_grad_(True)
-                        xn = fn[lo:hi].detach().requires_grad_(True) if fn is not None else None
-                        sigma, seg, rgb = _decode(kind, seq_a, seq_b, xn, xd)
-                        outs, gouts = [sigma, rgb], [g_flat[lo:hi, :1], g_flat[lo:hi, 16:48]]
-                        if seg is not None:
-                            outs.append(seg)
-                            gouts.append(g_flat[lo:hi, 1:16])
-                        inputs = [xd] + ([xn] if xn is not None else []) + [params[i] for i in live]
-                        res = torch.autograd.grad(outs, inputs, gouts, allow_unused=True)
-                    g_fd[lo:hi] = res[0]
-                    k = 1
-                    if xn is not None:
-                        g_fn[lo:hi] = res[1]
-                        k = 2
-                    for i, g in zip(live, res[k:]):
-                        if g is not None:
-                            g_params[i] += g
-                # 4. gather backward
-                _lib.check(lib.nfe_feature_mean_bwd(P(g_fd), *geom, P(g_denorm_cl), stream), "nfe_feature_mean_bwd")
-                if g_fn is not None:
-                    _lib.check(lib.nfe_feature_mean_bwd(P(g_fn), *geom, P(g_norm_cl), stream), "nfe_feature_mean_bwd")
+            # 2-4. gather + decoder backward of both passes
+            fb = _FieldBackward(kind, seq_a, seq_b, norm_cl, denorm_cl, ctx.affine, cfg.box_warp, ctx.needs_input_grad[5:], dev)
+            for depths, s, rec, g_rec in ((dc, s_c, st["rec_c"], g_rec_c), (df, s_f, st.get("rec_f"), g_rec_f)):
+                if s:
+                    fb.run_pass(n, rec, g_rec, rays=(o, d, depths))
             # 5. back to the reference layout
-
-            def to_ref(g_cl, shape):
-                out = torch.empty(shape, device=dev)
-                _lib.check(lib.nfe_planes_from_channel_last(P(g_cl), g_cl.shape[0] * 3, 32, h * w, P(out), stream), "nfe_planes_from_channel_last")
-                return out
             norm_shape, plane_shape = ctx.plane_shapes
-            g_planes = to_ref(g_denorm_cl, plane_shape) if (g_denorm_cl is not None and ctx.needs_input_grad[2]) else None
-            g_norm = to_ref(g_norm_cl, norm_shape) if (g_norm_cl is not None and ctx.needs_input_grad[1]) else None
-            if affine is not None:
-                g_scale = g_scale.reshape(ctx.stat_shapes[0]) if ctx.needs_input_grad[3] else None
-                g_shift = g_shift.reshape(ctx.stat_shapes[1]) if ctx.needs_input_grad[4] else None
+            stat = ctx.stat_shapes
+            g_norm, g_planes, g_scale, g_shift, g_params = fb.finish(norm_shape, plane_shape, ctx.needs_input_grad[1], ctx.needs_input_grad[2], stat,
+                                                                     ctx.needs_input_grad[3], ctx.needs_input_grad[4])
+        return (None, g_norm, g_planes, g_scale, g_shift) + tuple(g_params)
+
+
+class RunModelFunction(torch.autograd.Function):
+    """Differentiable run_model (renderer.py:142-148,259-287): the reference's density regulariser back-propagates through
+    G.sample_mixed(...)['sigma'] (training/loss.py:310-331, training/triplane.py:150-157).  Gradients reach the plane tensors (or
+    the statistics, under the single-gather identity) and the decoder parameters; the sample coordinates carry none."""
+
+    @staticmethod
+    def forward(ctx, state, norm_planes, planes, scale_src, shift_src, *params):
+        kind = state["kind"]
+        coords = state["coords"]
+        sigma_only = state["sigma_only"]
+        affine = _affine_of(scale_src, shift_src, state.get("affine_eps", 0.0))
+        geo_only = sigma_only and kind == ops.DEC_DISENTANGLED and state["cfg"]["precision"] != ops.PRECISIONS['fp32']
+        norm_cl = ops.planes_channel_last(norm_planes) if kind == ops.DEC_DISENTANGLED else None
+        denorm_cl = ops.planes_channel_last(planes) if affine is None else None
+        cfg = ops.make_cfg(kind, norm_cl if denorm_cl is None else denorm_cl, 2, 0, affine=affine, **state["cfg"])
+        out = ops.run_model_fwd(cfg, state["seq_a"], state["seq_b"], norm_cl, None if (geo_only and affine is not None) else denorm_cl, coords,
+                                sigma_only=sigma_only)
+        ctx.state, ctx.affine, ctx.box_warp = state, affine, cfg.box_warp
+        ctx.stat_shapes = None if scale_src is None else (scale_src.shape, shift_src.shape)
+        ctx.saved = (norm_cl, denorm_cl, None if sigma_only else out["rgb"])
+        ctx.plane_shapes = (None if norm_planes is None else norm_planes.shape, planes.shape)
+        ctx.keys = ("sigma",) if sigma_only else tuple(k for k in ("rgb", "sigma", "seg") if k in out)
+        return tuple(out[k] for k in ctx.keys)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        state = ctx.state
+        kind, seq_a, seq_b, coords = state["kind"], state["seq_a"], state["seq_b"], state["coords"]
+        norm_cl, denorm_cl, rgb = ctx.saved
+        n, m, _ = coords.shape
+        dev = coords.device
+        g = dict(zip(ctx.keys, grads))
+        # records {sigma, seg[15], rgb[32]} of the forward (only the colours are read: sigmoid derivative) and of the gradients
+        rec = torch.zeros((n * m, 48), device=dev)
+        g_rec = torch.zeros((n * m, 48), device=dev)
+        if rgb is not None:
+            rec[:, 16:48] = rgb.reshape(n * m, 32)
+        if g.get("sigma") is not None:
+            g_rec[:, 0:1] = g["sigma"].reshape(n * m, 1)
+        if g.get("seg") is not None:
+            g_rec[:, 1:16] = g["seg"].reshape(n * m, 15)
+        if g.get("rgb") is not None:
+            g_rec[:, 16:48] = g["rgb"].reshape(n * m, 32)
+        with torch.cuda.device(dev):
+            fb = _FieldBackward(kind, seq_a, seq_b, norm_cl, denorm_cl, ctx.affine, ctx.box_warp, ctx.needs_input_grad[5:], dev)
+            fb.run_pass(n, rec, g_rec, coords=coords)
+            norm_shape, plane_shape = ctx.plane_shapes
+            g_norm, g_planes, g_scale, g_shift, g_params = fb.finish(norm_shape, plane_shape, ctx.needs_input_grad[1], ctx.needs_input_grad[2],
+                                                                     ctx.stat_shapes, ctx.needs_input_grad[3], ctx.needs_input_grad[4])
         return (None, g_norm, g_planes, g_scale, g_shift) + tuple(g_params)
 
 
 class NormalizeFunction(torch.autograd.Function):
-    """normalize_plane with its analytic backward (triplane.py:56-65): n = (x - mean) / (std + 1e-8)."""
+    """normalize_plane with its analytic backward (triplane.py:56-65): n = (x - mean) / (std + 1e-8).
+    Returns (norm, mean, std, norm_cl): norm_cl is the channel-last staging written by the same kernel (None for tensors
+    that are not [N,96,H,W] tri-planes); triplane.normalize_plane registers it against the tensors the caller sees."""
 
     @staticmethod
     def forward(ctx, planes):
         mean, std = ops.plane_stats(planes)
+        norm_cl = None
         if planes.dim() == 4 and planes.shape[1] == 96 and planes.is_contiguous() and planes.dtype == torch.float32:
-            norm = ops.plane_normalize_staged(planes.detach(), mean, std)      # the raw set is staged on demand (single-gather identity: never)
+            # the raw set is staged on demand (single-gather identity: never)
+            norm, norm_cl, _ = ops.plane_normalize_staged(planes.detach(), mean, std, register=False)
         else:
             norm = ops.plane_normalize(planes, mean, std)
         ctx.save_for_backward(norm, std)
         ctx.hw = planes.shape[-1] * planes.shape[-2]
-        return norm, mean, std
+        if norm_cl is None:
+            return norm, mean, std, None
+        ctx.mark_non_differentiable(norm_cl)
+        return norm, mean, std, norm_cl
 
     @staticmethod
-    def backward(ctx, g_norm, g_mean, g_std):
+    def backward(ctx, g_norm, g_mean, g_std, _g_cl=None):
         norm, std = ctx.saved_tensors
         # d n_j / d x_i = (delta_ij - 1/N)/d - n_j * n_i * d / ((N-1) * std * d)   (std is the unbiased one), i.e.
         #   gx = (g - mean(g))/d - norm*sum(g*norm)/((N-1)*std) + g_mean/N + g_std*norm*d/((N-1)*std)
@@ -222,7 +331,7 @@ class DenormalizeFunction(torch.autograd.Function):
     def forward(ctx, planes, mean, std):
         ctx.save_for_backward(planes, std)
         ctx.stat_shape = mean.shape
-        return ops.plane_denormalize(planes, mean, std)
+        return ops.plane_denormalize(planes, mean, std, register=False)
 
     @staticmethod
     def backward(ctx, g):

@@ -359,7 +359,12 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     if ((int64_t)n * m == 0) return 0;
     const bool sigma_only = cfg->sigma_only != 0;
     const bool geo_only = sigma_only && cfg->kind == NFE_DEC_DISENTANGLED && cfg->precision != NFE_PREC_FP32;
-    NFE_REQUIRE((planes_denorm_cl || geo_only) && coords && sigma && (rgb || sigma_only), "nfe_run_model_fwd: null pointer");
+    // single-gather identity (cfg->affine_*): the de-normalised planes are norm*scale + shift and are not read
+    const bool affine = cfg->affine_scale && cfg->affine_shift && cfg->kind == NFE_DEC_DISENTANGLED && cfg->precision != NFE_PREC_FP32 &&
+                        getenv("NFE_TC_SIMPLE") == nullptr;
+    NFE_REQUIRE(!cfg->affine_scale || cfg->affine_items == 1 || cfg->affine_items == n, "nfe_run_model_fwd: affine statistics for %d items, batch is %d",
+                cfg->affine_items, n);
+    NFE_REQUIRE((planes_denorm_cl || geo_only || affine) && coords && sigma && (rgb || sigma_only), "nfe_run_model_fwd: null pointer");
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_run_model_fwd: the disentangled decoder needs the normalised planes");
     NFE_REQUIRE(cfg->kind == NFE_DEC_OSG || seg || sigma_only, "nfe_run_model_fwd: seg output missing");
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_run_model_fwd: plane batch %d does not match point batch %d", plane_batch, n);
@@ -367,6 +372,7 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     FieldArgs a = {};
     a.set_norm = planes_norm_cl; a.set_denorm = planes_denorm_cl; a.plane_batch = plane_batch; a.H = cfg->height; a.W = cfg->width;
     a.scale = (float)(2.0 / (double)cfg->box_warp);
+    if (affine) { a.affine_scale = cfg->affine_scale; a.affine_shift = cfg->affine_shift; a.affine_items = cfg->affine_items; }
     a.coords = coords; a.m = m; a.total = (int64_t)n * m; a.s_per_ray = 1;
     a.sigma = sigma; a.rgb = rgb; a.seg = seg;
     a.density_noise = cfg->density_noise; a.seed = cfg->seed; a.offset = cfg->offset;

@@ -68,6 +68,7 @@ struct Args {
     float* g_norm; float* g_raw;                      // channel-last plane gradients (zero-initialised by the caller)
     int plane_batch, H, W; float scale;
     const float* origins; const float* dirs; const float* depths;
+    const float* coords;                              // explicit sample positions [total,3] (run_model); rays are unused then
     int s_per_ray; int64_t m, total;
     const float* rec;                                 // forward records [total,48] (rgb for the sigmoid derivative)
     const float* g_rec;                               // d loss / d record [total,48]
@@ -243,11 +244,17 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
             for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
             int item = 0;
             if (idx < a.total) {
-                const int64_t ray = idx / a.s_per_ray;
-                const float t = __ldg(a.depths + idx);
-                const float* o = a.origins + ray * 3;
-                const float* d = a.dirs + ray * 3;
-                const float x = ray_point(__ldg(o), t, __ldg(d)), y = ray_point(__ldg(o + 1), t, __ldg(d + 1)), z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
+                float x, y, z;
+                if (a.coords) {
+                    const float* c = a.coords + idx * 3;
+                    x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
+                } else {
+                    const int64_t ray = idx / a.s_per_ray;
+                    const float t = __ldg(a.depths + idx);
+                    const float* o = a.origins + ray * 3;
+                    const float* d = a.dirs + ray * 3;
+                    x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
+                }
                 ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
                 item = (int)(idx / a.m);
                 const int item_off = a.plane_batch == 1 ? 0 : (int)(item * set_stride4);
@@ -596,33 +603,35 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
 
 using namespace nfe;
 
-NFE_EXPORT int nfe_field_bwd(int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width, float box_warp,
-                             const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays, int s_per_ray,
-                             const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec, const float* g_rec, float* g_planes_norm_cl,
-                             float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a, float* g_b2_a, float* g_w1_b, float* g_b1_b,
-                             float* g_w2_b, float* g_b2_b, const float* affine_scale, const float* affine_shift, int affine_items,
-                             float* g_affine_scale, float* g_affine_shift, nfe_stream_t stream)
+// shared by nfe_field_bwd (samples along rays) and nfe_run_model_bwd (explicit points: coords != NULL, s_per_ray = 1)
+static int field_bwd_launch(const char* who, int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width,
+                            float box_warp, const float* origins, const float* dirs, const float* depths, const float* coords, int n,
+                            int64_t n_rays, int s_per_ray, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec, const float* g_rec,
+                            float* g_planes_norm_cl, float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a, float* g_b2_a, float* g_w1_b,
+                            float* g_b1_b, float* g_w2_b, float* g_b2_b, const float* affine_scale, const float* affine_shift, int affine_items,
+                            float* g_affine_scale, float* g_affine_shift, nfe_stream_t stream)
 {
     const int64_t total = (int64_t)n * n_rays * s_per_ray;
     if (total == 0) return 0;
     const bool affine = affine_scale != nullptr;
-    NFE_REQUIRE(kind == NFE_DEC_DISENTANGLED, "nfe_field_bwd: only the DisentangledOSGDecoder has a fused backward (kind %d)", kind);
-    NFE_REQUIRE(planes_norm_cl && origins && dirs && depths && net_a && net_b && rec && g_rec && g_planes_norm_cl, "nfe_field_bwd: null pointer");
+    NFE_REQUIRE(kind == NFE_DEC_DISENTANGLED, "%s: only the DisentangledOSGDecoder has a fused backward (kind %d)", who, kind);
+    NFE_REQUIRE(planes_norm_cl && (coords || (origins && dirs && depths)) && net_a && net_b && rec && g_rec && g_planes_norm_cl, "%s: null pointer", who);
     if (affine) {
-        NFE_REQUIRE(affine_shift && g_affine_scale && g_affine_shift, "nfe_field_bwd: the single-gather backward needs shift and both statistics gradients");
-        NFE_REQUIRE(affine_items == n || affine_items == 1, "nfe_field_bwd: %d statistics rows for a batch of %d", affine_items, n);
+        NFE_REQUIRE(affine_shift && g_affine_scale && g_affine_shift, "%s: the single-gather backward needs shift and both statistics gradients", who);
+        NFE_REQUIRE(affine_items == n || affine_items == 1, "%s: %d statistics rows for a batch of %d", who, affine_items, n);
     } else {
-        NFE_REQUIRE(planes_cl && g_planes_cl, "nfe_field_bwd: null raw-plane pointer (and no affine statistics)");
+        NFE_REQUIRE(planes_cl && g_planes_cl, "%s: null raw-plane pointer (and no affine statistics)", who);
     }
-    NFE_REQUIRE(g_w1_a && g_b1_a && g_w2_a && g_b2_a && g_w1_b && g_b1_b && g_w2_b && g_b2_b, "nfe_field_bwd: null parameter-gradient pointer");
+    NFE_REQUIRE(g_w1_a && g_b1_a && g_w2_a && g_b2_a && g_w1_b && g_b1_b && g_w2_b && g_b2_b, "%s: null parameter-gradient pointer", who);
     NFE_REQUIRE(net_a->in_dim == FEAT && net_a->hidden == HIDDEN && net_a->out_dim == 16 && net_b->in_dim == FEAT && net_b->hidden == HIDDEN &&
-                net_b->out_dim == 32, "nfe_field_bwd: decoder widths must be 32-64-16 / 32-64-32");
-    NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_field_bwd: plane batch %d does not match ray batch %d", plane_batch, n);
-    NFE_REQUIRE((int64_t)plane_batch * height * width * 3 * (FEAT / 4) < (1ll << 31), "nfe_field_bwd: planes exceed the 32-bit texel offsets");
+                net_b->out_dim == 32, "%s: decoder widths must be 32-64-16 / 32-64-32", who);
+    NFE_REQUIRE(plane_batch == n || plane_batch == 1, "%s: plane batch %d does not match batch %d", who, plane_batch, n);
+    NFE_REQUIRE((int64_t)plane_batch * height * width * 3 * (FEAT / 4) < (1ll << 31), "%s: planes exceed the 32-bit texel offsets", who);
+    NFE_REQUIRE(box_warp != 0.0f, "%s: box_warp must be non-zero", who);
     fb::Args a = {};
     a.set_norm = planes_norm_cl; a.set_raw = planes_cl; a.g_norm = g_planes_norm_cl; a.g_raw = g_planes_cl;
     a.plane_batch = plane_batch; a.H = height; a.W = width; a.scale = (float)(2.0 / (double)box_warp);
-    a.origins = origins; a.dirs = dirs; a.depths = depths; a.s_per_ray = s_per_ray; a.m = n_rays * s_per_ray; a.total = total;
+    a.origins = origins; a.dirs = dirs; a.depths = depths; a.coords = coords; a.s_per_ray = s_per_ray; a.m = n_rays * s_per_ray; a.total = total;
     a.rec = rec; a.g_rec = g_rec;
     a.gw1[0] = g_w1_a; a.gb1[0] = g_b1_a; a.gw2[0] = g_w2_a; a.gb2[0] = g_b2_a;
     a.gw1[1] = g_w1_b; a.gb1[1] = g_b1_b; a.gw2[1] = g_w2_b; a.gb2[1] = g_b2_b;
@@ -633,7 +642,7 @@ NFE_EXPORT int nfe_field_bwd(int kind, const float* planes_norm_cl, const float*
     if (!configured[affine]) {
         cudaError_t e = affine ? cudaFuncSetAttribute(fb::field_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
                                : cudaFuncSetAttribute(fb::field_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        NFE_REQUIRE(e == cudaSuccess, "nfe_field_bwd: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        NFE_REQUIRE(e == cudaSuccess, "%s: cannot reserve %zu bytes of shared memory: %s", who, smem, cudaGetErrorString(e));
         configured[affine] = true;
     }
     const int64_t n_tiles = (total + TILE_M - 1) / TILE_M;
@@ -643,6 +652,30 @@ NFE_EXPORT int nfe_field_bwd(int kind, const float* planes_norm_cl, const float*
     else fb::field_bwd_kernel<false><<<grid, fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, *net_b);
     NFE_LAUNCH_CHECK("field_bwd_kernel");
     return 0;
+}
+
+NFE_EXPORT int nfe_field_bwd(int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width, float box_warp,
+                             const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays, int s_per_ray,
+                             const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec, const float* g_rec, float* g_planes_norm_cl,
+                             float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a, float* g_b2_a, float* g_w1_b, float* g_b1_b,
+                             float* g_w2_b, float* g_b2_b, const float* affine_scale, const float* affine_shift, int affine_items,
+                             float* g_affine_scale, float* g_affine_shift, nfe_stream_t stream)
+{
+    return field_bwd_launch("nfe_field_bwd", kind, planes_norm_cl, planes_cl, plane_batch, height, width, box_warp, origins, dirs, depths, nullptr, n,
+                            n_rays, s_per_ray, net_a, net_b, rec, g_rec, g_planes_norm_cl, g_planes_cl, g_w1_a, g_b1_a, g_w2_a, g_b2_a, g_w1_b, g_b1_b,
+                            g_w2_b, g_b2_b, affine_scale, affine_shift, affine_items, g_affine_scale, g_affine_shift, stream);
+}
+
+NFE_EXPORT int nfe_run_model_bwd(int kind, const float* planes_norm_cl, const float* planes_cl, int plane_batch, int height, int width, float box_warp,
+                                 const float* coords, int n, int64_t m, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* rec,
+                                 const float* g_rec, float* g_planes_norm_cl, float* g_planes_cl, float* g_w1_a, float* g_b1_a, float* g_w2_a,
+                                 float* g_b2_a, float* g_w1_b, float* g_b1_b, float* g_w2_b, float* g_b2_b, const float* affine_scale,
+                                 const float* affine_shift, int affine_items, float* g_affine_scale, float* g_affine_shift, nfe_stream_t stream)
+{
+    NFE_REQUIRE(coords || (int64_t)n * m == 0, "nfe_run_model_bwd: null coords");
+    return field_bwd_launch("nfe_run_model_bwd", kind, planes_norm_cl, planes_cl, plane_batch, height, width, box_warp, nullptr, nullptr, nullptr, coords,
+                            n, m, 1, net_a, net_b, rec, g_rec, g_planes_norm_cl, g_planes_cl, g_w1_a, g_b1_a, g_w2_a, g_b2_a, g_w1_b, g_b1_b, g_w2_b,
+                            g_b2_b, affine_scale, affine_shift, affine_items, g_affine_scale, g_affine_shift, stream);
 }
 
 #ifdef NFE_BWD_PROFILE

@@ -17,13 +17,19 @@ Contract (the usual one for CUDA graphs):
   * deterministic sampling only (`rendering_options['nfe_deterministic']=True`, or cameras/jitter supplied
     from outside): the Philox seed/offset of stochastic mode is a by-value launch argument and would be
     frozen into the graph, repeating the same jitter on every replay.  `capture` refuses a stochastic render;
-  * inference only (capture runs under torch.no_grad()).
+  * inference only (capture runs under torch.no_grad());
+  * warm-up and capture run in a fresh epoch of the plane registries (plane_registry.new_epoch): a staging buffer or
+    statistics recorded BEFORE the capture (e.g. by a normalize_plane outside the captured call, or kept by
+    `nfe_cache_planes`) is not visible inside, so the captured step re-stages from its static inputs and a replay after
+    `raw.copy_(new_planes)` renders the new planes.  Whatever the step registers itself (normalize_plane inside the
+    captured call) still hits, and is captured with it.
 
 The reference has no counterpart (eager ATen ops, training/volumetric_rendering/renderer.py:88-140).
 """
 import torch
 
 from . import _lib, ops
+from . import plane_registry as registry
 
 
 class GraphedCall:
@@ -47,19 +53,21 @@ def capture(fn, warmup=2, pool=None):
     philox0 = ops.philox_draws()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
-    with torch.no_grad(), torch.cuda.stream(side):
-        for _ in range(max(int(warmup), 1)):
-            fn()
-    torch.cuda.current_stream().wait_stream(side)
-    torch.cuda.synchronize()
-    if ops.philox_draws() != philox0:
-        raise RuntimeError("graphs.capture: the call draws random numbers (stochastic sampling or density noise); its Philox "
-                           "seed/offset would be frozen into the graph — capture a deterministic render "
-                           "(rendering_options['nfe_deterministic']=True, density_noise=0)")
+    with registry.new_epoch():
+        with torch.no_grad(), torch.cuda.stream(side):
+            for _ in range(max(int(warmup), 1)):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        if ops.philox_draws() != philox0:
+            raise RuntimeError("graphs.capture: the call draws random numbers (stochastic sampling or density noise); its Philox "
+                               "seed/offset would be frozen into the graph — capture a deterministic render "
+                               "(rendering_options['nfe_deterministic']=True, density_noise=0)")
     graph = torch.cuda.CUDAGraph()
     launches0 = _lib.launch_count()
-    with torch.no_grad(), torch.cuda.graph(graph, pool=pool):
-        outputs = fn()
+    with registry.new_epoch():
+        with torch.no_grad(), torch.cuda.graph(graph, pool=pool):
+            outputs = fn()
     kernels = _lib.launch_count() - launches0
     if kernels <= 0:
         raise RuntimeError("graphs.capture: the call launched no kernel of libnfe_b200.so")

@@ -10,6 +10,7 @@ import os
 import torch
 
 from . import _lib
+from . import plane_registry as registry
 from ._lib import DEC_DISENTANGLED, DEC_OSG, DEC_SEGMENTATION, NfeMlp, NfeRenderCfg  # noqa: F401
 
 
@@ -76,7 +77,7 @@ def plane_normalize(planes, mean, std):
     return out
 
 
-def plane_denormalize(norm, mean, std):
+def plane_denormalize(norm, mean, std, register=True):
     """norm*std + mean; statistics either per (batch, channel) or one item's, broadcast over the batch."""
     x = _cuda_f32(norm, "planes")
     hw = x.shape[-1] * x.shape[-2]
@@ -97,11 +98,22 @@ def plane_denormalize(norm, mean, std):
     with _Guard(x):
         _lib.check(_lib.load().nfe_plane_denormalize(_ptr(x), _ptr(mean), _ptr(std), slabs, stat, hw, _ptr(out), _stream(x)),
                    "nfe_plane_denormalize")
-    if x.dim() in (4, 5) and (x.shape[1] == 96 or (x.dim() == 5 and x.shape[1] == 3 and x.shape[2] == 32)):
-        k = stat // 96 if stat % 96 == 0 else 0
-        if k in (1, x.shape[0]):
-            _provenance_put(out, _key5(x), std.reshape(k, 96), mean.reshape(k, 96))
+    if register and x is norm:         # (a converted temporary cannot be identified later)
+        register_denormalized(out, norm, mean, std)
     return out
+
+
+def register_denormalized(out, norm, mean, std):
+    """Record out == norm*std + mean per (item, plane-major channel) when the statistics have that form (tri-plane tensors
+    with one statistics row per item, or one row for the whole batch): the single-gather identity then also holds after a
+    statistics swap (triplane.py:93-107)."""
+    if not (torch.is_tensor(mean) and torch.is_tensor(std)) or mean.numel() != std.numel():
+        return
+    if norm.dim() in (4, 5) and (norm.shape[1] == 96 or (norm.dim() == 5 and norm.shape[1] == 3 and norm.shape[2] == 32)):
+        stat = mean.numel()
+        k = stat // 96 if stat % 96 == 0 else 0
+        if k in (1, norm.shape[0]):
+            registry.provenance_put(out, norm, std.detach().reshape(k, 96).float(), mean.detach().reshape(k, 96).float())
 
 
 def resize_bilinear(x, size, antialias=True):
@@ -119,107 +131,42 @@ def resize_bilinear(x, size, antialias=True):
     return out
 
 
-_CL_CACHE = {}
-_CL_CACHE_MAX = 2
-
-
-def _version_of(t):
-    """Version counter of a tensor, the staleness check of the registries below.  Tensors created under torch.inference_mode()
-    do not track one (RuntimeError): they get a fresh object, which never compares equal, so every lookup misses and nothing is
-    registered for them — the renderer then stages and gathers both plane sets itself (correct, just not the fast path)."""
-    try:
-        return t._version
-    except RuntimeError:
-        return object()
+# Registries (plane_registry.py): staged channel-last copies and the provenance of de-normalised planes
+_key5 = registry.key5
+_version_of = registry.version_of
+provenance = registry.provenance
+provenance_attach = registry.provenance_attach
+provenance_sources = registry.provenance_sources
+note_path = registry.note
+path_counts = registry.counts
 
 
 def planes_channel_last(planes, cache=False):
     """[N,3,C,H,W] (reference layout) -> channel-last [N,3,H,W,C] staging buffer for the gather.
     With cache=True (rendering_options['nfe_cache_planes']) the staged copy is kept, keyed on
-    (address, shape, version), so a video sweep over fixed planes (utils.py:78-80) stages once; the
-    cache holds the source tensor alive so the address cannot be recycled under the key."""
+    (address, shape, version) and valid while the source tensor is alive, so a video sweep over fixed planes
+    (utils.py:78-80) stages once."""
     x = _cuda_f32(planes, "planes")
     if x.dim() != 5 or x.shape[1] != 3:
         raise RuntimeError(f"planes: expected [N,3,C,H,W], got {tuple(x.shape)}")
-    key = (x.data_ptr(), tuple(x.shape), _version_of(x), x.device.index)
-    if key in _CL_CACHE:      # staged by plane_normalize_staged, or kept from an earlier call with cache=True
-        return _CL_CACHE[key][1]
+    hit = registry.staged_get(x)      # staged by normalize_plane, or kept from an earlier call with cache=True
+    if hit is not None:
+        return hit
     n, p, c, h, w = x.shape
     out = torch.empty((n, p, h, w, c), device=x.device, dtype=torch.float32)
     with _Guard(x):
         _lib.check(_lib.load().nfe_planes_to_channel_last(_ptr(x), n * p, c, h * w, _ptr(out), _stream(x)), "nfe_planes_to_channel_last")
-    if cache:
-        _cache_put(key, x, out)
+    if cache and x is planes:         # (a converted temporary would die at once and take the entry with it)
+        registry.staged_put(planes, out)
     return out
 
 
-# Provenance of de-normalised planes: key(denorm tensor) -> (key(norm tensor), scale [K,96], shift [K,96], keep-alive refs).
-# Filled by plane_normalize_staged (raw = norm*(std+1e-8) + mean) and plane_denormalize (out = norm*std' + mean');
-# read by the disentangled renderer to gather the normalised planes only (single-gather identity, SURVEY.md §7.2).
-_PROVENANCE = {}
-_PROVENANCE_MAX = 4
-
-
-def _key5(t):
-    """Identity of a tri-plane tensor, the same for [N,96,H,W] and its [N,3,32,H,W] view."""
-    if t.dim() == 4:
-        n, c, h, w = t.shape
-        shape5 = (n, 3, c // 3, h, w)
-    else:
-        shape5 = tuple(t.shape)
-    return (t.data_ptr(), shape5, _version_of(t), t.device.index)
-
-
-def _provenance_put(denorm, norm_key, scale, shift):
-    if not isinstance(norm_key[2], int) or not isinstance(_version_of(denorm), int):
-        return                                  # inference tensors: no version counter, nothing to key on
-    while len(_PROVENANCE) >= _PROVENANCE_MAX:
-        _PROVENANCE.pop(next(iter(_PROVENANCE)))
-    _PROVENANCE[_key5(denorm)] = (norm_key, scale.reshape(scale.shape[0], -1).contiguous(), shift.reshape(shift.shape[0], -1).contiguous(), denorm)
-
-
-def provenance(norm_planes, denorm_planes):
-    """(scale, shift) if denorm_planes is known to be norm_planes*scale + shift per (item, channel), else None."""
-    hit = _PROVENANCE.get(_key5(denorm_planes))
-    if hit is None or hit[0] != _key5(norm_planes):
-        return None
-    return hit[1], hit[2]
-
-
-# Autograd sources of a provenance entry: the (possibly grad-tracked) statistics tensors the scale and shift came from,
-# scale = scale_src + eps.  Attached by triplane.normalize_plane / denormalize_plane on their differentiable paths so that
-# the training-step renderer can use the single-gather identity and send the statistics gradients back (autograd.py).
-_PROVENANCE_SRC = {}
-
-
-def provenance_attach(denorm, scale_src, eps, shift_src):
-    key = _key5(denorm)
-    if key in _PROVENANCE:
-        for k in [k for k in _PROVENANCE_SRC if k not in _PROVENANCE]:
-            _PROVENANCE_SRC.pop(k)
-        _PROVENANCE_SRC[key] = (scale_src, float(eps), shift_src)
-
-
-def provenance_sources(norm_planes, denorm_planes):
-    """(scale_src, eps, shift_src) for a (norm, denorm) pair with known provenance and attached sources, else None."""
-    if provenance(norm_planes, denorm_planes) is None:
-        return None
-    return _PROVENANCE_SRC.get(_key5(denorm_planes))
-
-
-def _cache_put(key, src, staged):
-    if not isinstance(key[2], int):
-        return
-    while len(_CL_CACHE) >= _CL_CACHE_MAX:
-        _CL_CACHE.pop(next(iter(_CL_CACHE)))
-    _CL_CACHE[key] = (src, staged)
-
-
-def plane_normalize_staged(planes, mean, std, stage_raw=False):
+def plane_normalize_staged(planes, mean, std, stage_raw=False, register=True):
     """normalize_plane for tri-plane tensors [N, 96, H, W]: one kernel writes the normalised planes AND the
-    channel-last staging of both the normalised and the raw planes, and registers the staged copies so that
-    the renderer called next on views of (norm, planes) (triplane.py:113-119) skips its own staging pass.
-    The registry keeps the two source tensors alive until the next call replaces them."""
+    channel-last staging of both the normalised and the raw planes.  Returns (norm, norm_cl, raw_cl|None).
+    register=True also records the staged copies and the provenance (raw == norm*(std+1e-8) + mean) so that the
+    renderer called next on views of (norm, planes) (triplane.py:113-119) skips its own staging pass and gathers
+    one plane set; the entries live as long as `planes` and the returned `norm` do."""
     x = _cuda_f32(planes, "planes")
     n, c96, h, w = x.shape
     norm = torch.empty_like(x)
@@ -228,17 +175,24 @@ def plane_normalize_staged(planes, mean, std, stage_raw=False):
     with _Guard(x):
         _lib.check(_lib.load().nfe_plane_normalize_staged(_ptr(x), _ptr(mean), _ptr(std), n * 3, h * w, _ptr(norm), _ptr(norm_cl), _ptr(raw_cl),
                                                           _stream(x)), "nfe_plane_normalize_staged")
-    _CL_CACHE.clear()
-    _cache_put(_key5(norm), norm, norm_cl)
+    if register:
+        register_normalized(planes, norm, mean, std, norm_cl, raw_cl)
+    return norm, norm_cl, raw_cl
+
+
+def register_normalized(planes, norm, mean, std, norm_cl, raw_cl=None):
+    """Record what normalize_plane knows about its input and output: the staged copies, and that the raw planes ARE the
+    de-normalisation of `norm` with their own statistics."""
+    n = planes.shape[0]
+    registry.staged_put(norm, norm_cl)
     if raw_cl is not None:
-        _cache_put(_key5(x), x, raw_cl)
-    # the raw planes ARE the de-normalisation of `norm` with their own statistics
-    _provenance_put(x, _key5(norm), std.reshape(n, -1) + 1e-8, mean.reshape(n, -1))
-    return norm
+        registry.staged_put(planes, raw_cl)
+    registry.provenance_put(planes, norm, std.detach().reshape(n, -1) + 1e-8, mean.detach().reshape(n, -1))
 
 
 def clear_plane_cache():
-    _CL_CACHE.clear()
+    """Drop every staged copy and provenance record (and the autograd sources attached to them)."""
+    registry.clear()
 
 
 # ------------------------------------------------------------------------------- rays
@@ -558,9 +512,15 @@ def render_fwd(cfg, seq_a, seq_b, planes_norm_cl, planes_denorm_cl, origins, dir
         pn = planes_norm_cl if (planes_norm_cl is None or shared_planes) else planes_norm_cl[i0:i1]
         pd = planes_denorm_cl if (planes_denorm_cl is None or shared_planes) else planes_denorm_cl[i0:i1]
         ccfg = cfg
-        if cfg.affine_scale and cfg.affine_items == n and (i0, i1) != (0, n):
-            ccfg = NfeRenderCfg.from_buffer_copy(cfg)                  # per-item statistics: shift to this chunk's items
-            ccfg.affine_scale, ccfg.affine_shift, ccfg.affine_items = cfg.affine_scale + i0 * 96 * 4, cfg.affine_shift + i0 * 96 * 4, cn
+        if (i0, i1, r0, r1) != (0, n, 0, r):
+            ccfg = NfeRenderCfg.from_buffer_copy(cfg)
+            if cfg.affine_scale and cfg.affine_items == n:             # per-item statistics: shift to this chunk's items
+                ccfg.affine_scale, ccfg.affine_shift, ccfg.affine_items = cfg.affine_scale + i0 * 96 * 4, cfg.affine_shift + i0 * 96 * 4, cn
+            # the kernels index their Philox streams by the LOCAL sample number: give every workspace chunk its own offsets
+            # (all 64 bits of the offset enter the counter; torch's generator advances it by 16 per call, far below 2^40),
+            # or all chunks would draw the same jitter and density noise
+            ccfg.offset = cfg.offset + (len(kept.setdefault("chunks", [])) << 40)
+            kept["chunks"].append((i0, i1, r0, r1))
         oo, dd, dcc = o[sl].contiguous(), d[sl].contiguous(), dc[sl].contiguous()     # no copies: whole items, or rays of one item
         outs = [rgb, seg, depth, wsum]
         if image and cr != r:

@@ -143,9 +143,14 @@ class ImportanceRenderer(torch.nn.Module):
         if not ray_origins.is_cuda:
             raise RuntimeError("ImportanceRenderer: expected CUDA tensors (this path has no CPU fallback)")
         assert opts['clamp_mode'] == 'softplus', "MipRayMarcher only supports `clamp_mode`=`softplus`!"
+        if torch.is_grad_enabled() and (ray_origins.requires_grad or ray_directions.requires_grad):
+            # the reference would back-propagate into the cameras (pose optimisation); no caller in the reference does, and
+            # silently detaching would be wrong
+            raise RuntimeError("ImportanceRenderer: gradients w.r.t. ray_origins / ray_directions are not built; detach the rays")
         deterministic = bool(opts.get('nfe_deterministic', False))
         desc = self._fused_decoder(decoder, norm_planes)
         if desc is None:
+            ops.note_path("render", "staged")
             if defer_clamp:
                 raise NotImplementedError("a ray-sharded render needs one of the reference's decoders (fused path)")
             return self._render_staged(norm_planes, planes, decoder, ray_origins, ray_directions, opts, deterministic)
@@ -163,6 +168,7 @@ class ImportanceRenderer(torch.nn.Module):
             affine = ops.provenance(norm_planes, planes)
         norm_cl = ops.planes_channel_last(norm_planes, cache) if kind == ops.DEC_DISENTANGLED else None
         denorm_cl = ops.planes_channel_last(planes, cache) if affine is None else None
+        ops.note_path("render", "single-gather" if affine is not None else ("two-gather" if kind == ops.DEC_DISENTANGLED else "one-set"))
         plane_batch = (norm_cl if denorm_cl is None else denorm_cl).shape[0]
         if plane_batch not in (1, ray_origins.shape[0]):
             raise RuntimeError(f"planes batch {plane_batch} does not match ray batch {ray_origins.shape[0]}")
@@ -208,17 +214,35 @@ class ImportanceRenderer(torch.nn.Module):
         # single-gather identity in training: planes known to be norm*scale + shift are never read; their gradient goes
         # through the statistics instead (autograd.RenderFunction, csrc/nfe_field_bwd.cu AFFINE)
         scale_src = shift_src = None
-        if (kind == ops.DEC_DISENTANGLED and state["cfg"]["precision"] != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True)
-                and os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1"):
-            src = ops.provenance_sources(norm_planes, planes)
-            if src is not None and src[0].numel() == src[2].numel() and src[0].numel() in (96, 96 * ray_origins.shape[0]):
-                scale_src, state["affine_eps"], shift_src = src
+        if kind == ops.DEC_DISENTANGLED and state["cfg"]["precision"] != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True):
+            scale_src, shift_src = self._affine_sources(norm_planes, planes, ray_origins.shape[0], state)
+        ops.note_path("render", "training-single-gather" if scale_src is not None else "training")
         out = RenderFunction.apply(state, norm_planes if kind == ops.DEC_DISENTANGLED else None, planes, scale_src, shift_src, *params)
         if kind == ops.DEC_OSG:
             rgb, depth, wsum, _ = out
             return rgb, None, depth, wsum
         rgb, seg, depth, wsum, _ = out
         return rgb, seg, depth, wsum
+
+    @staticmethod
+    def _affine_sources(norm_planes, planes, batch, state):
+        """(scale_src, shift_src) when the differentiable single-gather identity applies to this (norm, planes) pair, else
+        (None, None); sets state['affine_eps'].  The identity replaces the gradient into `planes` by gradients into the
+        normalised planes and the statistics `planes` is tied to (normalize_plane: planes is their root; denormalize_plane:
+        planes is their product), which is only the same thing while the autograd graph still has the shape it had when
+        the pair was made: `planes` must carry grad and `norm_planes` must be in the state it was registered in.  A pair
+        with one branch detached afterwards (renderer(norm.detach(), planes), renderer(norm, planes.detach())) takes the
+        two-gather backward, which honours the detach like the reference does."""
+        if os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") == "1":
+            return None, None
+        src = ops.provenance_sources(norm_planes, planes)
+        if src is None or src[0].numel() != src[2].numel() or src[0].numel() not in (96, 96 * batch):
+            return None, None
+        scale_src, eps, shift_src, norm_rg = src
+        if not planes.requires_grad or bool(norm_planes.requires_grad) != norm_rg:
+            return None, None
+        state["affine_eps"] = eps
+        return scale_src, shift_src
 
     def _render_staged(self, norm_planes, planes, decoder, ray_origins, ray_directions, opts, deterministic):
         """Any decoder callable: the reference's orchestration (renderer.py:99-140,320-363) over the stage
@@ -237,6 +261,8 @@ class ImportanceRenderer(torch.nn.Module):
             return col, sig, seg
 
         col_c, sig_c, seg_c = evaluate(depths_coarse, s_c)
+        # the stage kernels below have no backward: a decoder whose outputs carry grad must not be silently detached
+        ops._no_grad_needed(col_c, sig_c, seg_c)
         s_f = opts['depth_resolution_importance']
         white = opts.get('white_back', False)
         if s_f > 0:
@@ -258,18 +284,34 @@ class ImportanceRenderer(torch.nn.Module):
         desc = self._fused_decoder(decoder, norm_planes)
         if desc is not None:
             kind, seq_a, seq_b = desc
-            ops._no_grad_needed(norm_planes, planes, sample_coordinates, *decoder.parameters())
-            cache = bool(options.get('nfe_cache_planes', False))
             precision = ops.precision_of(options)
             sigma_only = bool(options.get('nfe_sigma_only', False))
-            # density-only queries with the disentangled decoder on the tensor-core path never touch the de-normalised planes
-            geo_only = sigma_only and kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32']
-            norm_cl = ops.planes_channel_last(norm_planes, cache) if kind == ops.DEC_DISENTANGLED else None
-            denorm_cl = None if geo_only else ops.planes_channel_last(planes, cache)
             noise = options.get('density_noise', 0) or 0.0
             seed, offset = ops.philox_state(sample_coordinates.device) if noise > 0 else (0, 0)
+            single = kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32'] and options.get('nfe_single_gather', True)
+            if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (norm_planes, planes, *decoder.parameters())):
+                # differentiable point queries (the density regulariser, loss.py:310-331): autograd.RunModelFunction
+                if sample_coordinates.requires_grad:
+                    raise RuntimeError("run_model: gradients w.r.t. sample_coordinates are not built (the reference's callers never ask for them)")
+                from .autograd import RunModelFunction
+                state = {"kind": kind, "seq_a": seq_a, "seq_b": seq_b, "coords": sample_coordinates.detach().float().contiguous(),
+                         "sigma_only": sigma_only,
+                         "cfg": dict(box_warp=options['box_warp'], density_noise=noise, seed=seed, offset=offset, precision=precision)}
+                scale_src, shift_src = self._affine_sources(norm_planes, planes, sample_coordinates.shape[0], state) if single else (None, None)
+                params = [p for seq in (seq_a, seq_b) if seq is not None for p in (seq[0].weight, seq[0].bias, seq[2].weight, seq[2].bias)]
+                outs = RunModelFunction.apply(state, norm_planes if kind == ops.DEC_DISENTANGLED else None, planes, scale_src, shift_src, *params)
+                keys = ("sigma",) if sigma_only else (("rgb", "sigma") if kind == ops.DEC_OSG else ("rgb", "sigma", "seg"))
+                return dict(zip(keys, outs))
+            ops._no_grad_needed(sample_coordinates)
+            cache = bool(options.get('nfe_cache_planes', False))
+            # density-only queries with the disentangled decoder on the tensor-core path never touch the de-normalised planes
+            geo_only = sigma_only and kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32']
+            affine = ops.provenance(norm_planes, planes) if (single and not geo_only) else None
+            norm_cl = ops.planes_channel_last(norm_planes, cache) if kind == ops.DEC_DISENTANGLED else None
+            denorm_cl = None if (geo_only or affine is not None) else ops.planes_channel_last(planes, cache)
+            ops.note_path("run_model", "single-gather" if (affine is not None or geo_only) else ("two-gather" if kind == ops.DEC_DISENTANGLED else "one-set"))
             cfg = ops.make_cfg(kind, norm_cl if denorm_cl is None else denorm_cl, 2, 0, options['box_warp'], density_noise=noise, seed=seed,
-                               offset=offset, precision=precision)
+                               offset=offset, precision=precision, affine=affine)
             return ops.run_model_fwd(cfg, seq_a, seq_b, norm_cl, denorm_cl, sample_coordinates, sigma_only=sigma_only)
         axes = self.plane_axes
         feats = sample_from_planes(axes, planes, sample_coordinates, padding_mode='zeros', box_warp=options['box_warp'])

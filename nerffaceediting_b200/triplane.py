@@ -88,25 +88,29 @@ def compute_mean_var(planes):
 
 def normalize_plane(planes):
     """(planes - mean) / (std + 1e-8) -> (norm_planes, mean, std) (triplane.py:61-65)."""
+    tri = planes.dim() == 4 and planes.shape[1] == 96 and planes.is_contiguous() and planes.dtype == torch.float32
     if torch.is_grad_enabled() and planes.requires_grad:
         from .autograd import NormalizeFunction
-        norm, mean, std = NormalizeFunction.apply(planes)
-        ops.provenance_attach(planes, std, 1e-8, mean)       # planes == norm*(std+1e-8) + mean: lets the renderer gather one set
+        norm, mean, std, norm_cl = NormalizeFunction.apply(planes)
+        if norm_cl is not None:
+            ops.register_normalized(planes, norm, mean, std, norm_cl)
+            ops.provenance_attach(planes, std, 1e-8, mean)       # planes == norm*(std+1e-8) + mean: lets the renderer gather one set
         return norm, mean, std
     mean, std = ops.plane_stats(planes)
-    if planes.dim() == 4 and planes.shape[1] == 96 and planes.is_contiguous() and planes.dtype == torch.float32:
-        # the generator's [N,96,H,W] tri-planes: also stage both plane sets for the renderer in the same pass
-        return ops.plane_normalize_staged(planes, mean, std), mean, std
+    if tri:
+        # the generator's [N,96,H,W] tri-planes: also stage the planes for the renderer in the same pass
+        return ops.plane_normalize_staged(planes, mean, std)[0], mean, std
     return ops.plane_normalize(planes, mean, std), mean, std
 
 
 def denormalize_plane(planes, mean, var):
     """planes * std + mean (triplane.py:66-68).  Statistics may belong to another identity (appearance
     swap), or to one batch item broadcast over the batch (triplane.py:98-103)."""
-    if torch.is_grad_enabled() and any(t.requires_grad for t in (planes, mean, var)):
+    if torch.is_grad_enabled() and any(torch.is_tensor(t) and t.requires_grad for t in (planes, mean, var)):
         from .autograd import DenormalizeFunction
         out = DenormalizeFunction.apply(planes, mean, var)
         if torch.is_tensor(mean) and torch.is_tensor(var):
-            ops.provenance_attach(out, var, 0.0, mean)
+            ops.register_denormalized(out, planes, mean, var)
+            ops.provenance_attach(out, var, 0.0, mean, norm_requires_grad=planes.requires_grad)
         return out
     return ops.plane_denormalize(planes, mean, var)

@@ -2,7 +2,7 @@
 
 Checkpoints and datasets are unavailable offline, so benches and parity tests run on
 random-init planes/decoders and on the camera schedule the reference's scripts use
-(gen_samples.py:156-172, gen_videos.py:126-130).  Nothing here touches the GPU kernels.
+(gen_samples.py:156-172, gen_videos.py:126-130).  Nothing here touches the GPU kernels; it is test and bench infrastructure, not part of the product package.
 """
 import math
 
@@ -23,14 +23,15 @@ FFHQ_RENDERING_OPTIONS = {
 }
 
 
-def hash_normal(seed, shape):
+def hash_normal(seed, shape, offset=0):
     """Bit-reproducible ~N(0,1) floats: splitmix64 of the element index, four 16-bit uniforms summed
     (Irwin-Hall) and rescaled.  Integer arithmetic plus exact double ops only, so the golden-vector
     generator (run beside the reference) and the tests (run anywhere) regenerate identical planes
-    instead of committing 25 MB fixtures."""
+    instead of committing 25 MB fixtures.  `offset` is the flat index of the first element, so that a large
+    tensor can be regenerated slice by slice: hash_normal(s, (a+b, ...))[a:] == hash_normal(s, (b, ...), offset=a*...)."""
     n = int(np.prod(shape))
     with np.errstate(over='ignore'):
-        z = np.arange(n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0xD1B54A32D192ED03)
+        z = np.arange(offset, offset + n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0xD1B54A32D192ED03)
         z = z + np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
         z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)

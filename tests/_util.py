@@ -19,6 +19,16 @@ def rel_err(a, b):
     return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-30))
 
 
+def elem_err(a, b, floor=1e-2):
+    """Element-wise relative error with an absolute floor: max over elements of |a-b| / max(|b|, floor * max|b|).
+    `rel_err` (max-norm) is the loosest reading of BASELINE.json's "1e-4 relative"; this is the strict one, and the floor
+    says from which magnitude on an element is held to it (elements below floor * max|b| are held to floor * max|b| * tol
+    absolute).  VERDICT r01 weak #1a."""
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = max(np.max(np.abs(b)), 1e-30)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), floor * scale)))
+
+
 def oracle_decoder(arrays, prefix, kind, lr=1.0):
     """(kind_id, net_a, net_b, color_dim, seg_dim) from saved state_dict arrays `<prefix>.<net>.<i>.<p>`."""
     def mlp(net):

@@ -25,7 +25,7 @@ REF = os.environ.get("NFE_REFERENCE", "/root/reference")
 sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 
-from nerffaceediting_b200 import synth  # noqa: E402
+import synth_inputs as synth  # noqa: E402
 from training.triplane import DisentangledOSGDecoder, OSGDecoder, SegmentationOSGDecoder  # noqa: E402
 from training.volumetric_rendering import math_utils as ref_math  # noqa: E402
 from training.volumetric_rendering.ray_marcher import MipRayMarcher2, SegMipRayMarcher2  # noqa: E402

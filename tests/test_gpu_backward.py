@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from nerffaceediting_b200 import synth
+import synth_inputs as synth
 from _util import golden, rel_err
 from test_gpu_parity import N, T, torch_decoder
 

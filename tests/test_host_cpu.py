@@ -11,7 +11,8 @@ import numpy as np
 import pytest
 import torch
 
-from nerffaceediting_b200 import _lib, ops, synth
+from nerffaceediting_b200 import _lib, ops
+import synth_inputs as synth
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REFERENCE = os.environ.get("NFE_REFERENCE", "/root/reference")
@@ -113,21 +114,107 @@ def test_plane_registries_key_on_version_and_tolerate_inference_tensors():
     """The staging / provenance registries key on (address, shape, version): a 4-D tensor and its 5-D view share a key, an
     in-place write invalidates it, and tensors made under torch.inference_mode() (no version counter) simply never hit."""
     from nerffaceediting_b200 import ops
+    from nerffaceediting_b200 import plane_registry as reg
+    reg.clear()
     norm, raw = torch.randn(2, 96, 4, 4), torch.randn(2, 96, 4, 4)
-    assert ops._key5(norm) == ops._key5(norm.view(2, 3, 32, 4, 4))
-    ops._provenance_put(raw, ops._key5(norm), torch.ones(2, 96), torch.zeros(2, 96))
+    assert reg.key5(norm) == reg.key5(norm.view(2, 3, 32, 4, 4))
+    reg.provenance_put(raw, norm, torch.ones(2, 96), torch.zeros(2, 96))
     hit = ops.provenance(norm.view(2, 3, 32, 4, 4), raw.view(2, 3, 32, 4, 4))
     assert hit is not None and hit[0].shape == (2, 96)
+    assert ops.provenance(raw, norm) is None                     # the pair is ordered
     raw.add_(1.0)                                               # stale: the version moved on
     assert ops.provenance(norm, raw) is None
     with torch.inference_mode():
         n2, r2 = torch.randn(1, 96, 4, 4), torch.randn(1, 96, 4, 4)
-        before = len(ops._PROVENANCE)
-        ops._provenance_put(r2, ops._key5(n2), torch.ones(1, 96), torch.zeros(1, 96))
-        assert len(ops._PROVENANCE) == before and ops.provenance(n2, r2) is None
-        ops._cache_put(ops._key5(n2), n2, n2)
-        assert ops._key5(n2) not in ops._CL_CACHE
-    ops._PROVENANCE.clear()
+        before = len(reg.PROVENANCE)
+        reg.provenance_put(r2, n2, torch.ones(1, 96), torch.zeros(1, 96))
+        assert len(reg.PROVENANCE) == before and ops.provenance(n2, r2) is None
+        reg.staged_put(n2, n2)
+        assert reg.staged_get(n2) is None
+    reg.clear()
+
+
+def test_plane_registries_never_hit_a_recycled_address():
+    """an entry must die with the tensors it describes.  Tensors that land on a freed tensor's address (the
+    caching allocator recycles blocks; here the same storage is re-wrapped) do not inherit its provenance or staging."""
+    import gc
+    from nerffaceediting_b200 import ops
+    from nerffaceediting_b200 import plane_registry as reg
+    reg.clear()
+    pool_n, pool_r = torch.zeros(2 * 96 * 16), torch.zeros(2 * 96 * 16)      # stand-ins for allocator blocks
+    norm, raw = pool_n.view(2, 96, 4, 4), pool_r.view(2, 96, 4, 4)
+    reg.provenance_put(raw, norm, torch.full((2, 96), 2.0), torch.zeros(2, 96))
+    reg.staged_put(norm, torch.ones(1))
+    assert ops.provenance(norm, raw) is not None and reg.staged_get(norm) is not None
+    key_n, key_r = reg.key5(norm), reg.key5(raw)
+    del norm, raw
+    gc.collect()
+    norm_other, raw_other = pool_n.view(2, 96, 4, 4), pool_r.view(2, 96, 4, 4)   # same address, shape, version: other tensors
+    assert reg.key5(norm_other) == key_n and reg.key5(raw_other) == key_r
+    assert ops.provenance(norm_other, raw_other) is None
+    assert reg.staged_get(norm_other) is None
+    assert len(reg.PROVENANCE) == 0 and len(reg.STAGED) == 0                    # dead entries are dropped on lookup
+    # ... while views and the registered objects themselves keep hitting
+    norm, raw = torch.randn(2, 96, 4, 4), torch.randn(2, 96, 4, 4)
+    reg.provenance_put(raw, norm, torch.ones(2, 96), torch.zeros(2, 96))
+    v_n, v_r = norm.view(2, 3, 32, 4, 4), raw.view(2, 3, 32, 4, 4)
+    del norm, raw
+    gc.collect()
+    assert ops.provenance(v_n, v_r) is not None                                 # a view keeps its base alive
+    ops.clear_plane_cache()
+    assert ops.provenance(v_n, v_r) is None and len(reg.SOURCES) == 0
+
+
+def test_plane_registries_capacity_epochs_and_counters():
+    """Several generators (G, G_ema, swap variants) coexist up to MAX_ENTRIES; a new epoch (graphs.capture) hides entries made
+    before it and retires those made inside it; counts() reports which path calls took."""
+    from nerffaceediting_b200 import plane_registry as reg
+    reg.clear()
+    reg.counts(reset=True)
+    pairs = [(torch.randn(1, 96, 2, 2), torch.randn(1, 96, 2, 2)) for _ in range(reg.MAX_ENTRIES + 2)]
+    for n_, r_ in pairs:
+        reg.provenance_put(r_, n_, torch.ones(1, 96), torch.zeros(1, 96))
+    assert len(reg.PROVENANCE) == reg.MAX_ENTRIES
+    assert reg.provenance(*pairs[0]) is None and reg.provenance(*pairs[1]) is None       # the oldest two left
+    assert all(reg.provenance(n_, r_) is not None for n_, r_ in pairs[2:])               # alternating between the rest never thrashes
+    n0, r0 = pairs[-1]
+    with reg.new_epoch():
+        assert reg.provenance(n0, r0) is None                      # made before the capture: invisible inside
+        n1, r1 = torch.randn(1, 96, 2, 2), torch.randn(1, 96, 2, 2)
+        reg.provenance_put(r1, n1, torch.ones(1, 96), torch.zeros(1, 96))
+        assert reg.provenance(n1, r1) is not None                  # made inside: visible inside
+    assert reg.provenance(n1, r1) is None                          # ... and retired with the capture
+    reg.note("render", "single-gather")
+    reg.note("render", "single-gather")
+    reg.note("render", "two-gather")
+    c = reg.counts(reset=True)
+    assert c["render:single-gather"] == 2 and c["render:two-gather"] == 1 and reg.counts() == {}
+    reg.clear()
+
+
+def test_plane_registries_are_thread_safe():
+    import threading
+    from nerffaceediting_b200 import plane_registry as reg
+    reg.clear()
+    errors = []
+
+    def worker(seed):
+        try:
+            g = torch.Generator().manual_seed(seed)
+            for _ in range(200):
+                n_, r_ = torch.randn(1, 96, 2, 2, generator=g), torch.randn(1, 96, 2, 2, generator=g)
+                reg.provenance_put(r_, n_, torch.ones(1, 96), torch.zeros(1, 96))
+                hit = reg.provenance(n_, r_)
+                assert hit is None or hit[0].shape == (1, 96)
+                reg.staged_put(n_, r_)
+                reg.staged_get(n_)
+        except Exception as e:      # noqa: BLE001
+            errors.append(e)
+    threads = [threading.Thread(target=worker, args=(i,)) for i in range(4)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors
+    reg.clear()
 
 
 def test_missing_library_fails_loudly(monkeypatch):
@@ -209,7 +296,7 @@ def test_synth_cameras_match_reference_camera_utils():
 import sys, math, torch
 sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
 import camera_utils
-from nerffaceediting_b200 import synth
+import synth_inputs as synth
 for h, v in ((math.pi/2, math.pi/2), (math.pi/2 - 0.4, math.pi/2 + 0.25)):
     ref = camera_utils.LookAtPoseSampler.sample(h, v, torch.tensor([0, 0, 0.2]), radius=2.7)
     assert torch.equal(ref, synth.look_at_cam2world([h], [v]))
