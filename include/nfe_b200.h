@@ -42,6 +42,13 @@ uint64_t nfe_launch_count(void);
 int nfe_timing_enable(int on);
 int nfe_timing_read(double* ms_by_stage, int64_t* count_by_stage, int n_stages, int reset);
 
+/* Measurement aid (no product path calls it): gathers random 128-byte lines of `table` ([n_lines,32] floats; 25 MB = one plane set
+ * keeps it L2-resident) the way the field kernel reads texels — LDG.128, 8 lanes per line, 4 lines per warp instruction, `depth`
+ * (4, 8 or 12) independent loads in flight per warp, one CTA of warps_per_cta warps per SM.  *host_lines_out = lines gathered by the
+ * launch; time it with events on `stream`.  bench.py reports the result as roofline.l2_gbs_measured. */
+int nfe_bench_l2_gather(const float* table, int64_t n_lines, int warps_per_cta, int depth, int iters, int64_t* host_lines_out,
+                        float* sink, nfe_stream_t stream);
+
 /* ---- plane statistics: TriPlaneGenerator.compute_mean_var / normalize_plane /
  *      denormalize_plane, training/triplane.py:56-68 (twins utils.py:146-158) ---------------
  * planes is [n_slabs, hw] (a slab = one (batch, channel) image).  std is sqrt of the unbiased

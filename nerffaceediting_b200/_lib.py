@@ -45,6 +45,7 @@ SIGNATURES = {
     "nfe_launch_count": (c_u64, []),
     "nfe_timing_enable": (c_int, [c_int]),
     "nfe_timing_read": (c_int, [ctypes.POINTER(c_double), ctypes.POINTER(c_i64), c_int, c_int]),
+    "nfe_bench_l2_gather": (c_int, [c_vp, c_i64, c_int, c_int, c_int, ctypes.POINTER(c_i64), c_vp, c_vp]),
     "nfe_plane_stats": (c_int, [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "nfe_plane_normalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "nfe_plane_denormalize": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),

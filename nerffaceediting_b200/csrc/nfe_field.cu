@@ -276,7 +276,11 @@ int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net
     if (precision != NFE_PREC_FP32) {
         // NFE_TC_SIMPLE=1 selects the single-role tensor-core kernel (kept as the readable baseline of the pipelined one)
         static const bool simple = getenv("NFE_TC_SIMPLE") != nullptr;
-        return simple ? launch_field_tc(kind, precision, a, net_a, net_b, stream) : launch_field_pipe(kind, precision, a, net_a, net_b, stream);
+        if (simple) return launch_field_tc(kind, precision, a, net_a, net_b, stream);
+        // NFE_FIELD_PIPE=1 selects round 1's kernel (4 epilogue warps, pre-pass inside the gather warps) for A/B runs
+        static const char* gen = getenv("NFE_FIELD_PIPE");
+        static const bool first_gen = gen && gen[0] == '1';
+        return first_gen ? launch_field_pipe(kind, precision, a, net_a, net_b, stream) : launch_field_pipe2(kind, precision, a, net_a, net_b, stream);
     }
     nfe_mlp none = {};
     switch (kind) {

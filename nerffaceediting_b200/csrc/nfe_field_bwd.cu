@@ -157,7 +157,9 @@ template <bool AFFINE>
 __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp geo, nfe_mlp app)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    Smem<AFFINE>& s = *reinterpret_cast<Smem<AFFINE>*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+    // (no integer round-up of the base: it strips the shared address space and every LDS/STS below becomes a generic LD/ST — round 1's
+    // build had 258 of those and 10 LDS/STS; the dynamic window starts 1024-byte aligned, the kernel has no static shared memory)
+    Smem<AFFINE>& s = *reinterpret_cast<Smem<AFFINE>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int net = warp >> 2;                       // epilogue role: warps 0-3 geo_net, 4-7 app_net
     const int row = (warp & 3) * 32 + lane;          // TMEM lane = tile row

@@ -47,6 +47,8 @@ int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net
 int launch_field_tc(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream);
 // warp-specialised pipelined tensor-core kernel (nfe_field_pipe.cu): the production path for the tensor-core modes
 int launch_field_pipe(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream);
+// second-generation pipelined kernel (nfe_field_pipe2.cu): two alternating epilogue groups, dedicated tap producers
+int launch_field_pipe2(int kind, int precision, const FieldArgs& a, const nfe_mlp* net_a, const nfe_mlp* net_b, cudaStream_t stream);
 int launch_decoder_tc(int kind, int precision, const nfe_mlp* net_a, const nfe_mlp* net_b, const float* feat_norm, const float* feat_denorm,
                       int n, int64_t m, float* rgb, float* sigma, float* seg, cudaStream_t stream);
 

@@ -99,6 +99,26 @@ class _Table:
         return len(self.d)
 
 
+def _as_batch_slice(t):
+    """(root, lo, hi) when `t` is a contiguous slice [lo:hi] along the batch axis of a larger registered-able tensor `root`
+    (its `_base`), else None.  sharding.render_sharded and the workspace chunking hand the renderer such slices of the
+    generator's planes; they inherit the root's staging and provenance, sliced the same way."""
+    root = getattr(t, "_base", None)
+    if root is None or not t.is_contiguous() or not root.is_contiguous() or t.dim() < 4 or root.dim() < 4:
+        return None
+    per_item = t[0].numel() if t.shape[0] else 0
+    if per_item == 0 or root.numel() % per_item or root[0].numel() != per_item:
+        return None
+    delta = t.storage_offset() - root.storage_offset()
+    if delta < 0 or delta % per_item:
+        return None
+    lo = delta // per_item
+    hi = lo + t.shape[0]
+    if hi > root.shape[0] or (lo, hi) == (0, root.shape[0]):
+        return None
+    return root, lo, hi
+
+
 STAGED = _Table()        # key5(src) -> channel-last copy
 PROVENANCE = _Table()    # key5(denorm) -> (key5(norm), scale [K,96], shift [K,96])
 SOURCES = _Table()       # key5(denorm) -> (scale_src, eps, shift_src): the autograd sources of scale / shift
@@ -106,6 +126,12 @@ SOURCES = _Table()       # key5(denorm) -> (scale_src, eps, shift_src): the auto
 
 def staged_get(src):
     hit = STAGED.get(key5(src))
+    if hit is None:
+        sl = _as_batch_slice(src)
+        if sl is not None:
+            root_hit = STAGED.get(key5(sl[0]))
+            if root_hit is not None and root_hit.shape[0] == sl[0].shape[0]:
+                hit = root_hit[sl[1]:sl[2]]
     note("staging", "hit" if hit is not None else "miss")
     return hit
 
@@ -123,9 +149,19 @@ def provenance_put(denorm, norm, scale, shift):
 def provenance(norm_planes, denorm_planes):
     """(scale, shift) if denorm_planes is known to be norm_planes*scale + shift per (item, channel), else None."""
     hit = PROVENANCE.get(key5(denorm_planes))
-    if hit is None or hit[0] != key5(norm_planes):
+    if hit is not None:
+        return (hit[1], hit[2]) if hit[0] == key5(norm_planes) else None
+    # the same batch slice of a registered pair
+    sd, sn = _as_batch_slice(denorm_planes), _as_batch_slice(norm_planes)
+    if sd is None or sn is None or (sd[1], sd[2]) != (sn[1], sn[2]):
         return None
-    return hit[1], hit[2]
+    hit = PROVENANCE.get(key5(sd[0]))
+    if hit is None or hit[0] != key5(sn[0]):
+        return None
+    scale, shift = hit[1], hit[2]
+    if scale.shape[0] == 1:                         # one statistics row for the whole batch
+        return scale, shift
+    return scale[sd[1]:sd[2]].contiguous(), shift[sd[1]:sd[2]].contiguous()
 
 
 def provenance_attach(denorm, scale_src, eps, shift_src, norm_requires_grad=True):

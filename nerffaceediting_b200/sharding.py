@@ -100,6 +100,7 @@ class ShardedRenderer:
     def __init__(self, renderer, group=None, overlap=True):
         self.renderer, self.group, self.overlap = renderer, group, overlap
         self._ring, self._events, self._i, self._stream = {}, {}, 0, None
+        self.last_packed = None          # this rank's packed [rgb|seg|depth|wsum] maps of the latest local_batch call
 
     def __call__(self, norm_planes, planes, decoder, ray_origins, ray_directions, rendering_options, local_batch=False):
         world = dist.get_world_size(self.group) if (dist.is_available() and dist.is_initialized()) else 1
@@ -131,6 +132,7 @@ class ShardedRenderer:
         main = torch.cuda.current_stream()
         main.wait_event(self._events[key])                       # the all-gather that last read this slot (two calls ago) is done
         torch.cat([rgb] + ([seg] if has_seg else []) + [depth, wsum], dim=-1, out=packed)
+        self.last_packed = packed
         if not self.overlap:
             _all_gather_into(full, packed, self.group)
             return PendingMaps(full, has_seg, None)

@@ -39,13 +39,24 @@ def _loss(g, tag, out, dev):
 
 
 def _check_decoder_grads(g, tag, dec, tol):
+    """Per parameter, max-norm error relative to that parameter's own gradient magnitude.  Gradients that are pure
+    cancellation noise in the reference itself (under the l1 density loss the last-layer bias gradient is a sum of +-c/N terms:
+    3e-10 against 1e-4 elsewhere) are only required to be noise here too."""
+    refs = {name: g[f"{tag}.g_dec.{name}"] for name, _ in dec.named_parameters()}
+    top = max(float(np.abs(r).max()) for r in refs.values())
     for name, p in dec.named_parameters():
-        ref = g[f"{tag}.g_dec.{name}"]
-        if not np.any(ref):
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, name        # e.g. app_net under the sigma-only loss
+        ref = refs[name]
+        if float(np.abs(ref).max()) < 1e-4 * top:
+            assert p.grad is None or float(p.grad.abs().max()) < 1e-4 * top, name      # e.g. app_net under the sigma-only loss
             continue
         assert p.grad is not None and p.grad.shape == ref.shape, name
         assert rel_err(N(p.grad), ref) < tol, name
+
+
+def _check_loss(loss, ref, mass, tol):
+    """A loss that is a signed sum of ~200 k terms is compared against the mass of its terms (sum of |term|) as well as against
+    its own, heavily cancelled, value: per-term errors of 1e-6 add up to 1e-3 of a loss of 0.9 whose terms sum to 8e4."""
+    assert abs(float(loss) - float(ref)) <= tol * max(1.0, abs(float(ref))) + 1e-7 * float(mass), (float(loss), float(ref), float(mass))
 
 
 @pytest.mark.parametrize("tag,precision", [("dis_sigma", "fp32"), ("dis_sigma", "bf16x3"), ("dis_all", "fp32"), ("dis_all", "bf16x3"),
@@ -72,14 +83,19 @@ def test_run_model_backward_vs_reference_autograd(dev, tag, precision):
     tol = TOL if precision == "fp32" else 2 * TOL
     assert rel_err(N(out["sigma"]), g[f"{tag}.out.sigma"]) < tol
     loss = _loss(g, tag, out, dev)
-    assert abs(float(loss.detach()) - float(g[f"{tag}.loss"])) <= tol * max(1.0, abs(float(g[f"{tag}.loss"])))
+    mass = 0.0 if tag == "dis_sigma" else sum(float((out[k].detach().abs() * T(g[w], dev).abs()).sum())
+                                              for k, w in (("rgb", "w_rgb"), ("sigma", "w_sig"), ("seg", "w_seg")) if k in out)
+    _check_loss(loss.detach(), g[f"{tag}.loss"], mass, tol)
     loss.backward()
     if np.any(g[f"{tag}.g_planes"]):
         assert rel_err(N(planes.grad), g[f"{tag}.g_planes"]) < tol
     else:
         assert planes.grad is None or float(planes.grad.abs().max()) == 0.0       # sigma of the disentangled decoder ignores the raw planes
     if norm is not None:
-        assert rel_err(N(norm.grad), g[f"{tag}.g_norm"]) < tol
+        if np.any(g[f"{tag}.g_norm"]):
+            assert rel_err(N(norm.grad), g[f"{tag}.g_norm"]) < tol
+        else:
+            assert norm.grad is None or float(norm.grad.abs().max()) == 0.0       # SegmentationOSGDecoder ignores the normalised planes
     _check_decoder_grads(g, tag, dec, tol)
 
 

@@ -192,6 +192,32 @@ def test_plane_registries_capacity_epochs_and_counters():
     reg.clear()
 
 
+def test_plane_registries_resolve_batch_slices():
+    """sharding / chunking pass batch slices of the generator's planes: they inherit staging and provenance, sliced alike."""
+    from nerffaceediting_b200 import plane_registry as reg
+    reg.clear()
+    norm, raw = torch.randn(4, 96, 2, 2), torch.randn(4, 96, 2, 2)
+    scale, shift = torch.arange(4 * 96.0).reshape(4, 96), -torch.arange(4 * 96.0).reshape(4, 96)
+    reg.provenance_put(raw, norm, scale, shift)
+    reg.staged_put(norm, torch.arange(4.0).reshape(4, 1).expand(4, 5).contiguous())
+    n5, r5 = norm.view(4, 3, 32, 2, 2), raw.view(4, 3, 32, 2, 2)
+    hit = reg.provenance(n5[1:3], r5[1:3])
+    assert hit is not None and torch.equal(hit[0], scale[1:3]) and torch.equal(hit[1], shift[1:3])
+    assert reg.provenance(n5[1:3], r5[2:4]) is None            # different slices of the pair
+    assert reg.provenance(n5[0:2], r5[0:2]) is not None
+    st = reg.staged_get(n5[2:4])
+    assert st is not None and torch.equal(st[:, 0], torch.tensor([2.0, 3.0]))
+    assert reg.staged_get(n5[:, 1:2]) is None                  # not a batch slice
+    # one statistics row for the whole batch (triplane.py:100-101): every slice shares it
+    out = torch.randn(4, 96, 2, 2)
+    reg.provenance_put(out, norm, scale[:1], shift[:1])
+    hit = reg.provenance(n5[3:4], out.view(4, 3, 32, 2, 2)[3:4])
+    assert hit is not None and hit[0].shape == (1, 96)
+    raw.add_(1)                                                 # an in-place write to the root invalidates its slices too
+    assert reg.provenance(n5[1:3], r5[1:3]) is None
+    reg.clear()
+
+
 def test_plane_registries_are_thread_safe():
     import threading
     from nerffaceediting_b200 import plane_registry as reg
