@@ -239,13 +239,15 @@ int nfe_feature_mean_fwd(const float* planes_cl, int plane_batch, int height, in
 int nfe_feature_mean_bwd(const float* g_feat, int plane_batch, int height, int width, float box_warp,
                          const float* origins, const float* dirs, const float* depths, int n, int64_t n_rays,
                          int s_per_ray, float* g_planes_cl, nfe_stream_t stream);
-/* Fused backward of gather + DisentangledOSGDecoder (triplane.py:249-270 and renderer.py:55-65 differentiated) for one
+/* Fused backward of gather + decoder (triplane.py:167-270 and renderer.py:55-65 differentiated) for one
  * pass of samples (sample idx = ray*s_per_ray + s at depth depths[idx]), on the tensor cores:
  * recomputes the plane-mean features and hidden activations, back-propagates the per-sample record gradients
  * g_rec [total,48] = d/d{sigma, seg[15], rgb[32]} (rec = the forward's records, for the colour sigmoid), scatter-adds
  * the feature gradients into the two channel-last plane gradients and ACCUMULATES the raw-parameter gradients
  * (shapes of the parameters; FullyConnectedLayer gains applied) — all gradient buffers are zero-initialised /
- * carried by the caller.  kind must be NFE_DEC_DISENTANGLED.
+ * carried by the caller.  kind: NFE_DEC_DISENTANGLED (net_a = geo_net on the normalised planes, net_b = app_net on the raw ones),
+ * NFE_DEC_SEGMENTATION (net_a = net, net_b = seg_net, both on the raw planes: planes_norm_cl / g_planes_norm_cl unused) or
+ * NFE_DEC_OSG (net_a = net alone: net_b and the g_*_b buffers may be NULL).
  * Single-gather backward: when affine_scale is non-NULL the raw planes are norm*scale + shift per (item, plane-major
  * channel) ([affine_items,96] floats each, affine_items = n or 1; what normalize_plane / denormalize_plane made,
  * triplane.py:61-68).  planes_cl / g_planes_cl are then unused (may be NULL): only the normalised planes are gathered,
@@ -271,6 +273,29 @@ int nfe_run_model_bwd(int kind, const float* planes_norm_cl, const float* planes
 /* channel-last [n_img, hw, 32] -> reference layout [n_img, 32, hw] (plane gradients back to [N,3,32,H,W]) */
 int nfe_planes_from_channel_last(const float* planes_cl, int64_t n_img, int channels, int64_t hw, float* out,
                                  nfe_stream_t stream);
+
+/* ---- training-side consumers of the rendered maps, training/loss.py:28-157,276-293 -------------------
+ * remap_seg (loss.py:28-53): BiSeNet's 19 face-parsing labels -> the generator's 15; other values pass through. */
+int nfe_remap_seg(const int64_t* labels19, int64_t n, int64_t* out, nfe_stream_t stream);
+/* torch.nn.CrossEntropyLoss()(logits [n,c,hw], labels [n,hw]) (loss.py:276-277): mean over all pixels of logsumexp - picked logit.
+ * loss is a device float[1]; acc_ws a device double[1] scratch.  bwd: g_logits = (softmax - onehot) * g_loss / (n*hw). */
+int nfe_seg_cross_entropy_fwd(const float* logits, const int64_t* labels, int n, int c, int64_t hw, float* loss, double* acc_ws,
+                              nfe_stream_t stream);
+int nfe_seg_cross_entropy_bwd(const float* logits, const int64_t* labels, int n, int c, int64_t hw, const float* g_loss,
+                              float* g_logits, nfe_stream_t stream);
+/* RGB-uv histogram distances (RGBuvHistBlock h=64 'inverse-quadratic' with intensity scale, compute_hist_dist,
+ * compute_seg_hist_dist, compute_whole_hist_dist: loss.py:57-157).  img [b,3,p] in (-1,1); seg [b,c_seg,p] logits whose argmax masks
+ * the pixels of each of the n_labels label ids (device int[n_labels]), or NULL with n_labels == 1 for the whole image;
+ * lin = torch.linspace(-3,3,64) (device); weights [n_labels] (SEG2WEIGHT, or {1}).  Outputs (device): hist_raw / hist_norm
+ * [n_labels,b,3,64,64], totals [n_labels,b], s_ws / dist [n_labels], loss [1] = sum_l weights[l] * Hellinger distance of items
+ * 1..b-1 to item 0 / (b-1).  bwd: g_img [b,3,p] (zero-initialised by the caller) += d(g_loss * loss)/d img; item 0 is the detached
+ * target and receives none; g_raw_ws is a [n_labels,b,3,64,64] scratch. */
+int nfe_hist_dist_fwd(const float* img, const float* seg, const int* label_ids, const float* lin, int b, int c_seg, int n_labels,
+                      int64_t p, float sigma, const float* weights, float* hist_raw, float* hist_norm, float* totals, float* s_ws,
+                      float* dist, float* loss, nfe_stream_t stream);
+int nfe_hist_dist_bwd(const float* img, const float* seg, const int* label_ids, const float* lin, int b, int c_seg, int n_labels,
+                      int64_t p, float sigma, const float* hist_raw, const float* hist_norm, const float* totals, const float* s_ws,
+                      const float* weights, const float* g_loss, float* g_raw_ws, float* g_img, nfe_stream_t stream);
 
 /* Depth clamp split out for sharded renders: depth = clamp(nan_to_num(depth, +inf), min, max)
  * with {min,max} read from device memory (ray_marcher.py:49-50,93-94). */

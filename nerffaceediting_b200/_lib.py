@@ -72,6 +72,11 @@ SIGNATURES = {
                               c_vp, c_vp] + [c_vp] * 8 + [c_vp, c_vp, c_int, c_vp, c_vp] + [c_vp]),
     "nfe_run_model_bwd": (c_int, [c_int, c_vp, c_vp, c_int, c_int, c_int, c_float, c_vp, c_int, c_i64, _MLP_P, _MLP_P, c_vp, c_vp,
                                   c_vp, c_vp] + [c_vp] * 8 + [c_vp, c_vp, c_int, c_vp, c_vp] + [c_vp]),
+    "nfe_remap_seg": (c_int, [c_vp, c_i64, c_vp, c_vp]),
+    "nfe_seg_cross_entropy_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "nfe_seg_cross_entropy_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_i64, c_vp, c_vp, c_vp]),
+    "nfe_hist_dist_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "nfe_hist_dist_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_i64, c_float, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "nfe_plane_normalize_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp]),
     "nfe_resize_bilinear": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "nfe_finish_depth": (c_int, [c_vp, c_i64, c_vp, c_vp]),

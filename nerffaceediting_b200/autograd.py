@@ -4,13 +4,15 @@ Forward is the same fused CUDA path as inference; its workspace (per-sample dens
 records of both passes) is kept for the backward.  Backward, per SURVEY.md §3.3 / §7.10:
 
   1. nfe_composite_bwd          ray gradients -> per-sample gradients (warp per ray, CUDA)
-  2. nfe_feature_mean_fwd       decoder inputs recomputed from the planes (no [N,3,M,32] tensors were saved)
-  3. decoder MLP backward       on library GEMMs (torch.addmm / autograd over [M,32] features): plain GEMMs,
-                                the one place this package uses cuBLAS
-  4. nfe_feature_mean_bwd       scatter-add of the feature gradients into channel-last plane gradients (CUDA,
-                                red.global.add.v4.f32 — atomic, hence ulp-level run-to-run noise like the
-                                reference's grid_sampler_2d_backward)
-  5. nfe_planes_from_channel_last   back to the reference's [N,3,32,H,W]
+  2. nfe_field_bwd / nfe_run_model_bwd   ONE tcgen05 kernel per pass for all three decoders: decoder inputs recomputed from
+                                the planes (no [N,3,M,32] tensors were saved), both MLPs back-propagated, parameter gradients
+                                accumulated in tensor memory, feature gradients scatter-added into channel-last plane gradients
+                                (red.global.add.v4.f32 — atomic, hence ulp-level run-to-run noise like the reference's
+                                grid_sampler_2d_backward)
+  3. nfe_planes_from_channel_last   back to the reference's [N,3,32,H,W]
+
+NFE_BWD_LIBRARY_GEMM=1 keeps the round-1 cross-check path (nfe_feature_mean_fwd -> decoder MLP backward on torch.addmm ->
+nfe_feature_mean_bwd) that the fused kernel is tested against; no product path uses it.
 
 Gradients reach the two plane tensors and the decoder parameters; sample positions carry none (camera labels
 are data and depths_fine is detached in the reference, renderer.py:198,211).
@@ -65,9 +67,9 @@ class _FieldBackward:
         self.g_scale = self.g_shift = None
         if affine is not None:
             self.g_scale, self.g_shift = torch.zeros_like(affine[0]), torch.zeros_like(affine[1])
-        # one tcgen05 kernel per pass (csrc/nfe_field_bwd.cu) for the disentangled decoder; the other two decoders (and
-        # NFE_BWD_LIBRARY_GEMM=1 as a cross-check) run the MLP backward on library GEMMs between two gather kernels
-        self.fused = kind == ops.DEC_DISENTANGLED and (affine is not None or os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1")
+        # one tcgen05 kernel per pass (csrc/nfe_field_bwd.cu, templated on the decoder kind); NFE_BWD_LIBRARY_GEMM=1 keeps the
+        # cross-check path: the MLP backward on library GEMMs (torch.addmm) between two gather kernels
+        self.fused = affine is not None or os.environ.get("NFE_BWD_LIBRARY_GEMM", "0") != "1"
         if self.fused:
             self.full = [g if g is not None else torch.zeros_like(p) for g, p in zip(self.g_params, self.params)]
 
@@ -77,8 +79,10 @@ class _FieldBackward:
         stream = torch.cuda.current_stream(self.dev).cuda_stream
         kind, affine = self.kind, self.affine
         if self.fused:
-            mlp_a, mlp_b = ops.MlpRef(self.seq_a, self.dev), ops.MlpRef(self.seq_b, self.dev)
-            tail = (mlp_a.ref(), mlp_b.ref(), P(rec), P(g_rec), P(self.g_norm_cl), P(self.g_denorm_cl), *[P(t) for t in self.full],
+            mlp_a = ops.MlpRef(self.seq_a, self.dev)
+            mlp_b = ops.MlpRef(self.seq_b, self.dev) if self.seq_b is not None else None
+            grads8 = [P(t) for t in self.full] + [None] * (8 - len(self.full))           # OSG has one net: no second set of parameter gradients
+            tail = (mlp_a.ref(), mlp_b.ref() if mlp_b else None, P(rec), P(g_rec), P(self.g_norm_cl), P(self.g_denorm_cl), *grads8,
                     P(affine[0]) if affine else None, P(affine[1]) if affine else None, affine[0].shape[0] if affine else 0,
                     P(self.g_scale), P(self.g_shift), stream)
             if coords is not None:

@@ -369,6 +369,7 @@ NFE_EXPORT int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a
     NFE_REQUIRE(!cfg->affine_scale || cfg->affine_items == 1 || cfg->affine_items == n, "nfe_run_model_fwd: affine statistics for %d items, batch is %d",
                 cfg->affine_items, n);
     NFE_REQUIRE((planes_denorm_cl || geo_only || affine) && coords && sigma && (rgb || sigma_only), "nfe_run_model_fwd: null pointer");
+    NFE_REQUIRE(!affine || m >= 128, "nfe_run_model_fwd: the single-gather identity needs at least 128 points per item (%lld)", (long long)m);
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_run_model_fwd: the disentangled decoder needs the normalised planes");
     NFE_REQUIRE(cfg->kind == NFE_DEC_OSG || seg || sigma_only, "nfe_run_model_fwd: seg output missing");
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_run_model_fwd: plane batch %d does not match point batch %d", plane_batch, n);

@@ -18,6 +18,11 @@
 // shared-memory tiles the other GEMMs read K-major, described MN-major (transposed) to the tensor core, so nothing
 // is transposed in software.
 //
+// KIND selects the decoder (triplane.py:167-270).  DISENTANGLED is the layout described above.  SEGMENTATION has `net`
+// (33 outputs: sigma + 32 colours) and `seg_net` (15 logits), BOTH on the raw-plane features: the raw set is gathered once and
+// written into both X column groups, dY = [dY_net (48, 33 used) | dY_seg (16, 15 used)], and dX_net + dX_seg scatter into the
+// raw-plane gradient.  OSG is SEGMENTATION without a second net (its weights are zeros, nothing of it is flushed).
+//
 // AFFINE = true is the backward of the forward's single-gather identity: the raw planes are known to be
 // norm*scale + shift per (item, plane, channel), so only the normalised set is gathered and only its gradient is
 // scattered.  With f_p the per-plane blend of the normalised planes and w_p the in-bounds tap-weight sum,
@@ -38,15 +43,21 @@ namespace fb {
 constexpr int THREADS = 256;
 constexpr int XA_COLS = 80, XA_LBO = 160, XA_SBO = (XA_COLS / 8) * XA_LBO, XA_BYTES = 16 * XA_SBO;   // [X_norm | X_raw | 1 0..0]
 constexpr int HC_COLS = 128, HC_LBO = 128, HC_SBO = (HC_COLS / 8) * HC_LBO, HC_BYTES = 16 * HC_SBO;  // [H_geo | H_app], later dpre
-constexpr int DY_COLS = 48, DY_LBO = 128, DY_SBO = (DY_COLS / 8) * DY_LBO, DY_BYTES = 16 * DY_SBO;   // [dY_geo(16) | dY_app(32)]
-constexpr int W2T_LBO = 128, W2T_SBO = 512, W2T_BYTES = 8 * W2T_SBO;     // B of G2: [N=64 x K<=32], element (j,o) = W2[o][j]
+// output-layer layout per decoder kind: real / padded output counts of the two nets; dY = [dY_0 (PAD0) | dY_1 (PAD1)]
+template <int KIND> struct Out;
+template <> struct Out<NFE_DEC_DISENTANGLED> { static constexpr int OUT0 = 16, PAD0 = 16, OUT1 = 32, PAD1 = 32; };   // geo | app
+template <> struct Out<NFE_DEC_SEGMENTATION> { static constexpr int OUT0 = 33, PAD0 = 48, OUT1 = 15, PAD1 = 16; };   // net | seg_net
+template <> struct Out<NFE_DEC_OSG> { static constexpr int OUT0 = 33, PAD0 = 48, OUT1 = 0, PAD1 = 16; };              // net | (none)
+constexpr int DY_LBO = 128;
+constexpr int W2T_LBO = 128, W2T_SBO = 768, W2T_BYTES = 8 * W2T_SBO;     // B of G2: [N=64 x K<=48], element (j,o) = W2[o][j]
 constexpr int W1T_LBO = 128, W1T_SBO = 1024, W1T_BYTES = 4 * W1T_SBO;    // B of G3: [N=32 x K=64], element (i,j) = W1[j][i]
 constexpr int GX_STRIDE = 68;                                            // fp32 dX staging row stride (floats), aliases hc
 // TMEM columns
 constexpr int C_PRE = 0, C_DH = 128, C_DX = 256, C_DW1 = 320, C_DW2 = 400, TMEM_ALLOC = 512;
 
-template <bool AFFINE>
+template <int KIND, bool AFFINE>
 struct Smem {
+    static constexpr int DY_COLS = Out<KIND>::PAD0 + Out<KIND>::PAD1, DY_SBO = (DY_COLS / 8) * DY_LBO, DY_BYTES = 16 * DY_SBO;
     alignas(128) unsigned char xa[2][XA_BYTES];
     alignas(128) unsigned char hc[2][HC_BYTES];
     alignas(128) unsigned char dy[2][DY_BYTES];
@@ -153,13 +164,18 @@ __device__ unsigned long long g_bwd_prof[16];
 #define BWD_MARK(slot) do { } while (0)
 #endif
 
-template <bool AFFINE>
+template <int KIND, bool AFFINE>
 __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp geo, nfe_mlp app)
 {
+    using O = Out<KIND>;
+    constexpr bool DIS = KIND == NFE_DEC_DISENTANGLED;
+    constexpr int DY_COLS = O::PAD0 + O::PAD1, DY_SBO = (DY_COLS / 8) * DY_LBO;
+    static_assert(!AFFINE || DIS, "the single-gather identity belongs to the disentangled decoder");
+    static_assert(C_DW2 + DY_COLS <= TMEM_ALLOC, "tensor memory");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     // (no integer round-up of the base: it strips the shared address space and every LDS/STS below becomes a generic LD/ST — round 1's
     // build had 258 of those and 10 LDS/STS; the dynamic window starts 1024-byte aligned, the kernel has no static shared memory)
-    Smem<AFFINE>& s = *reinterpret_cast<Smem<AFFINE>*>(smem_raw);
+    Smem<KIND, AFFINE>& s = *reinterpret_cast<Smem<KIND, AFFINE>*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int net = warp >> 2;                       // epilogue role: warps 0-3 geo_net, 4-7 app_net
     const int row = (warp & 3) * 32 + lane;          // TMEM lane = tile row
@@ -170,10 +186,11 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
     if (threadIdx.x == 0) { tc::mbar_init(&s.bar, 1); tc::mbar_fence_init(); }
     for (int n = 0; n < 2; ++n) {
         const nfe_mlp& p = n ? app : geo;
-        load_weights<2>(s.w1[n][0], B1_BYTES, p.w1, p.wgain1, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
-        load_weights_t(s.w2t[n][0], W2T_BYTES, p.w2, p.wgain2, HIDDEN, p.out_dim, n ? 32 : 16, HIDDEN, W2T_LBO, W2T_SBO);
-        load_weights_t(s.w1t[n][0], W1T_BYTES, p.w1, p.wgain1, FEAT, HIDDEN, HIDDEN, FEAT, W1T_LBO, W1T_SBO);
-        for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s.bias1[n][i] = folded_bias(p.b1, p.bgain1, i);
+        const bool present = n == 0 || O::OUT1 > 0;            // OSG has no second net: all-zero operands, nothing flushed
+        load_weights<2>(s.w1[n][0], B1_BYTES, p.w1, p.wgain1, present ? HIDDEN : 0, HIDDEN, FEAT, B1_LBO, B1_SBO);
+        load_weights_t(s.w2t[n][0], W2T_BYTES, p.w2, p.wgain2, HIDDEN, n ? O::OUT1 : O::OUT0, n ? O::PAD1 : O::PAD0, HIDDEN, W2T_LBO, W2T_SBO);
+        load_weights_t(s.w1t[n][0], W1T_BYTES, p.w1, p.wgain1, FEAT, present ? HIDDEN : 0, HIDDEN, FEAT, W1T_LBO, W1T_SBO);
+        for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s.bias1[n][i] = present ? folded_bias(p.b1, p.bgain1, i) : 0.0f;
     }
     for (int i = threadIdx.x; i < TILE_M * 16; i += blockDim.x) {
         const int r = i >> 4, c = 64 + (i & 15);
@@ -188,9 +205,10 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
     const uint32_t tmem = s.tmem_base;
     const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     uint32_t phase = 0;
-    float db2[32];
+    constexpr int DB2 = O::PAD0 > O::PAD1 ? O::PAD0 : O::PAD1;
+    float db2[DB2];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) db2[i] = 0.0f;
+    for (int i = 0; i < DB2; ++i) db2[i] = 0.0f;
 
     const int64_t n_tiles = (a.total + TILE_M - 1) / TILE_M;
     const int64_t set_stride4 = (int64_t)3 * a.H * a.W * (FEAT / 4);
@@ -337,9 +355,15 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                 TapSet ts;
                 float4 va[12], vb[12];
                 read_taps(r, ts);
-                gather_load(a.set_norm, ts, c4, va);
-                gather_load(a.set_raw, ts, c4, vb);
-                store_x(r, gather_reduce(va, ts), gather_reduce(vb, ts));
+                if constexpr (DIS) {
+                    gather_load(a.set_norm, ts, c4, va);
+                    gather_load(a.set_raw, ts, c4, vb);
+                    store_x(r, gather_reduce(va, ts), gather_reduce(vb, ts));
+                } else {                                       // both nets read the raw-plane features
+                    gather_load(a.set_raw, ts, c4, vb);
+                    const float4 f = gather_reduce(vb, ts);
+                    store_x(r, f, f);
+                }
             }
         }
         tc::fence_async_smem();
@@ -357,17 +381,20 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         }
         // record gradients (and the saved colours) of this thread's row: requested now, consumed after the softplus loop
         const bool live = base + row < a.total;
-        float4 pg[8], py[8];
+        float4 pg[9], py[8];
         {
             const float4* g4 = reinterpret_cast<const float4*>(a.g_rec + (base + row) * 48);
             const float4* r4 = reinterpret_cast<const float4*>(a.rec + (base + row) * 48);
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (net == 0) {
+            // records are {sigma, seg[15], rgb[32]}: the colour net needs d rgb and the saved rgb, the other one d sigma / d seg
+            const bool colour_net = DIS ? net == 1 : net == 0;
+            if (!colour_net) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) pg[i] = live ? __ldg(g4 + i) : z4;
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { pg[i] = live ? __ldg(g4 + 4 + i) : z4; py[i] = live ? __ldg(r4 + 4 + i) : z4; }
+                if (!DIS) pg[8] = live ? __ldg(g4) : z4;             // d sigma rides with the colours in `net` (33 outputs)
             }
         }
         tc::mbar_wait(&s.bar, phase); phase ^= 1;
@@ -391,34 +418,62 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                     store8(s.hc[0], s.hc[1], core_offset(row, 64 * net + q * 16 + c8 * 8, HC_LBO, HC_SBO), h8);
                 }
             }
-            if (net == 0) {
+            // colour gradients through rgb = s*1.002 - 0.001, s = sigmoid(out):  d rgb / d out = 1.002 * s * (1 - s), s from the saved rgb
+            auto colour_dy = [&](int c) {
+                const float4 g = pg[c >> 2], y = py[c >> 2];
+                const int i = c & 3;
+                const float gv = i == 0 ? g.x : i == 1 ? g.y : i == 2 ? g.z : g.w, yv = i == 0 ? y.x : i == 1 ? y.y : i == 2 ? y.z : y.w;
+                const float sg = (yv + 0.001f) * (1.0f / 1.002f);
+                return gv * 1.002f * sg * (1.0f - sg);
+            };
+            auto rec_g = [&](int c) {                                   // element c of the first 16 record gradients {d sigma, d seg[15]}
+                const float4 g = pg[c >> 2];
+                const int i = c & 3;
+                return i == 0 ? g.x : i == 1 ? g.y : i == 2 ? g.z : g.w;
+            };
+            if constexpr (DIS) {
+                if (net == 0) {                                         // geo_net: [d sigma, d seg[15]]
 #pragma unroll
-                for (int c8 = 0; c8 < 2; ++c8) {
-                    float d8[8];
-                    const float4 g0 = pg[2 * c8], g1 = pg[2 * c8 + 1];
-                    d8[0] = g0.x; d8[1] = g0.y; d8[2] = g0.z; d8[3] = g0.w; d8[4] = g1.x; d8[5] = g1.y; d8[6] = g1.z; d8[7] = g1.w;
+                    for (int c8 = 0; c8 < 2; ++c8) {
+                        float d8[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) db2[c8 * 8 + i] += d8[i];
-                    store8(s.dy[0], s.dy[1], core_offset(row, c8 * 8, DY_LBO, DY_SBO), d8);
+                        for (int i = 0; i < 8; ++i) { d8[i] = rec_g(c8 * 8 + i); db2[c8 * 8 + i] += d8[i]; }
+                        store8(s.dy[0], s.dy[1], core_offset(row, c8 * 8, DY_LBO, DY_SBO), d8);
+                    }
+                } else {                                                // app_net: 32 colours
+#pragma unroll
+                    for (int c8 = 0; c8 < 4; ++c8) {
+                        float d8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { d8[i] = colour_dy(c8 * 8 + i); db2[c8 * 8 + i] += d8[i]; }
+                        store8(s.dy[0], s.dy[1], core_offset(row, O::PAD0 + c8 * 8, DY_LBO, DY_SBO), d8);
+                    }
                 }
             } else {
+                if (net == 0) {                                         // net: [d sigma, 32 colours, 15 x 0]
 #pragma unroll
-                for (int c8 = 0; c8 < 4; ++c8) {
-                    float d8[8];
+                    for (int c8 = 0; c8 < O::PAD0 / 8; ++c8) {
+                        float d8[8];
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const float4 g = pg[2 * c8 + h], y = py[2 * c8 + h];
-                        // rgb = s*1.002 - 0.001 with s = sigmoid(out)  =>  d rgb / d out = 1.002 * s * (1 - s)
-                        const float gs[4] = {g.x, g.y, g.z, g.w}, ys[4] = {y.x, y.y, y.z, y.w};
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float sg = (ys[i] + 0.001f) * (1.0f / 1.002f);
-                            d8[4 * h + i] = gs[i] * 1.002f * sg * (1.0f - sg);
+                        for (int i = 0; i < 8; ++i) {
+                            const int k = c8 * 8 + i;
+                            d8[i] = k == 0 ? pg[8].x : (k <= 32 ? colour_dy(k - 1) : 0.0f);
+                            db2[k] += d8[i];
                         }
+                        store8(s.dy[0], s.dy[1], core_offset(row, c8 * 8, DY_LBO, DY_SBO), d8);
                     }
+                } else {                                                // seg_net: [d seg[15], 0]; absent in OSG
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) db2[c8 * 8 + i] += d8[i];
-                    store8(s.dy[0], s.dy[1], core_offset(row, 16 + c8 * 8, DY_LBO, DY_SBO), d8);
+                    for (int c8 = 0; c8 < O::PAD1 / 8; ++c8) {
+                        float d8[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int k = c8 * 8 + i;
+                            d8[i] = (O::OUT1 > 0 && k < 15) ? rec_g(k + 1) : 0.0f;
+                            db2[k] += d8[i];
+                        }
+                        store8(s.dy[0], s.dy[1], core_offset(row, O::PAD0 + c8 * 8, DY_LBO, DY_SBO), d8);
+                    }
                 }
             }
         }
@@ -431,8 +486,9 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         if (threadIdx.x == 0) {
             tc::fence_after_sync();
             constexpr uint32_t id2 = tc::make_idesc_bf16(TILE_M, HIDDEN);
-            issue_gemm<true>(tmem + C_DH, s.dy[0], s.dy[1], DY_LBO, DY_SBO, s.w2t[0][0], s.w2t[0][1], W2T_LBO, W2T_SBO, 16, id2);
-            issue_gemm<true>(tmem + C_DH + 64, s.dy[0] + 2 * DY_LBO, s.dy[1] + 2 * DY_LBO, DY_LBO, DY_SBO, s.w2t[1][0], s.w2t[1][1], W2T_LBO, W2T_SBO, 32, id2);
+            issue_gemm<true>(tmem + C_DH, s.dy[0], s.dy[1], DY_LBO, DY_SBO, s.w2t[0][0], s.w2t[0][1], W2T_LBO, W2T_SBO, O::PAD0, id2);
+            issue_gemm<true>(tmem + C_DH + 64, s.dy[0] + (O::PAD0 / 8) * DY_LBO, s.dy[1] + (O::PAD0 / 8) * DY_LBO, DY_LBO, DY_SBO, s.w2t[1][0], s.w2t[1][1],
+                             W2T_LBO, W2T_SBO, O::PAD1, id2);
             issue_gemm_rows(tmem + C_DW2, s.hc[0], s.hc[1], HC_LBO, HC_SBO, s.dy[0], s.dy[1], DY_LBO, DY_SBO, idesc_mn(TILE_M, DY_COLS), !first);
             tc::mma_commit(&s.bar);
         }
@@ -535,12 +591,13 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                 }
                 continue;
             }
+            if constexpr (!DIS) gr = make_float4(gn.x + gr.x, gn.y + gr.y, gn.z + gr.z, gn.w + gr.w);      // both nets read the raw planes
 #pragma unroll
             for (int i = 0; i < 12; ++i) {
                 const float w = s.tap_w[r][i];
                 if (w != 0.0f) {
                     const int64_t off = (int64_t)s.tap_off[r][i] * 4 + 4 * c4;
-                    red_add_v4(a.g_norm + off, make_float4(gn.x * w, gn.y * w, gn.z * w, gn.w * w));
+                    if constexpr (DIS) red_add_v4(a.g_norm + off, make_float4(gn.x * w, gn.y * w, gn.z * w, gn.w * w));
                     red_add_v4(a.g_raw + off, make_float4(gr.x * w, gr.y * w, gr.z * w, gr.w * w));
                 }
             }
@@ -557,7 +614,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
     // ---- parameter gradients of this CTA -> global (chain rule through the FullyConnectedLayer gains)
     if (!first) {
         tc::fence_after_sync();
-        if (warp < 4) {
+        if (warp < 4 && ((row >> 6) == 0 || O::OUT1 > 0)) {     // (OSG: the rows of the absent second net carry nothing)
             const int n = row >> 6, j = row & 63;               // accumulator row = hidden unit j of net n
             const nfe_mlp& p = n ? app : geo;
             const uint32_t la = tmem + ((uint32_t)(warp * 32) << 16);
@@ -577,18 +634,19 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                 float v[16];
                 tc::tmem_ld16(la + C_DW2 + q * 16, v);
                 tc::tmem_ld_wait();
-                const bool mine_q = n == 0 ? q == 0 : q >= 1;
-                if (mine_q) {
-                    const int o0 = n == 0 ? 0 : (q - 1) * 16;
+                // columns [0, PAD0) belong to net 0, [PAD0, PAD0 + PAD1) to net 1; only the real outputs of this row's net are flushed
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) atomicAdd(a.gw2[n] + (o0 + i) * HIDDEN + j, v[i] * p.wgain2);
+                for (int i = 0; i < 16; ++i) {
+                    const int c = q * 16 + i;
+                    const int o = n == 0 ? c : c - O::PAD0;
+                    if ((n == 0 ? c < O::PAD0 : c >= O::PAD0) && o < (n == 0 ? O::OUT0 : O::OUT1)) atomicAdd(a.gw2[n] + o * HIDDEN + j, v[i] * p.wgain2);
                 }
             }
         }
         // db2: column sums over the rows this thread handled, reduced over the warp
-        const int n_out = net ? 32 : 16;
+        const int n_out = net ? O::OUT1 : O::OUT0;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
+        for (int i = 0; i < DB2; ++i) {
             float v = db2[i];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -616,17 +674,22 @@ static int field_bwd_launch(const char* who, int kind, const float* planes_norm_
     const int64_t total = (int64_t)n * n_rays * s_per_ray;
     if (total == 0) return 0;
     const bool affine = affine_scale != nullptr;
-    NFE_REQUIRE(kind == NFE_DEC_DISENTANGLED, "%s: only the DisentangledOSGDecoder has a fused backward (kind %d)", who, kind);
-    NFE_REQUIRE(planes_norm_cl && (coords || (origins && dirs && depths)) && net_a && net_b && rec && g_rec && g_planes_norm_cl, "%s: null pointer", who);
+    const bool dis = kind == NFE_DEC_DISENTANGLED, osg = kind == NFE_DEC_OSG;
+    NFE_REQUIRE(kind == NFE_DEC_DISENTANGLED || kind == NFE_DEC_SEGMENTATION || kind == NFE_DEC_OSG, "%s: unknown decoder kind %d", who, kind);
+    NFE_REQUIRE((coords || (origins && dirs && depths)) && net_a && (net_b || osg) && rec && g_rec, "%s: null pointer", who);
+    NFE_REQUIRE(!dis || (planes_norm_cl && g_planes_norm_cl), "%s: the disentangled decoder needs the normalised planes and their gradient buffer", who);
     if (affine) {
+        NFE_REQUIRE(dis, "%s: the single-gather backward belongs to the disentangled decoder", who);
         NFE_REQUIRE(affine_shift && g_affine_scale && g_affine_shift, "%s: the single-gather backward needs shift and both statistics gradients", who);
         NFE_REQUIRE(affine_items == n || affine_items == 1, "%s: %d statistics rows for a batch of %d", who, affine_items, n);
     } else {
         NFE_REQUIRE(planes_cl && g_planes_cl, "%s: null raw-plane pointer (and no affine statistics)", who);
     }
-    NFE_REQUIRE(g_w1_a && g_b1_a && g_w2_a && g_b2_a && g_w1_b && g_b1_b && g_w2_b && g_b2_b, "%s: null parameter-gradient pointer", who);
-    NFE_REQUIRE(net_a->in_dim == FEAT && net_a->hidden == HIDDEN && net_a->out_dim == 16 && net_b->in_dim == FEAT && net_b->hidden == HIDDEN &&
-                net_b->out_dim == 32, "%s: decoder widths must be 32-64-16 / 32-64-32", who);
+    NFE_REQUIRE(g_w1_a && g_b1_a && g_w2_a && g_b2_a && (osg || (g_w1_b && g_b1_b && g_w2_b && g_b2_b)), "%s: null parameter-gradient pointer", who);
+    const int out_a = dis ? 16 : 33, out_b = dis ? 32 : 15;
+    NFE_REQUIRE(net_a->in_dim == FEAT && net_a->hidden == HIDDEN && net_a->out_dim == out_a &&
+                (osg || (net_b->in_dim == FEAT && net_b->hidden == HIDDEN && net_b->out_dim == out_b)),
+                "%s: decoder widths must be 32-64-%d%s", who, out_a, osg ? "" : (dis ? " / 32-64-32" : " / 32-64-15"));
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "%s: plane batch %d does not match batch %d", who, plane_batch, n);
     NFE_REQUIRE((int64_t)plane_batch * height * width * 3 * (FEAT / 4) < (1ll << 31), "%s: planes exceed the 32-bit texel offsets", who);
     NFE_REQUIRE(box_warp != 0.0f, "%s: box_warp must be non-zero", who);
@@ -639,19 +702,27 @@ static int field_bwd_launch(const char* who, int kind, const float* planes_norm_
     a.gw1[1] = g_w1_b; a.gb1[1] = g_b1_b; a.gw2[1] = g_w2_b; a.gb2[1] = g_b2_b;
     a.affine_scale = affine_scale; a.affine_shift = affine_shift; a.affine_items = affine_items;
     a.g_scale = g_affine_scale; a.g_shift = g_affine_shift;
-    const size_t smem = (affine ? sizeof(fb::Smem<true>) : sizeof(fb::Smem<false>)) + 128;
-    static bool configured[2] = {false, false};
-    if (!configured[affine]) {
-        cudaError_t e = affine ? cudaFuncSetAttribute(fb::field_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                               : cudaFuncSetAttribute(fb::field_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        NFE_REQUIRE(e == cudaSuccess, "%s: cannot reserve %zu bytes of shared memory: %s", who, smem, cudaGetErrorString(e));
-        configured[affine] = true;
-    }
+    const nfe_mlp none = {};
+    const nfe_mlp& nb = net_b ? *net_b : none;
     const int64_t n_tiles = (total + TILE_M - 1) / TILE_M;
     const int64_t cap = sm_count();
     const unsigned grid = (unsigned)(n_tiles < cap ? n_tiles : cap);
-    if (affine) fb::field_bwd_kernel<true><<<grid, fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, *net_b);
-    else fb::field_bwd_kernel<false><<<grid, fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, *net_b);
+    auto launch = [&](auto kernel, size_t smem, bool& configured) -> int {
+        if (!configured) {
+            cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            NFE_REQUIRE(e == cudaSuccess, "%s: cannot reserve %zu bytes of shared memory: %s", who, smem, cudaGetErrorString(e));
+            configured = true;
+        }
+        kernel<<<grid, fb::THREADS, smem, as_stream(stream)>>>(a, *net_a, nb);
+        return 0;
+    };
+    static bool configured[4] = {false, false, false, false};
+    int rc;
+    if (dis && affine) rc = launch(fb::field_bwd_kernel<NFE_DEC_DISENTANGLED, true>, sizeof(fb::Smem<NFE_DEC_DISENTANGLED, true>) + 128, configured[0]);
+    else if (dis) rc = launch(fb::field_bwd_kernel<NFE_DEC_DISENTANGLED, false>, sizeof(fb::Smem<NFE_DEC_DISENTANGLED, false>) + 128, configured[1]);
+    else if (osg) rc = launch(fb::field_bwd_kernel<NFE_DEC_OSG, false>, sizeof(fb::Smem<NFE_DEC_OSG, false>) + 128, configured[2]);
+    else rc = launch(fb::field_bwd_kernel<NFE_DEC_SEGMENTATION, false>, sizeof(fb::Smem<NFE_DEC_SEGMENTATION, false>) + 128, configured[3]);
+    if (rc) return rc;
     NFE_LAUNCH_CHECK("field_bwd_kernel");
     return 0;
 }

@@ -14,8 +14,8 @@
 //   warps  4-7   epilogue group 1: tiles 1, 3, 5, ...                      (two whole, independent epilogues interleave on every
 //                                                                          sub-partition instead of one epilogue split by columns)
 //   warp   8     MMA issuer (one elected thread)
-//   warps  9-11  tap producers: position -> texel offsets + bilinear weights; warp w makes the taps of tiles w, w+3, ... with all
-//                32 lanes busy (one sample per lane, four rounds per tile), up to two tiles ahead of the gather (3 tap buffers)
+//   warps  9-11  tap producers: position -> texel offsets + bilinear weights, one sample per lane; the four 32-sample chunks of a
+//                tile are dealt over the three warps, up to two tiles ahead of the gather (3 tap buffers)
 //   warps 12-19  gather: 8 lanes per sample, LDG.128 per tap, rolling one-pass-ahead texel pipeline, bf16 hi/lo feature tile
 //
 // Tensor memory: each epilogue group owns one accumulator set of 192 columns: D1A 64 | D1B 64 | D2 <= 64.  The hidden
@@ -23,6 +23,8 @@
 // of bf16 hi pairs + 8 of lo pairs out), from where the layer-2 MMAs take them as their A operand — no separate hidden
 // region, no shared-memory round trip.  Layer 1 of tile i+2 is issued as soon as layer 2 of tile i has consumed that region
 // (its own commit), i.e. while group g is still writing tile i's outputs, so an epilogue group never waits for a layer 1.
+#include <type_traits>
+
 #include "nfe_field_launch.cuh"
 #include "nfe_mlp_tc.cuh"
 
@@ -67,12 +69,20 @@ constexpr int REC_STAGE_STRIDE = 208;                       // bytes per staged 
 #ifndef NFE_P2_REGS_MISC
 #define NFE_P2_REGS_MISC 64
 #endif
+#ifndef NFE_P2_UNROLL_PASSES
+#define NFE_P2_UNROLL_PASSES 0      // unrolling the passes of a tile trades loop bookkeeping for instruction-cache misses: slower
+#endif
+#ifndef NFE_P2_ROLLED_MMA
+#define NFE_P2_ROLLED_MMA 0
+#endif
 #ifndef NFE_P2_REGS_GATHER
 #define NFE_P2_REGS_GATHER 88
 #endif
 constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8 > 96 ? 96 : (65536 / THREADS) / 8 * 8;       // 20 warps: 96, 24 warps: 80
 constexpr int REGS_EPI = NFE_P2_REGS_EPI, REGS_MISC = NFE_P2_REGS_MISC, REGS_GATHER = NFE_P2_REGS_GATHER;
-static_assert(!NFE_P2_SETMAXNREG || (8 * (REGS_EPI - REGS_LAUNCH) + GATHER_WARPS * (REGS_GATHER - REGS_LAUNCH) <= 4 * (REGS_LAUNCH - REGS_MISC)),
+static_assert(!NFE_P2_SETMAXNREG || (REGS_EPI >= REGS_LAUNCH && REGS_MISC <= REGS_LAUNCH), "epilogue groups only grow, the MMA / tap group only shrinks");
+static_assert(!NFE_P2_SETMAXNREG || (8 * (REGS_EPI - REGS_LAUNCH) + (REGS_GATHER > REGS_LAUNCH ? GATHER_WARPS * (REGS_GATHER - REGS_LAUNCH) : 0)
+                                     <= 4 * (REGS_LAUNCH - REGS_MISC) + (REGS_GATHER < REGS_LAUNCH ? GATHER_WARPS * (REGS_LAUNCH - REGS_GATHER) : 0)),
               "setmaxnreg.inc would wait forever");
 static_assert(!NFE_P2_SETMAXNREG || (2 * REGS_EPI + REGS_MISC + (GATHER_WARPS / 4) * REGS_GATHER) * 32 <= 16384, "register file of a sub-partition");
 
@@ -185,11 +195,19 @@ __device__ __forceinline__ void issue_layer2(uint32_t tmem_d, uint32_t tmem_h, c
 {
     bool acc = false;
     constexpr int TERMS = SPLIT ? 3 : 1;
+#if NFE_P2_ROLLED_MMA
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
     for (int t = 0; t < TERMS; ++t) {
         const uint32_t part = (t == 1) ? 8u : 0u;                        // hi*hi, lo*hi, hi*lo
         const unsigned char* b = (t == 2) ? b_lo : b_hi;
+#if NFE_P2_ROLLED_MMA
+#pragma unroll 1
+#else
 #pragma unroll
+#endif
         for (int ks = 0; ks < HIDDEN / 16; ++ks) {
             const uint64_t db = tc::make_desc(tc::smem_u32(b) + (ks * 2) * B2_LBO, B2_LBO, B2_SBO);
             tc::mma_bf16_ts(tmem_d, tmem_h + ks * 16 + part, db, idesc, acc);
@@ -279,7 +297,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
             tc::mbar_init(&s.d2_free[i], 4);
         }
         for (int i = 0; i < TAP_BUFS; ++i) {
-            tc::mbar_init(&s.taps_full[i], 1);
+            tc::mbar_init(&s.taps_full[i], TAP_WARPS);
             tc::mbar_init(&s.taps_empty[i], GATHER_WARPS);
         }
         tc::mbar_fence_init();
@@ -341,58 +359,66 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
             const bool has_next = it + 1 < n_my;
             P2_WAIT(1, &s.empty[st], ((it >> 1) & 1) ^ 1);      // slot released by the layer-1 commit two tiles ago
             if (rolling) {
-#pragma unroll 1
-                for (int p = 0; p < n_pass; ++p) {
-                    const int row = row0 + 4 * p;
-                    const uint4* cur = s.taps[tb][row];
-                    const bool more = p + 1 < n_pass;
-                    const bool fetch = more || has_next;
-                    if (!more && has_next) P2_WAIT(0, &s.taps_full[tb_next], ((it + 1) / TAP_BUFS) & 1);
-                    const uint4* nxt = more ? s.taps[tb][row + 4] : s.taps[tb_next][row0];
-                    float2 f01[3], f23[3], w_in[3];
+                // the passes of a tile are unrolled (shared-memory addresses become base + constant, no loop bookkeeping): the
+                // body is instantiated for the two pass counts a warp can own
+                auto tile_body = [&](auto np_tag) {
+                    constexpr int NP = decltype(np_tag)::value;
+                    const uint4* tap_row = s.taps[tb][row0];
+#if NFE_P2_UNROLL_PASSES
 #pragma unroll
-                    for (int pl = 0; pl < 3; ++pl) {
-                        const float4 w4 = *reinterpret_cast<const float4*>(&cur[3 + pl]);
-                        const float2 w0 = make_float2(w4.x, w4.x), w1 = make_float2(w4.y, w4.y), w2 = make_float2(w4.z, w4.z), w3 = make_float2(w4.w, w4.w);
-                        float2 a01 = fmul2(make_float2(va[4 * pl].x, va[4 * pl].y), w0), a23 = fmul2(make_float2(va[4 * pl].z, va[4 * pl].w), w0);
-                        a01 = ffma2(make_float2(va[4 * pl + 1].x, va[4 * pl + 1].y), w1, a01); a23 = ffma2(make_float2(va[4 * pl + 1].z, va[4 * pl + 1].w), w1, a23);
-                        a01 = ffma2(make_float2(va[4 * pl + 2].x, va[4 * pl + 2].y), w2, a01); a23 = ffma2(make_float2(va[4 * pl + 2].z, va[4 * pl + 2].w), w2, a23);
-                        a01 = ffma2(make_float2(va[4 * pl + 3].x, va[4 * pl + 3].y), w3, a01); a23 = ffma2(make_float2(va[4 * pl + 3].z, va[4 * pl + 3].w), w3, a23);
-                        f01[pl] = a01; f23[pl] = a23;
-                        w_in[pl] = fadd2(fadd2(fadd2(w0, w1), w2), w3);
-                        if (fetch) {             // refill the four registers just consumed with the next pass's texels
-                            const uint4 o4 = nxt[pl];
-                            va[4 * pl] = ldg_tap(set_r, o4.x, pl != 0); va[4 * pl + 1] = ldg_tap(set_r, o4.y, pl != 0);
-                            va[4 * pl + 2] = ldg_tap(set_r, o4.z, pl != 0); va[4 * pl + 3] = ldg_tap(set_r, o4.w, pl != 0);
-                        }
-                    }
-                    const float2 third2 = make_float2(1.0f / 3.0f, 1.0f / 3.0f);
-                    const float2 fa01 = fmul2(fadd2(fadd2(f01[0], f01[1]), f01[2]), third2), fa23 = fmul2(fadd2(fadd2(f23[0], f23[1]), f23[2]), third2);
-                    store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, make_float4(fa01.x, fa01.y, fa23.x, fa23.y));
-                    if (affine && !skip_b) {
-                        // single-gather identity: only the normalised planes are read; the de-normalised features are
-                        // s*f_p + m*w_in per plane (statistics: 6 L1-resident float4 loads per lane)
-                        const int item = a.affine_items == 1 ? 0 : (int)cur[6].x;
-                        const uint32_t rel = (uint32_t)(item - s.aff_item[tb]);
-                        // the tile's own table (shared memory) unless the sample sits more than one item past the tile's first
-                        // (only possible when an item has fewer than 128 samples): then straight from global memory
-                        const float4* gsc = reinterpret_cast<const float4*>(a.affine_scale + (int64_t)item * 96) + c4;
-                        const float4* gsh = reinterpret_cast<const float4*>(a.affine_shift + (int64_t)item * 96) + c4;
-                        const float4* ssc = reinterpret_cast<const float4*>(s.aff[tb][rel & 1u][0]) + c4;
-                        const float4* ssh = reinterpret_cast<const float4*>(s.aff[tb][rel & 1u][1]) + c4;
-                        float2 d01[3], d23[3];
+#else
+#pragma unroll 1
+#endif
+                    for (int p = 0; p < NP; ++p) {
+                        const int row = row0 + 4 * p;
+                        const uint4* cur = tap_row + 4 * p * 7;
+                        const bool more = p + 1 < NP;
+                        const bool fetch = more || has_next;
+                        if (!more && has_next) P2_WAIT(0, &s.taps_full[tb_next], ((it + 1) / TAP_BUFS) & 1);
+                        const uint4* nxt = more ? cur + 4 * 7 : s.taps[tb_next][row0];
+                        float2 f01[3], f23[3];
 #pragma unroll
                         for (int pl = 0; pl < 3; ++pl) {
-                            float4 scl, shf;
-                            if (rel < 2u) { scl = ssc[pl * 8]; shf = ssh[pl * 8]; }          // LDS (kept apart from the LDG path: one
-                            else { scl = __ldg(gsc + pl * 8); shf = __ldg(gsh + pl * 8); }  // selected pointer would be generic)
-                            d01[pl] = ffma2(make_float2(scl.x, scl.y), f01[pl], fmul2(make_float2(shf.x, shf.y), w_in[pl]));
-                            d23[pl] = ffma2(make_float2(scl.z, scl.w), f23[pl], fmul2(make_float2(shf.z, shf.w), w_in[pl]));
+                            const float4 w4 = *reinterpret_cast<const float4*>(&cur[3 + pl]);
+                            const float2 w0 = make_float2(w4.x, w4.x), w1 = make_float2(w4.y, w4.y), w2 = make_float2(w4.z, w4.z), w3 = make_float2(w4.w, w4.w);
+                            float2 a01 = fmul2(make_float2(va[4 * pl].x, va[4 * pl].y), w0), a23 = fmul2(make_float2(va[4 * pl].z, va[4 * pl].w), w0);
+                            a01 = ffma2(make_float2(va[4 * pl + 1].x, va[4 * pl + 1].y), w1, a01); a23 = ffma2(make_float2(va[4 * pl + 1].z, va[4 * pl + 1].w), w1, a23);
+                            a01 = ffma2(make_float2(va[4 * pl + 2].x, va[4 * pl + 2].y), w2, a01); a23 = ffma2(make_float2(va[4 * pl + 2].z, va[4 * pl + 2].w), w2, a23);
+                            a01 = ffma2(make_float2(va[4 * pl + 3].x, va[4 * pl + 3].y), w3, a01); a23 = ffma2(make_float2(va[4 * pl + 3].z, va[4 * pl + 3].w), w3, a23);
+                            f01[pl] = a01; f23[pl] = a23;
+                            if (fetch) {             // refill the four registers just consumed with the next pass's texels
+                                const uint4 o4 = nxt[pl];
+                                va[4 * pl] = ldg_tap(set_r, o4.x, pl != 0); va[4 * pl + 1] = ldg_tap(set_r, o4.y, pl != 0);
+                                va[4 * pl + 2] = ldg_tap(set_r, o4.z, pl != 0); va[4 * pl + 3] = ldg_tap(set_r, o4.w, pl != 0);
+                            }
                         }
-                        const float2 fb01 = fmul2(fadd2(fadd2(d01[0], d01[1]), d01[2]), third2), fb23 = fmul2(fadd2(fadd2(d23[0], d23[1]), d23[2]), third2);
-                        store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, make_float4(fb01.x, fb01.y, fb23.x, fb23.y));
+                        const float2 third2 = make_float2(1.0f / 3.0f, 1.0f / 3.0f);
+                        const float2 fa01 = fmul2(fadd2(fadd2(f01[0], f01[1]), f01[2]), third2), fa23 = fmul2(fadd2(fadd2(f23[0], f23[1]), f23[2]), third2);
+                        store_features4<SPLIT>(s.a1[st][0], row, 4 * c4, make_float4(fa01.x, fa01.y, fa23.x, fa23.y));
+                        if (affine && !skip_b) {
+                            // single-gather identity: only the normalised planes are read; the de-normalised features are
+                            // s*f_p + m*w_in per plane, statistics from the tile's table in shared memory (the launcher only
+                            // enables the identity when an item has at least TILE_M samples, so a tile touches at most two items)
+                            const uint4 meta = cur[6];                       // item, w_in of the three planes
+                            const float wi[3] = {__uint_as_float(meta.y), __uint_as_float(meta.z), __uint_as_float(meta.w)};
+                            const uint32_t rel = a.affine_items == 1 ? 0u : ((uint32_t)((int)meta.x - s.aff_item[tb]) & 1u);
+                            const float4* ssc = reinterpret_cast<const float4*>(s.aff[tb][rel][0]) + c4;
+                            const float4* ssh = reinterpret_cast<const float4*>(s.aff[tb][rel][1]) + c4;
+                            float2 d01[3], d23[3];
+#pragma unroll
+                            for (int pl = 0; pl < 3; ++pl) {
+                                const float4 scl = ssc[pl * 8], shf = ssh[pl * 8];
+                                const float2 w2_ = make_float2(wi[pl], wi[pl]);
+                                d01[pl] = ffma2(make_float2(scl.x, scl.y), f01[pl], fmul2(make_float2(shf.x, shf.y), w2_));
+                                d23[pl] = ffma2(make_float2(scl.z, scl.w), f23[pl], fmul2(make_float2(shf.z, shf.w), w2_));
+                            }
+                            const float2 fb01 = fmul2(fadd2(fadd2(d01[0], d01[1]), d01[2]), third2), fb23 = fmul2(fadd2(fadd2(d23[0], d23[1]), d23[2]), third2);
+                            store_features4<SPLIT>(s.a1[st][T::SETS - 1], row, 4 * c4, make_float4(fb01.x, fb01.y, fb23.x, fb23.y));
+                        }
                     }
-                }
+                };
+                if (n_pass == PER_LONG) tile_body(std::integral_constant<int, PER_LONG>{});
+                else tile_body(std::integral_constant<int, PER_LONG - 1>{});
             } else {
                 if (it > 0) P2_WAIT(0, &s.taps_full[tb], (it / TAP_BUFS) & 1);
 #pragma unroll 1
@@ -437,13 +463,14 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
 #endif
         const int64_t set_stride4 = (int64_t)3 * a.H * a.W * (FEAT / 4);     // float4 units
         const bool small = a.total < (1ll << 31);
-        // tile-wise deal: tap warp w produces the taps of tiles w, w + TAP_WARPS, ... all by itself (4 x 32 samples), into the tap
-        // buffer of that tile; with TAP_WARPS == TAP_BUFS every warp owns one buffer
-        for (int it = tw; it < n_my; it += TAP_WARPS) {
+        // row-wise deal: every tap warp works on every tile — the four 32-sample chunks of a tile go to warps 0 .. TAP_WARPS-1, the
+        // remaining ones rotate with the tile — so a tile's taps are ready after at most two rounds, not four (the gather asks for
+        // them two tiles after it released the buffer: what counts is the latency of one tile's taps, not only the throughput)
+        for (int it = 0; it < n_my; ++it) {
             const int tb = it % TAP_BUFS;
             if (it >= TAP_BUFS) P2_WAIT(2, &s.taps_empty[tb], ((it / TAP_BUFS) - 1) & 1);
             const int64_t base = ((int64_t)blockIdx.x + (int64_t)it * G) * TILE_M;
-            if (T::SETS == 2 && a.affine_scale != nullptr) {
+            if (tw == 0 && T::SETS == 2 && a.affine_scale != nullptr) {
                 const int item0 = a.affine_items == 1 ? 0 : (int)(small ? (uint32_t)base / (uint32_t)a.m : base / a.m);
                 if (lane == 0) s.aff_item[tb] = item0;
                 for (int i = lane; i < 2 * 2 * 24; i += 32) {           // 2 items x {scale, shift} x 24 float4
@@ -455,6 +482,8 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
             }
 #pragma unroll 1
             for (int h = 0; h < TILE_M / 32; ++h) {
+                const int owner = h < TAP_WARPS ? h : (it + h) % TAP_WARPS;
+                if (owner != tw) continue;
                 const int row = h * 32 + lane;
                 TapSet ts;
                 int item_idx = 0;
@@ -479,7 +508,10 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
                     for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
                 }
                 uint4* dst = s.taps[tb][row];
-                dst[6] = make_uint4((uint32_t)item_idx, 0u, 0u, 0u);
+                // batch item and, per plane, the sum of the in-bounds tap weights (what the single-gather identity multiplies the
+                // shift by; summed in the order the gather warps used to, so results are bit-identical)
+                dst[6] = make_uint4((uint32_t)item_idx, __float_as_uint(((ts.w[0] + ts.w[1]) + ts.w[2]) + ts.w[3]),
+                                    __float_as_uint(((ts.w[4] + ts.w[5]) + ts.w[6]) + ts.w[7]), __float_as_uint(((ts.w[8] + ts.w[9]) + ts.w[10]) + ts.w[11]));
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
                     dst[q] = make_uint4((uint32_t)ts.off4[4 * q], (uint32_t)ts.off4[4 * q + 1], (uint32_t)ts.off4[4 * q + 2], (uint32_t)ts.off4[4 * q + 3]);

@@ -91,6 +91,10 @@ NFE_EXPORT int nfe_render_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, c
     NFE_REQUIRE(!cfg->affine_scale || (cfg->affine_items == 1 || cfg->affine_items == n), "nfe_render_fwd: affine statistics for %d items, batch is %d",
                 cfg->affine_items, n);
     NFE_REQUIRE((planes_denorm_cl || affine) && origins && dirs && depths_coarse && rgb && depth && wsum, "nfe_render_fwd: null pointer");
+    // the field kernel keeps the statistics of two batch items per 128-sample tile: an item must span at least one tile in each pass
+    NFE_REQUIRE(!affine || (n_rays * cfg->s_c >= 128 && (cfg->s_f == 0 || n_rays * cfg->s_f >= 128)),
+                "nfe_render_fwd: the single-gather identity needs at least 128 samples per item and pass (%lld rays x %d / %d)", (long long)n_rays,
+                cfg->s_c, cfg->s_f);
     NFE_REQUIRE(cfg->kind != NFE_DEC_DISENTANGLED || planes_norm_cl, "nfe_render_fwd: the disentangled decoder needs the normalised planes");
     NFE_REQUIRE(cfg->seg_dim == 0 || seg, "nfe_render_fwd: seg output missing");
     NFE_REQUIRE(plane_batch == n || plane_batch == 1, "nfe_render_fwd: plane batch %d does not match ray batch %d", plane_batch, n);

@@ -162,7 +162,8 @@ class ImportanceRenderer(torch.nn.Module):
         cache = bool(opts.get('nfe_cache_planes', False))
         precision = ops.precision_of(opts)
         affine = None
-        if kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True):
+        if (kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True)
+                and self._single_gather_fits(ray_origins.shape[1], opts)):
             # planes known to be norm*scale + shift per channel (normalize_plane / denormalize_plane made them):
             # gather the normalised planes only and rebuild the de-normalised features from the statistics
             affine = ops.provenance(norm_planes, planes)
@@ -194,6 +195,16 @@ class ImportanceRenderer(torch.nn.Module):
                     depth.view(n, 1, side, side), wsum)
         return rgb, seg, depth, wsum
 
+    @staticmethod
+    def _single_gather_fits(samples_axis, opts=None):
+        """The field kernel keeps the statistics of at most two batch items per 128-sample tile, so the single-gather identity
+        needs every item to hold at least one tile's worth of samples in each pass (always true for renders; tiny point
+        queries simply read both plane sets)."""
+        if opts is None:
+            return samples_axis >= 128
+        s_f = opts['depth_resolution_importance']
+        return samples_axis * min(opts['depth_resolution'], s_f if s_f > 0 else opts['depth_resolution']) >= 128
+
     def _render_training(self, kind, seq_a, seq_b, norm_planes, planes, ray_origins, ray_directions, opts, deterministic):
         """Differentiable forward (BASELINE config 4): same fused kernels, workspace kept for the backward
         (autograd.RenderFunction).  Gradients flow to the plane tensors and the decoder parameters."""
@@ -214,7 +225,8 @@ class ImportanceRenderer(torch.nn.Module):
         # single-gather identity in training: planes known to be norm*scale + shift are never read; their gradient goes
         # through the statistics instead (autograd.RenderFunction, csrc/nfe_field_bwd.cu AFFINE)
         scale_src = shift_src = None
-        if kind == ops.DEC_DISENTANGLED and state["cfg"]["precision"] != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True):
+        if (kind == ops.DEC_DISENTANGLED and state["cfg"]["precision"] != ops.PRECISIONS['fp32'] and opts.get('nfe_single_gather', True)
+                and self._single_gather_fits(ray_origins.shape[1], opts)):
             scale_src, shift_src = self._affine_sources(norm_planes, planes, ray_origins.shape[0], state)
         ops.note_path("render", "training-single-gather" if scale_src is not None else "training")
         out = RenderFunction.apply(state, norm_planes if kind == ops.DEC_DISENTANGLED else None, planes, scale_src, shift_src, *params)
@@ -288,7 +300,8 @@ class ImportanceRenderer(torch.nn.Module):
             sigma_only = bool(options.get('nfe_sigma_only', False))
             noise = options.get('density_noise', 0) or 0.0
             seed, offset = ops.philox_state(sample_coordinates.device) if noise > 0 else (0, 0)
-            single = kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32'] and options.get('nfe_single_gather', True)
+            single = (kind == ops.DEC_DISENTANGLED and precision != ops.PRECISIONS['fp32'] and options.get('nfe_single_gather', True)
+                      and self._single_gather_fits(sample_coordinates.shape[1]))
             if torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in (norm_planes, planes, *decoder.parameters())):
                 # differentiable point queries (the density regulariser, loss.py:310-331): autograd.RunModelFunction
                 if sample_coordinates.requires_grad:

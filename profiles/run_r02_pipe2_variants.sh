@@ -10,9 +10,9 @@ for spec in "$@"; do
   name="${spec%%|*}"; flags="${spec#*|}"
   echo "=== $name: $flags"
   $NV $flags -DNFE_PIPE_PROFILE -c $CS/nfe_field_pipe2.cu -o $CS/_obj/nfe_field_pipe2.o 2>&1 | grep -E "error|spill" ; relink
-  python profiles/pipe2_role_profile.py 2>&1 | tail -4
+  timeout 120 python profiles/pipe2_role_profile.py 2>&1 | tail -4
   $NV $flags -c $CS/nfe_field_pipe2.cu -o $CS/_obj/nfe_field_pipe2.o 2>&1 | grep -E "error" ; relink
-  python bench.py --steps 30 --warmup 5 --no-cpu-baseline > gpurun_out/p2_${name}.json 2> gpurun_out/p2_${name}.err
+  timeout 180 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --no-extras > gpurun_out/p2_${name}.json 2> gpurun_out/p2_${name}.err
   python - <<PY
 import json
 try:
