@@ -49,7 +49,7 @@ template <> struct Out<NFE_DEC_DISENTANGLED> { static constexpr int OUT0 = 16, P
 template <> struct Out<NFE_DEC_SEGMENTATION> { static constexpr int OUT0 = 33, PAD0 = 48, OUT1 = 15, PAD1 = 16; };   // net | seg_net
 template <> struct Out<NFE_DEC_OSG> { static constexpr int OUT0 = 33, PAD0 = 48, OUT1 = 0, PAD1 = 16; };              // net | (none)
 constexpr int DY_LBO = 128;
-constexpr int W2T_LBO = 128, W2T_SBO = 768, W2T_BYTES = 8 * W2T_SBO;     // B of G2: [N=64 x K<=48], element (j,o) = W2[o][j]
+constexpr int W2T_LBO = 128;                                             // B of G2: [N=64 x K=PADn], element (j,o) = W2[o][j]
 constexpr int W1T_LBO = 128, W1T_SBO = 1024, W1T_BYTES = 4 * W1T_SBO;    // B of G3: [N=32 x K=64], element (i,j) = W1[j][i]
 constexpr int GX_STRIDE = 68;                                            // fp32 dX staging row stride (floats), aliases hc
 // TMEM columns
@@ -58,6 +58,8 @@ constexpr int C_PRE = 0, C_DH = 128, C_DX = 256, C_DW1 = 320, C_DW2 = 400, TMEM_
 template <int KIND, bool AFFINE>
 struct Smem {
     static constexpr int DY_COLS = Out<KIND>::PAD0 + Out<KIND>::PAD1, DY_SBO = (DY_COLS / 8) * DY_LBO, DY_BYTES = 16 * DY_SBO;
+    static constexpr int KMAX = Out<KIND>::PAD0 > Out<KIND>::PAD1 ? Out<KIND>::PAD0 : Out<KIND>::PAD1;
+    static constexpr int W2T_SBO = (KMAX / 8) * W2T_LBO, W2T_BYTES = 8 * W2T_SBO;        // 512 / 4 KB (disentangled), 768 / 6 KB (33 outputs)
     alignas(128) unsigned char xa[2][XA_BYTES];
     alignas(128) unsigned char hc[2][HC_BYTES];
     alignas(128) unsigned char dy[2][DY_BYTES];
@@ -170,6 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
     using O = Out<KIND>;
     constexpr bool DIS = KIND == NFE_DEC_DISENTANGLED;
     constexpr int DY_COLS = O::PAD0 + O::PAD1, DY_SBO = (DY_COLS / 8) * DY_LBO;
+    constexpr int W2T_SBO = Smem<KIND, AFFINE>::W2T_SBO, W2T_BYTES = Smem<KIND, AFFINE>::W2T_BYTES;
     static_assert(!AFFINE || DIS, "the single-gather identity belongs to the disentangled decoder");
     static_assert(C_DW2 + DY_COLS <= TMEM_ALLOC, "tensor memory");
     extern __shared__ __align__(128) unsigned char smem_raw[];

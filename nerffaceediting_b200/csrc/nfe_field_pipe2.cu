@@ -60,11 +60,14 @@ constexpr int REC_STAGE_STRIDE = 208;                       // bytes per staged 
 
 // Register re-deal (setmaxnreg works on groups of four warps).  At launch every thread has what 640 threads allow (96).
 // Only registers a warp group RELEASES can be claimed by another (asking for more blocks forever), hence the static_assert.
+// Measured at c2 (ms per launch, profiles/pipe2_variants_r02.txt): uniform 96: 0.355; epilogue/gather/misc = 104/104/64: 0.331
+// (the default); 96/112/56: 0.347; 104/112/48 and 112/104/48: 0.340-0.342 (at 48 the MMA-issuing thread spills and paces
+// everything); 12 gather warps at 80-88 registers: 0.445-0.57 (spills in the gather loop).
 #ifndef NFE_P2_SETMAXNREG
-#define NFE_P2_SETMAXNREG 0
+#define NFE_P2_SETMAXNREG 1
 #endif
 #ifndef NFE_P2_REGS_EPI
-#define NFE_P2_REGS_EPI 112
+#define NFE_P2_REGS_EPI 104
 #endif
 #ifndef NFE_P2_REGS_MISC
 #define NFE_P2_REGS_MISC 64
@@ -76,7 +79,7 @@ constexpr int REC_STAGE_STRIDE = 208;                       // bytes per staged 
 #define NFE_P2_ROLLED_MMA 0
 #endif
 #ifndef NFE_P2_REGS_GATHER
-#define NFE_P2_REGS_GATHER 88
+#define NFE_P2_REGS_GATHER 104
 #endif
 constexpr int REGS_LAUNCH = (65536 / THREADS) / 8 * 8 > 96 ? 96 : (65536 / THREADS) / 8 * 8;       // 20 warps: 96, 24 warps: 80
 constexpr int REGS_EPI = NFE_P2_REGS_EPI, REGS_MISC = NFE_P2_REGS_MISC, REGS_GATHER = NFE_P2_REGS_GATHER;

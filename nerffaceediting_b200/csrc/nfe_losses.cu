@@ -491,7 +491,13 @@ NFE_EXPORT int nfe_hist_dist_bwd(const float* img, const float* seg, const int* 
     cudaStream_t st = as_stream(stream);
     hist_dist_bwd_kernel<<<n_labels * b, 256, 0, st>>>(hist_raw, hist_norm, totals, s_ws, weights, g_loss, b, g_raw_ws);
     NFE_LAUNCH_CHECK("hist_dist_bwd_kernel");
-    const size_t smem = sizeof(float) * (HB + 2 * HCHUNK) * (HB + 1);
+    const size_t smem = sizeof(float) * (HB + 2 * HCHUNK) * (HB + 1);           // 49.9 KB: above the 48 KB default
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(hist_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        NFE_REQUIRE(e == cudaSuccess, "nfe_hist_dist_bwd: cannot reserve %zu bytes of shared memory: %s", smem, cudaGetErrorString(e));
+        configured = true;
+    }
     hist_bwd_kernel<<<dim3(3, b, n_labels), HTHREADS, smem, st>>>(a, g_raw_ws, g_img);      // g_img zero-initialised by the caller
     NFE_LAUNCH_CHECK("hist_bwd_kernel");
     return 0;

@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TARGETS = [os.path.join(ROOT, "nerffaceediting_b200", "lib", "libnfe_b200.so"), os.path.join(ROOT, "profiles", "microbench", "_bin", "l2_gather")]
-KEY = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "SYNCS", "LDG", "STG", "RED", "ATOMG", "LDS", "STS", "LD", "ST",
+KEY = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "LDGSTS", "SYNCS", "USETMAXREG", "LDG", "STG", "RED", "REDG", "ATOMG", "LDS", "STS", "LD", "ST",
        "MUFU", "F2FP", "FFMA2", "FFMA", "HMMA", "NANOSLEEP", "BAR", "LDL", "STL"]
 
 
