@@ -308,6 +308,29 @@ int nfe_run_model_fwd(const nfe_render_cfg* cfg, const nfe_mlp* net_a, const nfe
                       const float* coords, int n, int64_t m, float* rgb, float* sigma, float* seg,
                       void* workspace, int64_t workspace_bytes, nfe_stream_t stream);
 
+/* ---- backbone / super-resolution plugins ----------------------------------------------------
+ * Element types of the activations these ops move (arithmetic is fp32 inside). */
+enum { NFE_DTYPE_F32 = 0, NFE_DTYPE_F16 = 1, NFE_DTYPE_BF16 = 2 };
+
+/* bias_act: replaces the reference's bias_act plugin entry `bias_act(x, b, xref, yref, dy, grad, dim, act, alpha, gain, clamp)`
+ * (torch_utils/ops/bias_act.cpp:34-99, kernel bias_act.cu:27-151; Python torch_utils/ops/bias_act.py:51-209).
+ * x, xref, yref, dy, y: size_x elements of `dtype` in ONE dense memory order (contiguous or channels-last: the caller passes the
+ * order it holds, as the reference does).  b: size_b elements or NULL; element i takes b[(i / step_b) % size_b] (step_b = stride of
+ * the bias dimension).  act = the reference's cuda_idx (1 linear, 2 relu, 3 lrelu, 4 tanh, 5 sigmoid, 6 elu, 7 selu, 8 softplus,
+ * 9 swish).  grad 0: y = clamp(gain * act(x + b)); grad 1: x is dy, y = dx (needs yref, swish needs xref);
+ * grad 2: x is the incoming second-order gradient, dy the first-order one.  clamp < 0 disables clamping. */
+int nfe_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y, int64_t size_x,
+                 int size_b, int64_t step_b, int dtype, int grad, int act, float alpha, float gain, float clamp, nfe_stream_t stream);
+
+/* upfirdn2d: replaces the reference's plugin entry `upfirdn2d(x, f, upx, upy, downx, downy, padx0, padx1, pady0, pady1, flip, gain)`
+ * (torch_utils/ops/upfirdn2d.cpp:20-107, kernels upfirdn2d.cu:33-204; Python torch_utils/ops/upfirdn2d.py:117-214): zero-insert
+ * up-sampling, zero padding (negative = crop), FIR filtering with f [fh,fw] (fp32; true convolution unless flip_filter), decimation.
+ * x [n,c,in_h,in_w] and y [n,c,out_h,out_w] with explicit element strides {batch, channel, row, column};
+ * out = (in*up + pad0 + pad1 - f + down) / down. */
+int nfe_upfirdn2d(const void* x, const float* f, void* y, int n, int c, int in_h, int in_w, int out_h, int out_w, int fh, int fw,
+                  const int64_t* x_strides, const int64_t* y_strides, int upx, int upy, int downx, int downy, int padx0, int padx1,
+                  int pady0, int pady1, int flip_filter, float gain, int dtype, nfe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

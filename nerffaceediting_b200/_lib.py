@@ -81,6 +81,8 @@ SIGNATURES = {
     "nfe_resize_bilinear": (c_int, [c_vp, c_i64, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "nfe_finish_depth": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "nfe_run_model_fwd": (c_int, [_CFG_P, _MLP_P, _MLP_P, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "nfe_bias_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_int, c_float, c_float, c_float, c_vp]),
+    "nfe_upfirdn2d": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 8 + [ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)] + [c_int] * 9 + [c_float, c_int, c_vp]),
 }
 
 _lib = None

@@ -280,7 +280,8 @@ int launch_field(int kind, int precision, const FieldArgs& a, const nfe_mlp* net
         // NFE_FIELD_PIPE=1 selects round 1's kernel (4 epilogue warps, pre-pass inside the gather warps) for A/B runs
         static const char* gen = getenv("NFE_FIELD_PIPE");
         static const bool first_gen = gen && gen[0] == '1';
-        return first_gen ? launch_field_pipe(kind, precision, a, net_a, net_b, stream) : launch_field_pipe2(kind, precision, a, net_a, net_b, stream);
+        // (the experimental quad-order walk, NFE_QUAD_ORDER, only exists in round 1's kernel)
+        return (first_gen || a.quad_stride != 0) ? launch_field_pipe(kind, precision, a, net_a, net_b, stream) : launch_field_pipe2(kind, precision, a, net_a, net_b, stream);
     }
     nfe_mlp none = {};
     switch (kind) {

@@ -52,7 +52,10 @@ constexpr int PASSES_PER_TILE = TILE_M / 4;                 // a pass = 4 sample
 constexpr int PER_LONG = (PASSES_PER_TILE + GATHER_WARPS - 1) / GATHER_WARPS;
 constexpr int LONG_WARPS = PASSES_PER_TILE - (PER_LONG - 1) * GATHER_WARPS;
 static_assert(LONG_WARPS >= 1 && LONG_WARPS <= GATHER_WARPS && PER_LONG >= 2, "bad gather split");
-constexpr int TAP_BUFS = 3;
+#ifndef NFE_P2_TAP_BUFS
+#define NFE_P2_TAP_BUFS 3
+#endif
+constexpr int TAP_BUFS = NFE_P2_TAP_BUFS;                   // tap buffers: the tap warps run up to TAP_BUFS - 1 tiles ahead of the gather
 constexpr int GROUP_COLS = 192;                             // D1A 64 | D1B 64 | D2A | D2B (<= 64 together)
 constexpr int P2_TMEM_COLS = 512;
 constexpr int COL_D2 = 128;
@@ -158,32 +161,40 @@ __device__ __forceinline__ float2 rgb_activation2(float2 x)
 // hidden = softplus(D1 + b1) for this thread's row, written back over the accumulator columns it came from: the 16 fp32
 // columns [16q, 16q+16) become 8 columns of packed bf16 hi parts at 16q and 8 columns of lo parts at 16q+8.
 // Softplus in base-2 units: with t = x*log2(e), softplus(x) = ln2 * (max(t,0) + log2(1 + 2^-|t|)).
+#ifndef NFE_P2_HIDDEN_UNROLL
+#define NFE_P2_HIDDEN_UNROLL 1      // copies of the 16-column body in the loop (1: smallest code; the kernel is instruction-cache sensitive)
+#endif
+constexpr int HIDDEN_UNROLL = NFE_P2_HIDDEN_UNROLL;
 template <bool SPLIT>
 __device__ __forceinline__ void hidden_in_place(uint32_t taddr, const float* bias1_log2)
 {
     const float2 k2 = make_float2(LOG2E, LOG2E), one2 = make_float2(1.0f, 1.0f), neg2 = make_float2(-1.0f, -1.0f);
-#pragma unroll
+#pragma unroll HIDDEN_UNROLL
     for (int q = 0; q < HIDDEN / 16; ++q) {
         float v[16];
         tc::tmem_ld16(taddr + q * 16, v);
         tc::tmem_ld_wait();
         uint32_t hi[8], lo[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float2 t = ffma2(make_float2(v[2 * i], v[2 * i + 1]), k2, *reinterpret_cast<const float2*>(bias1_log2 + q * 16 + 2 * i));
-            float e0, e1, l0, l1;
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-fabsf(t.x)));
-            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-fabsf(t.y)));
-            const float2 s1 = fadd2(make_float2(e0, e1), one2);
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(s1.x));
-            asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(s1.y));
-            const float2 hh = fadd2(make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f)), make_float2(l0, l1));
-            const __nv_bfloat162 p = __floats2bfloat162_rn(hh.x, hh.y);
-            hi[i] = *reinterpret_cast<const uint32_t*>(&p);
-            if (SPLIT) {
-                const float2 d = ffma2(__bfloat1622float2(p), neg2, hh);      // h - bf16(h), exact
-                const __nv_bfloat162 r = __floats2bfloat162_rn(d.x, d.y);
-                lo[i] = *reinterpret_cast<const uint32_t*>(&r);
+        for (int i = 0; i < 4; ++i) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias1_log2 + q * 16 + 4 * i);
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const float2 t = ffma2(make_float2(v[4 * i + 2 * j], v[4 * i + 2 * j + 1]), k2, j ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
+                float e0, e1, l0, l1;
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-fabsf(t.x)));
+                asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-fabsf(t.y)));
+                const float2 s1 = fadd2(make_float2(e0, e1), one2);
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l0) : "f"(s1.x));
+                asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l1) : "f"(s1.y));
+                const float2 hh = fadd2(make_float2(fmaxf(t.x, 0.0f), fmaxf(t.y, 0.0f)), make_float2(l0, l1));
+                const __nv_bfloat162 p = __floats2bfloat162_rn(hh.x, hh.y);
+                hi[2 * i + j] = *reinterpret_cast<const uint32_t*>(&p);
+                if (SPLIT) {
+                    const float2 d = ffma2(__bfloat1622float2(p), neg2, hh);      // h - bf16(h), exact
+                    const __nv_bfloat162 r = __floats2bfloat162_rn(d.x, d.y);
+                    lo[2 * i + j] = *reinterpret_cast<const uint32_t*>(&r);
+                }
             }
         }
         tmem_st8(taddr + q * 16, hi);
@@ -221,30 +232,18 @@ __device__ __forceinline__ void issue_layer2(uint32_t tmem_d, uint32_t tmem_h, c
 
 struct SampleRef { int64_t idx; int item; int64_t ray; };
 
-// Tile row -> sample (plain order: sample L is index L; quad order: see FieldArgs::quad_stride)
+// Tile row -> sample.  Plain order only: sample L is index L (the quad-order walk of FieldArgs::quad_stride stays with round 1's kernel)
 __device__ __forceinline__ SampleRef sample_of(const FieldArgs& a, int64_t L, bool small)
 {
     SampleRef r;
-    if (a.quad_stride == 0) {
-        r.idx = L;
-        if (small) {                    // everything fits 31 bits: 32-bit divisions (the 64-bit ones are subroutine calls)
-            r.item = (int)((uint32_t)L / (uint32_t)a.m);
-            r.ray = (int64_t)((uint32_t)L / (uint32_t)a.s_per_ray);
-        } else {
-            r.item = (int)(L / a.m);
-            r.ray = L / a.s_per_ray;
-        }
-        return r;
+    r.idx = L;
+    if (small) {                    // everything fits 31 bits: 32-bit divisions (the 64-bit ones are subroutine calls)
+        r.item = (int)((uint32_t)L / (uint32_t)a.m);
+        r.ray = (int64_t)((uint32_t)L / (uint32_t)a.s_per_ray);
+    } else {
+        r.item = (int)(L / a.m);
+        r.ray = L / a.s_per_ray;
     }
-    const uint32_t S = (uint32_t)a.s_per_ray, per_quad = 4u * S, res = (uint32_t)a.quad_stride;
-    const uint32_t quad = (uint32_t)(L / per_quad), within = (uint32_t)(L % per_quad);
-    const uint32_t s = within >> 2, ray_in_quad = within & 3u;
-    const uint32_t quads_per_item = (uint32_t)(a.rays_per_item >> 2);
-    const uint32_t item = quad / quads_per_item, q = quad % quads_per_item;
-    const uint32_t qrow = q / res, col = q % res;
-    r.ray = (int64_t)item * a.rays_per_item + (int64_t)(4u * qrow + ray_in_quad) * res + col;
-    r.idx = r.ray * S + s;
-    r.item = (int)item;
     return r;
 }
 
@@ -469,51 +468,89 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
         // row-wise deal: every tap warp works on every tile — the four 32-sample chunks of a tile go to warps 0 .. TAP_WARPS-1, the
         // remaining ones rotate with the tile — so a tile's taps are ready after at most two rounds, not four (the gather asks for
         // them two tiles after it released the buffer: what counts is the latency of one tile's taps, not only the throughput)
-        for (int it = 0; it < n_my; ++it) {
-            const int tb = it % TAP_BUFS;
-            if (it >= TAP_BUFS) P2_WAIT(2, &s.taps_empty[tb], ((it / TAP_BUFS) - 1) & 1);
-            const int64_t base = ((int64_t)blockIdx.x + (int64_t)it * G) * TILE_M;
-            if (tw == 0 && T::SETS == 2 && a.affine_scale != nullptr) {
-                const int item0 = a.affine_items == 1 ? 0 : (int)(small ? (uint32_t)base / (uint32_t)a.m : base / a.m);
-                if (lane == 0) s.aff_item[tb] = item0;
-                for (int i = lane; i < 2 * 2 * 24; i += 32) {           // 2 items x {scale, shift} x 24 float4
-                    const int rel = i / 48, which = (i / 24) & 1, c = i % 24;
-                    const int item = min(item0 + rel, a.affine_items - 1);
-                    const float* src = (which ? a.affine_shift : a.affine_scale) + (int64_t)item * 96;
-                    reinterpret_cast<float4*>(s.aff[tb][rel][which])[c] = __ldg(reinterpret_cast<const float4*>(src) + c);
+        // The inputs of a chunk (depth + ray, or the point) are fetched one chunk ahead: the loads of the warp's NEXT chunk — which
+        // may belong to the next tile; they touch no tap buffer, so they need no barrier — are in flight while this chunk's taps
+        // are computed, instead of heading a dependent chain of ~1000 cycles per chunk.
+        struct Raw { float t, o[3], d[3]; int item; bool live; };
+        auto owner_of = [&](int it, int h) { return h < TAP_WARPS ? h : (it + h) % TAP_WARPS; };
+        auto advance = [&](int& it, int& h) {                      // next chunk this warp owns (it == n_my: none left)
+            for (;;) {
+                if (++h == TILE_M / 32) { h = 0; if (++it >= n_my) return; }
+                if (owner_of(it, h) == tw) return;
+            }
+        };
+        auto fetch = [&](int it, int h) {
+            Raw r;
+            r.t = 0.0f; r.item = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) r.o[k] = r.d[k] = 0.0f;
+            const int64_t L = ((int64_t)blockIdx.x + (int64_t)it * G) * TILE_M + h * 32 + lane;
+            r.live = it < n_my && L < a.total;
+            if (r.live) {
+                const SampleRef sr = sample_of(a, L, small);
+                r.item = sr.item;
+                if (a.coords) {
+                    const float* c = a.coords + sr.idx * 3;
+                    r.o[0] = __ldg(c); r.o[1] = __ldg(c + 1); r.o[2] = __ldg(c + 2);
+                } else {
+                    r.t = __ldg(a.depths + sr.idx);
+                    const float* o = a.origins + sr.ray * 3;
+                    const float* d = a.dirs + sr.ray * 3;
+#pragma unroll
+                    for (int k = 0; k < 3; ++k) { r.o[k] = __ldg(o + k); r.d[k] = __ldg(d + k); }
                 }
             }
+            return r;
+        };
+        // one loop body, run once more than there are chunks: iteration k fetches chunk k and turns chunk k-1 into taps
+        int it = 0, h = -1;
+        if (n_my > 0) advance(it, h);
+        Raw cur;
+        cur.live = false;
+        int cit = -1, ch = 0;
 #pragma unroll 1
-            for (int h = 0; h < TILE_M / 32; ++h) {
-                const int owner = h < TAP_WARPS ? h : (it + h) % TAP_WARPS;
-                if (owner != tw) continue;
-                const int row = h * 32 + lane;
+        for (;;) {
+            const Raw nxt = fetch(it, h);                          // it == n_my: nothing to fetch, live = false
+            if (cit < 0) {
+                if (it >= n_my) break;
+                cur = nxt; cit = it; ch = h;
+                advance(it, h);
+                continue;
+            }
+            const int tb = cit % TAP_BUFS;
+            const bool first = ch == tw;                               // chunk h = tw is the first one a warp owns in every tile
+            if (first) {
+                if (cit >= TAP_BUFS) P2_WAIT(2, &s.taps_empty[tb], ((cit / TAP_BUFS) - 1) & 1);
+                if (tw == 0 && T::SETS == 2 && a.affine_scale != nullptr) {
+                    const int64_t base = ((int64_t)blockIdx.x + (int64_t)cit * G) * TILE_M;
+                    const int item0 = a.affine_items == 1 ? 0 : (int)(small ? (uint32_t)base / (uint32_t)a.m : base / a.m);
+                    if (lane == 0) s.aff_item[tb] = item0;
+                    for (int i = lane; i < 2 * 2 * 24; i += 32) {           // 2 items x {scale, shift} x 24 float4
+                        const int rel = i / 48, which = (i / 24) & 1, c = i % 24;
+                        const int item = min(item0 + rel, a.affine_items - 1);
+                        const float* src = (which ? a.affine_shift : a.affine_scale) + (int64_t)item * 96;
+                        reinterpret_cast<float4*>(s.aff[tb][rel][which])[c] = __ldg(reinterpret_cast<const float4*>(src) + c);
+                    }
+                }
+            }
+            {
+                const int row = ch * 32 + lane;
                 TapSet ts;
-                int item_idx = 0;
 #pragma unroll
                 for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
-                if (base + row < a.total) {
-                    const SampleRef sr = sample_of(a, base + row, small);
+                if (cur.live) {
                     float x, y, z;
-                    if (a.coords) {
-                        const float* c = a.coords + sr.idx * 3;
-                        x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
-                    } else {
-                        const float t = __ldg(a.depths + sr.idx);
-                        const float* o = a.origins + sr.ray * 3;
-                        const float* d = a.dirs + sr.ray * 3;
-                        x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
-                    }
+                    if (a.coords) { x = cur.o[0]; y = cur.o[1]; z = cur.o[2]; }
+                    else { x = ray_point(cur.o[0], cur.t, cur.d[0]); y = ray_point(cur.o[1], cur.t, cur.d[1]); z = ray_point(cur.o[2], cur.t, cur.d[2]); }
                     ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
-                    item_idx = sr.item;
-                    const int item_off = a.plane_batch == 1 ? 0 : (int)(sr.item * set_stride4);
+                    const int item_off = a.plane_batch == 1 ? 0 : (int)(cur.item * set_stride4);
 #pragma unroll
                     for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
                 }
                 uint4* dst = s.taps[tb][row];
                 // batch item and, per plane, the sum of the in-bounds tap weights (what the single-gather identity multiplies the
                 // shift by; summed in the order the gather warps used to, so results are bit-identical)
-                dst[6] = make_uint4((uint32_t)item_idx, __float_as_uint(((ts.w[0] + ts.w[1]) + ts.w[2]) + ts.w[3]),
+                dst[6] = make_uint4((uint32_t)cur.item, __float_as_uint(((ts.w[0] + ts.w[1]) + ts.w[2]) + ts.w[3]),
                                     __float_as_uint(((ts.w[4] + ts.w[5]) + ts.w[6]) + ts.w[7]), __float_as_uint(((ts.w[8] + ts.w[9]) + ts.w[10]) + ts.w[11]));
 #pragma unroll
                 for (int q = 0; q < 3; ++q)
@@ -522,8 +559,13 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
                 for (int q = 0; q < 3; ++q)
                     dst[3 + q] = make_uint4(__float_as_uint(ts.w[4 * q]), __float_as_uint(ts.w[4 * q + 1]), __float_as_uint(ts.w[4 * q + 2]), __float_as_uint(ts.w[4 * q + 3]));
             }
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&s.taps_full[tb]);
+            if (it != cit) {                                       // that was the warp's last chunk of tile cit
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&s.taps_full[tb]);
+            }
+            if (it >= n_my) break;
+            cur = nxt; cit = it; ch = h;
+            advance(it, h);
         }
     } else if (warp == MMA_WARP) {
         // ================================================================ MMA issuer (one thread)
@@ -587,121 +629,154 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
             const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * G;
             P2_WAIT(8, &s.d1_full[gi], ph);
             tc::fence_after_sync();
-            hidden_in_place<SPLIT>(lane_addr + COL_D1A, s.bias1[0]);
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&s.a2a_full[gi]);
-            if (has_b) {
-                hidden_in_place<SPLIT>(lane_addr + COL_D1B, s.bias1[T::HAS_B ? 1 : 0]);     // overlaps the net-A layer-2 MMA
+            // one copy of the hidden stage serves both nets (net B's overlaps the net-A layer-2 MMA)
+#pragma unroll 1
+            for (int net = 0; net < (has_b ? 2 : 1); ++net) {
+                hidden_in_place<SPLIT>(lane_addr + (net ? COL_D1B : COL_D1A), s.bias1[T::HAS_B ? net : 0]);
                 tc::fence_before_sync();
                 __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&s.a2b_full[gi]);
+                if (lane == 0) tc::mbar_arrive(net ? &s.a2b_full[gi] : &s.a2a_full[gi]);
             }
             P2_WAIT(9, &s.d2a_full[gi], ph);
             tc::fence_after_sync();
             // ---- outputs
-            const bool live = tile * TILE_M + row < a.total;
-            const int64_t idx = live ? sample_of(a, tile * TILE_M + row, false).idx : 0;
-            float outa[T::N_A];
-#pragma unroll
-            for (int q = 0; q < T::N_A / 16; ++q) {
-                float v[16];
-                tc::tmem_ld16(lane_addr + COL_D2 + q * 16, v);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float2 o2 = fadd2(make_float2(v[2 * i], v[2 * i + 1]), *reinterpret_cast<const float2*>(&s.bias2a[q * 16 + 2 * i]));
-                    outa[q * 16 + 2 * i] = o2.x; outa[q * 16 + 2 * i + 1] = o2.y;
-                }
-            }
-            float sig = outa[0];
-            if (a.density_noise > 0.0f && live) {
-                const uint4 r = philox4x32(a.seed, (uint64_t)idx, a.offset);
-                sig += normal2(r.x, r.y).x * a.density_noise;
-            }
-            if (live) a.sigma[idx] = sig;
-            if (a.sigma_only) {                                       // nothing else is written
-                tc::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(&s.d2_free[gi]);
-                continue;
-            }
-            // staged records need the tile's rows to be consecutive samples (plain order)
-            const bool staged = a.rec && a.quad_stride == 0;
-            float4* rec = a.rec ? (staged ? reinterpret_cast<float4*>(s.recbuf[gi][row]) : reinterpret_cast<float4*>(a.rec + idx * 48)) : nullptr;
-            float4* rgb4 = rec ? rec + 4 : reinterpret_cast<float4*>(a.rgb + idx * 32);
+            const int64_t L = tile * TILE_M + row;                   // plain order: tile row = sample index
+            const bool live = L < a.total;
+            const int64_t idx = live ? L : 0;
+            // Every output row is assembled in record layout [sigma, seg 15 | rgb 32] in this thread's shared-memory staging row
+            // (STS only, never a generic store), then the warp copies its 32 rows out in coalesced 16-byte chunks — to the
+            // records, or to the rgb / seg outputs when the caller asked for those.
+            float4* rec = reinterpret_cast<float4*>(s.recbuf[gi][row]);
+            bool done = false;
             if constexpr (KIND == NFE_DEC_DISENTANGLED) {
-                if (live) {
-                    if (rec) {
-                        rec[0] = make_float4(sig, outa[1], outa[2], outa[3]);
+                // the production decoder keeps ONE copy of each 16-column step (rolled loops): with four roles sharing every
+                // sub-partition's instruction cache, code size is time (profiles/pipe2_variants_r02.txt)
+                {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + COL_D2, v);
+                    tc::tmem_ld_wait();
 #pragma unroll
-                        for (int c = 1; c < 4; ++c) rec[c] = make_float4(outa[4 * c], outa[4 * c + 1], outa[4 * c + 2], outa[4 * c + 3]);
-                    } else {
+                    for (int c = 0; c < 4; ++c) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&s.bias2a[4 * c]);
+                        const float2 lo2 = fadd2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b4.x, b4.y));
+                        const float2 hi2 = fadd2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b4.z, b4.w));
+                        float4 o = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                        if (c == 0) {
+                            if (a.density_noise > 0.0f && live) {
+                                const uint4 r = philox4x32(a.seed, (uint64_t)idx, a.offset);
+                                o.x += normal2(r.x, r.y).x * a.density_noise;
+                            }
+                            if (live) a.sigma[idx] = o.x;
+                        }
+                        rec[c] = o;
+                    }
+                }
+                done = a.sigma_only;
+                if (!done) {
+                    P2_WAIT(10, &s.d2b_full[gi], ph);
+                    tc::fence_after_sync();
+#pragma unroll 1
+                    for (int q = 0; q < T::N_B / 16; ++q) {
+                        float v[16];
+                        tc::tmem_ld16(lane_addr + COL_D2 + T::N_A + q * 16, v);
+                        tc::tmem_ld_wait();
 #pragma unroll
-                        for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outa[1 + c];
+                        for (int c = 0; c < 4; ++c) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(&s.bias2b[q * 16 + 4 * c]);
+                            const float2 lo2 = rgb_activation2(fadd2(make_float2(v[4 * c], v[4 * c + 1]), make_float2(b4.x, b4.y)));
+                            const float2 hi2 = rgb_activation2(fadd2(make_float2(v[4 * c + 2], v[4 * c + 3]), make_float2(b4.z, b4.w)));
+                            rec[4 + 4 * q + c] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                        }
                     }
                 }
             } else {
-                if (live) {
-                    if (rec && !T::HAS_B) {
+                // OSG / segmentation decoders (sigma shares net A's output row with the colours): straight-line code
+                float outa[T::N_A];
+#pragma unroll
+                for (int q = 0; q < T::N_A / 16; ++q) {
+                    float v[16];
+                    tc::tmem_ld16(lane_addr + COL_D2 + q * 16, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float2 o2 = fadd2(make_float2(v[2 * i], v[2 * i + 1]), *reinterpret_cast<const float2*>(&s.bias2a[q * 16 + 2 * i]));
+                        outa[q * 16 + 2 * i] = o2.x; outa[q * 16 + 2 * i + 1] = o2.y;
+                    }
+                }
+                float sig = outa[0];
+                if (a.density_noise > 0.0f && live) {
+                    const uint4 r = philox4x32(a.seed, (uint64_t)idx, a.offset);
+                    sig += normal2(r.x, r.y).x * a.density_noise;
+                }
+                if (live) a.sigma[idx] = sig;
+                done = a.sigma_only;
+                if (!done) {
+                    if (!T::HAS_B) {
                         rec[0] = make_float4(sig, 0.f, 0.f, 0.f);
                         rec[1] = rec[2] = rec[3] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int c = 0; c < 8; ++c)
-                        rgb4[c] = make_float4(rgb_activation(outa[1 + 4 * c]), rgb_activation(outa[2 + 4 * c]),
-                                              rgb_activation(outa[3 + 4 * c]), rgb_activation(outa[4 + 4 * c]));
-                }
-            }
-            if constexpr (T::HAS_B) {
-                P2_WAIT(10, &s.d2b_full[gi], ph);
-                tc::fence_after_sync();
-                float outb[T::N_B];
+                        rec[4 + c] = make_float4(rgb_activation(outa[1 + 4 * c]), rgb_activation(outa[2 + 4 * c]),
+                                                 rgb_activation(outa[3 + 4 * c]), rgb_activation(outa[4 + 4 * c]));
+                    if constexpr (T::HAS_B) {
+                        P2_WAIT(10, &s.d2b_full[gi], ph);
+                        tc::fence_after_sync();
+                        float outb[T::N_B];
 #pragma unroll
-                for (int q = 0; q < T::N_B / 16; ++q) {
-                    float v[16];
-                    tc::tmem_ld16(lane_addr + COL_D2 + T::N_A + q * 16, v);
-                    tc::tmem_ld_wait();
+                        for (int q = 0; q < T::N_B / 16; ++q) {
+                            float v[16];
+                            tc::tmem_ld16(lane_addr + COL_D2 + T::N_A + q * 16, v);
+                            tc::tmem_ld_wait();
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float2 o2 = fadd2(make_float2(v[2 * i], v[2 * i + 1]), *reinterpret_cast<const float2*>(&s.bias2b[q * 16 + 2 * i]));
-                        outb[q * 16 + 2 * i] = o2.x; outb[q * 16 + 2 * i + 1] = o2.y;
-                    }
-                }
-                if (live) {
-                    if constexpr (KIND == NFE_DEC_DISENTANGLED) {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) {
-                            const float2 lo2 = rgb_activation2(make_float2(outb[4 * c], outb[4 * c + 1]));
-                            const float2 hi2 = rgb_activation2(make_float2(outb[4 * c + 2], outb[4 * c + 3]));
-                            rgb4[c] = make_float4(lo2.x, lo2.y, hi2.x, hi2.y);
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 o2 = fadd2(make_float2(v[2 * i], v[2 * i + 1]), *reinterpret_cast<const float2*>(&s.bias2b[q * 16 + 2 * i]));
+                                outb[q * 16 + 2 * i] = o2.x; outb[q * 16 + 2 * i + 1] = o2.y;
+                            }
                         }
-                    } else if (rec) {
                         rec[0] = make_float4(sig, outb[0], outb[1], outb[2]);
 #pragma unroll
                         for (int c = 1; c < 4; ++c) rec[c] = make_float4(outb[4 * c - 1], outb[4 * c], outb[4 * c + 1], outb[4 * c + 2]);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 15; ++c) a.seg[idx * 15 + c] = outb[c];
                     }
                 }
             }
             tc::fence_before_sync();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&s.d2_free[gi]);
-            if (staged) {
-                // 16-byte chunk c of the warp's 32 records sits at row c/12, chunk c%12 of the staging rows
-                const int64_t r0 = tile * TILE_M + wq * 32;
-                const int n_chunks = (int)min((int64_t)32, a.total - r0) * 12;
-                float4* gdst = reinterpret_cast<float4*>(a.rec + r0 * 48);
-                int r = lane / 12, c = lane % 12;
-#pragma unroll
-                for (int k = 0; k < 12; ++k) {
-                    const int ch = k * 32 + lane;
-                    const float4 v = *reinterpret_cast<const float4*>(s.recbuf[gi][wq * 32 + r] + c * 16);
-                    if (ch < n_chunks) gdst[ch] = v;
-                    r += 2; c += 8;
-                    if (c >= 12) { c -= 12; r += 1; }
+            if (!done) {
+                // rows of this warp: tile rows wq*32 .. +31 = samples L0 .. L0+31, one contiguous run of every output
+                const int64_t L0 = tile * TILE_M + wq * 32;
+                const int n_rows = (int)min((int64_t)32, a.total - L0);
+                const unsigned char* rows = s.recbuf[gi][wq * 32];
+                if (a.rec) {
+                    float4* gdst = reinterpret_cast<float4*>(a.rec + L0 * 48);
+                    int r = lane / 12, c = lane % 12;                  // chunk k*32 + lane = row r, 16-byte chunk c of the record
+#pragma unroll 4
+                    for (int k = 0; k < 12; ++k) {
+                        const float4 v = *reinterpret_cast<const float4*>(rows + r * REC_STAGE_STRIDE + c * 16);
+                        if (r < n_rows) gdst[k * 32 + lane] = v;
+                        r += 2; c += 8;
+                        if (c >= 12) { c -= 12; r += 1; }
+                    }
+                } else {
+                    float4* gdst = reinterpret_cast<float4*>(a.rgb + L0 * 32);
+#pragma unroll 4
+                    for (int k = 0; k < 8; ++k) {                      // colours: 8 chunks per row
+                        const int r = 4 * k + (lane >> 3);
+                        const float4 v = *reinterpret_cast<const float4*>(rows + r * REC_STAGE_STRIDE + (4 + (lane & 7)) * 16);
+                        if (r < n_rows) gdst[k * 32 + lane] = v;
+                    }
+                    if constexpr (KIND != NFE_DEC_OSG) {
+                        float* sdst = a.seg + L0 * 15;
+                        int r = lane / 15, c = lane % 15;              // labels: float k*32 + lane = row r, logit c
+#pragma unroll 5
+                        for (int k = 0; k < 15; ++k) {
+                            const float v = *reinterpret_cast<const float*>(rows + r * REC_STAGE_STRIDE + (1 + c) * 4);
+                            if (r < n_rows) sdst[k * 32 + lane] = v;
+                            r += 2; c += 2;
+                            if (c >= 15) { c -= 15; r += 1; }
+                        }
+                    }
                 }
                 __syncwarp();          // the rows are rewritten by the group's next tile
             }

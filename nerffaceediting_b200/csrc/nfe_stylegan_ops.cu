@@ -1,0 +1,362 @@
+// Backbone / super-resolution elementwise plugins (first step): the two custom ops every StyleGAN2 layer of the
+// reference calls around its convolution,
+//
+//   bias_act    torch_utils/ops/bias_act.py:51-209 (plugin bias_act.cpp:34-99, bias_act.cu:27-151): y = clamp(gain * act(x + b[dim])),
+//               its first derivative (grad = 1: dx from dy and the saved x / y) and second derivative (grad = 2), 9 activations
+//   upfirdn2d   torch_utils/ops/upfirdn2d.py:117-214 (plugin upfirdn2d.cpp:20-107, upfirdn2d.cu:33-204): zero-insert upsampling,
+//               zero padding / cropping, FIR filtering, decimation, in one pass
+//
+// Both are memory-bound: bias_act moves 16 bytes per thread and access with the bias index computed once per vector; the FIR
+// fast path (up = down = 1, rows contiguous: what conv2d_resample runs after every transposed convolution, conv2d_resample.py:128-129)
+// stages the input tile in shared memory and gives every thread a 4 x 2 block of outputs, so an output costs ~1.3 shared-memory
+// 16-byte reads instead of fw*fh L1 reads; every other configuration (the 3-channel image up-sampling of the skip connection,
+// strided layouts) takes the generic one-thread-per-output kernel, which only visits the taps that land on a real input sample.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "nfe_common.cuh"
+
+namespace nfe {
+
+namespace sg {
+
+template <class T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__half>(__half v) { return __half2float(v); }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <class T> __device__ __forceinline__ T from_f(float v);
+template <> __device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half from_f<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+
+// ---------------------------------------------------------------------------------------------- bias_act
+constexpr float SELU_SCALE = 1.0507009873554804934193349852946f;
+constexpr float SELU_ALPHA = 1.6732632423543772848170429916717f;
+constexpr float EXP_RANGE = 80.0f;
+
+// One element.  G == 0: x is the input, returns clamp(gain * act(x + b)).  G == 1: x is dy, returns d/dx of the forward at the saved
+// point times dy; G == 2: x is the incoming second-order gradient, dy the first-order one.  xref = saved input + b (only swish needs
+// it), yref = saved forward output.  Same case analysis as the reference kernel (bias_act.cu:56-135), written from the formulas.
+template <int A>
+__device__ __forceinline__ float bias_act_one(int G, float x, float b, float xref, float yref, float dy, float alpha, float gain, float clamp)
+{
+    if (G == 0) x += b; else xref += b;
+    const float yy = gain != 0.0f ? yref / gain : 0.0f;
+    float y = 0.0f;
+    if (A == 1) { if (G <= 1) y = x; }
+    if (A == 2) { if (G == 0) y = x > 0.0f ? x : 0.0f; if (G == 1) y = yy > 0.0f ? x : 0.0f; }
+    if (A == 3) { if (G == 0) y = x > 0.0f ? x : x * alpha; if (G == 1) y = yy > 0.0f ? x : x * alpha; }
+    if (A == 4) {
+        if (G == 0) y = tanhf(x);
+        if (G == 1) y = x * (1.0f - yy * yy);
+        if (G == 2) y = x * (1.0f - yy * yy) * (-2.0f * yy);
+    }
+    if (A == 5) {
+        if (G == 0) y = x < -EXP_RANGE ? 0.0f : 1.0f / (expf(-x) + 1.0f);
+        if (G == 1) y = x * yy * (1.0f - yy);
+        if (G == 2) y = x * yy * (1.0f - yy) * (1.0f - 2.0f * yy);
+    }
+    if (A == 6) {
+        if (G == 0) y = x >= 0.0f ? x : expm1f(x);
+        if (G == 1) y = yy >= 0.0f ? x : x * (yy + 1.0f);
+        if (G == 2) y = yy >= 0.0f ? 0.0f : x * (yy + 1.0f);
+    }
+    if (A == 7) {
+        if (G == 0) y = x >= 0.0f ? SELU_SCALE * x : (SELU_SCALE * SELU_ALPHA) * expm1f(x);
+        if (G == 1) y = yy >= 0.0f ? x * SELU_SCALE : x * (yy + SELU_SCALE * SELU_ALPHA);
+        if (G == 2) y = yy >= 0.0f ? 0.0f : x * (yy + SELU_SCALE * SELU_ALPHA);
+    }
+    if (A == 8) {
+        if (G == 0) y = x > 20.0f ? x : log1pf(expf(x));            // torch.nn.functional.softplus (threshold 20), bias_act.py:32
+        if (G == 1) y = x * (1.0f - expf(-yy));
+        if (G == 2) { const float c = expf(-yy); y = x * c * (1.0f - c); }
+    }
+    if (A == 9) {
+        if (G == 0) y = x < -EXP_RANGE ? 0.0f : x / (expf(-x) + 1.0f);
+        else {
+            const float c = expf(xref), d = c + 1.0f;
+            if (G == 1) y = xref > 0.5f * EXP_RANGE ? x : x * c * (xref + d) / (d * d);
+            else y = xref > 0.5f * EXP_RANGE ? 0.0f : x * c * (xref * (2.0f - d) + 2.0f * d) / (d * d * d);
+            yref = xref < -EXP_RANGE ? 0.0f : xref / (expf(-xref) + 1.0f) * gain;
+        }
+    }
+    y *= gain * dy;
+    if (clamp >= 0.0f) {
+        if (G == 0) y = (y > -clamp && y < clamp) ? y : (y >= 0.0f ? clamp : -clamp);
+        else y = (yref > -clamp && yref < clamp) ? y : 0.0f;
+    }
+    return y;
+}
+
+struct BiasActArgs {
+    const void *x, *b, *xref, *yref, *dy;
+    void* y;
+    int64_t size_x;
+    int size_b;
+    int64_t step_b;
+    int grad;
+    float alpha, gain, clamp;
+};
+
+template <class T> struct Vec { static constexpr int N = 16 / sizeof(T); };
+
+// 16 bytes per access.  MODE 0: all elements of a vector share one bias entry (step_b % N == 0: NCHW with H*W % N == 0);
+// MODE 1: consecutive elements take consecutive bias entries (step_b == 1 and size_b % N == 0: channels-last / [M, C] activations);
+// MODE 2: scalar fallback (any shape, any alignment).
+template <class T, int A, int MODE>
+__global__ void __launch_bounds__(256) bias_act_kernel(BiasActArgs p)
+{
+    constexpr int N = Vec<T>::N;
+    const T* x = static_cast<const T*>(p.x);
+    const T* b = static_cast<const T*>(p.b);
+    const T* xref = static_cast<const T*>(p.xref);
+    const T* yref = static_cast<const T*>(p.yref);
+    const T* dy = static_cast<const T*>(p.dy);
+    T* y = static_cast<T*>(p.y);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    if (MODE == 2) {
+        for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.size_x; i += stride) {
+            const float bv = b ? to_f(b[(i / p.step_b) % p.size_b]) : 0.0f;
+            y[i] = from_f<T>(bias_act_one<A>(p.grad, to_f(x[i]), bv, xref ? to_f(xref[i]) : 0.0f, yref ? to_f(yref[i]) : 0.0f,
+                                             dy ? to_f(dy[i]) : 1.0f, p.alpha, p.gain, p.clamp));
+        }
+        return;
+    }
+    struct alignas(16) Pack { T v[N]; };
+    const int64_t n_vec = p.size_x / N;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_vec; v += stride) {
+        const int64_t i0 = v * N;
+        const Pack px = reinterpret_cast<const Pack*>(x)[v];
+        Pack pr, pyr, pdy, pb, out;
+        if (xref) pr = reinterpret_cast<const Pack*>(xref)[v];
+        if (yref) pyr = reinterpret_cast<const Pack*>(yref)[v];
+        if (dy) pdy = reinterpret_cast<const Pack*>(dy)[v];
+        float b0 = 0.0f;
+        if (b) {
+            if (MODE == 0) b0 = to_f(b[(i0 / p.step_b) % p.size_b]);
+            else pb = *reinterpret_cast<const Pack*>(b + i0 % p.size_b);
+        }
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const float bv = (b && MODE == 1) ? to_f(pb.v[k]) : b0;
+            out.v[k] = from_f<T>(bias_act_one<A>(p.grad, to_f(px.v[k]), bv, xref ? to_f(pr.v[k]) : 0.0f, yref ? to_f(pyr.v[k]) : 0.0f,
+                                                 dy ? to_f(pdy.v[k]) : 1.0f, p.alpha, p.gain, p.clamp));
+        }
+        reinterpret_cast<Pack*>(y)[v] = out;
+    }
+}
+
+template <class T, int A>
+int bias_act_launch(const BiasActArgs& p, cudaStream_t stream)
+{
+    constexpr int N = Vec<T>::N;
+    auto aligned = [](const void* q) { return q == nullptr || (reinterpret_cast<uintptr_t>(q) & 15) == 0; };
+    const bool vec_ok = p.size_x % N == 0 && aligned(p.x) && aligned(p.xref) && aligned(p.yref) && aligned(p.dy) && aligned(p.y);
+    int mode = 2;
+    if (vec_ok && (!p.b || p.step_b % N == 0)) mode = 0;
+    else if (vec_ok && p.step_b == 1 && p.size_b % N == 0 && aligned(p.b)) mode = 1;
+    const int64_t work = mode == 2 ? p.size_x : p.size_x / N;
+    const int blocks = (int)std::min<int64_t>((work + 255) / 256, (int64_t)sm_count() * 8);
+    if (mode == 0) bias_act_kernel<T, A, 0><<<blocks, 256, 0, stream>>>(p);
+    else if (mode == 1) bias_act_kernel<T, A, 1><<<blocks, 256, 0, stream>>>(p);
+    else bias_act_kernel<T, A, 2><<<blocks, 256, 0, stream>>>(p);
+    return check_launch("bias_act_kernel");
+}
+
+template <class T>
+int bias_act_dispatch(int act, const BiasActArgs& p, cudaStream_t stream)
+{
+    switch (act) {
+    case 1: return bias_act_launch<T, 1>(p, stream);
+    case 2: return bias_act_launch<T, 2>(p, stream);
+    case 3: return bias_act_launch<T, 3>(p, stream);
+    case 4: return bias_act_launch<T, 4>(p, stream);
+    case 5: return bias_act_launch<T, 5>(p, stream);
+    case 6: return bias_act_launch<T, 6>(p, stream);
+    case 7: return bias_act_launch<T, 7>(p, stream);
+    case 8: return bias_act_launch<T, 8>(p, stream);
+    case 9: return bias_act_launch<T, 9>(p, stream);
+    }
+    set_error("nfe_bias_act: act must be 1..9 (bias_act.py:23-33 cuda_idx), got %d", act);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------- upfirdn2d
+struct UpfirdnArgs {
+    const void* x;
+    const float* f;
+    void* y;
+    int n, c, in_h, in_w, out_h, out_w, fh, fw;
+    int64_t xs[4], ys[4];                 // element strides of x and y: batch, channel, row, column
+    int upx, upy, downx, downy, padx0, pady0;
+    int flip;
+    float gain;
+};
+
+// y[oy,ox] = gain * sum_{ky,kx} F[ky,kx] * u[oy*downy + ky, ox*downx + kx], u = zero-inserted, zero-padded x, F = f flipped unless
+// flip_filter (upfirdn2d.py:169-214).  Only the taps that land on a real sample are visited.
+template <class T>
+__global__ void __launch_bounds__(256) upfirdn2d_generic_kernel(UpfirdnArgs p)
+{
+    const int64_t total = (int64_t)p.n * p.c * p.out_h * p.out_w;
+    const T* x = static_cast<const T*>(p.x);
+    T* y = static_cast<T*>(p.y);
+    // the fastest-varying index of the thread order follows y's unit stride (NCHW: column, channels-last: channel)
+    const bool cl = p.ys[1] == 1 && p.c > 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        int ox, oy, ch, nb;
+        int64_t r = i;
+        if (cl) { ch = (int)(r % p.c); r /= p.c; ox = (int)(r % p.out_w); r /= p.out_w; oy = (int)(r % p.out_h); nb = (int)(r / p.out_h); }
+        else { ox = (int)(r % p.out_w); r /= p.out_w; oy = (int)(r % p.out_h); r /= p.out_h; ch = (int)(r % p.c); nb = (int)(r / p.c); }
+        const int my = oy * p.downy - p.pady0, mx = ox * p.downx - p.padx0;      // u row my + pady0 + ky holds x row (my + ky) / upy
+        // first tap whose row / column is a multiple of the up-sampling factor
+        int ky0 = ((-my) % p.upy + p.upy) % p.upy, kx0 = ((-mx) % p.upx + p.upx) % p.upx;
+        const T* xb = x + nb * p.xs[0] + ch * p.xs[1];
+        float acc = 0.0f;
+        for (int ky = ky0; ky < p.fh; ky += p.upy) {
+            const int iy = (my + ky) / p.upy;
+            if (iy < 0 || iy >= p.in_h) continue;
+            const int fy = p.flip ? ky : p.fh - 1 - ky;
+            for (int kx = kx0; kx < p.fw; kx += p.upx) {
+                const int ix = (mx + kx) / p.upx;
+                if (ix < 0 || ix >= p.in_w) continue;
+                const int fx = p.flip ? kx : p.fw - 1 - kx;
+                acc = fmaf(to_f(xb[iy * p.xs[2] + ix * p.xs[3]]), __ldg(p.f + fy * p.fw + fx), acc);
+            }
+        }
+        y[nb * p.ys[0] + ch * p.ys[1] + oy * p.ys[2] + ox * p.ys[3]] = from_f<T>(acc * p.gain);
+    }
+}
+
+// FIR fast path: up = down = 1, unit column stride on both sides, filter at most 8 x 8.  A CTA owns a 16 x 128 output tile of one
+// (batch, channel) plane; thread (tx, ty) computes the 2 rows x 4 columns at (2 ty, 4 tx) from the staged (16 + fh - 1) x (128 + 8)
+// input tile with 16-byte shared-memory reads (three per input row cover 4 + 7 columns).
+constexpr int FIR_TW = 128, FIR_TH = 16, FIR_MAXF = 8, FIR_PITCH = FIR_TW + 12;
+
+template <class T>
+__global__ void __launch_bounds__(256) upfirdn2d_fir_kernel(UpfirdnArgs p, int tiles_x, int tiles_y)
+{
+    __shared__ __align__(16) float tile[(FIR_TH + FIR_MAXF - 1) * FIR_PITCH];
+    __shared__ float filt[FIR_MAXF * FIR_MAXF];
+    const T* x = static_cast<const T*>(p.x);
+    T* y = static_cast<T*>(p.y);
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    if (threadIdx.x < p.fh * p.fw) {
+        const int ky = threadIdx.x / p.fw, kx = threadIdx.x % p.fw;
+        filt[threadIdx.x] = __ldg(p.f + (p.flip ? ky : p.fh - 1 - ky) * p.fw + (p.flip ? kx : p.fw - 1 - kx)) * p.gain;
+    }
+    const int64_t n_tiles = (int64_t)p.n * p.c * tiles_y * tiles_x;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int bx = (int)(t % tiles_x), by = (int)((t / tiles_x) % tiles_y);
+        const int64_t plane = t / ((int64_t)tiles_x * tiles_y);
+        const int ch = (int)(plane % p.c), nb = (int)(plane / p.c);
+        const int ox0 = bx * FIR_TW, oy0 = by * FIR_TH;
+        const T* xb = x + nb * p.xs[0] + ch * p.xs[1];
+        const int rows = FIR_TH + p.fh - 1, cols = FIR_TW + p.fw - 1;
+        __syncthreads();                                   // previous tile fully consumed (and the filter visible)
+        for (int r = ty; r < rows; r += 8) {
+            const int iy = oy0 + r - p.pady0;
+            const bool row_ok = iy >= 0 && iy < p.in_h;
+            for (int cc = tx; cc < cols; cc += 32) {
+                const int ix = ox0 + cc - p.padx0;
+                tile[r * FIR_PITCH + cc] = (row_ok && ix >= 0 && ix < p.in_w) ? to_f(xb[iy * p.xs[2] + ix]) : 0.0f;
+            }
+        }
+        __syncthreads();
+        float acc[2][4] = {};
+        for (int r = 0; r < p.fh + 1; ++r) {                // input rows 2 ty + r, r = 0 .. fh: output row j uses filter row r - j
+            const float4* src = reinterpret_cast<const float4*>(&tile[(2 * ty + r) * FIR_PITCH + 4 * tx]);
+            const float4 a = src[0], b = src[1], c = src[2];
+            const float in[12] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int ky = r - j;
+                if (ky < 0 || ky >= p.fh) continue;
+#pragma unroll
+                for (int kx = 0; kx < FIR_MAXF; ++kx) {
+                    if (kx >= p.fw) break;
+                    const float w = filt[ky * p.fw + kx];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) acc[j][i] = fmaf(in[i + kx], w, acc[j][i]);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int oy = oy0 + 2 * ty + j;
+            if (oy >= p.out_h) continue;
+            T* dst = y + nb * p.ys[0] + ch * p.ys[1] + oy * p.ys[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ox = ox0 + 4 * tx + i;
+                if (ox < p.out_w) dst[ox] = from_f<T>(acc[j][i]);
+            }
+        }
+    }
+}
+
+template <class T>
+int upfirdn2d_launch(const UpfirdnArgs& p, cudaStream_t stream)
+{
+    const int64_t total = (int64_t)p.n * p.c * p.out_h * p.out_w;
+    if (total == 0) return 0;
+    const bool fir = p.upx == 1 && p.upy == 1 && p.downx == 1 && p.downy == 1 && p.xs[3] == 1 && p.ys[3] == 1 && p.fw <= FIR_MAXF &&
+                     p.fh <= FIR_MAXF && p.out_w >= 32;
+    if (fir) {
+        const int tiles_x = (p.out_w + FIR_TW - 1) / FIR_TW, tiles_y = (p.out_h + FIR_TH - 1) / FIR_TH;
+        const int64_t n_tiles = (int64_t)p.n * p.c * tiles_x * tiles_y;
+        const int blocks = (int)std::min<int64_t>(n_tiles, (int64_t)sm_count() * 8);
+        upfirdn2d_fir_kernel<T><<<blocks, 256, 0, stream>>>(p, tiles_x, tiles_y);
+        return check_launch("upfirdn2d_fir_kernel");
+    }
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)sm_count() * 16);
+    upfirdn2d_generic_kernel<T><<<blocks, 256, 0, stream>>>(p);
+    return check_launch("upfirdn2d_generic_kernel");
+}
+
+}  // namespace sg
+}  // namespace nfe
+
+using namespace nfe;
+
+NFE_EXPORT int nfe_bias_act(const void* x, const void* b, const void* xref, const void* yref, const void* dy, void* y, int64_t size_x,
+                            int size_b, int64_t step_b, int dtype, int grad, int act, float alpha, float gain, float clamp, nfe_stream_t stream)
+{
+    NFE_REQUIRE(size_x >= 0 && (size_x == 0 || (x && y)), "nfe_bias_act: null x / y");
+    NFE_REQUIRE(grad >= 0 && grad <= 2, "nfe_bias_act: grad must be 0, 1 or 2, got %d", grad);
+    NFE_REQUIRE(!b || (size_b > 0 && step_b > 0), "nfe_bias_act: bias needs size_b > 0 and step_b > 0");
+    NFE_REQUIRE(grad == 0 || yref || act == 1 || act == 9, "nfe_bias_act: grad >= 1 needs the saved output (yref)");
+    NFE_REQUIRE(!(act == 9 && grad > 0) || xref, "nfe_bias_act: swish gradients need the saved input (xref)");
+    NFE_REQUIRE(grad < 2 || dy, "nfe_bias_act: grad == 2 needs dy");
+    if (size_x == 0) return 0;
+    sg::BiasActArgs p{x, b, xref, yref, dy, y, size_x, b ? size_b : 1, b ? step_b : 1, grad, alpha, gain, clamp};
+    if (dtype == NFE_DTYPE_F32) return sg::bias_act_dispatch<float>(act, p, as_stream(stream));
+    if (dtype == NFE_DTYPE_F16) return sg::bias_act_dispatch<__half>(act, p, as_stream(stream));
+    if (dtype == NFE_DTYPE_BF16) return sg::bias_act_dispatch<__nv_bfloat16>(act, p, as_stream(stream));
+    set_error("nfe_bias_act: dtype must be NFE_DTYPE_F32 / F16 / BF16, got %d", dtype);
+    return 1;
+}
+
+NFE_EXPORT int nfe_upfirdn2d(const void* x, const float* f, void* y, int n, int c, int in_h, int in_w, int out_h, int out_w, int fh, int fw,
+                             const int64_t* x_strides, const int64_t* y_strides, int upx, int upy, int downx, int downy, int padx0,
+                             int padx1, int pady0, int pady1, int flip_filter, float gain, int dtype, nfe_stream_t stream)
+{
+    NFE_REQUIRE(x && f && y && x_strides && y_strides, "nfe_upfirdn2d: null pointer");
+    NFE_REQUIRE(n >= 0 && c >= 0 && in_h > 0 && in_w > 0 && fh >= 1 && fw >= 1, "nfe_upfirdn2d: bad shape");
+    NFE_REQUIRE(upx >= 1 && upy >= 1 && downx >= 1 && downy >= 1, "nfe_upfirdn2d: scaling factors must be >= 1");
+    // upfirdn2d.cpp:55-58 / upfirdn2d.py:185-187: the up-sampled, padded image must not be smaller than the filter
+    const int64_t up_w = (int64_t)in_w * upx + padx0 + padx1, up_h = (int64_t)in_h * upy + pady0 + pady1;
+    NFE_REQUIRE(up_w >= fw && up_h >= fh, "nfe_upfirdn2d: up-sampled image (%lld x %lld) smaller than the filter (%d x %d)", (long long)up_h,
+                (long long)up_w, fh, fw);
+    NFE_REQUIRE(out_w == (up_w - fw + downx) / downx && out_h == (up_h - fh + downy) / downy, "nfe_upfirdn2d: output must be %lld x %lld, got %d x %d",
+                (long long)((up_h - fh + downy) / downy), (long long)((up_w - fw + downx) / downx), out_h, out_w);
+    sg::UpfirdnArgs p;
+    p.x = x; p.f = f; p.y = y; p.n = n; p.c = c; p.in_h = in_h; p.in_w = in_w; p.out_h = out_h; p.out_w = out_w; p.fh = fh; p.fw = fw;
+    for (int i = 0; i < 4; ++i) { p.xs[i] = x_strides[i]; p.ys[i] = y_strides[i]; }
+    p.upx = upx; p.upy = upy; p.downx = downx; p.downy = downy; p.padx0 = padx0; p.pady0 = pady0; p.flip = flip_filter ? 1 : 0; p.gain = gain;
+    if (dtype == NFE_DTYPE_F32) return sg::upfirdn2d_launch<float>(p, as_stream(stream));
+    if (dtype == NFE_DTYPE_F16) return sg::upfirdn2d_launch<__half>(p, as_stream(stream));
+    if (dtype == NFE_DTYPE_BF16) return sg::upfirdn2d_launch<__nv_bfloat16>(p, as_stream(stream));
+    set_error("nfe_upfirdn2d: dtype must be NFE_DTYPE_F32 / F16 / BF16, got %d", dtype);
+    return 1;
+}
