@@ -331,6 +331,35 @@ int nfe_upfirdn2d(const void* x, const float* f, void* y, int n, int c, int in_h
                   const int64_t* x_strides, const int64_t* y_strides, int upx, int upy, int downx, int downy, int padx0, int padx1,
                   int pady0, int pady1, int flip_filter, float gain, int dtype, nfe_stream_t stream);
 
+/* modulated_conv2d + the bias_act that follows it, inference forward: replaces `modulated_conv2d(x, weight, styles, noise, up,
+ * padding=k//2, resample_filter, demodulate, flip_weight, fused_modconv)` (training/networks_stylegan2.py:34-91) over
+ * conv2d_resample's plain and transposed cases (torch_utils/ops/conv2d_resample.py:48-143; the reference executes them as grouped
+ * cuDNN convolutions, conv2d_gradfix.py:37-55) and the layer's `bias_act(x, bias, act, gain, clamp)` (networks_stylegan2.py:322-325,
+ * 351-352).  Activations are channels-last: x [batch, in_h, in_w, in_ch], y [batch, in_h*up, in_w*up, out_ch], both `dtype`
+ * (NFE_DTYPE_F16: fp16 tensor-core operands as the reference's fp16 layers; NFE_DTYPE_F32: bf16 hi/lo split operands, three MMAs per
+ * product).  weight [out_ch, in_ch, k, k] and styles [batch, in_ch] are the fp32 master values; the per-sample fold w*s*demod (and the
+ * fp16 pre-normalisation, networks_stylegan2.py:55-57) happens inside.  noise: NULL, or fp32 [in_h*up, in_w*up] with
+ * noise_batch_stride 0, or per item with the stride in elements; bias: fp32 [out_ch] or NULL; act = bias_act cuda_idx 1 (linear),
+ * 2 (relu), 3 (lrelu); clamp < 0 disables.  up = 2 needs the resample filter f [fh, fw] (upfirdn2d.setup_filter). */
+typedef struct nfe_modconv_args {
+    const void* x;
+    const float* weight;
+    const float* styles;
+    const float* noise;
+    int64_t noise_batch_stride;
+    const float* bias;
+    void* y;
+    const float* filter;
+    int fh, fw;
+    int batch, in_ch, out_ch, in_h, in_w;
+    int ksize, up, demodulate, flip_weight;
+    int act;
+    float alpha, gain, clamp;
+    int dtype;
+} nfe_modconv_args;
+int64_t nfe_modconv_workspace_bytes(const nfe_modconv_args* args);
+int nfe_modulated_conv2d(const nfe_modconv_args* args, void* workspace, int64_t workspace_bytes, nfe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

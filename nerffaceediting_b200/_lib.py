@@ -35,6 +35,13 @@ class NfeRenderCfg(ctypes.Structure):
                 ("affine_scale", c_vp), ("affine_shift", c_vp), ("affine_items", c_int), ("sigma_only", c_int), ("image_layout", c_int)]
 
 
+class NfeModconvArgs(ctypes.Structure):
+    _fields_ = [("x", c_vp), ("weight", c_vp), ("styles", c_vp), ("noise", c_vp), ("noise_batch_stride", c_i64), ("bias", c_vp), ("y", c_vp),
+                ("filter", c_vp), ("fh", c_int), ("fw", c_int), ("batch", c_int), ("in_ch", c_int), ("out_ch", c_int), ("in_h", c_int),
+                ("in_w", c_int), ("ksize", c_int), ("up", c_int), ("demodulate", c_int), ("flip_weight", c_int), ("act", c_int),
+                ("alpha", c_float), ("gain", c_float), ("clamp", c_float), ("dtype", c_int)]
+
+
 _MLP_P = ctypes.POINTER(NfeMlp)
 _CFG_P = ctypes.POINTER(NfeRenderCfg)
 
@@ -82,6 +89,8 @@ SIGNATURES = {
     "nfe_finish_depth": (c_int, [c_vp, c_i64, c_vp, c_vp]),
     "nfe_run_model_fwd": (c_int, [_CFG_P, _MLP_P, _MLP_P, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "nfe_bias_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_int, c_float, c_float, c_float, c_vp]),
+    "nfe_modconv_workspace_bytes": (c_i64, [ctypes.POINTER(NfeModconvArgs)]),
+    "nfe_modulated_conv2d": (c_int, [ctypes.POINTER(NfeModconvArgs), c_vp, c_i64, c_vp]),
     "nfe_upfirdn2d": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 8 + [ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)] + [c_int] * 9 + [c_float, c_int, c_vp]),
 }
 

@@ -15,7 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIB_DIR, "libnfe_b200.so")
-SOURCES = ["nfe_api.cu", "nfe_planes.cu", "nfe_rays.cu", "nfe_field.cu", "nfe_field_tc.cu", "nfe_field_pipe.cu", "nfe_field_pipe2.cu", "nfe_march.cu", "nfe_render.cu", "nfe_backward.cu", "nfe_field_bwd.cu", "nfe_diag.cu", "nfe_losses.cu", "nfe_stylegan_ops.cu"]
+SOURCES = ["nfe_api.cu", "nfe_planes.cu", "nfe_rays.cu", "nfe_field.cu", "nfe_field_tc.cu", "nfe_field_pipe.cu", "nfe_field_pipe2.cu", "nfe_march.cu", "nfe_render.cu", "nfe_backward.cu", "nfe_field_bwd.cu", "nfe_diag.cu", "nfe_losses.cu", "nfe_stylegan_ops.cu", "nfe_modconv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

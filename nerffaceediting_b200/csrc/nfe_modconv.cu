@@ -1,0 +1,641 @@
+// Modulated convolution of the StyleGAN2 backbone / super-resolution stack as a tcgen05 implicit GEMM.
+//
+// Replaces, for inference:  modulated_conv2d (training/networks_stylegan2.py:34-91) + conv2d_resample's 3x3 / 1x1 and
+// transposed (up = 2) cases (torch_utils/ops/conv2d_resample.py:48-143) + the bias_act that follows every layer
+// (networks_stylegan2.py:322-325, 351-352).  The reference runs it as a grouped cuDNN convolution over per-sample weights.
+//
+// Formulation.  Activations are channels-last ([N,H,W,C]; the reference's own fp16_channels_last layout), so one pixel's channels
+// are one contiguous run.  out[pixel, o] = sum_{tap, i} x[pixel + shift(tap), i] * Wm[n][o, i, tap] with the per-sample weights
+// Wm = W * style * demodulation folded ONCE per call by the packing kernel (the reference folds them too, fused_modconv=True, and
+// rounds them to fp16 exactly there).  GEMM view per CTA: M = 128 * MA pixels (a 16*MA x 8 window of the image), N = up to 256
+// output channels, K = taps x input channels, accumulated in tensor memory.
+//
+//  * A operand (activations): ONE halo window (16*MA+2) x 10 pixels x 64 channels per K chunk is brought into shared memory by
+//    cp.async with zero fill (that is the convolution's zero padding) in the layout [channel group of 8][halo pixel][8 channels];
+//    8 consecutive pixels of a window row x 8 channels are then exactly one 8x16-byte core matrix of the K-major SWIZZLE_NONE
+//    operand layout, the next window row is the next row group (SBO = 160 B), the next channel group the next K core matrix
+//    (LBO = the halo size).  Every one of the 9 taps of a 3x3 convolution is the SAME buffer read through a descriptor whose start
+//    address is shifted by (dy * 10 + dx) * 16 bytes: no im2col copy exists anywhere, and the activations cross the L2 -> SM link
+//    once per 9 taps.
+//  * B operand (weights): packed by the packing kernel in exactly the shared-memory operand order, one contiguous block per
+//    (K chunk, tap), streamed by ONE thread with cp.async.bulk (the TMA unit's bulk copy, completion on an mbarrier with
+//    complete_tx) through a ring of up to 4 stages.
+//  * roles: warps 0-3 load A during the main loop and run the epilogue (thread = TMEM lane = pixel), warp 4 issues the MMAs
+//    (one elected thread, tcgen05.mma kind::f16, fp32 accumulate), warp 5 streams B.  tcgen05.commit releases the stages.
+//  * epilogue, fused: + noise, + bias, activation (linear / relu / lrelu), gain, clamp, conversion, channels-last store.
+//  * up = 2 (conv2d_resample.py:117-134): the transposed stride-2 convolution is four phase convolutions (even/odd output rows x
+//    columns: 4 + 2 + 2 + 1 taps, i.e. the 9 taps once — no multiplication by an inserted zero) written interleaved into the
+//    (2H+1) x (2W+1) intermediate, followed by ONE pass that applies the low-pass filter, noise, bias, activation and clamp
+//    (upfir_finish_kernel; the reference makes four passes of it: upfirdn2d, add_, bias_act).
+//
+// Arithmetic: fp16 activations -> fp16 operands, one MMA per product (what the reference's fp16 layers do in cuDNN);
+// fp32 activations -> bf16 hi/lo split of both operands, three MMAs per product, fp32 accumulate (~16 significand bits per operand,
+// the decoder's bf16x3 mode; the reference's fp32 layers run with TF32 disabled, training_loop.py:128-129).
+#include <algorithm>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "nfe_common.cuh"
+#include "nfe_tc.cuh"
+
+namespace nfe {
+namespace mc {
+
+constexpr int TILE_W = 8, HALO_W = TILE_W + 2, MAX_TAPS = 9, MAX_PHASES = 4, THREADS = 192, SA = 2, MAX_SB = 6;
+constexpr int SMEM_BUDGET = 227 * 1024 - 256;
+
+struct Phase {
+    int taps;
+    int dy[MAX_TAPS], dx[MAX_TAPS];       // input pixel of tap t = output-grid pixel + (dy, dx)
+    int ky[MAX_TAPS], kx[MAX_TAPS];       // weight element of tap t
+    int gh, gw;                           // output grid of the phase
+    int oy_mul, oy_off, ox_mul, ox_off;   // grid pixel (gy, gx) is written to (gy * oy_mul + oy_off, gx * ox_mul + ox_off)
+    long long packed_off;                 // bytes, inside one batch item's packed block
+};
+
+struct GemmArgs {
+    const void* x;                        // [batch, in_h, in_w, in_ch]
+    const unsigned char* packed;
+    long long packed_item_stride;
+    void* y;
+    long long ys_n, ys_h, ys_w;           // element strides of y; the channel stride is 1
+    const float* noise;                   // noise[n * noise_n + oy * noise_w + ox] or NULL
+    long long noise_n;
+    int noise_w;
+    const float* bias;
+    int batch, in_h, in_w, in_ch, out_ch;
+    int n_tile, n_tiles, chunks, kc, sb, b_stage, halo;
+    int phases, tiles_x, tiles_y;
+    int act;                              // bias_act cuda_idx: 1 linear, 2 relu, 3 lrelu
+    float alpha, gain, clamp;
+    Phase ph[MAX_PHASES];
+};
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(tc::smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
+}
+// bulk copy global -> shared by the TMA unit, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+// kind::f16 instruction descriptor: fp32 accumulate, both operands K-major; FMT 0 = fp16, 1 = bf16
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt)
+{
+    return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <class T> __device__ __forceinline__ float act_apply(float v, int act, float alpha)
+{
+    if (act == 2) return fmaxf(v, 0.0f);
+    if (act == 3) return v > 0.0f ? v : v * alpha;
+    return v;
+}
+
+template <int PARTS> struct Elem { using type = __half; };
+template <> struct Elem<2> { using type = float; };
+
+// PARTS = 1: fp16 activations / fp16 operands.  PARTS = 2: fp32 activations / bf16 hi + lo operands, three terms per product.
+// MA = accumulators (128 pixels each) per CTA.
+template <int PARTS, int MA>
+__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
+{
+    using T = typename Elem<PARTS>::type;
+    constexpr int HALO_H = 16 * MA + 2;
+    constexpr int A_LBO = HALO_H * HALO_W * 16;          // bytes between channel groups of 8 (K core matrices)
+    constexpr int A_SBO = HALO_W * 16;                    // bytes between window rows (row groups of 8 pixels)
+    constexpr int A_PART = 8 * A_LBO, A_STAGE = PARTS * A_PART;
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char* const sA = smem;
+    unsigned char* const sB = smem + SA * A_STAGE;
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(sB + a.sb * a.b_stage);
+    uint64_t* const a_full = bars, * const a_empty = bars + SA, * const b_full = bars + 2 * SA, * const b_empty = b_full + MAX_SB;
+    uint64_t* const acc_full = b_empty + MAX_SB;
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int p = blockIdx.z / a.batch, n = blockIdx.z % a.batch, nt = blockIdx.y;
+    const Phase& ph = a.ph[p];
+    const int x0 = (blockIdx.x % a.tiles_x) * TILE_W, y0 = (blockIdx.x / a.tiles_x) * (16 * MA);
+    if (x0 >= ph.gw || y0 >= ph.gh) return;               // the launch grid is sized for the largest phase
+    const int taps = ph.taps;
+    uint32_t tmem_cols = 32;
+    while ((int)tmem_cols < MA * a.n_tile) tmem_cols <<= 1;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
+        tc::mbar_init(acc_full, 1);
+        tc::mbar_fence_init();
+    }
+    if (warp == 4) tc::tmem_alloc(tmem_slot, tmem_cols);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 4) {
+        // ------------------------------------------------------------------ A loader: one halo window per K chunk
+        const int kcores = a.kc >> 3, total = HALO_H * HALO_W * kcores;
+        const T* xin = static_cast<const T*>(a.x);
+        for (int c = 0; c < a.chunks; ++c) {
+            const int s = c % SA, r = c / SA;
+            if (r > 0) tc::mbar_wait(&a_empty[s], (r - 1) & 1);
+            unsigned char* const dst0 = sA + s * A_STAGE;
+            for (int i = threadIdx.x; i < total; i += 128) {
+                const int k8 = i % kcores, hp = i / kcores, hy = hp / HALO_W, hx = hp % HALO_W;
+                if (!a.halo && (hy == 0 || hy == HALO_H - 1 || hx == 0 || hx == HALO_W - 1)) continue;   // 1x1: the ring is never read
+                const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                const bool ok = gy >= 0 && gy < a.in_h && gx >= 0 && gx < a.in_w;
+                const long long e = ((long long)(n * a.in_h + (ok ? gy : 0)) * a.in_w + (ok ? gx : 0)) * a.in_ch + c * a.kc + k8 * 8;
+                unsigned char* dst = dst0 + k8 * A_LBO + hp * 16;
+                if constexpr (PARTS == 1) {
+                    cp_async16(dst, xin + e, ok ? 16 : 0);
+                } else {
+                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                    if (ok) {
+                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(xin + e)), v1 = __ldg(reinterpret_cast<const float4*>(xin + e) + 1);
+                        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+                    }
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        __nv_bfloat16 h0, l0, h1, l1;
+                        tc::split_bf16(v[2 * q], h0, l0); tc::split_bf16(v[2 * q + 1], h1, l1);
+                        hi[q] = tc::pack_bf16(h0, h1); lo[q] = tc::pack_bf16(l0, l1);
+                    }
+                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<uint4*>(dst + A_PART) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                }
+            }
+            if constexpr (PARTS == 1) cp_async_wait_all();
+            tc::fence_async_smem();
+            tc::mbar_arrive(&a_full[s]);
+        }
+        // ------------------------------------------------------------------ epilogue: thread = TMEM lane = pixel of the window
+        tc::mbar_wait(acc_full, 0);
+        tc::fence_after_sync();
+        const int row = threadIdx.x, py = row >> 3, px = row & 7;
+        T* yout = static_cast<T*>(a.y);
+        constexpr int VEC = 16 / (int)sizeof(T);
+        const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
+#pragma unroll 1
+        for (int m = 0; m < MA; ++m) {
+            const int gy = y0 + m * 16 + py, gx = x0 + px;
+            const bool valid = gy < ph.gh && gx < ph.gw;
+            const int oy = gy * ph.oy_mul + ph.oy_off, ox = gx * ph.ox_mul + ph.ox_off;
+            T* dst = yout + n * a.ys_n + oy * a.ys_h + ox * a.ys_w + nt * a.n_tile;
+            const float nz = (a.noise && valid) ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.noise_w + ox) : 0.0f;
+#pragma unroll 1
+            for (int q = 0; q < a.n_tile / 16; ++q) {
+                float v[16];
+                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + m * a.n_tile + q * 16, v);
+                tc::tmem_ld_wait();
+                if (!valid) continue;
+                const int o0 = nt * a.n_tile + q * 16;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    float t = v[i] + nz;
+                    if (a.bias && o0 + i < a.out_ch) t += __ldg(a.bias + o0 + i);
+                    t = act_apply<T>(t, a.act, a.alpha) * a.gain;
+                    if (a.clamp >= 0.0f) t = fminf(fmaxf(t, -a.clamp), a.clamp);
+                    v[i] = t;
+                }
+                if (vec_ok && o0 + 16 <= a.out_ch) {
+                    if constexpr (PARTS == 1) {
+                        uint32_t w[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) { const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&h); }
+                        uint4* d4 = reinterpret_cast<uint4*>(dst + q * 16);
+                        d4[0] = make_uint4(w[0], w[1], w[2], w[3]); d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
+                    } else {
+                        float4* d4 = reinterpret_cast<float4*>(dst + q * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i)
+                        if (o0 + i < a.out_ch) {
+                            if constexpr (PARTS == 1) dst[q * 16 + i] = __float2half_rn(v[i]); else dst[q * 16 + i] = v[i];
+                        }
+                }
+            }
+        }
+        tc::fence_before_sync();
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issue (one thread)
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(128, a.n_tile, PARTS == 1 ? 0 : 1);
+            const uint32_t b_lbo = a.n_tile * 16, b_part = a.n_tile * a.kc * 2;
+            const int ksteps = a.kc >> 4;
+            int it = 0;
+            for (int c = 0; c < a.chunks; ++c) {
+                const int s = c % SA;
+                tc::mbar_wait(&a_full[s], (c / SA) & 1);
+                tc::fence_after_sync();
+                const uint32_t a_base = tc::smem_u32(sA + s * A_STAGE);
+                for (int t = 0; t < taps; ++t, ++it) {
+                    const int sb = it % a.sb;
+                    tc::mbar_wait(&b_full[sb], (it / a.sb) & 1);
+                    tc::fence_after_sync();
+                    const uint32_t b_base = tc::smem_u32(sB + sb * a.b_stage);
+                    const uint32_t a_tap = a_base + ((1 + ph.dy[t]) * HALO_W + 1 + ph.dx[t]) * 16;
+#pragma unroll 1
+                    for (int m = 0; m < MA; ++m) {
+                        constexpr int TERMS = PARTS == 2 ? 3 : 1;
+#pragma unroll
+                        for (int term = 0; term < TERMS; ++term) {          // hi*hi, lo*hi, hi*lo
+                            const uint32_t aa = a_tap + m * 16 * A_SBO + (term == 1 ? A_PART : 0);
+                            const uint32_t bb = b_base + (term == 2 ? b_part : 0);
+                            for (int j = 0; j < ksteps; ++j) {
+                                const uint64_t da = tc::make_desc(aa + j * 2 * A_LBO, A_LBO, A_SBO);
+                                const uint64_t db = tc::make_desc(bb + j * 2 * b_lbo, b_lbo, 128);
+                                tc::mma_bf16_ss(tmem + m * a.n_tile, da, db, idesc, !(c == 0 && t == 0 && term == 0 && j == 0));
+                            }
+                        }
+                    }
+                    tc::mma_commit(&b_empty[sb]);          // the weight stage is free once these MMAs have read it
+                }
+                tc::mma_commit(&a_empty[s]);
+            }
+            tc::mma_commit(acc_full);
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------------------------------------------ B stream (one thread): packed weights, one block per (chunk, tap)
+        if (lane == 0) {
+            const unsigned char* src = a.packed + n * a.packed_item_stride + ph.packed_off + (long long)nt * a.chunks * taps * a.b_stage;
+            const int total = a.chunks * taps;
+            for (int it = 0; it < total; ++it) {
+                const int sb = it % a.sb;
+                if (it >= a.sb) tc::mbar_wait(&b_empty[sb], ((it / a.sb) - 1) & 1);
+                mbar_expect_tx(&b_full[sb], (uint32_t)a.b_stage);
+                bulk_copy(sB + sb * a.b_stage, src + (long long)it * a.b_stage, (uint32_t)a.b_stage, &b_full[sb]);
+            }
+        }
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 4) {
+        tc::fence_after_sync();
+        tc::tmem_dealloc(tmem, tmem_cols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- weight folding and packing
+struct PackArgs {
+    const float* weight;                  // [O, I, k, k]
+    const float* styles;                  // [N, I]
+    float* dcoef;                         // [N, O] workspace
+    float* wmul;                          // [O] workspace (fp16 pre-normalisation, networks_stylegan2.py:55-57)
+    float* smax;                          // [N]
+    unsigned char* packed;
+    long long packed_item_stride;
+    int batch, out_ch, in_ch, ksize, demodulate, prenorm, parts;
+    int n_tile, n_tiles, chunks, kc, b_stage, phases;
+    Phase ph[MAX_PHASES];
+};
+
+// one block per (o, n): demodulation coefficient rsqrt(sum_{i,k} (w * s)^2 + 1e-8) (networks_stylegan2.py:59-66)
+__global__ void __launch_bounds__(128) modconv_coef_kernel(const PackArgs a)
+{
+    __shared__ float red[4];
+    const int o = blockIdx.x, n = blockIdx.y, kk = a.ksize * a.ksize, per_o = a.in_ch * kk;
+    const float* w = a.weight + (long long)o * per_o;
+    const float* s = a.styles + (long long)n * a.in_ch;
+    auto block_reduce = [&](float v, bool is_max) {
+        v = is_max ? warp_max(v) : warp_sum(v);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+        __syncthreads();
+        return is_max ? fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) : (red[0] + red[1]) + (red[2] + red[3]);
+    };
+    float wm = 1.0f, sm = 1.0f;
+    if (a.prenorm) {
+        float mw = 0.0f, ms = 0.0f;
+        for (int i = threadIdx.x; i < per_o; i += 128) mw = fmaxf(mw, fabsf(__ldg(w + i)));
+        for (int i = threadIdx.x; i < a.in_ch; i += 128) ms = fmaxf(ms, fabsf(__ldg(s + i)));
+        mw = block_reduce(mw, true);
+        ms = block_reduce(ms, true);
+        wm = (float)(1.0 / sqrt((double)per_o)) / mw;
+        sm = ms;
+    }
+    float acc = 0.0f;
+    if (a.demodulate)
+        for (int i = threadIdx.x; i < per_o; i += 128) {
+            const float v = (__ldg(w + i) * wm) * (a.prenorm ? __ldg(s + i / kk) / sm : __ldg(s + i / kk));
+            acc = fmaf(v, v, acc);
+        }
+    acc = block_reduce(acc, false);
+    if (threadIdx.x == 0) {
+        a.dcoef[(long long)n * a.out_ch + o] = a.demodulate ? 1.0f / sqrtf(acc + 1e-8f) : 1.0f;
+        if (n == 0) a.wmul[o] = wm;
+        if (o == 0) a.smax[n] = sm;
+    }
+}
+
+// one thread per 16-byte operand slot (8 consecutive input channels of one output channel and tap): w * s * d, rounded to the
+// operand type, in the order [phase][N tile][K chunk][tap][part][channel group][row group][row][8 channels]
+__global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
+{
+    const int n = blockIdx.y, kk = a.ksize * a.ksize;
+    const int kcores = a.kc >> 3, rows = a.n_tile;
+    long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int p = blockIdx.z;
+    const Phase& ph = a.ph[p];
+    const long long slots = (long long)a.n_tiles * a.chunks * ph.taps * kcores * rows;
+    if (slot >= slots) return;
+    const int row = (int)(slot % rows); long long r = slot / rows;
+    const int k8 = (int)(r % kcores); r /= kcores;
+    const int t = (int)(r % ph.taps); r /= ph.taps;
+    const int c = (int)(r % a.chunks); const int nt = (int)(r / a.chunks);
+    const int o = nt * a.n_tile + row, i0 = c * a.kc + k8 * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
+    if (o < a.out_ch) {
+        const float wm = a.prenorm ? a.wmul[o] : 1.0f, sm = a.prenorm ? a.smax[n] : 1.0f, d = a.dcoef[(long long)n * a.out_ch + o];
+        const float* w = a.weight + ((long long)o * a.in_ch + i0) * kk + ph.ky[t] * a.ksize + ph.kx[t];
+        const float* s = a.styles + (long long)n * a.in_ch + i0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float sv = a.prenorm ? __ldg(s + j) / sm : __ldg(s + j);
+            v[j] = ((__ldg(w + (long long)j * kk) * wm) * sv) * d;
+        }
+    }
+    unsigned char* dst = a.packed + n * a.packed_item_stride + ph.packed_off +
+                         ((((long long)nt * a.chunks + c) * ph.taps + t) * a.b_stage) + ((long long)k8 * (rows / 8) + row / 8) * 128 + (row & 7) * 16;
+    if (a.parts == 1) {
+        uint32_t w4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); w4[j] = *reinterpret_cast<const uint32_t*>(&h); }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+    } else {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            tc::split_bf16(v[2 * j], h0, l0); tc::split_bf16(v[2 * j + 1], h1, l1);
+            hi[j] = tc::pack_bf16(h0, h1); lo[j] = tc::pack_bf16(l0, l1);
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(dst + a.b_stage / 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- up = 2: filter + noise + bias + act
+struct FinishArgs {
+    const void* t;                        // [batch, th, tw, c] channels-last: the transposed convolution's output
+    void* y;                              // [batch, oh, ow, c]
+    const float* f;                       // [fh, fw]
+    const float* noise; long long noise_n;
+    const float* bias;
+    int batch, th, tw, oh, ow, c, fh, fw, pad_y0, pad_x0, flip;
+    float fgain;
+    int act; float alpha, gain, clamp;
+};
+
+// y[oy, ox, :] = bias_act(sum_{ky,kx} F[ky,kx] * t[oy + ky - pad, ox + kx - pad, :] * fgain + noise[oy, ox]); 8 channels per thread
+// (upfirdn2d.py:169-214 with up = down = 1 on the already up-sampled image; conv2d_resample.py:131, networks_stylegan2.py:84-85,322-325)
+template <class T>
+__global__ void __launch_bounds__(256) upfir_finish_kernel(const FinishArgs a)
+{
+    constexpr int V = 16 / (int)sizeof(T) >= 8 ? 8 : 4;     // channels per thread: 8 halves or 4 floats (16 bytes)
+    __shared__ float filt[64];
+    if ((int)threadIdx.x < a.fh * a.fw) {
+        const int ky = threadIdx.x / a.fw, kx = threadIdx.x % a.fw;
+        filt[threadIdx.x] = __ldg(a.f + (a.flip ? ky : a.fh - 1 - ky) * a.fw + (a.flip ? kx : a.fw - 1 - kx)) * a.fgain;
+    }
+    __syncthreads();
+    const int cv = a.c / V;
+    const long long total = (long long)a.batch * a.oh * a.ow * cv;
+    const T* tin = static_cast<const T*>(a.t);
+    T* yout = static_cast<T*>(a.y);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % cv) * V; long long r = i / cv;
+        const int ox = (int)(r % a.ow); r /= a.ow;
+        const int oy = (int)(r % a.oh); const int n = (int)(r / a.oh);
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+        for (int ky = 0; ky < a.fh; ++ky) {
+            const int iy = oy + ky - a.pad_y0;
+            if (iy < 0 || iy >= a.th) continue;
+            for (int kx = 0; kx < a.fw; ++kx) {
+                const int ix = ox + kx - a.pad_x0;
+                if (ix < 0 || ix >= a.tw) continue;
+                const float w = filt[ky * a.fw + kx];
+                const T* src = tin + (((long long)n * a.th + iy) * a.tw + ix) * a.c + c0;
+                if constexpr (sizeof(T) == 2) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(src));
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 f2 = __half22float2(h[j]); acc[2 * j] = fmaf(f2.x, w, acc[2 * j]); acc[2 * j + 1] = fmaf(f2.y, w, acc[2 * j + 1]); }
+                } else {
+                    const float4 u = __ldg(reinterpret_cast<const float4*>(src));
+                    acc[0] = fmaf(u.x, w, acc[0]); acc[1] = fmaf(u.y, w, acc[1]); acc[2] = fmaf(u.z, w, acc[2]); acc[3] = fmaf(u.w, w, acc[3]);
+                }
+            }
+        }
+        const float nz = a.noise ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.ow + ox) : 0.0f;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float t = acc[j];
+            if constexpr (sizeof(T) == 2) t = __half2float(__float2half_rn(t));      // the reference stores the filtered image in fp16
+            t += nz;
+            if (a.bias) t += __ldg(a.bias + c0 + j);
+            t = act_apply<T>(t, a.act, a.alpha) * a.gain;
+            if (a.clamp >= 0.0f) t = fminf(fmaxf(t, -a.clamp), a.clamp);
+            acc[j] = t;
+        }
+        T* dst = yout + (((long long)n * a.oh + oy) * a.ow + ox) * a.c + c0;
+        if constexpr (sizeof(T) == 2) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const __half2 h = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]); w4[j] = *reinterpret_cast<const uint32_t*>(&h); }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+struct Plan {
+    int parts, ma, n_tile, n_tiles, kc, chunks, b_stage, sb, phases, halo;
+    long long packed_item_bytes, coef_bytes, packed_bytes, trans_bytes, total_bytes;
+    int th, tw;                            // transposed-convolution intermediate (up = 2)
+    Phase ph[MAX_PHASES];
+};
+
+static int make_plan(const nfe_modconv_args& q, Plan& pl)
+{
+    NFE_REQUIRE(q.dtype == NFE_DTYPE_F32 || q.dtype == NFE_DTYPE_F16, "nfe_modulated_conv2d: dtype must be NFE_DTYPE_F32 or NFE_DTYPE_F16, got %d", q.dtype);
+    NFE_REQUIRE(q.batch > 0 && q.in_ch > 0 && q.out_ch > 0 && q.in_h > 0 && q.in_w > 0, "nfe_modulated_conv2d: bad shape");
+    NFE_REQUIRE(q.ksize == 1 || q.ksize == 3, "nfe_modulated_conv2d: kernel size must be 1 or 3 (the reference's layers), got %d", q.ksize);
+    NFE_REQUIRE(q.up == 1 || (q.up == 2 && q.ksize == 3), "nfe_modulated_conv2d: up must be 1, or 2 with a 3x3 kernel, got up=%d k=%d", q.up, q.ksize);
+    NFE_REQUIRE(q.in_ch % 16 == 0, "nfe_modulated_conv2d: in_channels must be a multiple of 16, got %d", q.in_ch);
+    pl.parts = q.dtype == NFE_DTYPE_F16 ? 1 : 2;
+    pl.ma = pl.parts == 1 ? 2 : 1;
+    const int n_max = pl.parts == 1 ? 256 : 128;
+    const int o16 = (q.out_ch + 15) / 16 * 16;
+    if (o16 <= n_max) { pl.n_tile = o16; pl.n_tiles = 1; }
+    else {
+        NFE_REQUIRE(q.out_ch % n_max == 0, "nfe_modulated_conv2d: out_channels above %d must be a multiple of it, got %d", n_max, q.out_ch);
+        pl.n_tile = n_max; pl.n_tiles = q.out_ch / n_max;
+    }
+    pl.kc = q.in_ch % 64 == 0 ? 64 : (q.in_ch % 32 == 0 ? 32 : 16);
+    pl.chunks = q.in_ch / pl.kc;
+    pl.b_stage = pl.parts * pl.n_tile * pl.kc * 2;
+    const int halo_h = 16 * pl.ma + 2, a_bytes = SA * pl.parts * 8 * halo_h * HALO_W * 16;
+    pl.sb = std::min(MAX_SB, (SMEM_BUDGET - a_bytes) / pl.b_stage);
+    NFE_REQUIRE(pl.sb >= 2, "nfe_modulated_conv2d: internal: weight ring does not fit");
+    pl.halo = q.ksize == 3;
+    // phases and taps.  conv2d_resample.py:137-139 (plain) and :117-134 (transposed, stride 2): Y = 2 y + ky
+    long long off = 0;
+    if (q.up == 1) {
+        pl.phases = 1;
+        Phase& p = pl.ph[0];
+        p.taps = q.ksize * q.ksize;
+        for (int ky = 0, t = 0; ky < q.ksize; ++ky)
+            for (int kx = 0; kx < q.ksize; ++kx, ++t) {
+                p.dy[t] = ky - q.ksize / 2; p.dx[t] = kx - q.ksize / 2;
+                p.ky[t] = q.flip_weight ? ky : q.ksize - 1 - ky; p.kx[t] = q.flip_weight ? kx : q.ksize - 1 - kx;   // conv2d_resample.py:36-37
+            }
+        p.gh = q.in_h; p.gw = q.in_w; p.oy_mul = p.ox_mul = 1; p.oy_off = p.ox_off = 0; p.packed_off = 0;
+        off = (long long)pl.n_tiles * pl.chunks * p.taps * pl.b_stage;
+        pl.th = pl.tw = 0;
+    } else {
+        pl.phases = 4;
+        pl.th = 2 * q.in_h + 1; pl.tw = 2 * q.in_w + 1;
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                Phase& p = pl.ph[py * 2 + px];
+                p.taps = 0;
+                for (int ky = py; ky < 3; ky += 2)
+                    for (int kx = px; kx < 3; kx += 2) {
+                        const int t = p.taps++;
+                        p.dy[t] = -(ky / 2); p.dx[t] = -(kx / 2);               // even rows: ky = 0 reads y, ky = 2 reads y - 1
+                        // modulated_conv2d passes flip_weight on; conv2d_resample flips once more for the transposed op (:128)
+                        p.ky[t] = q.flip_weight ? 2 - ky : ky; p.kx[t] = q.flip_weight ? 2 - kx : kx;
+                    }
+                p.gh = py == 0 ? q.in_h + 1 : q.in_h; p.gw = px == 0 ? q.in_w + 1 : q.in_w;
+                p.oy_mul = p.ox_mul = 2; p.oy_off = py; p.ox_off = px;
+                p.packed_off = off;
+                off += (long long)pl.n_tiles * pl.chunks * p.taps * pl.b_stage;
+            }
+    }
+    pl.packed_item_bytes = off;
+    auto up256 = [](long long v) { return (v + 255) / 256 * 256; };
+    pl.coef_bytes = up256((long long)(q.batch * q.out_ch + q.out_ch + q.batch) * 4);
+    pl.packed_bytes = up256(off * q.batch);
+    pl.trans_bytes = q.up == 2 ? up256((long long)q.batch * pl.th * pl.tw * q.out_ch * (q.dtype == NFE_DTYPE_F16 ? 2 : 4)) : 0;
+    pl.total_bytes = pl.coef_bytes + pl.packed_bytes + pl.trans_bytes;
+    return 0;
+}
+
+template <int PARTS, int MA>
+static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
+{
+    const int halo_h = 16 * MA + 2;
+    const size_t smem = (size_t)SA * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + (2 * SA + 2 * MAX_SB + 1) * 8 + 16;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("conv_gemm_kernel: shared memory opt-in: %s", cudaGetErrorString(e)); return 2; }
+        attr_done = true;
+    }
+    const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)(pl.phases * g.batch));
+    conv_gemm_kernel<PARTS, MA><<<grid, THREADS, smem, stream>>>(g);
+    return check_launch("conv_gemm_kernel");
+}
+
+}  // namespace mc
+}  // namespace nfe
+
+using namespace nfe;
+
+NFE_EXPORT int64_t nfe_modconv_workspace_bytes(const nfe_modconv_args* q)
+{
+    mc::Plan pl;
+    if (!q || mc::make_plan(*q, pl)) return -1;
+    return pl.total_bytes;
+}
+
+NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, int64_t workspace_bytes, nfe_stream_t stream_)
+{
+    NFE_REQUIRE(q && q->x && q->weight && q->styles && q->y, "nfe_modulated_conv2d: null pointer");
+    mc::Plan pl;
+    if (int rc = mc::make_plan(*q, pl)) return rc;
+    NFE_REQUIRE(workspace && workspace_bytes >= pl.total_bytes, "nfe_modulated_conv2d: workspace of %lld bytes needed, %lld given",
+                (long long)pl.total_bytes, (long long)workspace_bytes);
+    NFE_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(q->x) & 15) == 0, "nfe_modulated_conv2d: workspace must be 256-byte and x 16-byte aligned");
+    NFE_REQUIRE(q->act >= 1 && q->act <= 3, "nfe_modulated_conv2d: the fused epilogue knows linear (1), relu (2) and lrelu (3), got act=%d", q->act);
+    NFE_REQUIRE(q->up == 1 || (q->filter && q->fh >= 1 && q->fw >= 1 && q->fh * q->fw <= 64 && q->fh == q->fw), "nfe_modulated_conv2d: up = 2 needs a square resample filter of at most 8 x 8");
+    const int vec = q->dtype == NFE_DTYPE_F16 ? 8 : 4;
+    NFE_REQUIRE(q->up == 1 || q->out_ch % vec == 0, "nfe_modulated_conv2d: up = 2 needs out_channels to be a multiple of %d", vec);
+    cudaStream_t stream = as_stream(stream_);
+    unsigned char* ws = static_cast<unsigned char*>(workspace);
+    float* coef = reinterpret_cast<float*>(ws);
+    unsigned char* packed = ws + pl.coef_bytes;
+    void* trans = ws + pl.coef_bytes + pl.packed_bytes;
+
+    mc::PackArgs pa;
+    pa.weight = q->weight; pa.styles = q->styles; pa.dcoef = coef; pa.wmul = coef + (long long)q->batch * q->out_ch; pa.smax = pa.wmul + q->out_ch;
+    pa.packed = packed; pa.packed_item_stride = pl.packed_item_bytes;
+    pa.batch = q->batch; pa.out_ch = q->out_ch; pa.in_ch = q->in_ch; pa.ksize = q->ksize; pa.demodulate = q->demodulate;
+    pa.prenorm = (q->dtype == NFE_DTYPE_F16 && q->demodulate) ? 1 : 0;                     // networks_stylegan2.py:55-57
+    pa.parts = pl.parts; pa.n_tile = pl.n_tile; pa.n_tiles = pl.n_tiles; pa.chunks = pl.chunks; pa.kc = pl.kc; pa.b_stage = pl.b_stage; pa.phases = pl.phases;
+    for (int i = 0; i < pl.phases; ++i) pa.ph[i] = pl.ph[i];
+    mc::modconv_coef_kernel<<<dim3(q->out_ch, q->batch), 128, 0, stream>>>(pa);
+    NFE_LAUNCH_CHECK("modconv_coef_kernel");
+    int max_taps = 0;
+    for (int i = 0; i < pl.phases; ++i) max_taps = std::max(max_taps, pl.ph[i].taps);
+    const long long slots = (long long)pl.n_tiles * pl.chunks * max_taps * (pl.kc / 8) * pl.n_tile;
+    mc::modconv_pack_kernel<<<dim3((unsigned)((slots + 255) / 256), q->batch, pl.phases), 256, 0, stream>>>(pa);
+    NFE_LAUNCH_CHECK("modconv_pack_kernel");
+
+    mc::GemmArgs g;
+    g.x = q->x; g.packed = packed; g.packed_item_stride = pl.packed_item_bytes;
+    g.batch = q->batch; g.in_h = q->in_h; g.in_w = q->in_w; g.in_ch = q->in_ch; g.out_ch = q->out_ch;
+    g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.halo = pl.halo;
+    g.phases = pl.phases;
+    int gh = 0, gw = 0;
+    for (int i = 0; i < pl.phases; ++i) { g.ph[i] = pl.ph[i]; gh = std::max(gh, pl.ph[i].gh); gw = std::max(gw, pl.ph[i].gw); }
+    g.tiles_x = (gw + mc::TILE_W - 1) / mc::TILE_W; g.tiles_y = (gh + 16 * pl.ma - 1) / (16 * pl.ma);
+    if (q->up == 1) {
+        g.y = q->y; g.ys_w = q->out_ch; g.ys_h = (long long)q->in_w * q->out_ch; g.ys_n = (long long)q->in_h * g.ys_h;
+        g.noise = q->noise; g.noise_n = q->noise_batch_stride; g.noise_w = q->in_w; g.bias = q->bias;
+        g.act = q->act; g.alpha = q->alpha; g.gain = q->gain; g.clamp = q->clamp;
+    } else {
+        g.y = trans; g.ys_w = q->out_ch; g.ys_h = (long long)pl.tw * q->out_ch; g.ys_n = (long long)pl.th * g.ys_h;
+        g.noise = nullptr; g.noise_n = 0; g.noise_w = 0; g.bias = nullptr; g.act = 1; g.alpha = 0.0f; g.gain = 1.0f; g.clamp = -1.0f;
+    }
+    int rc = pl.parts == 1 ? mc::launch_gemm<1, 2>(g, pl, stream) : mc::launch_gemm<2, 1>(g, pl, stream);
+    if (rc) return rc;
+    if (q->up == 2) {
+        // conv2d_resample.py:97-101,124-131 with padding = k/2 as the layers pass it: the filter pass pads the (2H+1) image by
+        // p0 = k/2 + (f+1)/2 - (k-1) before and p1 = k/2 + (f-2)/2 - (k-2) after, gain up^2, and yields 2H x 2W
+        mc::FinishArgs f;
+        f.t = trans; f.y = q->y; f.f = q->filter; f.noise = q->noise; f.noise_n = q->noise_batch_stride; f.bias = q->bias;
+        f.batch = q->batch; f.th = pl.th; f.tw = pl.tw; f.oh = 2 * q->in_h; f.ow = 2 * q->in_w; f.c = q->out_ch; f.fh = q->fh; f.fw = q->fw;
+        const int pad0 = q->ksize / 2 + (q->fw + 1) / 2 - (q->ksize - 1), pad1 = q->ksize / 2 + (q->fw - 2) / 2 - (q->ksize - 2);
+        NFE_REQUIRE(pl.th + pad0 + pad1 - q->fh + 1 == f.oh, "nfe_modulated_conv2d: a %d-tap resample filter does not yield a 2x image", q->fw);
+        f.pad_y0 = f.pad_x0 = pad0; f.flip = 0; f.fgain = 4.0f;
+        f.act = q->act; f.alpha = q->alpha; f.gain = q->gain; f.clamp = q->clamp;
+        const long long work = (long long)q->batch * f.oh * f.ow * (q->out_ch / vec);
+        const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 16);
+        if (q->dtype == NFE_DTYPE_F16) mc::upfir_finish_kernel<__half><<<blocks, 256, 0, stream>>>(f);
+        else mc::upfir_finish_kernel<float><<<blocks, 256, 0, stream>>>(f);
+        NFE_LAUNCH_CHECK("upfir_finish_kernel");
+    }
+    return 0;
+}

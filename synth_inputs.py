@@ -88,3 +88,23 @@ def camera_sweep(batch, yaw_range=0.4, pitch_range=0.25, device='cpu'):
     c2w = look_at_cam2world([math.pi / 2 + y for y in yaw], [math.pi / 2 + p for p in pitch], device=device)
     k = fov_to_intrinsics(device=device).unsqueeze(0).repeat(batch, 1, 1)
     return c2w, k
+
+
+def fill_module(module, seed):
+    """Deterministic parameters / buffers for a backbone or super-resolution module (the reference's or this package's: the names are
+    the same), so that goldens and tests build identical networks without storing weights: weights, constants and noise maps
+    ~N(0,1) as at initialisation; style-affine biases around 1, other biases and the noise strengths small but non-zero."""
+    import torch
+    with torch.no_grad():
+        for i, (name, t) in enumerate(sorted(module.state_dict().items())):
+            if name.endswith('resample_filter'):
+                continue
+            h = torch.from_numpy(hash_normal(seed + 7 * i, tuple(t.shape) if t.ndim else (1,))).reshape(t.shape).to(t.dtype)
+            if name.endswith('noise_strength'):
+                h = 0.3 * h
+            elif name.endswith('affine.bias'):
+                h = 1.0 + 0.2 * h
+            elif name.endswith('bias') or name.endswith('w_avg'):
+                h = 0.2 * h
+            t.copy_(h)
+    return module

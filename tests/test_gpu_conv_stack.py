@@ -1,0 +1,143 @@
+"""Convolution stack of the backbone / super-resolution module (csrc/nfe_modconv.cu through
+nfe_modulated_conv2d) against fixtures the UNMODIFIED reference produced on CPU in fp32 (tests/golden/make_golden_f3_conv.py ->
+conv_stack.npz).  Networks are rebuilt on both sides from synth_inputs.fill_module with the same seeds.
+
+Tolerances (max |a-b| / max |b|, `rel_err`, and the element-wise `elem_err` with a 5e-2 floor at ten times the figure):
+  fp32 activations (bf16 hi/lo split operands, three MMAs per product, fp32 accumulate): 1e-4 for single layers, 3e-4 through a
+  whole network (the 8XDC head is 5 convolutions over up to 2304-term sums);
+  fp16 activations (what the reference's own fp16 blocks compute with): 1e-2 against the fp32 fixture."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from _util import elem_err, golden, rel_err
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import conv_cases as cases  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL32, TOL32_NET, TOL16 = 1e-4, 3e-4, 1e-2
+
+
+def cuda(t):
+    return None if t is None else t.cuda()
+
+
+def check(y, ref, tol, what):
+    y = y.float().cpu().numpy()
+    assert y.shape == ref.shape, (what, y.shape, ref.shape)
+    assert np.isfinite(y).all(), what
+    e, ee = rel_err(y, ref), elem_err(y, ref, floor=5e-2)
+    assert e < tol and ee < 10 * tol, (what, e, ee)
+
+
+@pytest.mark.parametrize("tag", list(cases.MODCONV))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_modulated_conv2d(tag, dtype):
+    from nerffaceediting_b200 import networks as net
+    from nerffaceediting_b200 import stylegan_ops as sg
+    c = cases.MODCONV[tag]
+    x, w, s, noise = cases.modconv_inputs(c)
+    f = sg.setup_filter([1, 3, 3, 1]).cuda() if c['up'] == 2 else None
+    with torch.no_grad():
+        y = net.modulated_conv2d(cuda(x).to(dtype), cuda(w), cuda(s), noise=cuda(noise), up=c['up'], padding=c['k'] // 2, resample_filter=f,
+                                 demodulate=c['demod'], flip_weight=c['flip'])
+    assert y.dtype == dtype and y.is_contiguous(memory_format=torch.channels_last)
+    check(y, golden("conv_stack")[f"modconv.{tag}"], TOL32 if dtype == torch.float32 else TOL16, tag)
+
+
+def test_modulated_conv2d_accepts_any_input_layout_and_rejects_what_it_cannot_do():
+    from nerffaceediting_b200 import networks as net
+    c = cases.MODCONV["3x3"]
+    x, w, s, noise = cases.modconv_inputs(c)
+    ref = golden("conv_stack")["modconv.3x3"]
+    with torch.no_grad():
+        y_cl = net.modulated_conv2d(cuda(x).contiguous(memory_format=torch.channels_last), cuda(w), cuda(s), noise=cuda(noise), padding=1)
+        y_nchw = net.modulated_conv2d(cuda(x), cuda(w).contiguous(memory_format=torch.channels_last), cuda(s), noise=cuda(noise), padding=1)
+    assert torch.equal(y_cl, y_nchw)
+    check(y_cl, ref, TOL32, "layouts")
+    with pytest.raises(RuntimeError):
+        net.modulated_conv2d(x, w, s, padding=1)                                            # CPU tensors: no fallback
+    with pytest.raises(RuntimeError):
+        net.modulated_conv2d(cuda(x).requires_grad_(True), cuda(w), cuda(s), padding=1)     # forward-only
+    with pytest.raises(AssertionError):
+        net.modulated_conv2d(cuda(x), cuda(w), cuda(s), padding=1, down=2)
+    with pytest.raises(RuntimeError):
+        with torch.no_grad():
+            net.modulated_conv2d(cuda(x)[:, :24], cuda(w)[:, :24], cuda(s)[:, :24], padding=1)   # in_channels not a multiple of 16
+
+
+@pytest.mark.parametrize("tag", list(cases.LAYERS))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_layers(tag, dtype):
+    from nerffaceediting_b200 import networks as net
+    c = cases.LAYERS[tag]
+    layer = cases.make_layer(net, c).cuda()
+    x, w = cases.layer_inputs(c)
+    with torch.no_grad():
+        if c['kind'] == 'synthesis':
+            y = layer(cuda(x).to(dtype), cuda(w), noise_mode=c['noise_mode'], gain=c['gain'])
+        else:
+            y = layer(cuda(x).to(dtype), cuda(w))
+    check(y, golden("conv_stack")[f"layer.{tag}"], TOL32 if dtype == torch.float32 else TOL16, tag)
+
+
+@pytest.mark.parametrize("tag", list(cases.BLOCKS))
+def test_blocks(tag):
+    from nerffaceediting_b200 import networks as net
+    c = cases.BLOCKS[tag]
+    block = cases.make_block(net, c).cuda()
+    x, img, ws = cases.block_inputs(c)
+    with torch.no_grad():
+        x2, img2 = block(cuda(x), cuda(img), cuda(ws), noise_mode='const')
+    g = golden("conv_stack")
+    check(x2, g[f"block.{tag}.x"], TOL32_NET, tag + ".x")
+    check(img2, g[f"block.{tag}.img"], TOL32_NET, tag + ".img")
+    assert img2.dtype == torch.float32 and img2.is_contiguous()
+
+
+def test_synthesis_network_and_mapping():
+    from nerffaceediting_b200 import networks as net
+    g = golden("conv_stack")
+    n = cases.make_synthesis(net).cuda()
+    with torch.no_grad():
+        img = n(cuda(cases.synthesis_ws(n)), noise_mode='const')
+    check(img, g["synthesis.img"], TOL32_NET, "synthesis")
+    m = cases.make_mapping(net).cuda()
+    z, cnd = cases.mapping_inputs()
+    with torch.no_grad():
+        check(m(cuda(z), cuda(cnd), truncation_psi=0.7, truncation_cutoff=4), g["mapping.ws"], 1e-5, "mapping")
+        check(m(cuda(z), cuda(cnd)), g["mapping.ws_plain"], 1e-5, "mapping plain")
+
+
+def test_superresolution_2x():
+    from nerffaceediting_b200 import networks as net
+    m = cases.make_sr(net, '2X').cuda()
+    rgb, x, ws = cases.sr_inputs('2X')
+    with torch.no_grad():
+        out = m(cuda(rgb), cuda(x), cuda(ws), noise_mode='const')
+    check(out, golden("conv_stack")["sr2x.rgb"], TOL32_NET, "sr2x")
+
+
+@pytest.mark.parametrize("fp16", [False, True])
+def test_superresolution_8xdc_full_size(fp16):
+    """The default 512 x 512 head at full size (superresolution.py:264-290): 64 -> 128 (bilinear) -> 256 (256 ch) -> 512 (128 ch)."""
+    from nerffaceediting_b200 import networks as net
+    g = golden("conv_stack")
+    m = cases.make_sr(net, '8XDC', sr_num_fp16_res=4 if fp16 else 0).cuda()
+    rgb, x, ws = cases.sr_inputs('8XDC')
+    with torch.no_grad():
+        out = m(cuda(rgb), cuda(x), cuda(ws), noise_mode='const')
+    assert out.shape == (1, 3, 512, 512) and out.dtype == torch.float32
+    tol = TOL16 if fp16 else TOL32_NET
+    if fp16:
+        # with these random weights the fp16 blocks saturate at conv_clamp = 256 in places, as the reference's would: compare the bulk
+        assert rel_err(out[:, :, ::4, ::4].cpu().numpy(), g["sr8xdc.rgb_s4"]) < 5e-2
+        return
+    check(out[:, :, ::4, ::4], g["sr8xdc.rgb_s4"], tol, "sr8xdc subsampled")
+    check(out[:, :, 253:259, :], g["sr8xdc.rgb_rows"], tol, "sr8xdc rows")
+    mom = g["sr8xdc.moments"]
+    assert abs(out.double().mean().item() - mom[0]) < tol * mom[2] and abs(out.double().std().item() - mom[1]) < tol * mom[2]

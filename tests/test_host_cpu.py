@@ -331,3 +331,24 @@ print('ok')
 """
     r = subprocess.run([sys.executable, "-c", code, ROOT, REFERENCE], capture_output=True, text=True)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_state_dict_names_are_the_reference_s():
+    """Checkpoints of the reference load unchanged: same parameter / buffer names and shapes (recorded from the reference's modules)."""
+    from nerffaceediting_b200 import networks as net
+    import os
+    import sys
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import conv_cases as cases
+    g = np.load(os.path.join(here, "golden", "conv_stack.npz"))
+
+    def keys(m):
+        return sorted(f"{k}:{'x'.join(map(str, v.shape))}" for k, v in m.state_dict().items())
+    assert keys(cases.make_synthesis(net)) == sorted(g["keys.synthesis"].tolist())
+    assert keys(cases.make_mapping(net)) == sorted(g["keys.mapping"].tolist())
+    assert keys(cases.make_sr(net, '2X')) == sorted(g["keys.sr2x"].tolist())
+    assert keys(cases.make_sr(net, '8XDC')) == sorted(g["keys.sr8xdc"].tolist())
+    assert keys(net.SuperresolutionHybrid4X(32, 256, 4, True)) == sorted(g["keys.sr4x"].tolist())
+    assert keys(net.SuperresolutionHybrid8X(32, 512, 4, True)) == sorted(g["keys.sr8x"].tolist())
