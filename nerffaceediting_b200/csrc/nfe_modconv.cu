@@ -42,7 +42,7 @@ namespace nfe {
 namespace mc {
 
 constexpr int TILE_W = 8, HALO_W = TILE_W + 2, MAX_TAPS = 9, MAX_PHASES = 4, THREADS = 192, SA = 2, MAX_SB = 6;
-constexpr int SMEM_BUDGET = 227 * 1024 - 256;
+constexpr int SMEM_BUDGET = 227 * 1024 - 256 - 1024;
 
 struct Phase {
     int taps;
@@ -92,6 +92,14 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt)
     return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+#ifdef NFE_MC_PROFILE
+__device__ unsigned long long g_mc_prof[16];
+#define MC_WAIT(slot, bar, par) do { const long long t0_ = clock64(); tc::mbar_wait(bar, par); prof_[slot] += clock64() - t0_; } while (0)
+#define MC_FLUSH(slot) atomicAdd(&g_mc_prof[slot], (unsigned long long)prof_[slot])
+#else
+#define MC_WAIT(slot, bar, par) tc::mbar_wait(bar, par)
+#endif
+
 template <class T> __device__ __forceinline__ float act_apply(float v, int act, float alpha)
 {
     if (act == 2) return fmaxf(v, 0.0f);
@@ -119,7 +127,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
     uint64_t* const a_full = bars, * const a_empty = bars + SA, * const b_full = bars + 2 * SA, * const b_empty = b_full + MAX_SB;
     uint64_t* const acc_full = b_empty + MAX_SB;
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 160);       // this N tile's bias, zero where there is none
 
+#ifdef NFE_MC_PROFILE
+    long long prof_[12] = {};
+    const long long t_cta0 = clock64();
+#endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int p = blockIdx.z / a.batch, n = blockIdx.z % a.batch, nt = blockIdx.y;
     const Phase& ph = a.ph[p];
@@ -136,54 +149,78 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
         tc::mbar_fence_init();
     }
     if (warp == 4) tc::tmem_alloc(tmem_slot, tmem_cols);
+    for (int i = threadIdx.x; i < a.n_tile; i += THREADS) {
+        const int o = blockIdx.y * a.n_tile + i;
+        s_bias[i] = (a.bias && o < a.out_ch) ? __ldg(a.bias + o) : 0.0f;
+    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *tmem_slot;
+#ifdef NFE_MC_PROFILE
+    const long long t_role0 = clock64();
+    if (threadIdx.x == 0) { prof_[10] = t_role0 - t_cta0; MC_FLUSH(10); atomicAdd(&g_mc_prof[9], 1ull); }
+#endif
 
     if (warp < 4) {
         // ------------------------------------------------------------------ A loader: one halo window per K chunk
-        const int kcores = a.kc >> 3, total = HALO_H * HALO_W * kcores;
+        const int kcores = a.kc >> 3;
         const T* xin = static_cast<const T*>(a.x);
         for (int c = 0; c < a.chunks; ++c) {
             const int s = c % SA, r = c / SA;
-            if (r > 0) tc::mbar_wait(&a_empty[s], (r - 1) & 1);
+            if (r > 0) MC_WAIT(3, &a_empty[s], (r - 1) & 1);
             unsigned char* const dst0 = sA + s * A_STAGE;
-            for (int i = threadIdx.x; i < total; i += 128) {
-                const int k8 = i % kcores, hp = i / kcores, hy = hp / HALO_W, hx = hp % HALO_W;
-                if (!a.halo && (hy == 0 || hy == HALO_H - 1 || hx == 0 || hx == HALO_W - 1)) continue;   // 1x1: the ring is never read
-                const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
-                const bool ok = gy >= 0 && gy < a.in_h && gx >= 0 && gx < a.in_w;
-                const long long e = ((long long)(n * a.in_h + (ok ? gy : 0)) * a.in_w + (ok ? gx : 0)) * a.in_ch + c * a.kc + k8 * 8;
-                unsigned char* dst = dst0 + k8 * A_LBO + hp * 16;
-                if constexpr (PARTS == 1) {
-                    cp_async16(dst, xin + e, ok ? 16 : 0);
-                } else {
-                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    if (ok) {
-                        const float4 v0 = __ldg(reinterpret_cast<const float4*>(xin + e)), v1 = __ldg(reinterpret_cast<const float4*>(xin + e) + 1);
-                        v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-                    }
-                    uint32_t hi[4], lo[4];
+            // thread = (channel group k8, pixel slot): 16 halo pixels x 8 channel groups per pass, the pixel index advanced
+            // incrementally (no divisions); 8 consecutive threads read one pixel's 64 channels, i.e. one contiguous run
+            const int k8 = threadIdx.x & 7;
+            int hy = (threadIdx.x >> 3) / HALO_W, hx = (threadIdx.x >> 3) % HALO_W;
+            if (k8 < kcores)
+                for (int hp = threadIdx.x >> 3; hp < HALO_H * HALO_W; hp += 16) {
+                    const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                    const bool ring = hy == 0 || hy == HALO_H - 1 || hx == 0 || hx == HALO_W - 1;
+                    const bool ok = (unsigned)gy < (unsigned)a.in_h && (unsigned)gx < (unsigned)a.in_w;
+                    unsigned char* dst = dst0 + k8 * A_LBO + hp * 16;
+                    hx += 6; hy += 1;                            // + 16 pixels = one window row and 6 columns
+                    if (hx >= HALO_W) { hx -= HALO_W; hy += 1; }
+                    if (!a.halo && ring) continue;               // 1x1: the ring is never read
+                    const T* src = xin + (((long long)(n * a.in_h + (ok ? gy : 0)) * a.in_w + (ok ? gx : 0)) * a.in_ch + c * a.kc + k8 * 8);
+                    if constexpr (PARTS == 1) {
+                        cp_async16(dst, src, ok ? 16 : 0);
+                    } else {
+                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (ok) {
+                            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
+                            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
+                        }
+                        uint32_t hi[4], lo[4];
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        __nv_bfloat16 h0, l0, h1, l1;
-                        tc::split_bf16(v[2 * q], h0, l0); tc::split_bf16(v[2 * q + 1], h1, l1);
-                        hi[q] = tc::pack_bf16(h0, h1); lo[q] = tc::pack_bf16(l0, l1);
+                        for (int q = 0; q < 4; ++q) {
+                            __nv_bfloat16 h0, l0, h1, l1;
+                            tc::split_bf16(v[2 * q], h0, l0); tc::split_bf16(v[2 * q + 1], h1, l1);
+                            hi[q] = tc::pack_bf16(h0, h1); lo[q] = tc::pack_bf16(l0, l1);
+                        }
+                        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                        *reinterpret_cast<uint4*>(dst + A_PART) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
-                    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                    *reinterpret_cast<uint4*>(dst + A_PART) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                 }
-            }
             if constexpr (PARTS == 1) cp_async_wait_all();
             tc::fence_async_smem();
             tc::mbar_arrive(&a_full[s]);
         }
         // ------------------------------------------------------------------ epilogue: thread = TMEM lane = pixel of the window
-        tc::mbar_wait(acc_full, 0);
+#ifdef NFE_MC_PROFILE
+        if (threadIdx.x == 0) { prof_[4] = clock64() - t_role0 - prof_[3]; MC_FLUSH(3); MC_FLUSH(4); }
+        const long long t_e0 = clock64();
+#endif
+        MC_WAIT(5, acc_full, 0);
         tc::fence_after_sync();
+#ifdef NFE_MC_PROFILE
+        const long long t_e1 = clock64();
+#endif
         const int row = threadIdx.x, py = row >> 3, px = row & 7;
         T* yout = static_cast<T*>(a.y);
+        const float neg_slope = a.act == 1 ? 1.0f : (a.act == 2 ? 0.0f : a.alpha);
+        const float gain_pos = a.gain, gain_neg = a.gain * neg_slope, clampv = a.clamp >= 0.0f ? a.clamp : __int_as_float(0x7f800000);
         constexpr int VEC = 16 / (int)sizeof(T);
         const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
 #pragma unroll 1
@@ -201,12 +238,15 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
                 if (!valid) continue;
                 const int o0 = nt * a.n_tile + q * 16;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    float t = v[i] + nz;
-                    if (a.bias && o0 + i < a.out_ch) t += __ldg(a.bias + o0 + i);
-                    t = act_apply<T>(t, a.act, a.alpha) * a.gain;
-                    if (a.clamp >= 0.0f) t = fminf(fmaxf(t, -a.clamp), a.clamp);
-                    v[i] = t;
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + q * 16 + 4 * i4);      // same address in every lane: broadcast
+                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float t = (v[4 * i4 + j] + nz) + bb[j];
+                        t *= t > 0.0f ? gain_pos : gain_neg;          // linear / relu / lrelu as one slope pair (bias_act.cu:66-75), then the gain
+                        v[4 * i4 + j] = fminf(fmaxf(t, -clampv), clampv);
+                    }
                 }
                 if (vec_ok && o0 + 16 <= a.out_ch) {
                     if constexpr (PARTS == 1) {
@@ -230,6 +270,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
             }
         }
         tc::fence_before_sync();
+#ifdef NFE_MC_PROFILE
+        if (threadIdx.x == 0) { prof_[6] = clock64() - t_e1; MC_FLUSH(5); MC_FLUSH(6); (void)t_e0; }
+#endif
     } else if (warp == 4) {
         // ------------------------------------------------------------------ MMA issue (one thread)
         if (lane == 0) {
@@ -239,12 +282,12 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
             int it = 0;
             for (int c = 0; c < a.chunks; ++c) {
                 const int s = c % SA;
-                tc::mbar_wait(&a_full[s], (c / SA) & 1);
+                MC_WAIT(0, &a_full[s], (c / SA) & 1);
                 tc::fence_after_sync();
                 const uint32_t a_base = tc::smem_u32(sA + s * A_STAGE);
                 for (int t = 0; t < taps; ++t, ++it) {
                     const int sb = it % a.sb;
-                    tc::mbar_wait(&b_full[sb], (it / a.sb) & 1);
+                    MC_WAIT(1, &b_full[sb], (it / a.sb) & 1);
                     tc::fence_after_sync();
                     const uint32_t b_base = tc::smem_u32(sB + sb * a.b_stage);
                     const uint32_t a_tap = a_base + ((1 + ph.dy[t]) * HALO_W + 1 + ph.dx[t]) * 16;
@@ -267,6 +310,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
                 tc::mma_commit(&a_empty[s]);
             }
             tc::mma_commit(acc_full);
+#ifdef NFE_MC_PROFILE
+            prof_[2] = clock64() - t_role0; MC_FLUSH(0); MC_FLUSH(1); MC_FLUSH(2);
+#endif
         }
         __syncwarp();
     } else {
@@ -276,10 +322,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
             const int total = a.chunks * taps;
             for (int it = 0; it < total; ++it) {
                 const int sb = it % a.sb;
-                if (it >= a.sb) tc::mbar_wait(&b_empty[sb], ((it / a.sb) - 1) & 1);
+                if (it >= a.sb) MC_WAIT(7, &b_empty[sb], ((it / a.sb) - 1) & 1);
                 mbar_expect_tx(&b_full[sb], (uint32_t)a.b_stage);
                 bulk_copy(sB + sb * a.b_stage, src + (long long)it * a.b_stage, (uint32_t)a.b_stage, &b_full[sb]);
             }
+#ifdef NFE_MC_PROFILE
+            MC_FLUSH(7);
+#endif
         }
         __syncwarp();
     }
@@ -288,6 +337,9 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem, tmem_cols);
     }
+#ifdef NFE_MC_PROFILE
+    if (threadIdx.x == 0) atomicAdd(&g_mc_prof[8], (unsigned long long)(clock64() - t_cta0));
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------- weight folding and packing
@@ -546,7 +598,7 @@ template <int PARTS, int MA>
 static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
-    const size_t smem = (size_t)SA * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + (2 * SA + 2 * MAX_SB + 1) * 8 + 16;
+    const size_t smem = (size_t)SA * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 192 + 256 * 4;   // A ring | B ring | 17 mbarriers + the TMEM slot (160 bytes reserved) | bias table
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -639,3 +691,14 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     }
     return 0;
 }
+
+#ifdef NFE_MC_PROFILE
+// debug builds only: where the roles of conv_gemm_kernel wait (profiles/modconv_role_profile.py)
+NFE_EXPORT int nfe_debug_modconv_profile(unsigned long long* out16, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out16, mc::g_mc_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(mc::g_mc_prof, z, sizeof(z)); }
+    return 0;
+}
+#endif
