@@ -20,13 +20,16 @@
 //  * B operand (weights): packed by the packing kernel in exactly the shared-memory operand order, one contiguous block per
 //    (K chunk, tap), streamed by ONE thread with cp.async.bulk (the TMA unit's bulk copy, completion on an mbarrier with
 //    complete_tx) through a ring of up to 4 stages.
-//  * roles: warps 0-3 load A during the main loop and run the epilogue (thread = TMEM lane = pixel), warp 4 issues the MMAs
-//    (one elected thread, tcgen05.mma kind::f16, fp32 accumulate), warp 5 streams B.  tcgen05.commit releases the stages.
+//  * roles: warps 0-3 load A during the main loop, warp 4 issues the MMAs (one elected thread, tcgen05.mma kind::f16, fp32
+//    accumulate), warp 5 streams B, tcgen05.commit releases the stages; all eight warps run the epilogue (thread = TMEM lane =
+//    pixel; warps w and w + 4 share a lane quarter and split the columns).
 //  * epilogue, fused: + noise, + bias, activation (linear / relu / lrelu), gain, clamp, conversion, channels-last store.
 //  * up = 2 (conv2d_resample.py:117-134): the transposed stride-2 convolution is four phase convolutions (even/odd output rows x
-//    columns: 4 + 2 + 2 + 1 taps, i.e. the 9 taps once — no multiplication by an inserted zero) written interleaved into the
-//    (2H+1) x (2W+1) intermediate, followed by ONE pass that applies the low-pass filter, noise, bias, activation and clamp
-//    (upfir_finish_kernel; the reference makes four passes of it: upfirdn2d, add_, bias_act).
+//    columns: 4 + 2 + 2 + 1 taps, i.e. the 9 taps once — no multiplication by an inserted zero).  ONE CTA computes all four phases of
+//    its window: the halo is loaded once, every tap's MMAs go to the accumulator of the tap's phase (4 accumulators x up to 128
+//    columns of tensor memory), and the epilogue writes them interleaved into the (2H+1) x (2W+1) intermediate; ONE pass then
+//    applies the low-pass filter, noise, bias, activation and clamp (upfir_finish_kernel; the reference makes four passes of it:
+//    upfirdn2d, add_, bias_act).
 //
 // Arithmetic: fp16 activations -> fp16 operands, one MMA per product (what the reference's fp16 layers do in cuDNN);
 // fp32 activations -> bf16 hi/lo split of both operands, three MMAs per product, fp32 accumulate (~16 significand bits per operand,
@@ -41,16 +44,24 @@
 namespace nfe {
 namespace mc {
 
-constexpr int TILE_W = 8, HALO_W = TILE_W + 2, MAX_TAPS = 9, MAX_PHASES = 4, THREADS = 192, SA = 2, MAX_SB = 6;
+constexpr int TILE_W = 8, HALO_W = TILE_W + 2, MAX_TAPS = 9, THREADS = 256, MAX_SA = 4, MAX_SB = 6;
+// halo stages: the small fp16 window (up = 2: little MMA work per K chunk, the loads must run several chunks ahead) gets four
+__host__ __device__ constexpr int stages_a(int parts, int ma) { return (parts == 1 && ma == 1) ? 4 : 2; }
 constexpr int SMEM_BUDGET = 227 * 1024 - 256 - 1024;
 
-struct Phase {
-    int taps;
-    int dy[MAX_TAPS], dx[MAX_TAPS];       // input pixel of tap t = output-grid pixel + (dy, dx)
+constexpr int MAX_ACC = 4;
+
+// Taps and accumulators of one launch.  Plain convolution: every tap feeds every accumulator, accumulator m = window rows
+// 16 m .. 16 m + 15.  up = 2: accumulator = output phase (row parity, column parity), each tap feeds the one phase it belongs to.
+struct TapPlan {
+    int taps, n_acc;
+    int dy[MAX_TAPS], dx[MAX_TAPS];       // input pixel of tap t = window pixel + (dy, dx)
     int ky[MAX_TAPS], kx[MAX_TAPS];       // weight element of tap t
-    int gh, gw;                           // output grid of the phase
-    int oy_mul, oy_off, ox_mul, ox_off;   // grid pixel (gy, gx) is written to (gy * oy_mul + oy_off, gx * ox_mul + ox_off)
-    long long packed_off;                 // bytes, inside one batch item's packed block
+    unsigned acc_mask[MAX_TAPS];          // accumulators tap t feeds
+    int row_off[MAX_ACC];                 // first window row of the accumulator's 128 pixels
+    int gh[MAX_ACC], gw[MAX_ACC];         // output grid of the accumulator
+    int oy_off[MAX_ACC], ox_off[MAX_ACC]; // grid pixel (gy, gx) is written to (gy * o_mul + oy_off, gx * o_mul + ox_off)
+    int o_mul;
 };
 
 struct GemmArgs {
@@ -64,18 +75,19 @@ struct GemmArgs {
     int noise_w;
     const float* bias;
     int batch, in_h, in_w, in_ch, out_ch;
-    int n_tile, n_tiles, chunks, kc, sb, b_stage, halo;
-    int phases, tiles_x, tiles_y;
+    int n_tile, n_tiles, chunks, kc, sb, b_stage, halo, stage_ok;
+    int tiles_x, tiles_y;
     int act;                              // bias_act cuda_idx: 1 linear, 2 relu, 3 lrelu
     float alpha, gain, clamp;
-    Phase ph[MAX_PHASES];
+    TapPlan tp;
 };
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src, int src_bytes)
 {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(tc::smem_u32(dst)), "l"(src), "r"(src_bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(tc::smem_u32(bar)), "r"(bytes) : "memory");
@@ -85,6 +97,15 @@ __device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t b
 {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
+}
+// one lane of the (converged) warp; the callers keep their control flow warp-uniform so that descriptors and barrier addresses
+// live in uniform registers: a divergent `if (lane == 0)` loop makes the compiler wrap every tcgen05.mma in an ELECT / R2UR
+// waterfall (~24 dependent instructions, ~180 cycles per MMA measured against the 128 the tensor core needs)
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 // kind::f16 instruction descriptor: fp32 accumulate, both operands K-major; FMT 0 = fp16, 1 = bf16
 __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt)
@@ -111,7 +132,7 @@ template <int PARTS> struct Elem { using type = __half; };
 template <> struct Elem<2> { using type = float; };
 
 // PARTS = 1: fp16 activations / fp16 operands.  PARTS = 2: fp32 activations / bf16 hi + lo operands, three terms per product.
-// MA = accumulators (128 pixels each) per CTA.
+// MA = window height in units of 16 rows (the window is 16 MA x 8 pixels).
 template <int PARTS, int MA>
 __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
 {
@@ -119,31 +140,30 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
     constexpr int HALO_H = 16 * MA + 2;
     constexpr int A_LBO = HALO_H * HALO_W * 16;          // bytes between channel groups of 8 (K core matrices)
     constexpr int A_SBO = HALO_W * 16;                    // bytes between window rows (row groups of 8 pixels)
-    constexpr int A_PART = 8 * A_LBO, A_STAGE = PARTS * A_PART;
+    constexpr int A_PART = 8 * A_LBO, A_STAGE = PARTS * A_PART, SA = stages_a(PARTS, MA);
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* const sA = smem;
     unsigned char* const sB = smem + SA * A_STAGE;
     uint64_t* const bars = reinterpret_cast<uint64_t*>(sB + a.sb * a.b_stage);
-    uint64_t* const a_full = bars, * const a_empty = bars + SA, * const b_full = bars + 2 * SA, * const b_empty = b_full + MAX_SB;
+    uint64_t* const a_full = bars, * const a_empty = bars + MAX_SA, * const b_full = bars + 2 * MAX_SA, * const b_empty = b_full + MAX_SB;
     uint64_t* const acc_full = b_empty + MAX_SB;
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
-    float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 160);       // this N tile's bias, zero where there is none
+    float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);       // this N tile's bias, zero where there is none
 
 #ifdef NFE_MC_PROFILE
     long long prof_[12] = {};
     const long long t_cta0 = clock64();
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int p = blockIdx.z / a.batch, n = blockIdx.z % a.batch, nt = blockIdx.y;
-    const Phase& ph = a.ph[p];
+    const int n = blockIdx.z, nt = blockIdx.y;
+    const TapPlan& tp = a.tp;
     const int x0 = (blockIdx.x % a.tiles_x) * TILE_W, y0 = (blockIdx.x / a.tiles_x) * (16 * MA);
-    if (x0 >= ph.gw || y0 >= ph.gh) return;               // the launch grid is sized for the largest phase
-    const int taps = ph.taps;
+    const int taps = tp.taps, n_acc = tp.n_acc;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < MA * a.n_tile) tmem_cols <<= 1;
+    while ((int)tmem_cols < n_acc * a.n_tile) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < SA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
+        for (int i = 0; i < MAX_SA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
         tc::mbar_init(acc_full, 1);
         tc::mbar_fence_init();
@@ -168,6 +188,10 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
         const T* xin = static_cast<const T*>(a.x);
         for (int c = 0; c < a.chunks; ++c) {
             const int s = c % SA, r = c / SA;
+            if constexpr (PARTS == 1) {
+                // up to SA - 1 chunks stay in flight: chunk c - (SA - 1) is handed to the MMA thread before this one is requested
+                if (c >= SA - 1) { cp_async_wait_group<SA - 2>(); tc::fence_async_smem(); tc::mbar_arrive(&a_full[(c - (SA - 1)) % SA]); }
+            }
             if (r > 0) MC_WAIT(3, &a_empty[s], (r - 1) & 1);
             unsigned char* const dst0 = sA + s * A_STAGE;
             // thread = (channel group k8, pixel slot): 16 halo pixels x 8 channel groups per pass, the pixel index advanced
@@ -203,13 +227,101 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
                         *reinterpret_cast<uint4*>(dst + A_PART) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
                     }
                 }
-            if constexpr (PARTS == 1) cp_async_wait_all();
-            tc::fence_async_smem();
-            tc::mbar_arrive(&a_full[s]);
+            if constexpr (PARTS == 1) {
+                cp_async_commit();
+            } else {
+                tc::fence_async_smem();
+                tc::mbar_arrive(&a_full[s]);
+            }
         }
-        // ------------------------------------------------------------------ epilogue: thread = TMEM lane = pixel of the window
+        if constexpr (PARTS == 1) {
+            cp_async_wait_group<0>();
+            tc::fence_async_smem();
+            for (int c = a.chunks > SA - 1 ? a.chunks - (SA - 1) : 0; c < a.chunks; ++c) tc::mbar_arrive(&a_full[c % SA]);
+        }
 #ifdef NFE_MC_PROFILE
         if (threadIdx.x == 0) { prof_[4] = clock64() - t_role0 - prof_[3]; MC_FLUSH(3); MC_FLUSH(4); }
+#endif
+    } else if (warp == 4) {
+        // ------------------------------------------------------------------ MMA issue (one thread).  The descriptors differ only in
+        // their 14-bit address field (bytes >> 4), so each one is the constant part plus an add: the issuing thread stays far below
+        // the tensor core's 64-128 cycles per instruction.  Every lane runs the loop; one elected lane issues.
+        {
+            const bool leader = elect_one();
+            const uint32_t idesc = make_idesc(128, a.n_tile, PARTS == 1 ? 0 : 1);
+            const uint32_t b_lbo = a.n_tile * 16, b_part16 = (a.n_tile * a.kc * 2) >> 4, a_part16 = A_PART >> 4;
+            const uint64_t da0 = tc::make_desc(0, A_LBO, A_SBO), db0 = tc::make_desc(0, b_lbo, 128);
+            const uint32_t a_k16 = (2 * A_LBO) >> 4, b_k16 = (2 * b_lbo) >> 4;
+            const int ksteps = a.kc >> 4;
+            uint32_t row16[MAX_ACC], tap16[MAX_TAPS], tmask[MAX_TAPS];
+#pragma unroll
+            for (int m = 0; m < MAX_ACC; ++m) row16[m] = (uint32_t)(tp.row_off[m] * A_SBO) >> 4;
+#pragma unroll
+            for (int t = 0; t < MAX_TAPS; ++t) { tap16[t] = (uint32_t)((1 + tp.dy[t]) * HALO_W + 1 + tp.dx[t]); tmask[t] = tp.acc_mask[t]; }
+            int sb = 0;
+            uint32_t sb_par = 0, started = 0;        // started: accumulators that hold a partial sum already
+            for (int c = 0; c < a.chunks; ++c) {
+                const int s = c % SA;
+                MC_WAIT(0, &a_full[s], (c / SA) & 1);
+                tc::fence_after_sync();
+                const uint32_t a_base16 = tc::smem_u32(sA + s * A_STAGE) >> 4;
+#pragma unroll
+                for (int t = 0; t < MAX_TAPS; ++t) {
+                    if (t >= taps) break;
+                    MC_WAIT(1, &b_full[sb], sb_par);
+                    tc::fence_after_sync();
+                    const uint32_t b16 = tc::smem_u32(sB + sb * a.b_stage) >> 4, a16 = a_base16 + tap16[t];
+#pragma unroll
+                    for (int m = 0; m < MAX_ACC; ++m) {
+                        if (m >= n_acc || !((tmask[t] >> m) & 1u)) continue;
+                        constexpr int TERMS = PARTS == 2 ? 3 : 1;
+                        uint32_t accf = (started >> m) & 1u;
+#pragma unroll
+                        for (int term = 0; term < TERMS; ++term) {          // hi*hi, lo*hi, hi*lo
+                            const uint32_t aa = a16 + row16[m] + (term == 1 ? a_part16 : 0), bb = b16 + (term == 2 ? b_part16 : 0);
+#pragma unroll 4
+                            for (int j = 0; j < ksteps; ++j) {
+                                if (leader) tc::mma_bf16_ss(tmem + m * a.n_tile, da0 + (aa + j * a_k16), db0 + (bb + j * b_k16), idesc, accf);
+                                accf = 1u;
+                            }
+                        }
+                        started |= 1u << m;
+                    }
+                    if (leader) tc::mma_commit(&b_empty[sb]);          // the weight stage is free once these MMAs have read it
+                    if (++sb == a.sb) { sb = 0; sb_par ^= 1u; }
+                }
+                if (leader) tc::mma_commit(&a_empty[s]);
+            }
+            if (leader) tc::mma_commit(acc_full);
+#ifdef NFE_MC_PROFILE
+            if (lane == 0) { prof_[2] = clock64() - t_role0; MC_FLUSH(0); MC_FLUSH(1); MC_FLUSH(2); }
+#endif
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ------------------------------------------------------------------ B stream (one thread): packed weights, one block per (chunk, tap)
+        if (lane == 0) {
+            const unsigned char* src = a.packed + n * a.packed_item_stride + (long long)nt * a.chunks * taps * a.b_stage;
+            const int total = a.chunks * taps;
+            int sb = 0;
+            uint32_t sb_par = 1;                    // parity of the PREVIOUS use of the stage
+            for (int it = 0; it < total; ++it) {
+                if (it >= a.sb) MC_WAIT(7, &b_empty[sb], sb_par);
+                mbar_expect_tx(&b_full[sb], (uint32_t)a.b_stage);
+                bulk_copy(sB + sb * a.b_stage, src, (uint32_t)a.b_stage, &b_full[sb]);
+                src += a.b_stage;
+                if (++sb == a.sb) { sb = 0; sb_par ^= 1u; }
+            }
+#ifdef NFE_MC_PROFILE
+            MC_FLUSH(7);
+#endif
+        }
+        __syncwarp();
+    }
+    {
+        // ------------------------------------------------------------------ epilogue, all eight warps: thread = TMEM lane = pixel of the
+        // window; warps w and w + 4 share a lane quarter and take alternate 16-column groups
+#ifdef NFE_MC_PROFILE
         const long long t_e0 = clock64();
 #endif
         MC_WAIT(5, acc_full, 0);
@@ -217,25 +329,38 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
 #ifdef NFE_MC_PROFILE
         const long long t_e1 = clock64();
 #endif
-        const int row = threadIdx.x, py = row >> 3, px = row & 7;
+        const int row = (warp & 3) * 32 + lane, py = row >> 3, px = row & 7, grp = warp >> 2;
         T* yout = static_cast<T*>(a.y);
         const float neg_slope = a.act == 1 ? 1.0f : (a.act == 2 ? 0.0f : a.alpha);
         const float gain_pos = a.gain, gain_neg = a.gain * neg_slope, clampv = a.clamp >= 0.0f ? a.clamp : __int_as_float(0x7f800000);
         constexpr int VEC = 16 / (int)sizeof(T);
         const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
+        const int nq = a.n_tile / 16;
+        const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        // Stores: a thread holds 16 channels of ONE pixel, so a direct store instruction would touch 32 different lines with 16 bytes
+        // each (measured: the epilogue ran at the speed of its 8192 partial-sector stores).  The tile is staged through the (now idle)
+        // operand rings instead — pixel rows of n_tile channels at a pitch of 16 bytes more, which spreads the lanes over the banks —
+        // and written out one whole pixel row (up to 512 contiguous bytes) per warp instruction.
+        const int row_bytes = a.n_tile * (int)sizeof(T), pitch = row_bytes + 16;
+        const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
 #pragma unroll 1
-        for (int m = 0; m < MA; ++m) {
-            const int gy = y0 + m * 16 + py, gx = x0 + px;
-            const bool valid = gy < ph.gh && gx < ph.gw;
-            const int oy = gy * ph.oy_mul + ph.oy_off, ox = gx * ph.ox_mul + ph.ox_off;
+        for (int m = 0; m < n_acc; ++m) {
+            const int gy = y0 + tp.row_off[m] + py, gx = x0 + px;
+            const bool valid = gy < tp.gh[m] && gx < tp.gw[m];
+            const int oy = gy * tp.o_mul + tp.oy_off[m], ox = gx * tp.o_mul + tp.ox_off[m];
             T* dst = yout + n * a.ys_n + oy * a.ys_h + ox * a.ys_w + nt * a.n_tile;
             const float nz = (a.noise && valid) ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.noise_w + ox) : 0.0f;
+            unsigned char* const stage = smem + (m & 1) * (128 * pitch);
+            float nxt[16];
+            if (grp < nq) tc::tmem_ld16(t_lane + m * a.n_tile + grp * 16, nxt);      // software pipeline: the next group loads while this one is processed
 #pragma unroll 1
-            for (int q = 0; q < a.n_tile / 16; ++q) {
+            for (int q = grp; q < nq; q += 2) {
                 float v[16];
-                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + m * a.n_tile + q * 16, v);
                 tc::tmem_ld_wait();
-                if (!valid) continue;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = nxt[i];
+                if (q + 2 < nq) tc::tmem_ld16(t_lane + m * a.n_tile + (q + 2) * 16, nxt);
+                if (!valid && !staged) continue;
                 const int o0 = nt * a.n_tile + q * 16;
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
@@ -248,15 +373,16 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
                         v[4 * i4 + j] = fminf(fmaxf(t, -clampv), clampv);
                     }
                 }
-                if (vec_ok && o0 + 16 <= a.out_ch) {
+                if (staged || (vec_ok && o0 + 16 <= a.out_ch)) {
+                    unsigned char* out = staged ? stage + row * pitch + q * 16 * (int)sizeof(T) : reinterpret_cast<unsigned char*>(dst + q * 16);
                     if constexpr (PARTS == 1) {
                         uint32_t w[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) { const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&h); }
-                        uint4* d4 = reinterpret_cast<uint4*>(dst + q * 16);
+                        uint4* d4 = reinterpret_cast<uint4*>(out);
                         d4[0] = make_uint4(w[0], w[1], w[2], w[3]); d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
                     } else {
-                        float4* d4 = reinterpret_cast<float4*>(dst + q * 16);
+                        float4* d4 = reinterpret_cast<float4*>(out);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
@@ -268,69 +394,21 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
                         }
                 }
             }
+            if (staged) {
+                __syncthreads();                            // the tile is complete (every warp is in the epilogue by now)
+                const int chunks16 = row_bytes >> 4;        // 16-byte pieces per pixel row: at most 32
+                for (int r = warp; r < 128; r += 8) {
+                    const int ry = y0 + tp.row_off[m] + (r >> 3), rx = x0 + (r & 7);
+                    if (ry >= tp.gh[m] || rx >= tp.gw[m] || lane >= chunks16) continue;
+                    T* g = yout + n * a.ys_n + (ry * tp.o_mul + tp.oy_off[m]) * a.ys_h + (rx * tp.o_mul + tp.ox_off[m]) * a.ys_w + nt * a.n_tile;
+                    reinterpret_cast<uint4*>(g)[lane] = *reinterpret_cast<const uint4*>(stage + r * pitch + lane * 16);
+                }
+            }
         }
         tc::fence_before_sync();
 #ifdef NFE_MC_PROFILE
-        if (threadIdx.x == 0) { prof_[6] = clock64() - t_e1; MC_FLUSH(5); MC_FLUSH(6); (void)t_e0; }
+        if (threadIdx.x == 0) { prof_[6] = clock64() - t_e1; prof_[5] = t_e1 - t_e0; atomicAdd(&g_mc_prof[5], (unsigned long long)prof_[5]); MC_FLUSH(6); }
 #endif
-    } else if (warp == 4) {
-        // ------------------------------------------------------------------ MMA issue (one thread)
-        if (lane == 0) {
-            const uint32_t idesc = make_idesc(128, a.n_tile, PARTS == 1 ? 0 : 1);
-            const uint32_t b_lbo = a.n_tile * 16, b_part = a.n_tile * a.kc * 2;
-            const int ksteps = a.kc >> 4;
-            int it = 0;
-            for (int c = 0; c < a.chunks; ++c) {
-                const int s = c % SA;
-                MC_WAIT(0, &a_full[s], (c / SA) & 1);
-                tc::fence_after_sync();
-                const uint32_t a_base = tc::smem_u32(sA + s * A_STAGE);
-                for (int t = 0; t < taps; ++t, ++it) {
-                    const int sb = it % a.sb;
-                    MC_WAIT(1, &b_full[sb], (it / a.sb) & 1);
-                    tc::fence_after_sync();
-                    const uint32_t b_base = tc::smem_u32(sB + sb * a.b_stage);
-                    const uint32_t a_tap = a_base + ((1 + ph.dy[t]) * HALO_W + 1 + ph.dx[t]) * 16;
-#pragma unroll 1
-                    for (int m = 0; m < MA; ++m) {
-                        constexpr int TERMS = PARTS == 2 ? 3 : 1;
-#pragma unroll
-                        for (int term = 0; term < TERMS; ++term) {          // hi*hi, lo*hi, hi*lo
-                            const uint32_t aa = a_tap + m * 16 * A_SBO + (term == 1 ? A_PART : 0);
-                            const uint32_t bb = b_base + (term == 2 ? b_part : 0);
-                            for (int j = 0; j < ksteps; ++j) {
-                                const uint64_t da = tc::make_desc(aa + j * 2 * A_LBO, A_LBO, A_SBO);
-                                const uint64_t db = tc::make_desc(bb + j * 2 * b_lbo, b_lbo, 128);
-                                tc::mma_bf16_ss(tmem + m * a.n_tile, da, db, idesc, !(c == 0 && t == 0 && term == 0 && j == 0));
-                            }
-                        }
-                    }
-                    tc::mma_commit(&b_empty[sb]);          // the weight stage is free once these MMAs have read it
-                }
-                tc::mma_commit(&a_empty[s]);
-            }
-            tc::mma_commit(acc_full);
-#ifdef NFE_MC_PROFILE
-            prof_[2] = clock64() - t_role0; MC_FLUSH(0); MC_FLUSH(1); MC_FLUSH(2);
-#endif
-        }
-        __syncwarp();
-    } else {
-        // ------------------------------------------------------------------ B stream (one thread): packed weights, one block per (chunk, tap)
-        if (lane == 0) {
-            const unsigned char* src = a.packed + n * a.packed_item_stride + ph.packed_off + (long long)nt * a.chunks * taps * a.b_stage;
-            const int total = a.chunks * taps;
-            for (int it = 0; it < total; ++it) {
-                const int sb = it % a.sb;
-                if (it >= a.sb) MC_WAIT(7, &b_empty[sb], ((it / a.sb) - 1) & 1);
-                mbar_expect_tx(&b_full[sb], (uint32_t)a.b_stage);
-                bulk_copy(sB + sb * a.b_stage, src + (long long)it * a.b_stage, (uint32_t)a.b_stage, &b_full[sb]);
-            }
-#ifdef NFE_MC_PROFILE
-            MC_FLUSH(7);
-#endif
-        }
-        __syncwarp();
     }
     __syncthreads();
     if (warp == 4) {
@@ -352,8 +430,8 @@ struct PackArgs {
     unsigned char* packed;
     long long packed_item_stride;
     int batch, out_ch, in_ch, ksize, demodulate, prenorm, parts;
-    int n_tile, n_tiles, chunks, kc, b_stage, phases;
-    Phase ph[MAX_PHASES];
+    int n_tile, n_tiles, chunks, kc, b_stage;
+    TapPlan tp;
 };
 
 // one block per (o, n): demodulation coefficient rsqrt(sum_{i,k} (w * s)^2 + 1e-8) (networks_stylegan2.py:59-66)
@@ -395,14 +473,13 @@ __global__ void __launch_bounds__(128) modconv_coef_kernel(const PackArgs a)
 }
 
 // one thread per 16-byte operand slot (8 consecutive input channels of one output channel and tap): w * s * d, rounded to the
-// operand type, in the order [phase][N tile][K chunk][tap][part][channel group][row group][row][8 channels]
+// operand type, in the order [N tile][K chunk][tap][part][channel group][row group][row][8 channels]
 __global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
 {
     const int n = blockIdx.y, kk = a.ksize * a.ksize;
     const int kcores = a.kc >> 3, rows = a.n_tile;
     long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int p = blockIdx.z;
-    const Phase& ph = a.ph[p];
+    const TapPlan& ph = a.tp;
     const long long slots = (long long)a.n_tiles * a.chunks * ph.taps * kcores * rows;
     if (slot >= slots) return;
     const int row = (int)(slot % rows); long long r = slot / rows;
@@ -423,7 +500,7 @@ __global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
             v[j] = ((__ldg(w + (long long)j * kk) * wm) * sv) * d;
         }
     }
-    unsigned char* dst = a.packed + n * a.packed_item_stride + ph.packed_off +
+    unsigned char* dst = a.packed + n * a.packed_item_stride +
                          ((((long long)nt * a.chunks + c) * ph.taps + t) * a.b_stage) + ((long long)k8 * (rows / 8) + row / 8) * 128 + (row & 7) * 16;
     if (a.parts == 1) {
         uint32_t w4[4];
@@ -522,22 +599,26 @@ __global__ void __launch_bounds__(256) upfir_finish_kernel(const FinishArgs a)
 
 // ---------------------------------------------------------------------------------------------- host side
 struct Plan {
-    int parts, ma, n_tile, n_tiles, kc, chunks, b_stage, sb, phases, halo;
+    int parts, ma, n_tile, n_tiles, kc, chunks, b_stage, sb, halo;
     long long packed_item_bytes, coef_bytes, packed_bytes, trans_bytes, total_bytes;
     int th, tw;                            // transposed-convolution intermediate (up = 2)
-    Phase ph[MAX_PHASES];
+    int grid_h, grid_w;                    // pixel grid the windows tile
+    TapPlan tp;
 };
 
 static int make_plan(const nfe_modconv_args& q, Plan& pl)
 {
     NFE_REQUIRE(q.dtype == NFE_DTYPE_F32 || q.dtype == NFE_DTYPE_F16, "nfe_modulated_conv2d: dtype must be NFE_DTYPE_F32 or NFE_DTYPE_F16, got %d", q.dtype);
     NFE_REQUIRE(q.batch > 0 && q.in_ch > 0 && q.out_ch > 0 && q.in_h > 0 && q.in_w > 0, "nfe_modulated_conv2d: bad shape");
+    NFE_REQUIRE(q.batch <= 65535, "nfe_modulated_conv2d: batch above 65535");
     NFE_REQUIRE(q.ksize == 1 || q.ksize == 3, "nfe_modulated_conv2d: kernel size must be 1 or 3 (the reference's layers), got %d", q.ksize);
     NFE_REQUIRE(q.up == 1 || (q.up == 2 && q.ksize == 3), "nfe_modulated_conv2d: up must be 1, or 2 with a 3x3 kernel, got up=%d k=%d", q.up, q.ksize);
     NFE_REQUIRE(q.in_ch % 16 == 0, "nfe_modulated_conv2d: in_channels must be a multiple of 16, got %d", q.in_ch);
     pl.parts = q.dtype == NFE_DTYPE_F16 ? 1 : 2;
-    pl.ma = pl.parts == 1 ? 2 : 1;
-    const int n_max = pl.parts == 1 ? 256 : 128;
+    // plain: two 128-pixel accumulators x 256 columns (fp16) or one x 128 (fp32 split: the operand rings are twice as wide);
+    // up = 2: a 128-pixel window, four phase accumulators x 128 columns.  512 columns of tensor memory either way.
+    pl.ma = (pl.parts == 1 && q.up == 1) ? 2 : 1;
+    const int n_max = (pl.parts == 1 && q.up == 1) ? 256 : 128;
     const int o16 = (q.out_ch + 15) / 16 * 16;
     if (o16 <= n_max) { pl.n_tile = o16; pl.n_tiles = 1; }
     else {
@@ -547,48 +628,52 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     pl.kc = q.in_ch % 64 == 0 ? 64 : (q.in_ch % 32 == 0 ? 32 : 16);
     pl.chunks = q.in_ch / pl.kc;
     pl.b_stage = pl.parts * pl.n_tile * pl.kc * 2;
-    const int halo_h = 16 * pl.ma + 2, a_bytes = SA * pl.parts * 8 * halo_h * HALO_W * 16;
+    const int halo_h = 16 * pl.ma + 2, a_bytes = stages_a(pl.parts, pl.ma) * pl.parts * 8 * halo_h * HALO_W * 16;
     pl.sb = std::min(MAX_SB, (SMEM_BUDGET - a_bytes) / pl.b_stage);
     NFE_REQUIRE(pl.sb >= 2, "nfe_modulated_conv2d: internal: weight ring does not fit");
     pl.halo = q.ksize == 3;
-    // phases and taps.  conv2d_resample.py:137-139 (plain) and :117-134 (transposed, stride 2): Y = 2 y + ky
-    long long off = 0;
+    TapPlan& p = pl.tp;
+    p = TapPlan{};
     if (q.up == 1) {
-        pl.phases = 1;
-        Phase& p = pl.ph[0];
+        // conv2d_resample.py:137-139: correlation with the weight as stored (flip_weight) or flipped (conv2d_resample.py:36-37)
         p.taps = q.ksize * q.ksize;
+        p.n_acc = pl.ma;
         for (int ky = 0, t = 0; ky < q.ksize; ++ky)
             for (int kx = 0; kx < q.ksize; ++kx, ++t) {
                 p.dy[t] = ky - q.ksize / 2; p.dx[t] = kx - q.ksize / 2;
-                p.ky[t] = q.flip_weight ? ky : q.ksize - 1 - ky; p.kx[t] = q.flip_weight ? kx : q.ksize - 1 - kx;   // conv2d_resample.py:36-37
+                p.ky[t] = q.flip_weight ? ky : q.ksize - 1 - ky; p.kx[t] = q.flip_weight ? kx : q.ksize - 1 - kx;
+                p.acc_mask[t] = (1u << pl.ma) - 1u;
             }
-        p.gh = q.in_h; p.gw = q.in_w; p.oy_mul = p.ox_mul = 1; p.oy_off = p.ox_off = 0; p.packed_off = 0;
-        off = (long long)pl.n_tiles * pl.chunks * p.taps * pl.b_stage;
+        for (int m = 0; m < pl.ma; ++m) { p.row_off[m] = 16 * m; p.gh[m] = q.in_h; p.gw[m] = q.in_w; p.oy_off[m] = p.ox_off[m] = 0; }
+        p.o_mul = 1;
+        pl.grid_h = q.in_h; pl.grid_w = q.in_w;
         pl.th = pl.tw = 0;
     } else {
-        pl.phases = 4;
+        // conv2d_resample.py:117-134: conv_transpose2d(stride 2): T[2 y + ky, 2 x + kx] += x[y, x] * w[ky, kx], so output rows of
+        // parity py take ky = py (from y) and, for py = 0, also ky = 2 (from y - 1); the even phases have one more row / column
         pl.th = 2 * q.in_h + 1; pl.tw = 2 * q.in_w + 1;
+        p.n_acc = 4;
+        p.taps = 0;
+        for (int ky = 0; ky < 3; ++ky)
+            for (int kx = 0; kx < 3; ++kx) {
+                const int t = p.taps++, py = ky & 1, px = kx & 1;
+                p.dy[t] = -(ky / 2); p.dx[t] = -(kx / 2);
+                // modulated_conv2d passes flip_weight on; conv2d_resample flips once more for the transposed op (:128)
+                p.ky[t] = q.flip_weight ? 2 - ky : ky; p.kx[t] = q.flip_weight ? 2 - kx : kx;
+                p.acc_mask[t] = 1u << (py * 2 + px);
+            }
         for (int py = 0; py < 2; ++py)
             for (int px = 0; px < 2; ++px) {
-                Phase& p = pl.ph[py * 2 + px];
-                p.taps = 0;
-                for (int ky = py; ky < 3; ky += 2)
-                    for (int kx = px; kx < 3; kx += 2) {
-                        const int t = p.taps++;
-                        p.dy[t] = -(ky / 2); p.dx[t] = -(kx / 2);               // even rows: ky = 0 reads y, ky = 2 reads y - 1
-                        // modulated_conv2d passes flip_weight on; conv2d_resample flips once more for the transposed op (:128)
-                        p.ky[t] = q.flip_weight ? 2 - ky : ky; p.kx[t] = q.flip_weight ? 2 - kx : kx;
-                    }
-                p.gh = py == 0 ? q.in_h + 1 : q.in_h; p.gw = px == 0 ? q.in_w + 1 : q.in_w;
-                p.oy_mul = p.ox_mul = 2; p.oy_off = py; p.ox_off = px;
-                p.packed_off = off;
-                off += (long long)pl.n_tiles * pl.chunks * p.taps * pl.b_stage;
+                const int m = py * 2 + px;
+                p.row_off[m] = 0; p.gh[m] = py == 0 ? q.in_h + 1 : q.in_h; p.gw[m] = px == 0 ? q.in_w + 1 : q.in_w; p.oy_off[m] = py; p.ox_off[m] = px;
             }
+        p.o_mul = 2;
+        pl.grid_h = q.in_h + 1; pl.grid_w = q.in_w + 1;
     }
-    pl.packed_item_bytes = off;
+    pl.packed_item_bytes = (long long)pl.n_tiles * pl.chunks * p.taps * pl.b_stage;
     auto up256 = [](long long v) { return (v + 255) / 256 * 256; };
     pl.coef_bytes = up256((long long)(q.batch * q.out_ch + q.out_ch + q.batch) * 4);
-    pl.packed_bytes = up256(off * q.batch);
+    pl.packed_bytes = up256(pl.packed_item_bytes * q.batch);
     pl.trans_bytes = q.up == 2 ? up256((long long)q.batch * pl.th * pl.tw * q.out_ch * (q.dtype == NFE_DTYPE_F16 ? 2 : 4)) : 0;
     pl.total_bytes = pl.coef_bytes + pl.packed_bytes + pl.trans_bytes;
     return 0;
@@ -598,14 +683,14 @@ template <int PARTS, int MA>
 static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
-    const size_t smem = (size_t)SA * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 192 + 256 * 4;   // A ring | B ring | 17 mbarriers + the TMEM slot (160 bytes reserved) | bias table
+    const size_t smem = (size_t)stages_a(PARTS, MA) * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 256 + 256 * 4;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table
     static bool attr_done = false;
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("conv_gemm_kernel: shared memory opt-in: %s", cudaGetErrorString(e)); return 2; }
         attr_done = true;
     }
-    const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)(pl.phases * g.batch));
+    const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)g.batch);
     conv_gemm_kernel<PARTS, MA><<<grid, THREADS, smem, stream>>>(g);
     return check_launch("conv_gemm_kernel");
 }
@@ -645,24 +730,24 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     pa.packed = packed; pa.packed_item_stride = pl.packed_item_bytes;
     pa.batch = q->batch; pa.out_ch = q->out_ch; pa.in_ch = q->in_ch; pa.ksize = q->ksize; pa.demodulate = q->demodulate;
     pa.prenorm = (q->dtype == NFE_DTYPE_F16 && q->demodulate) ? 1 : 0;                     // networks_stylegan2.py:55-57
-    pa.parts = pl.parts; pa.n_tile = pl.n_tile; pa.n_tiles = pl.n_tiles; pa.chunks = pl.chunks; pa.kc = pl.kc; pa.b_stage = pl.b_stage; pa.phases = pl.phases;
-    for (int i = 0; i < pl.phases; ++i) pa.ph[i] = pl.ph[i];
+    pa.parts = pl.parts; pa.n_tile = pl.n_tile; pa.n_tiles = pl.n_tiles; pa.chunks = pl.chunks; pa.kc = pl.kc; pa.b_stage = pl.b_stage;
+    pa.tp = pl.tp;
     mc::modconv_coef_kernel<<<dim3(q->out_ch, q->batch), 128, 0, stream>>>(pa);
     NFE_LAUNCH_CHECK("modconv_coef_kernel");
-    int max_taps = 0;
-    for (int i = 0; i < pl.phases; ++i) max_taps = std::max(max_taps, pl.ph[i].taps);
-    const long long slots = (long long)pl.n_tiles * pl.chunks * max_taps * (pl.kc / 8) * pl.n_tile;
-    mc::modconv_pack_kernel<<<dim3((unsigned)((slots + 255) / 256), q->batch, pl.phases), 256, 0, stream>>>(pa);
+    const long long slots = (long long)pl.n_tiles * pl.chunks * pl.tp.taps * (pl.kc / 8) * pl.n_tile;
+    mc::modconv_pack_kernel<<<dim3((unsigned)((slots + 255) / 256), q->batch), 256, 0, stream>>>(pa);
     NFE_LAUNCH_CHECK("modconv_pack_kernel");
 
     mc::GemmArgs g;
     g.x = q->x; g.packed = packed; g.packed_item_stride = pl.packed_item_bytes;
     g.batch = q->batch; g.in_h = q->in_h; g.in_w = q->in_w; g.in_ch = q->in_ch; g.out_ch = q->out_ch;
     g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.halo = pl.halo;
-    g.phases = pl.phases;
-    int gh = 0, gw = 0;
-    for (int i = 0; i < pl.phases; ++i) { g.ph[i] = pl.ph[i]; gh = std::max(gh, pl.ph[i].gh); gw = std::max(gw, pl.ph[i].gw); }
-    g.tiles_x = (gw + mc::TILE_W - 1) / mc::TILE_W; g.tiles_y = (gh + 16 * pl.ma - 1) / (16 * pl.ma);
+    {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
+        const long long rings = (long long)mc::stages_a(pl.parts, pl.ma) * pl.parts * 8 * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
+        g.stage_ok = 2ll * 128 * (pl.n_tile * (pl.parts == 1 ? 2 : 4) + 16) <= rings ? 1 : 0;
+    }
+    g.tp = pl.tp;
+    g.tiles_x = (pl.grid_w + mc::TILE_W - 1) / mc::TILE_W; g.tiles_y = (pl.grid_h + 16 * pl.ma - 1) / (16 * pl.ma);
     if (q->up == 1) {
         g.y = q->y; g.ys_w = q->out_ch; g.ys_h = (long long)q->in_w * q->out_ch; g.ys_n = (long long)q->in_h * g.ys_h;
         g.noise = q->noise; g.noise_n = q->noise_batch_stride; g.noise_w = q->in_w; g.bias = q->bias;
@@ -671,7 +756,7 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
         g.y = trans; g.ys_w = q->out_ch; g.ys_h = (long long)pl.tw * q->out_ch; g.ys_n = (long long)pl.th * g.ys_h;
         g.noise = nullptr; g.noise_n = 0; g.noise_w = 0; g.bias = nullptr; g.act = 1; g.alpha = 0.0f; g.gain = 1.0f; g.clamp = -1.0f;
     }
-    int rc = pl.parts == 1 ? mc::launch_gemm<1, 2>(g, pl, stream) : mc::launch_gemm<2, 1>(g, pl, stream);
+    int rc = pl.parts == 2 ? mc::launch_gemm<2, 1>(g, pl, stream) : (pl.ma == 2 ? mc::launch_gemm<1, 2>(g, pl, stream) : mc::launch_gemm<1, 1>(g, pl, stream));
     if (rc) return rc;
     if (q->up == 2) {
         // conv2d_resample.py:97-101,124-131 with padding = k/2 as the layers pass it: the filter pass pads the (2H+1) image by
