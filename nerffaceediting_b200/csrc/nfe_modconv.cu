@@ -44,9 +44,13 @@
 namespace nfe {
 namespace mc {
 
-constexpr int TILE_W = 8, HALO_W = TILE_W + 2, MAX_TAPS = 9, THREADS = 256, MAX_SA = 4, MAX_SB = 6;
-// halo stages: the small fp16 window (up = 2: little MMA work per K chunk, the loads must run several chunks ahead) gets four
-__host__ __device__ constexpr int stages_a(int parts, int ma) { return (parts == 1 && ma == 1) ? 4 : 2; }
+#ifdef NFE_MC_EXP_ALIGNED      // timing experiment only (wrong results): window rows at a 128-byte pitch, no column shifts
+constexpr int HALO_W = 8;
+#else
+constexpr int HALO_W = 10;
+#endif
+constexpr int TILE_W = 8, MAX_TAPS = 9, THREADS = 256, MAX_SA = 4, MAX_SB = 6;
+
 constexpr int SMEM_BUDGET = 227 * 1024 - 256 - 1024;
 
 constexpr int MAX_ACC = 4;
@@ -98,6 +102,15 @@ __device__ __forceinline__ void bulk_copy(void* dst, const void* src, uint32_t b
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(tc::smem_u32(bar)) : "memory");
 }
+// bulk copy shared -> global (TMA unit), tracked by the issuing thread's bulk groups
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(tc::smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // one lane of the (converged) warp; the callers keep their control flow warp-uniform so that descriptors and barrier addresses
 // live in uniform registers: a divergent `if (lane == 0)` loop makes the compiler wrap every tcgen05.mma in an ELECT / R2UR
 // waterfall (~24 dependent instructions, ~180 cycles per MMA measured against the 128 the tensor core needs)
@@ -133,14 +146,15 @@ template <> struct Elem<2> { using type = float; };
 
 // PARTS = 1: fp16 activations / fp16 operands.  PARTS = 2: fp32 activations / bf16 hi + lo operands, three terms per product.
 // MA = window height in units of 16 rows (the window is 16 MA x 8 pixels).
-template <int PARTS, int MA>
-__global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
+// SA = halo stages (up = 2 has little MMA work per K chunk, its loads must run several chunks ahead: four).
+template <int PARTS, int MA, int SA>
+__global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 2 : 1) conv_gemm_kernel(const GemmArgs a)
 {
     using T = typename Elem<PARTS>::type;
     constexpr int HALO_H = 16 * MA + 2;
     constexpr int A_LBO = HALO_H * HALO_W * 16;          // bytes between channel groups of 8 (K core matrices)
     constexpr int A_SBO = HALO_W * 16;                    // bytes between window rows (row groups of 8 pixels)
-    constexpr int A_PART = 8 * A_LBO, A_STAGE = PARTS * A_PART, SA = stages_a(PARTS, MA);
+    constexpr int A_PART = 8 * A_LBO, A_STAGE = PARTS * A_PART;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* const sA = smem;
     unsigned char* const sB = smem + SA * A_STAGE;
@@ -257,7 +271,14 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
 #pragma unroll
             for (int m = 0; m < MAX_ACC; ++m) row16[m] = (uint32_t)(tp.row_off[m] * A_SBO) >> 4;
 #pragma unroll
-            for (int t = 0; t < MAX_TAPS; ++t) { tap16[t] = (uint32_t)((1 + tp.dy[t]) * HALO_W + 1 + tp.dx[t]); tmask[t] = tp.acc_mask[t]; }
+            for (int t = 0; t < MAX_TAPS; ++t) {
+#ifdef NFE_MC_EXP_ALIGNED
+                tap16[t] = (uint32_t)((1 + tp.dy[t]) * HALO_W);
+#else
+                tap16[t] = (uint32_t)((1 + tp.dy[t]) * HALO_W + 1 + tp.dx[t]);
+#endif
+                tmask[t] = tp.acc_mask[t];
+            }
             int sb = 0;
             uint32_t sb_par = 0, started = 0;        // started: accumulators that hold a partial sum already
             for (int c = 0; c < a.chunks; ++c) {
@@ -320,7 +341,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
     }
     {
         // ------------------------------------------------------------------ epilogue, all eight warps: thread = TMEM lane = pixel of the
-        // window; warps w and w + 4 share a lane quarter and take alternate 16-column groups
+        // window; warps w and w + 4 share a lane quarter and take alternate accumulators
 #ifdef NFE_MC_PROFILE
         const long long t_e0 = clock64();
 #endif
@@ -337,30 +358,32 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
         const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
         const int nq = a.n_tile / 16;
         const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        // Stores: a thread holds 16 channels of ONE pixel, so a direct store instruction would touch 32 different lines with 16 bytes
-        // each (measured: the epilogue ran at the speed of its 8192 partial-sector stores).  The tile is staged through the (now idle)
-        // operand rings instead — pixel rows of n_tile channels at a pitch of 16 bytes more, which spreads the lanes over the banks —
-        // and written out one whole pixel row (up to 512 contiguous bytes) per warp instruction.
+        // Stores: a thread holds 16 channels of ONE pixel at a time, so direct store instructions touch 32 different lines with 16
+        // bytes each (measured: the epilogue then runs at the speed of its 8192 partial-sector stores).  Instead every thread builds
+        // its pixel's whole row of n_tile channels in the (now idle) operand rings — at a pitch of 16 bytes more than the row, which
+        // spreads the lanes over the banks — and hands the finished row (up to 512 contiguous bytes) to the TMA unit as one bulk
+        // store: no block-wide synchronisation, no copy-out loop.
         const int row_bytes = a.n_tile * (int)sizeof(T), pitch = row_bytes + 16;
         const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
+        unsigned char* const my_row = smem + (grp * 128 + row) * pitch;
 #pragma unroll 1
-        for (int m = 0; m < n_acc; ++m) {
+        for (int m = grp; m < n_acc; m += 2) {
             const int gy = y0 + tp.row_off[m] + py, gx = x0 + px;
             const bool valid = gy < tp.gh[m] && gx < tp.gw[m];
             const int oy = gy * tp.o_mul + tp.oy_off[m], ox = gx * tp.o_mul + tp.ox_off[m];
             T* dst = yout + n * a.ys_n + oy * a.ys_h + ox * a.ys_w + nt * a.n_tile;
             const float nz = (a.noise && valid) ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.noise_w + ox) : 0.0f;
-            unsigned char* const stage = smem + (m & 1) * (128 * pitch);
+            if (staged && m >= 2) bulk_wait_read();                      // the row buffer is free once the previous bulk store has read it
             float nxt[16];
-            if (grp < nq) tc::tmem_ld16(t_lane + m * a.n_tile + grp * 16, nxt);      // software pipeline: the next group loads while this one is processed
+            tc::tmem_ld16(t_lane + m * a.n_tile, nxt);                   // software pipeline: the next group loads while this one is processed
 #pragma unroll 1
-            for (int q = grp; q < nq; q += 2) {
+            for (int q = 0; q < nq; ++q) {
                 float v[16];
                 tc::tmem_ld_wait();
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = nxt[i];
-                if (q + 2 < nq) tc::tmem_ld16(t_lane + m * a.n_tile + (q + 2) * 16, nxt);
-                if (!valid && !staged) continue;
+                if (q + 1 < nq) tc::tmem_ld16(t_lane + m * a.n_tile + (q + 1) * 16, nxt);
+                if (!valid) continue;
                 const int o0 = nt * a.n_tile + q * 16;
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
@@ -374,7 +397,7 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
                     }
                 }
                 if (staged || (vec_ok && o0 + 16 <= a.out_ch)) {
-                    unsigned char* out = staged ? stage + row * pitch + q * 16 * (int)sizeof(T) : reinterpret_cast<unsigned char*>(dst + q * 16);
+                    unsigned char* out = staged ? my_row + q * 16 * (int)sizeof(T) : reinterpret_cast<unsigned char*>(dst + q * 16);
                     if constexpr (PARTS == 1) {
                         uint32_t w[8];
 #pragma unroll
@@ -394,17 +417,13 @@ __global__ void __launch_bounds__(THREADS, 1) conv_gemm_kernel(const GemmArgs a)
                         }
                 }
             }
-            if (staged) {
-                __syncthreads();                            // the tile is complete (every warp is in the epilogue by now)
-                const int chunks16 = row_bytes >> 4;        // 16-byte pieces per pixel row: at most 32
-                for (int r = warp; r < 128; r += 8) {
-                    const int ry = y0 + tp.row_off[m] + (r >> 3), rx = x0 + (r & 7);
-                    if (ry >= tp.gh[m] || rx >= tp.gw[m] || lane >= chunks16) continue;
-                    T* g = yout + n * a.ys_n + (ry * tp.o_mul + tp.oy_off[m]) * a.ys_h + (rx * tp.o_mul + tp.ox_off[m]) * a.ys_w + nt * a.n_tile;
-                    reinterpret_cast<uint4*>(g)[lane] = *reinterpret_cast<const uint4*>(stage + r * pitch + lane * 16);
-                }
+            if (staged && valid) {
+                tc::fence_async_smem();                     // this thread's row, written through the generic proxy, is read by the async proxy
+                bulk_store(dst, my_row, (uint32_t)row_bytes);
+                bulk_commit();
             }
         }
+        if (staged) bulk_wait_all();                        // shared memory must outlive the reads, the kernel the writes
         tc::fence_before_sync();
 #ifdef NFE_MC_PROFILE
         if (threadIdx.x == 0) { prof_[6] = clock64() - t_e1; prof_[5] = t_e1 - t_e0; atomicAdd(&g_mc_prof[5], (unsigned long long)prof_[5]); MC_FLUSH(6); }
@@ -597,9 +616,84 @@ __global__ void __launch_bounds__(256) upfir_finish_kernel(const FinishArgs a)
     }
 }
 
+// Tiled form for filters of at most 4 x 4 (the reference's [1,3,3,1]): a block owns 16 x 16 output pixels x one 128-byte channel
+// slice (64 halves / 32 floats), stages the (16 + f - 1)^2 input pixels of that slice in shared memory once (the generic kernel
+// above re-reads every input pixel 16 times through L1 / L2: measured 3x the time the bytes need) and then every thread computes
+// 16 bytes of channels per output pixel from 16-byte shared-memory reads.
+constexpr int FT = 16, FT_IN = FT + 3;
+
+template <class T>
+__global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArgs a, int tiles_x, int tiles_y, int slices)
+{
+    constexpr int V = 16 / (int)sizeof(T);                   // channels per 16 bytes
+    __shared__ __align__(16) unsigned char tile[FT_IN * FT_IN * 128];
+    __shared__ float filt[16];
+    if ((int)threadIdx.x < a.fh * a.fw) {
+        const int ky = threadIdx.x / a.fw, kx = threadIdx.x % a.fw;
+        filt[threadIdx.x] = __ldg(a.f + (a.flip ? ky : a.fh - 1 - ky) * a.fw + (a.flip ? kx : a.fw - 1 - kx)) * a.fgain;
+    }
+    const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x, sl = blockIdx.y % slices, n = blockIdx.y / slices;
+    const int ox0 = bx * FT, oy0 = by * FT, c_base = sl * 8 * V;
+    const int groups = min(8, (a.c - c_base) / V);          // 16-byte channel groups of this slice
+    const T* tin = static_cast<const T*>(a.t);
+    T* yout = static_cast<T*>(a.y);
+    const int in_w = FT + a.fw - 1, in_h = FT + a.fh - 1, g = threadIdx.x & 7;
+    if (g < groups)
+        for (int p = threadIdx.x >> 3; p < in_h * in_w; p += 32) {
+            const int iy = oy0 + p / in_w - a.pad_y0, ix = ox0 + p % in_w - a.pad_x0;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (iy >= 0 && iy < a.th && ix >= 0 && ix < a.tw)
+                v = __ldg(reinterpret_cast<const uint4*>(tin + (((long long)n * a.th + iy) * a.tw + ix) * a.c + c_base) + g);
+            *reinterpret_cast<uint4*>(tile + ((p / in_w) * FT_IN + p % in_w) * 128 + g * 16) = v;
+        }
+    __syncthreads();
+    if (g >= groups) return;
+    for (int p = threadIdx.x >> 3; p < FT * FT; p += 32) {
+        const int py = p / FT, px = p % FT, oy = oy0 + py, ox = ox0 + px;
+        if (oy >= a.oh || ox >= a.ow) continue;
+        float acc[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+        for (int ky = 0; ky < a.fh; ++ky)
+            for (int kx = 0; kx < a.fw; ++kx) {
+                const float w = filt[ky * a.fw + kx];
+                const uint4 u = *reinterpret_cast<const uint4*>(tile + ((py + ky) * FT_IN + px + kx) * 128 + g * 16);
+                if constexpr (sizeof(T) == 2) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { const float2 f2 = __half22float2(h[j]); acc[2 * j] = fmaf(f2.x, w, acc[2 * j]); acc[2 * j + 1] = fmaf(f2.y, w, acc[2 * j + 1]); }
+                } else {
+                    acc[0] = fmaf(__uint_as_float(u.x), w, acc[0]); acc[1] = fmaf(__uint_as_float(u.y), w, acc[1]);
+                    acc[2] = fmaf(__uint_as_float(u.z), w, acc[2]); acc[3] = fmaf(__uint_as_float(u.w), w, acc[3]);
+                }
+            }
+        const float nz = a.noise ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.ow + ox) : 0.0f;
+        const int c0 = c_base + g * V;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            float t = acc[j];
+            if constexpr (sizeof(T) == 2) t = __half2float(__float2half_rn(t));      // the reference stores the filtered image in fp16
+            t += nz;
+            if (a.bias) t += __ldg(a.bias + c0 + j);
+            t = act_apply<T>(t, a.act, a.alpha) * a.gain;
+            if (a.clamp >= 0.0f) t = fminf(fmaxf(t, -a.clamp), a.clamp);
+            acc[j] = t;
+        }
+        T* dst = yout + (((long long)n * a.oh + oy) * a.ow + ox) * a.c + c0;
+        if constexpr (sizeof(T) == 2) {
+            uint32_t w4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { const __half2 h = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]); w4[j] = *reinterpret_cast<const uint32_t*>(&h); }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        } else {
+            *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- host side
 struct Plan {
-    int parts, ma, n_tile, n_tiles, kc, chunks, b_stage, sb, halo;
+    int parts, ma, sa, n_tile, n_tiles, kc, chunks, b_stage, sb, halo;
     long long packed_item_bytes, coef_bytes, packed_bytes, trans_bytes, total_bytes;
     int th, tw;                            // transposed-convolution intermediate (up = 2)
     int grid_h, grid_w;                    // pixel grid the windows tile
@@ -617,7 +711,6 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     pl.parts = q.dtype == NFE_DTYPE_F16 ? 1 : 2;
     // plain: two 128-pixel accumulators x 256 columns (fp16) or one x 128 (fp32 split: the operand rings are twice as wide);
     // up = 2: a 128-pixel window, four phase accumulators x 128 columns.  512 columns of tensor memory either way.
-    pl.ma = (pl.parts == 1 && q.up == 1) ? 2 : 1;
     const int n_max = (pl.parts == 1 && q.up == 1) ? 256 : 128;
     const int o16 = (q.out_ch + 15) / 16 * 16;
     if (o16 <= n_max) { pl.n_tile = o16; pl.n_tiles = 1; }
@@ -628,8 +721,15 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     pl.kc = q.in_ch % 64 == 0 ? 64 : (q.in_ch % 32 == 0 ? 32 : 16);
     pl.chunks = q.in_ch / pl.kc;
     pl.b_stage = pl.parts * pl.n_tile * pl.kc * 2;
-    const int halo_h = 16 * pl.ma + 2, a_bytes = stages_a(pl.parts, pl.ma) * pl.parts * 8 * halo_h * HALO_W * 16;
-    pl.sb = std::min(MAX_SB, (SMEM_BUDGET - a_bytes) / pl.b_stage);
+    // An MMA with M = 128 costs the tensor core at least ~128 cycles (its A-operand fetch) whatever N is, so tiles of N <= 128 run
+    // at half rate at best and the epilogue weighs twice as much: for those the CTA is made small enough (one 128-pixel window,
+    // <= 113 KB of shared memory, <= 256 columns of tensor memory) for TWO CTAs per SM, whose main loops and epilogues overlap.
+    const bool twin = pl.parts == 1 && q.up == 1 && pl.n_tile <= 128;
+    pl.ma = (pl.parts == 1 && q.up == 1 && !twin) ? 2 : 1;
+    pl.sa = (pl.parts == 1 && q.up == 2) ? 4 : 2;
+    const int halo_h = 16 * pl.ma + 2, a_bytes = pl.sa * pl.parts * 8 * halo_h * HALO_W * 16;
+    const int budget = twin ? (SMEM_BUDGET + 1280) / 2 - 1280 - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM
+    pl.sb = std::min(MAX_SB, (budget - a_bytes) / pl.b_stage);
     NFE_REQUIRE(pl.sb >= 2, "nfe_modulated_conv2d: internal: weight ring does not fit");
     pl.halo = q.ksize == 3;
     TapPlan& p = pl.tp;
@@ -679,19 +779,20 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     return 0;
 }
 
-template <int PARTS, int MA>
+template <int PARTS, int MA, int SA>
 static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
-    const size_t smem = (size_t)stages_a(PARTS, MA) * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 256 + 256 * 4;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table
+    const size_t smem = (size_t)SA * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 256 + 256 * 4;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) { set_error("conv_gemm_kernel: shared memory opt-in: %s", cudaGetErrorString(e)); return 2; }
         attr_done = true;
     }
     const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)g.batch);
-    conv_gemm_kernel<PARTS, MA><<<grid, THREADS, smem, stream>>>(g);
+    conv_gemm_kernel<PARTS, MA, SA><<<grid, THREADS, smem, stream>>>(g);
     return check_launch("conv_gemm_kernel");
 }
 
@@ -743,7 +844,7 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     g.batch = q->batch; g.in_h = q->in_h; g.in_w = q->in_w; g.in_ch = q->in_ch; g.out_ch = q->out_ch;
     g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.halo = pl.halo;
     {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
-        const long long rings = (long long)mc::stages_a(pl.parts, pl.ma) * pl.parts * 8 * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
+        const long long rings = (long long)pl.sa * pl.parts * 8 * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
         g.stage_ok = 2ll * 128 * (pl.n_tile * (pl.parts == 1 ? 2 : 4) + 16) <= rings ? 1 : 0;
     }
     g.tp = pl.tp;
@@ -756,7 +857,8 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
         g.y = trans; g.ys_w = q->out_ch; g.ys_h = (long long)pl.tw * q->out_ch; g.ys_n = (long long)pl.th * g.ys_h;
         g.noise = nullptr; g.noise_n = 0; g.noise_w = 0; g.bias = nullptr; g.act = 1; g.alpha = 0.0f; g.gain = 1.0f; g.clamp = -1.0f;
     }
-    int rc = pl.parts == 2 ? mc::launch_gemm<2, 1>(g, pl, stream) : (pl.ma == 2 ? mc::launch_gemm<1, 2>(g, pl, stream) : mc::launch_gemm<1, 1>(g, pl, stream));
+    int rc = pl.parts == 2 ? mc::launch_gemm<2, 1, 2>(g, pl, stream)
+             : (pl.ma == 2 ? mc::launch_gemm<1, 2, 2>(g, pl, stream) : (pl.sa == 4 ? mc::launch_gemm<1, 1, 4>(g, pl, stream) : mc::launch_gemm<1, 1, 2>(g, pl, stream)));
     if (rc) return rc;
     if (q->up == 2) {
         // conv2d_resample.py:97-101,124-131 with padding = k/2 as the layers pass it: the filter pass pads the (2H+1) image by
@@ -768,11 +870,20 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
         NFE_REQUIRE(pl.th + pad0 + pad1 - q->fh + 1 == f.oh, "nfe_modulated_conv2d: a %d-tap resample filter does not yield a 2x image", q->fw);
         f.pad_y0 = f.pad_x0 = pad0; f.flip = 0; f.fgain = 4.0f;
         f.act = q->act; f.alpha = q->alpha; f.gain = q->gain; f.clamp = q->clamp;
-        const long long work = (long long)q->batch * f.oh * f.ow * (q->out_ch / vec);
-        const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 16);
-        if (q->dtype == NFE_DTYPE_F16) mc::upfir_finish_kernel<__half><<<blocks, 256, 0, stream>>>(f);
-        else mc::upfir_finish_kernel<float><<<blocks, 256, 0, stream>>>(f);
-        NFE_LAUNCH_CHECK("upfir_finish_kernel");
+        const int slices = (q->out_ch + 8 * vec - 1) / (8 * vec);
+        if (q->fh <= 4 && q->fw <= 4 && (long long)q->batch * slices <= 65535) {
+            const int tiles_x = (f.ow + mc::FT - 1) / mc::FT, tiles_y = (f.oh + mc::FT - 1) / mc::FT;
+            const dim3 grid((unsigned)(tiles_x * tiles_y), (unsigned)(q->batch * slices));
+            if (q->dtype == NFE_DTYPE_F16) mc::upfir_finish_tiled_kernel<__half><<<grid, 256, 0, stream>>>(f, tiles_x, tiles_y, slices);
+            else mc::upfir_finish_tiled_kernel<float><<<grid, 256, 0, stream>>>(f, tiles_x, tiles_y, slices);
+            NFE_LAUNCH_CHECK("upfir_finish_tiled_kernel");
+        } else {
+            const long long work = (long long)q->batch * f.oh * f.ow * (q->out_ch / vec);
+            const int blocks = (int)std::min<long long>((work + 255) / 256, (long long)sm_count() * 16);
+            if (q->dtype == NFE_DTYPE_F16) mc::upfir_finish_kernel<__half><<<blocks, 256, 0, stream>>>(f);
+            else mc::upfir_finish_kernel<float><<<blocks, 256, 0, stream>>>(f);
+            NFE_LAUNCH_CHECK("upfir_finish_kernel");
+        }
     }
     return 0;
 }
