@@ -572,6 +572,38 @@ def main():
         except Exception as exc:    # noqa: BLE001
             extras["c4_training_step"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+        try:
+            # the consumer of the rendered feature image.  The default super-resolution head
+            # (SuperresolutionHybrid8XDC, superresolution.py:264-290: 32 x 64^2 features -> 3 x 512^2, fp16 blocks as train.py sets
+            # them) at this workload's batch, and its largest layer alone against the tensor roofline.
+            import synth_inputs as synth
+            from nerffaceediting_b200 import networks as nfe_net
+            nb = wl["batch"]
+            with torch.no_grad():
+                sr = synth.fill_module(nfe_net.SuperresolutionHybrid8XDC(32, 512, 4, True), 3).to(device).eval()
+                feat = torch.randn(nb, 32, res, res, device=device)
+                ws_sr = torch.randn(nb, 14, 512, device=device)
+                ms_sr = quick(lambda: sr(feat[:, :3].contiguous(), feat, ws_sr, noise_mode='const'), 5, 2)
+                layer = synth.fill_module(nfe_net.SynthesisLayer(256, 256, w_dim=512, resolution=256, conv_clamp=256), 11).to(device).eval()
+                xl = torch.randn(nb, 256, 256, 256, device=device, dtype=torch.float16).contiguous(memory_format=torch.channels_last)
+                wl_ = torch.randn(nb, 512, device=device)
+                ms_l = quick(lambda: layer(xl, wl_, noise_mode='const'), 10, 3)
+            flop_l = 2.0 * nb * 256 * 256 * 9 * 256 * 256
+            pk = measured_peaks()[2]
+            tpeak = float(pk.get("bf16_tflops_sustained", 0) or 0)
+            extras["f3_conv_stack"] = {
+                "sr_head": {"value": nb / (ms_sr * 1e-3), "unit": "images/s", "ms": ms_sr, "workload": f"SuperresolutionHybrid8XDC, batch {nb}, fp16 blocks, 195.6 GFLOP of convolutions per image",
+                            "conv_tflops": nb * 195.6 / ms_sr},
+                "layer_256x256_at_256": {"ms": ms_l, "tflops": flop_l / ms_l / 1e9, "dtype": "f16 operands, f32 accumulate",
+                                         "roofline": {"bound": "tensor", "achieved": flop_l / ms_l / 1e9, "peak": tpeak or None, "unit": "TFLOP/s",
+                                                      "frac": (flop_l / ms_l / 1e9 / tpeak) if tpeak else None,
+                                                      "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (dense 16-bit tensor rate)"}},
+                "note": "modulated convolutions as tcgen05 implicit GEMMs (csrc/nfe_modconv.cu); the whole layer call is timed: weight fold + pack, "
+                        "GEMM with fused noise / bias / lrelu / clamp epilogue"}
+            del sr, feat, layer, xl
+        except Exception as exc:    # noqa: BLE001
+            extras["f3_conv_stack"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         ms_step = ms_total / steps
         total_rays = rays_per_rank * world

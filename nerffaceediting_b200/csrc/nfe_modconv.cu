@@ -725,7 +725,9 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     // at half rate at best and the epilogue weighs twice as much: for those the CTA is made small enough (one 128-pixel window,
     // <= 113 KB of shared memory, <= 256 columns of tensor memory) for TWO CTAs per SM, whose main loops and epilogues overlap.
     const bool twin = pl.parts == 1 && q.up == 1 && pl.n_tile <= 128;
-    pl.ma = (pl.parts == 1 && q.up == 1 && !twin) ? 2 : 1;
+    // a layer whose 256-pixel windows would not even give every SM one CTA (the backbone's 4^2 .. 32^2 blocks) takes 128-pixel windows
+    const long long ctas_256 = (long long)((q.in_h + 31) / 32) * ((q.in_w + TILE_W - 1) / TILE_W) * pl.n_tiles * q.batch;
+    pl.ma = (pl.parts == 1 && q.up == 1 && !twin && ctas_256 >= sm_count()) ? 2 : 1;
     pl.sa = (pl.parts == 1 && q.up == 2) ? 4 : 2;
     const int halo_h = 16 * pl.ma + 2, a_bytes = pl.sa * pl.parts * 8 * halo_h * HALO_W * 16;
     const int budget = twin ? (SMEM_BUDGET + 1280) / 2 - 1280 - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM

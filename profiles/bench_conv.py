@@ -58,7 +58,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--sr-only", action="store_true", help="two calls of the fp16 SR head and nothing else (for a launch list under ncu)")
     a = ap.parse_args()
+    if a.sr_only:
+        with torch.no_grad():
+            sr = synth.fill_module(net.SuperresolutionHybrid8XDC(32, 512, 4, True), 3).cuda().eval()
+            x = torch.randn(a.batch, 32, 64, 64, device="cuda")
+            ws = torch.randn(a.batch, 14, 512, device="cuda")
+            for _ in range(2):
+                sr(x[:, :3].contiguous(), x, ws, noise_mode='const')
+            torch.cuda.synchronize()
+        return
     n = a.batch
     out = {"batch": n, "device": torch.cuda.get_device_name(0)}
     layers = []
