@@ -352,3 +352,30 @@ def test_state_dict_names_are_the_reference_s():
     assert keys(cases.make_sr(net, '8XDC')) == sorted(g["keys.sr8xdc"].tolist())
     assert keys(net.SuperresolutionHybrid4X(32, 256, 4, True)) == sorted(g["keys.sr4x"].tolist())
     assert keys(net.SuperresolutionHybrid8X(32, 512, 4, True)) == sorted(g["keys.sr8x"].tolist())
+
+
+def test_modconv_plan_and_argument_checks_run_on_the_host(built):
+    """nfe_modconv_workspace_bytes is pure host code (tile plan of conv_gemm_kernel): the struct layout the ctypes mirror assumes, the
+    scratch sizes of known layers and the rejected configurations, without a GPU."""
+    lib = _lib.load()
+    A = _lib.NfeModconvArgs
+    assert A.noise_batch_stride.offset == 4 * 8 and A.fh.offset == 8 * 8 and ctypes.sizeof(A) == 8 * 8 + 16 * 4      # 8 pointer-sized + 16 x 4 bytes
+
+    def need(**kw):
+        base = dict(batch=8, in_ch=256, out_ch=256, in_h=256, in_w=256, ksize=3, up=1, demodulate=1, flip_weight=1, act=3, alpha=0.2, gain=1.0,
+                    clamp=256.0, dtype=1)
+        base.update(kw)
+        return lib.nfe_modconv_workspace_bytes(A(**base))
+    up256 = lambda v: (v + 255) // 256 * 256                                                                          # noqa: E731
+    coef = up256((8 * 256 + 256 + 8) * 4)
+    # fp16, plain 3x3: per item 9 taps x 256 x 256 halves of packed weights
+    assert need() == coef + up256(8 * 9 * 256 * 256 * 2)
+    # fp32: hi + lo parts
+    assert need(dtype=0) == coef + up256(8 * 9 * 256 * 256 * 2 * 2)
+    # up = 2: the same nine taps + the (2H+1)^2 intermediate in the activation type
+    assert need(up=2, in_h=128, in_w=128) == coef + up256(8 * 9 * 256 * 256 * 2) + up256(8 * 257 * 257 * 256 * 2)
+    # 1x1 to 3 channels (ToRGB): the output tile is padded to 16 rows
+    assert need(ksize=1, out_ch=3, demodulate=0) == up256((8 * 3 + 3 + 8) * 4) + up256(8 * 16 * 256 * 2)
+    for bad in (dict(in_ch=24), dict(ksize=5), dict(up=2, ksize=1), dict(up=3), dict(dtype=2), dict(out_ch=384), dict(batch=0)):
+        assert need(**bad) == -1, bad
+        assert lib.nfe_last_error()
