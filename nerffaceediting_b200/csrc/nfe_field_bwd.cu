@@ -96,19 +96,21 @@ __host__ __device__ constexpr uint32_t idesc_mn(int M, int N) { return tc::make_
 
 // D (+)= A^T-view * B^T-view contracting over the 128 tile rows; both tiles are stored K-major [rows x cols] with
 // (lbo,sbo); read MN-major the roles swap: stride between 8-row K blocks = sbo, between 8-column MN blocks = lbo
-__device__ __forceinline__ void issue_gemm_rows(uint32_t tmem_d, const unsigned char* a_hi, const unsigned char* a_lo, int a_lbo, int a_sbo,
+__device__ __forceinline__ void issue_gemm_rows(bool leader, uint32_t tmem_d, const unsigned char* a_hi, const unsigned char* a_lo, int a_lbo, int a_sbo,
                                                 const unsigned char* b_hi, const unsigned char* b_lo, int b_lbo, int b_sbo, uint32_t idesc, bool accumulate)
 {
-    bool acc = accumulate;
+    // every lane of the issuing warp runs this (warp-uniform arguments), the elected one issues; descriptors = constant part + an add
+    const uint64_t da0 = tc::make_desc(0, a_sbo, a_lbo), db0 = tc::make_desc(0, b_sbo, b_lbo);
+    const uint32_t ah = tc::smem_u32(a_hi) >> 4, al = tc::smem_u32(a_lo) >> 4, bh = tc::smem_u32(b_hi) >> 4, bl = tc::smem_u32(b_lo) >> 4;
+    const uint32_t ak = (uint32_t)(2 * a_sbo) >> 4, bk = (uint32_t)(2 * b_sbo) >> 4;
+    uint32_t acc = accumulate ? 1u : 0u;
 #pragma unroll
     for (int t = 0; t < 3; ++t) {
-        const unsigned char* a = (t == 1) ? a_lo : a_hi;
-        const unsigned char* b = (t == 2) ? b_lo : b_hi;
+        const uint32_t a = (t == 1) ? al : ah, b = (t == 2) ? bl : bh;
+#pragma unroll
         for (int ks = 0; ks < TILE_M / 16; ++ks) {
-            const uint64_t da = tc::make_desc(tc::smem_u32(a) + ks * 2 * a_sbo, a_sbo, a_lbo);
-            const uint64_t db = tc::make_desc(tc::smem_u32(b) + ks * 2 * b_sbo, b_sbo, b_lbo);
-            tc::mma_bf16_ss(tmem_d, da, db, idesc, acc);
-            acc = true;
+            if (leader) tc::mma_bf16_ss(tmem_d, da0 + (a + ks * ak), db0 + (b + ks * bk), idesc, acc);
+            acc = 1u;
         }
     }
 }
@@ -374,13 +376,15 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         BWD_MARK(0);
 
         // ---- G1: pre = X W1^T for both nets
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {                    // warp 0, warp-uniform; the elected lane issues (tc::elect_one)
+            const bool leader = tc::elect_one();
             tc::fence_after_sync();
             constexpr uint32_t id1 = tc::make_idesc_bf16(TILE_M, HIDDEN);
+#pragma unroll
             for (int n = 0; n < 2; ++n)
-                issue_gemm<true>(tmem + C_PRE + 64 * n, s.xa[0] + 4 * n * XA_LBO, s.xa[1] + 4 * n * XA_LBO, XA_LBO, XA_SBO, s.w1[n][0], s.w1[n][1],
+                issue_gemm<true>(leader, tmem + C_PRE + 64 * n, s.xa[0] + 4 * n * XA_LBO, s.xa[1] + 4 * n * XA_LBO, XA_LBO, XA_SBO, s.w1[n][0], s.w1[n][1],
                                  B1_LBO, B1_SBO, FEAT, id1);
-            tc::mma_commit(&s.bar);
+            if (leader) tc::mma_commit(&s.bar);
         }
         // record gradients (and the saved colours) of this thread's row: requested now, consumed after the softplus loop
         const bool live = base + row < a.total;
@@ -486,14 +490,15 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         BWD_MARK(2);
 
         // ---- G2: dH = dY W2;  G4: dW2^T += H^T dY (contraction over the tile rows)
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            const bool leader = tc::elect_one();
             tc::fence_after_sync();
             constexpr uint32_t id2 = tc::make_idesc_bf16(TILE_M, HIDDEN);
-            issue_gemm<true>(tmem + C_DH, s.dy[0], s.dy[1], DY_LBO, DY_SBO, s.w2t[0][0], s.w2t[0][1], W2T_LBO, W2T_SBO, O::PAD0, id2);
-            issue_gemm<true>(tmem + C_DH + 64, s.dy[0] + (O::PAD0 / 8) * DY_LBO, s.dy[1] + (O::PAD0 / 8) * DY_LBO, DY_LBO, DY_SBO, s.w2t[1][0], s.w2t[1][1],
+            issue_gemm<true>(leader, tmem + C_DH, s.dy[0], s.dy[1], DY_LBO, DY_SBO, s.w2t[0][0], s.w2t[0][1], W2T_LBO, W2T_SBO, O::PAD0, id2);
+            issue_gemm<true>(leader, tmem + C_DH + 64, s.dy[0] + (O::PAD0 / 8) * DY_LBO, s.dy[1] + (O::PAD0 / 8) * DY_LBO, DY_LBO, DY_SBO, s.w2t[1][0], s.w2t[1][1],
                              W2T_LBO, W2T_SBO, O::PAD1, id2);
-            issue_gemm_rows(tmem + C_DW2, s.hc[0], s.hc[1], HC_LBO, HC_SBO, s.dy[0], s.dy[1], DY_LBO, DY_SBO, idesc_mn(TILE_M, DY_COLS), !first);
-            tc::mma_commit(&s.bar);
+            issue_gemm_rows(leader, tmem + C_DW2, s.hc[0], s.hc[1], HC_LBO, HC_SBO, s.dy[0], s.dy[1], DY_LBO, DY_SBO, idesc_mn(TILE_M, DY_COLS), !first);
+            if (leader) tc::mma_commit(&s.bar);
         }
         tc::mbar_wait(&s.bar, phase); phase ^= 1;
         tc::fence_after_sync();
@@ -522,14 +527,16 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
         BWD_MARK(4);
 
         // ---- G3: dX = dpre W1;  G5: [dW1 | db1] += dpre^T [X | 1]
-        if (threadIdx.x == 0) {
+        if (threadIdx.x < 32) {
+            const bool leader = tc::elect_one();
             tc::fence_after_sync();
             constexpr uint32_t id3 = tc::make_idesc_bf16(TILE_M, FEAT);
+#pragma unroll
             for (int n = 0; n < 2; ++n)
-                issue_gemm<true>(tmem + C_DX + 32 * n, s.hc[0] + 8 * n * HC_LBO, s.hc[1] + 8 * n * HC_LBO, HC_LBO, HC_SBO, s.w1t[n][0], s.w1t[n][1],
+                issue_gemm<true>(leader, tmem + C_DX + 32 * n, s.hc[0] + 8 * n * HC_LBO, s.hc[1] + 8 * n * HC_LBO, HC_LBO, HC_SBO, s.w1t[n][0], s.w1t[n][1],
                                  W1T_LBO, W1T_SBO, HIDDEN, id3);
-            issue_gemm_rows(tmem + C_DW1, s.hc[0], s.hc[1], HC_LBO, HC_SBO, s.xa[0], s.xa[1], XA_LBO, XA_SBO, idesc_mn(TILE_M, XA_COLS), !first);
-            tc::mma_commit(&s.bar);
+            issue_gemm_rows(leader, tmem + C_DW1, s.hc[0], s.hc[1], HC_LBO, HC_SBO, s.xa[0], s.xa[1], XA_LBO, XA_SBO, idesc_mn(TILE_M, XA_COLS), !first);
+            if (leader) tc::mma_commit(&s.bar);
         }
         tc::mbar_wait(&s.bar, phase); phase ^= 1;
         tc::fence_after_sync();

@@ -203,11 +203,14 @@ __device__ __forceinline__ void hidden_in_place(uint32_t taddr, const float* bia
     tc::tmem_st_wait();
 }
 
-// One thread issues D (+)= H * W2^T with H taken from tensor memory in the in-place layout of hidden_in_place
+// D (+)= H * W2^T with H taken from tensor memory in the in-place layout of hidden_in_place; every lane of the MMA warp calls it, the
+// elected one issues
 template <bool SPLIT>
-__device__ __forceinline__ void issue_layer2(uint32_t tmem_d, uint32_t tmem_h, const unsigned char* b_hi, const unsigned char* b_lo, uint32_t idesc)
+__device__ __forceinline__ void issue_layer2(bool leader, uint32_t tmem_d, uint32_t tmem_h, const unsigned char* b_hi, const unsigned char* b_lo, uint32_t idesc)
 {
-    bool acc = false;
+    uint32_t acc = 0;
+    const uint64_t db0 = tc::make_desc(0, B2_LBO, B2_SBO);
+    const uint32_t bh = tc::smem_u32(b_hi) >> 4, bl = tc::smem_u32(b_lo) >> 4;
     constexpr int TERMS = SPLIT ? 3 : 1;
 #if NFE_P2_ROLLED_MMA
 #pragma unroll 1
@@ -216,16 +219,15 @@ __device__ __forceinline__ void issue_layer2(uint32_t tmem_d, uint32_t tmem_h, c
 #endif
     for (int t = 0; t < TERMS; ++t) {
         const uint32_t part = (t == 1) ? 8u : 0u;                        // hi*hi, lo*hi, hi*lo
-        const unsigned char* b = (t == 2) ? b_lo : b_hi;
+        const uint32_t b = (t == 2) ? bl : bh;
 #if NFE_P2_ROLLED_MMA
 #pragma unroll 1
 #else
 #pragma unroll
 #endif
         for (int ks = 0; ks < HIDDEN / 16; ++ks) {
-            const uint64_t db = tc::make_desc(tc::smem_u32(b) + (ks * 2) * B2_LBO, B2_LBO, B2_SBO);
-            tc::mma_bf16_ts(tmem_d, tmem_h + ks * 16 + part, db, idesc, acc);
-            acc = true;
+            if (leader) tc::mma_bf16_ts(tmem_d, tmem_h + ks * 16 + part, db0 + (b + ks * ((2 * B2_LBO) >> 4)), idesc, acc);
+            acc = 1;
         }
     }
 }
@@ -568,11 +570,13 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
             advance(it, h);
         }
     } else if (warp == MMA_WARP) {
-        // ================================================================ MMA issuer (one thread)
+        // ================================================================ MMA issuer: every lane runs the (warp-uniform) loop, one
+        // elected lane issues — see tc::elect_one
 #if NFE_P2_SETMAXNREG
         regs_dec<REGS_MISC>();
 #endif
-        if (lane == 0) {
+        {
+            const bool leader = tc::elect_one();
             constexpr uint32_t idesc1 = tc::make_idesc_bf16(TILE_M, HIDDEN);
             constexpr uint32_t idesc2a = tc::make_idesc_bf16(TILE_M, T::N_A);
             constexpr uint32_t idesc2b = tc::make_idesc_bf16(TILE_M, T::N_B);
@@ -582,12 +586,14 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
                 const uint32_t tb = tmem + st * GROUP_COLS;
                 P2_WAIT(3, &s.full[st], (it >> 1) & 1);          // features landed
                 tc::fence_after_sync();
-                issue_gemm<SPLIT>(tb + COL_D1A, s.a1[st][0][0], s.a1[st][0][P], A1_LBO, A1_SBO, s.b1[0][0], s.b1[0][P], B1_LBO, B1_SBO, FEAT, idesc1);
+                issue_gemm<SPLIT>(leader, tb + COL_D1A, s.a1[st][0][0], s.a1[st][0][P], A1_LBO, A1_SBO, s.b1[0][0], s.b1[0][P], B1_LBO, B1_SBO, FEAT, idesc1);
                 if (has_b)
-                    issue_gemm<SPLIT>(tb + COL_D1B, s.a1[st][T::SETS - 1][0], s.a1[st][T::SETS - 1][P], A1_LBO, A1_SBO, s.b1[T::HAS_B ? 1 : 0][0],
+                    issue_gemm<SPLIT>(leader, tb + COL_D1B, s.a1[st][T::SETS - 1][0], s.a1[st][T::SETS - 1][P], A1_LBO, A1_SBO, s.b1[T::HAS_B ? 1 : 0][0],
                                       s.b1[T::HAS_B ? 1 : 0][P], B1_LBO, B1_SBO, FEAT, idesc1);
-                tc::mma_commit(&s.empty[st]);                       // ring slot reusable once these MMAs have read it
-                tc::mma_commit(&s.d1_full[st]);
+                if (leader) {
+                    tc::mma_commit(&s.empty[st]);                   // ring slot reusable once these MMAs have read it
+                    tc::mma_commit(&s.d1_full[st]);
+                }
             };
             if (n_my > 0) layer1(0);
             if (n_my > 1) layer1(1);
@@ -599,13 +605,13 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
                 P2_WAIT(4, &s.a2a_full[gi], ph);
                 if (it >= 2) P2_WAIT(5, &s.d2_free[gi], ph ^ 1);
                 tc::fence_after_sync();
-                issue_layer2<SPLIT>(tb + COL_D2, tb + COL_D1A, s.b2a[0], s.b2a[P], idesc2a);
-                tc::mma_commit(&s.d2a_full[gi]);
+                issue_layer2<SPLIT>(leader, tb + COL_D2, tb + COL_D1A, s.b2a[0], s.b2a[P], idesc2a);
+                if (leader) tc::mma_commit(&s.d2a_full[gi]);
                 if (has_b) {
                     P2_WAIT(6, &s.a2b_full[gi], ph);
                     tc::fence_after_sync();
-                    issue_layer2<SPLIT>(tb + COL_D2 + T::N_A, tb + COL_D1B, s.b2b[0], s.b2b[P], idesc2b);
-                    tc::mma_commit(&s.d2b_full[gi]);
+                    issue_layer2<SPLIT>(leader, tb + COL_D2 + T::N_A, tb + COL_D1B, s.b2b[0], s.b2b[P], idesc2b);
+                    if (leader) tc::mma_commit(&s.d2b_full[gi]);
                 }
                 // layer 1 of the group's NEXT tile goes in as soon as layer 2 has consumed the hidden tile (our own commit),
                 // i.e. while the group is still writing this tile's outputs

@@ -103,24 +103,33 @@ __device__ __forceinline__ void store_features4(unsigned char (*a1)[A1_BYTES], i
     }
 }
 
-// One thread issues a whole GEMM: D (+)= A * B^T over K (multiple of 16), with the three split terms.
+// A whole GEMM: D (+)= A * B^T over K (multiple of 16), with the three split terms.  Called by every lane of the issuing warp
+// (warp-uniform arguments); only `leader` (tc::elect_one()) issues.  The descriptors differ in their address field alone, so each is the
+// constant part plus an add.  The one-argument-less form is for callers that are a single thread already.
+template <bool SPLIT>
+__device__ __forceinline__ void issue_gemm(bool leader, uint32_t tmem_d, const unsigned char* a_hi, const unsigned char* a_lo, int a_lbo, int a_sbo,
+                                           const unsigned char* b_hi, const unsigned char* b_lo, int b_lbo, int b_sbo, int K, uint32_t idesc)
+{
+    const uint64_t da0 = tc::make_desc(0, a_lbo, a_sbo), db0 = tc::make_desc(0, b_lbo, b_sbo);
+    const uint32_t ah = tc::smem_u32(a_hi) >> 4, al = tc::smem_u32(a_lo) >> 4, bh = tc::smem_u32(b_hi) >> 4, bl = tc::smem_u32(b_lo) >> 4;
+    const uint32_t ak = (uint32_t)(2 * a_lbo) >> 4, bk = (uint32_t)(2 * b_lbo) >> 4;
+    uint32_t acc = 0;
+    constexpr int TERMS = SPLIT ? 3 : 1;
+#pragma unroll
+    for (int t = 0; t < TERMS; ++t) {
+        const uint32_t a = (t == 1) ? al : ah, b = (t == 2) ? bl : bh;   // hi*hi, lo*hi, hi*lo
+#pragma unroll 4
+        for (int k = 0; k < (K >> 4); ++k) {
+            if (leader) tc::mma_bf16_ss(tmem_d, da0 + (a + k * ak), db0 + (b + k * bk), idesc, acc);
+            acc = 1;
+        }
+    }
+}
 template <bool SPLIT>
 __device__ __forceinline__ void issue_gemm(uint32_t tmem_d, const unsigned char* a_hi, const unsigned char* a_lo, int a_lbo, int a_sbo,
                                            const unsigned char* b_hi, const unsigned char* b_lo, int b_lbo, int b_sbo, int K, uint32_t idesc)
 {
-    bool acc = false;
-    constexpr int TERMS = SPLIT ? 3 : 1;
-#pragma unroll
-    for (int t = 0; t < TERMS; ++t) {
-        const unsigned char* a = (t == 1) ? a_lo : a_hi;   // hi*hi, lo*hi, hi*lo
-        const unsigned char* b = (t == 2) ? b_lo : b_hi;
-        for (int k = 0; k < K; k += 16) {
-            const uint64_t da = tc::make_desc(tc::smem_u32(a) + (k >> 3) * a_lbo, a_lbo, a_sbo);
-            const uint64_t db = tc::make_desc(tc::smem_u32(b) + (k >> 3) * b_lbo, b_lbo, b_sbo);
-            tc::mma_bf16_ss(tmem_d, da, db, idesc, acc);
-            acc = true;
-        }
-    }
+    issue_gemm<SPLIT>(true, tmem_d, a_hi, a_lo, a_lbo, a_sbo, b_hi, b_lo, b_lbo, b_sbo, K, idesc);
 }
 
 template <int KIND, bool SPLIT>

@@ -59,6 +59,16 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
         :: "r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"((uint32_t)accumulate) : "memory");
 }
 
+// One lane of the (converged) warp.  MMA-issuing code keeps its control flow warp-uniform and predicates only the tcgen05
+// instructions on this: inside a divergent `if (lane == 0)` region the compiler has to wrap every tcgen05.mma in an ELECT /
+// R2UR.BROADCAST waterfall loop to get descriptors into uniform registers (~24 dependent instructions, ~180 cycles per MMA measured).
+__device__ __forceinline__ bool elect_one()
+{
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when they complete
 __device__ __forceinline__ void mma_commit(uint64_t* mbar)
 {
