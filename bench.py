@@ -572,6 +572,23 @@ def main():
         except Exception as exc:    # noqa: BLE001
             extras["c4_training_step"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+        for name_x, k_x in (("c3", 5), ("c5", 3)):
+            try:
+                # the other BASELINE shapes, so that the driver's run times them too: configs[2] (batch 32,
+                # 128^2 rays) and configs[4] (one identity under 64 poses, 256^2 rays, 96+96 samples)
+                wlx = WORKLOADS[name_x]
+                rawx_host, decx, c2wx, kx_, optsx = make_inputs(torch, wlx, torch.device("cpu"), 3000)
+                optsx["nfe_precision"] = args.precision
+                rawx, decx, c2wx, kx_ = rawx_host.to(device), decx.to(device), c2wx.to(device), kx_.to(device)
+                with torch.no_grad():
+                    ms_x = quick(lambda: hot_path_step(torch, mods, rawx, decx, c2wx, kx_, wlx["res"], optsx), k_x, 2)
+                rays_x = wlx["batch"] * wlx["res"] ** 2
+                extras[name_x] = {"value": rays_x / (ms_x * 1e-3), "unit": "rays/s", "ms_per_step": ms_x, "workload": wlx["desc"],
+                                  "samples_per_s": rays_x * (wlx["s_c"] + wlx["s_f"]) / (ms_x * 1e-3)}
+                del rawx, rawx_host
+                torch.cuda.empty_cache()
+            except Exception as exc:    # noqa: BLE001
+                extras[name_x] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
         try:
             # the consumer of the rendered feature image.  The default super-resolution head
             # (SuperresolutionHybrid8XDC, superresolution.py:264-290: 32 x 64^2 features -> 3 x 512^2, fp16 blocks as train.py sets
