@@ -621,6 +621,36 @@ def main():
         except Exception as exc:    # noqa: BLE001
             extras["f3_conv_stack"] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
 
+        for tag_g, g16 in (("full_generator", 0), ("full_generator_fp16_backbone", 4)):
+            try:
+                # BASELINE configs[1] in full: mapping + StyleGAN2 tri-plane backbone + decoders + renderer + super-resolution, 512^2 output,
+                # 64^2 neural resolution, batch 8 — this package's TriPlaneGenerator with the reference's default sizes (train.py:150-151,
+                # 183-184,225-245,343-355: cbase 32768, cmax 512, map depth 2, fp32 backbone, fp16 super-resolution blocks).  The second
+                # variant runs the backbone's high resolutions in fp16 as well (--g_num_fp16_res 4).
+                import synth_inputs as synth
+                from nerffaceediting_b200 import triplane as nfe_triplane
+                rk = dict(synth.FFHQ_RENDERING_OPTIONS, superresolution_module='training.superresolution.SuperresolutionHybrid8XDC', sr_antialias=True,
+                          superresolution_noise_mode='none', c_gen_conditioning_zero=False, c_scale=1.0, decoder_lr_mul=1, nfe_deterministic=True,
+                          nfe_precision=args.precision)
+                nb = wl["batch"]
+                with torch.no_grad():
+                    G = nfe_triplane.TriPlaneGenerator(z_dim=512, c_dim=25, w_dim=512, img_resolution=512, img_channels=3, sr_num_fp16_res=4,
+                                                       mapping_kwargs=dict(num_layers=2), rendering_kwargs=rk, channel_base=32768, channel_max=512,
+                                                       num_fp16_res=g16, conv_clamp=256 if g16 else None, fused_modconv_default='inference_only',
+                                                       sr_kwargs=dict(channel_base=32768, channel_max=512, fused_modconv_default='inference_only'))
+                    G = synth.fill_module(G, 77).to(device).eval()
+                    zg = torch.randn(nb, 512, device=device)
+                    cam = torch.cat([c2w.reshape(nb, 16), k.reshape(nb, 9)], dim=1).float()
+                    ms_g = quick(lambda: G(zg, cam, noise_mode='const'), 5, 2)
+                extras[tag_g] = {"value": rays_per_rank / (ms_g * 1e-3), "unit": "rays/s", "images_per_s": nb / (ms_g * 1e-3), "ms_per_step": ms_g,
+                                 "workload": f"configs[1] full generator synthesis: batch {nb}, 512^2 output, 64^2 neural resolution, 48+48 samples, "
+                                             f"backbone {'fp16 from 32^2 up' if g16 else 'fp32 (bf16x3 tensor-core arithmetic)'}, super-resolution fp16, "
+                                             "random-init weights"}
+                del G
+                torch.cuda.empty_cache()
+            except Exception as exc:    # noqa: BLE001
+                extras[tag_g] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         ms_step = ms_total / steps
         total_rays = rays_per_rank * world

@@ -5,6 +5,7 @@
     MappingNetwork                                     networks_stylegan2.py:193-270
     SynthesisLayer, ToRGBLayer                         networks_stylegan2.py:276-357
     SynthesisBlock ('orig' and 'skip'), SynthesisNetwork   networks_stylegan2.py:365-526
+    Generator (the StyleGAN2 backbone)                 networks_stylegan2.py:529-557
     SuperresolutionHybrid8XDC / 8X / 4X / 2X           training/superresolution.py:29-125,264-290
 
 with the reference's constructor arguments, parameter / buffer names (state dicts load unchanged) and call signatures.  Every
@@ -307,7 +308,7 @@ class SynthesisNetwork(torch.nn.Module):
                 self.num_ws += block.num_torgb
             setattr(self, f'b{res}', block)
 
-    def forward(self, ws, **block_kwargs):
+    def forward(self, ws, update_emas=False, **block_kwargs):
         _no_grad(ws)
         assert ws.shape[1:] == (self.num_ws, self.w_dim)
         ws = ws.to(torch.float32)
@@ -320,6 +321,21 @@ class SynthesisNetwork(torch.nn.Module):
         for res, cur_ws in zip(self.block_resolutions, block_ws):
             x, img = getattr(self, f'b{res}')(x, img, cur_ws, **block_kwargs)
         return img
+
+
+class Generator(torch.nn.Module):
+    """networks_stylegan2.py:529-557: mapping + synthesis (the `StyleGAN2Backbone` of training/triplane.py:14,47)."""
+
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, mapping_kwargs={}, **synthesis_kwargs):
+        super().__init__()
+        self.z_dim, self.c_dim, self.w_dim, self.img_resolution, self.img_channels = z_dim, c_dim, w_dim, img_resolution, img_channels
+        self.synthesis = SynthesisNetwork(w_dim=w_dim, img_resolution=img_resolution, img_channels=img_channels, **synthesis_kwargs)
+        self.num_ws = self.synthesis.num_ws
+        self.mapping = MappingNetwork(z_dim=z_dim, c_dim=c_dim, w_dim=w_dim, num_ws=self.num_ws, **mapping_kwargs)
+
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False, **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return self.synthesis(ws, **synthesis_kwargs)
 
 
 class _SuperresolutionHybrid(torch.nn.Module):

@@ -114,3 +114,108 @@ def denormalize_plane(planes, mean, var):
             ops.provenance_attach(out, var, 0.0, mean, norm_requires_grad=planes.requires_grad)
         return out
     return ops.plane_denormalize(planes, mean, var)
+
+
+class TriPlaneGenerator(torch.nn.Module):
+    """The whole generator of training/triplane.py:18-165 (BASELINE configs[1]: mapping + StyleGAN2 tri-plane backbone + decoders +
+    renderer + super-resolution), composed of this package's modules only: same constructor, attribute / state-dict names
+    (`backbone.mapping.fc0.weight`, `backbone.synthesis.b64.conv1.weight`, `decoder.geo_net.0.weight`, `superresolution.block1...`) and
+    methods (`mapping`, `synthesis`, `sample`, `sample_mixed`, `forward`), so `G2.load_state_dict(G.state_dict())` moves a checkpoint over.
+    Inference (the convolution stack is forward-only); the plane statistics go through `normalize_plane`, which stages the planes and
+    registers their provenance, so the renderer takes the single-gather path."""
+
+    def __init__(self, z_dim, c_dim, w_dim, img_resolution, img_channels, sr_num_fp16_res=0, mapping_kwargs={}, rendering_kwargs={},
+                 sr_kwargs={}, disable_disentangle=False, disable_alignment=False, **synthesis_kwargs):
+        super().__init__()
+        from . import networks
+        from .ray_sampler import RaySampler
+        from .renderer import DisentangledImportanceRenderer
+        self.z_dim, self.c_dim, self.w_dim, self.img_resolution, self.img_channels = z_dim, c_dim, w_dim, img_resolution, img_channels
+        self.disable_disentangle, self.disable_alignment = disable_disentangle, disable_alignment
+        assert not self.disable_alignment or disable_disentangle
+        self.renderer = DisentangledImportanceRenderer()
+        self.ray_sampler = RaySampler()
+        self.backbone = networks.Generator(z_dim, c_dim, w_dim, img_resolution=256, img_channels=32 * 3, mapping_kwargs=mapping_kwargs, **synthesis_kwargs)
+        sr_cls = getattr(networks, rendering_kwargs['superresolution_module'].split('.')[-1])        # 'training.superresolution.SuperresolutionHybrid8XDC'
+        self.superresolution = sr_cls(channels=32, img_resolution=img_resolution, sr_num_fp16_res=sr_num_fp16_res,
+                                      sr_antialias=rendering_kwargs['sr_antialias'], **sr_kwargs)
+        dec_opts = {'decoder_lr_mul': rendering_kwargs.get('decoder_lr_mul', 1), 'decoder_output_dim': 32, 'decoder_seg_dim': 15}
+        self.decoder = DisentangledOSGDecoder(32, dec_opts) if not self.disable_alignment else SegmentationOSGDecoder(32, dec_opts)
+        self.neural_rendering_resolution = 64
+        self.rendering_kwargs = rendering_kwargs
+        self._last_planes = None
+
+    compute_mean_var = staticmethod(compute_mean_var)
+    normalize_plane = staticmethod(normalize_plane)
+    denormalize_plane = staticmethod(denormalize_plane)
+
+    def mapping(self, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False):
+        if self.rendering_kwargs['c_gen_conditioning_zero']:
+            c = torch.zeros_like(c)
+        return self.backbone.mapping(z, c * self.rendering_kwargs.get('c_scale', 0), truncation_psi=truncation_psi,
+                                     truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+
+    def _planes(self, ws, update_emas=False, **synthesis_kwargs):
+        return self.backbone.synthesis(ws, update_emas=update_emas, **synthesis_kwargs)
+
+    def synthesis(self, ws, c, neural_rendering_resolution=None, update_emas=False, cache_backbone=False, use_cached_backbone=False,
+                  planes_mean=None, planes_var=None, **synthesis_kwargs):
+        cam2world_matrix = c[:, :16].view(-1, 4, 4)
+        intrinsics = c[:, 16:25].view(-1, 3, 3)
+        if neural_rendering_resolution is None:
+            neural_rendering_resolution = self.neural_rendering_resolution
+        else:
+            self.neural_rendering_resolution = neural_rendering_resolution
+        ray_origins, ray_directions = self.ray_sampler(cam2world_matrix, intrinsics, neural_rendering_resolution)
+        N, M, _ = ray_origins.shape
+        if use_cached_backbone and self._last_planes is not None:
+            planes = self._last_planes
+        else:
+            planes = self._planes(ws, update_emas=update_emas, **synthesis_kwargs)
+        if not self.disable_disentangle:
+            norm_planes, mean, var = self.normalize_plane(planes)
+            if planes_mean is not None and planes_var is not None:              # appearance swap (triplane.py:98-103)
+                if type(planes_mean) == int and type(planes_var) == int:
+                    planes = self.denormalize_plane(norm_planes, mean[planes_mean][None, ...], var[planes_var][None, ...])
+                else:
+                    planes = self.denormalize_plane(norm_planes, planes_mean, planes_var)
+        else:
+            norm_planes = mean = var = None
+        if cache_backbone:
+            self._last_planes = planes
+        if not self.disable_disentangle:
+            norm_planes = norm_planes.view(len(norm_planes), 3, 32, norm_planes.shape[-2], norm_planes.shape[-1])
+        planes = planes.view(len(planes), 3, 32, planes.shape[-2], planes.shape[-1])
+        feature_samples, seg_samples, depth_samples, weights_samples = self.renderer(
+            norm_planes if not self.disable_disentangle else planes, planes, self.decoder, ray_origins, ray_directions, self.rendering_kwargs)
+        H = W = self.neural_rendering_resolution
+        feature_image = feature_samples.permute(0, 2, 1).reshape(N, feature_samples.shape[-1], H, W).contiguous()
+        seg_image = seg_samples.permute(0, 2, 1).reshape(N, seg_samples.shape[-1], H, W).contiguous()
+        depth_image = depth_samples.permute(0, 2, 1).reshape(N, 1, H, W)
+        rgb_image = feature_image[:, :3]
+        sr_image = self.superresolution(rgb_image, feature_image, ws, noise_mode=self.rendering_kwargs['superresolution_noise_mode'],
+                                        **{k: synthesis_kwargs[k] for k in synthesis_kwargs.keys() if k != 'noise_mode'})
+        return {'image': sr_image, 'image_seg': seg_image, 'image_raw': rgb_image, 'image_depth': depth_image, 'plane_mean': mean, 'plane_var': var}
+
+    def _run_model(self, ws, coordinates, directions, update_emas, synthesis_kwargs):
+        planes = self._planes(ws, update_emas=update_emas, **synthesis_kwargs)
+        norm_planes = None
+        if not self.disable_disentangle:
+            norm_planes, _, _ = self.normalize_plane(planes)
+            norm_planes = norm_planes.view(len(norm_planes), 3, 32, norm_planes.shape[-2], norm_planes.shape[-1])
+        planes = planes.view(len(planes), 3, 32, planes.shape[-2], planes.shape[-1])
+        return self.renderer.run_model(norm_planes if not self.disable_disentangle else planes, planes, self.decoder, coordinates, directions,
+                                       self.rendering_kwargs)
+
+    def sample(self, coordinates, directions, z, c, truncation_psi=1, truncation_cutoff=None, update_emas=False, **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return self._run_model(ws, coordinates, directions, update_emas, synthesis_kwargs)
+
+    def sample_mixed(self, coordinates, directions, ws, truncation_psi=1, truncation_cutoff=None, update_emas=False, **synthesis_kwargs):
+        return self._run_model(ws, coordinates, directions, update_emas, synthesis_kwargs)
+
+    def forward(self, z, c, truncation_psi=1, truncation_cutoff=None, neural_rendering_resolution=None, update_emas=False, cache_backbone=False,
+                use_cached_backbone=False, planes_mean=None, planes_var=None, **synthesis_kwargs):
+        ws = self.mapping(z, c, truncation_psi=truncation_psi, truncation_cutoff=truncation_cutoff, update_emas=update_emas)
+        return self.synthesis(ws, c, update_emas=update_emas, neural_rendering_resolution=neural_rendering_resolution, cache_backbone=cache_backbone,
+                              use_cached_backbone=use_cached_backbone, planes_mean=planes_mean, planes_var=planes_var, **synthesis_kwargs)

@@ -113,3 +113,33 @@ def sr_inputs(which):
     x = T(c['seed'], (c['n'], 32, c['feed_res'], c['feed_res']))
     ws = T(c['seed'] + 1, (c['n'], 14, 512))
     return x[:, :3].contiguous(), x, ws
+
+
+# ---- the whole generator (training/triplane.py:18-165; BASELINE configs[1]) with a narrow backbone so that the CPU reference is quick
+GENERATORS = {
+    'g128': dict(seed=800, n=2, img_resolution=128, sr='SuperresolutionHybrid2X'),
+    'g512': dict(seed=900, n=1, img_resolution=512, sr='SuperresolutionHybrid8XDC'),
+}
+
+
+def generator_rendering_kwargs(c):
+    rk = dict(synth.FFHQ_RENDERING_OPTIONS)
+    rk.update(superresolution_module='training.superresolution.' + c['sr'], sr_antialias=True, superresolution_noise_mode='none',
+              c_gen_conditioning_zero=False, c_scale=1.0, decoder_lr_mul=1, nfe_deterministic=True)
+    return rk
+
+
+def make_generator(cls, which):
+    c = GENERATORS[which]
+    g = cls(z_dim=64, c_dim=25, w_dim=512, img_resolution=c['img_resolution'], img_channels=3, sr_num_fp16_res=0,
+            mapping_kwargs=dict(num_layers=2), rendering_kwargs=generator_rendering_kwargs(c), channel_base=4096, channel_max=32, num_fp16_res=0)
+    return synth.fill_module(g, c['seed'] + 5).eval()
+
+
+def generator_inputs(which):
+    c = GENERATORS[which]
+    z = T(c['seed'], (c['n'], 64))
+    c2w, k = synth.camera_sweep(c['n'])
+    cam = torch.cat([c2w.reshape(c['n'], 16), k.reshape(c['n'], 9)], dim=1).float()
+    pts = 0.4 * T(c['seed'] + 1, (c['n'], 600, 3))
+    return z, cam, pts

@@ -379,3 +379,18 @@ def test_modconv_plan_and_argument_checks_run_on_the_host(built):
     for bad in (dict(in_ch=24), dict(ksize=5), dict(up=2, ksize=1), dict(up=3), dict(dtype=2), dict(out_ch=384), dict(batch=0)):
         assert need(**bad) == -1, bad
         assert lib.nfe_last_error()
+
+
+def test_generator_state_dict_names_are_the_reference_s():
+    """The whole-generator mirror (BASELINE configs[1]) accepts the reference's checkpoints: names and shapes recorded from the
+    reference's TriPlaneGenerator (tests/golden/make_golden_generator.py)."""
+    import numpy as np
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(here, "golden"))
+    import conv_cases as cases
+    from nerffaceediting_b200 import triplane
+    g = np.load(os.path.join(here, "golden", "generator.npz"))
+    for which in cases.GENERATORS:
+        G = cases.make_generator(triplane.TriPlaneGenerator, which)
+        keys = sorted(f"{k}:{'x'.join(map(str, v.shape))}" for k, v in G.state_dict().items())
+        assert keys == sorted(g[f"keys.{which}"].tolist())
