@@ -51,7 +51,7 @@ constexpr int HALO_W = 10;
 #endif
 constexpr int TILE_W = 8, MAX_TAPS = 9, THREADS = 256, MAX_SA = 4, MAX_SB = 6;
 
-constexpr int SMEM_BUDGET = 227 * 1024 - 256 - 1024;
+constexpr int SMEM_BUDGET = 227 * 1024 - 256 - 1024 - 128;
 
 constexpr int MAX_ACC = 4;
 
@@ -147,14 +147,15 @@ template <> struct Elem<2> { using type = float; };
 // PARTS = 1: fp16 activations / fp16 operands.  PARTS = 2: fp32 activations / bf16 hi + lo operands, three terms per product.
 // MA = window height in units of 16 rows (the window is 16 MA x 8 pixels).
 // SA = halo stages (up = 2 has little MMA work per K chunk, its loads must run several chunks ahead: four).
-template <int PARTS, int MA, int SA>
+// KG = channel groups of 8 a halo stage holds (8 = chunks of 64 channels; 4 = chunks of 32, the split-operand wide tile).
+template <int PARTS, int MA, int SA, int KG>
 __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 2 : 1) conv_gemm_kernel(const GemmArgs a)
 {
     using T = typename Elem<PARTS>::type;
     constexpr int HALO_H = 16 * MA + 2;
     constexpr int A_LBO = HALO_H * HALO_W * 16;          // bytes between channel groups of 8 (K core matrices)
     constexpr int A_SBO = HALO_W * 16;                    // bytes between window rows (row groups of 8 pixels)
-    constexpr int A_PART = 8 * A_LBO, A_STAGE = PARTS * A_PART;
+    constexpr int A_PART = KG * A_LBO, A_STAGE = PARTS * A_PART;
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* const sA = smem;
     unsigned char* const sB = smem + SA * A_STAGE;
@@ -163,6 +164,9 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
     uint64_t* const acc_full = b_empty + MAX_SB;
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);       // this N tile's bias, zero where there is none
+    uint32_t* const s_tap16 = reinterpret_cast<uint32_t*>(s_bias + 256);      // per tap: descriptor offset of its shifted window (16-byte units)
+    uint32_t* const s_tmask = s_tap16 + MAX_TAPS;                              // per tap: accumulators it feeds
+    uint32_t* const s_row16 = s_tmask + MAX_TAPS;                              // per accumulator: descriptor offset of its first window row
 
 #ifdef NFE_MC_PROFILE
     long long prof_[12] = {};
@@ -183,6 +187,15 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
         tc::mbar_fence_init();
     }
     if (warp == 4) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (threadIdx.x < MAX_TAPS) {
+#ifdef NFE_MC_EXP_ALIGNED
+        s_tap16[threadIdx.x] = (uint32_t)((1 + tp.dy[threadIdx.x]) * HALO_W);
+#else
+        s_tap16[threadIdx.x] = (uint32_t)((1 + tp.dy[threadIdx.x]) * HALO_W + 1 + tp.dx[threadIdx.x]);
+#endif
+        s_tmask[threadIdx.x] = tp.acc_mask[threadIdx.x];
+    }
+    if (threadIdx.x < MAX_ACC) s_row16[threadIdx.x] = (uint32_t)(tp.row_off[threadIdx.x] * (HALO_W * 16)) >> 4;
     for (int i = threadIdx.x; i < a.n_tile; i += THREADS) {
         const int o = blockIdx.y * a.n_tile + i;
         s_bias[i] = (a.bias && o < a.out_ch) ? __ldg(a.bias + o) : 0.0f;
@@ -209,38 +222,53 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
             if (r > 0) MC_WAIT(3, &a_empty[s], (r - 1) & 1);
             unsigned char* const dst0 = sA + s * A_STAGE;
             // thread = (channel group k8, pixel slot): 16 halo pixels x 8 channel groups per pass, the pixel index advanced
-            // incrementally (no divisions); 8 consecutive threads read one pixel's 64 channels, i.e. one contiguous run
+            // incrementally (no divisions); 8 consecutive threads read one pixel's 64 channels, i.e. one contiguous run.  The fp32
+            // path (loads through registers: split into bf16 hi + lo) requests FOUR pixels' loads before it converts and stores any
+            // of them: one pixel at a time it ran at one DRAM latency per pixel (27 k cycles per chunk measured).
             const int k8 = threadIdx.x & 7;
             int hy = (threadIdx.x >> 3) / HALO_W, hx = (threadIdx.x >> 3) % HALO_W;
-            if (k8 < kcores)
-                for (int hp = threadIdx.x >> 3; hp < HALO_H * HALO_W; hp += 16) {
-                    const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
-                    const bool ring = hy == 0 || hy == HALO_H - 1 || hx == 0 || hx == HALO_W - 1;
-                    const bool ok = (unsigned)gy < (unsigned)a.in_h && (unsigned)gx < (unsigned)a.in_w;
-                    unsigned char* dst = dst0 + k8 * A_LBO + hp * 16;
-                    hx += 6; hy += 1;                            // + 16 pixels = one window row and 6 columns
-                    if (hx >= HALO_W) { hx -= HALO_W; hy += 1; }
-                    if (!a.halo && ring) continue;               // 1x1: the ring is never read
-                    const T* src = xin + (((long long)(n * a.in_h + (ok ? gy : 0)) * a.in_w + (ok ? gx : 0)) * a.in_ch + c * a.kc + k8 * 8);
-                    if constexpr (PARTS == 1) {
-                        cp_async16(dst, src, ok ? 16 : 0);
-                    } else {
-                        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        if (ok) {
-                            const float4 v0 = __ldg(reinterpret_cast<const float4*>(src)), v1 = __ldg(reinterpret_cast<const float4*>(src) + 1);
-                            v[0] = v0.x; v[1] = v0.y; v[2] = v0.z; v[3] = v0.w; v[4] = v1.x; v[5] = v1.y; v[6] = v1.z; v[7] = v1.w;
-                        }
-                        uint32_t hi[4], lo[4];
+            if (k8 < kcores) {
+                constexpr int BATCH = PARTS == 1 ? 1 : 4;
+                for (int hp0 = threadIdx.x >> 3; hp0 < HALO_H * HALO_W; hp0 += 16 * BATCH) {
+                    float4 v0[BATCH], v1[BATCH];
+                    unsigned char* dsts[BATCH];
+                    bool live[BATCH];
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            __nv_bfloat16 h0, l0, h1, l1;
-                            tc::split_bf16(v[2 * q], h0, l0); tc::split_bf16(v[2 * q + 1], h1, l1);
-                            hi[q] = tc::pack_bf16(h0, h1); lo[q] = tc::pack_bf16(l0, l1);
+                    for (int b = 0; b < BATCH; ++b) {
+                        const int hp = hp0 + 16 * b;
+                        const int gy = y0 - 1 + hy, gx = x0 - 1 + hx;
+                        const bool ring = hy == 0 || hy == HALO_H - 1 || hx == 0 || hx == HALO_W - 1;
+                        const bool ok = (unsigned)gy < (unsigned)a.in_h && (unsigned)gx < (unsigned)a.in_w;
+                        dsts[b] = dst0 + k8 * A_LBO + hp * 16;
+                        live[b] = hp < HALO_H * HALO_W && !(!a.halo && ring);       // 1x1: the ring is never read
+                        hx += 6; hy += 1;                            // + 16 pixels = one window row and 6 columns
+                        if (hx >= HALO_W) { hx -= HALO_W; hy += 1; }
+                        const T* src = xin + (((long long)(n * a.in_h + (ok ? gy : 0)) * a.in_w + (ok ? gx : 0)) * a.in_ch + c * a.kc + k8 * 8);
+                        if constexpr (PARTS == 1) {
+                            if (live[b]) cp_async16(dsts[b], src, ok ? 16 : 0);
+                        } else {
+                            v0[b] = v1[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (live[b] && ok) { v0[b] = __ldg(reinterpret_cast<const float4*>(src)); v1[b] = __ldg(reinterpret_cast<const float4*>(src) + 1); }
                         }
-                        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                        *reinterpret_cast<uint4*>(dst + A_PART) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                    }
+                    if constexpr (PARTS == 2) {
+#pragma unroll
+                        for (int b = 0; b < BATCH; ++b) {
+                            if (!live[b]) continue;
+                            const float v[8] = {v0[b].x, v0[b].y, v0[b].z, v0[b].w, v1[b].x, v1[b].y, v1[b].z, v1[b].w};
+                            uint32_t hi[4], lo[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                __nv_bfloat16 h0, l0, h1, l1;
+                                tc::split_bf16(v[2 * q], h0, l0); tc::split_bf16(v[2 * q + 1], h1, l1);
+                                hi[q] = tc::pack_bf16(h0, h1); lo[q] = tc::pack_bf16(l0, l1);
+                            }
+                            *reinterpret_cast<uint4*>(dsts[b]) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+                            *reinterpret_cast<uint4*>(dsts[b] + A_PART) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                        }
                     }
                 }
+            }
             if constexpr (PARTS == 1) {
                 cp_async_commit();
             } else {
@@ -262,48 +290,48 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
         // the tensor core's 64-128 cycles per instruction.  Every lane runs the loop; one elected lane issues.
         {
             const bool leader = elect_one();
+#ifdef NFE_MC_EXP_FMT0
+            const uint32_t idesc = make_idesc(128, a.n_tile, 0);
+#else
             const uint32_t idesc = make_idesc(128, a.n_tile, PARTS == 1 ? 0 : 1);
+#endif
             const uint32_t b_lbo = a.n_tile * 16, b_part16 = (a.n_tile * a.kc * 2) >> 4, a_part16 = A_PART >> 4;
             const uint64_t da0 = tc::make_desc(0, A_LBO, A_SBO), db0 = tc::make_desc(0, b_lbo, 128);
             const uint32_t a_k16 = (2 * A_LBO) >> 4, b_k16 = (2 * b_lbo) >> 4;
             const int ksteps = a.kc >> 4;
-            uint32_t row16[MAX_ACC], tap16[MAX_TAPS], tmask[MAX_TAPS];
-#pragma unroll
-            for (int m = 0; m < MAX_ACC; ++m) row16[m] = (uint32_t)(tp.row_off[m] * A_SBO) >> 4;
-#pragma unroll
-            for (int t = 0; t < MAX_TAPS; ++t) {
-#ifdef NFE_MC_EXP_ALIGNED
-                tap16[t] = (uint32_t)((1 + tp.dy[t]) * HALO_W);
-#else
-                tap16[t] = (uint32_t)((1 + tp.dy[t]) * HALO_W + 1 + tp.dx[t]);
-#endif
-                tmask[t] = tp.acc_mask[t];
-            }
+            // The loop nest stays ROLLED (tap and accumulator tables in shared memory, filled at start-up): unrolled over taps x
+            // accumulators x terms it was 16 k instructions in the split-operand build and ran out of the instruction cache — ~500
+            // cycles per MMA measured there against the 143 of the (already 7 k instruction) fp16 build.
             int sb = 0;
             uint32_t sb_par = 0, started = 0;        // started: accumulators that hold a partial sum already
+#ifdef NFE_MC_EXP_TERMS1
+            constexpr int TERMS = 1;
+#else
+            constexpr int TERMS = PARTS == 2 ? 3 : 1;
+#endif
+#pragma unroll 1
             for (int c = 0; c < a.chunks; ++c) {
                 const int s = c % SA;
                 MC_WAIT(0, &a_full[s], (c / SA) & 1);
                 tc::fence_after_sync();
                 const uint32_t a_base16 = tc::smem_u32(sA + s * A_STAGE) >> 4;
-#pragma unroll
-                for (int t = 0; t < MAX_TAPS; ++t) {
-                    if (t >= taps) break;
+#pragma unroll 1
+                for (int t = 0; t < taps; ++t) {
                     MC_WAIT(1, &b_full[sb], sb_par);
                     tc::fence_after_sync();
-                    const uint32_t b16 = tc::smem_u32(sB + sb * a.b_stage) >> 4, a16 = a_base16 + tap16[t];
-#pragma unroll
-                    for (int m = 0; m < MAX_ACC; ++m) {
-                        if (m >= n_acc || !((tmask[t] >> m) & 1u)) continue;
-                        constexpr int TERMS = PARTS == 2 ? 3 : 1;
+                    const uint32_t b16 = tc::smem_u32(sB + sb * a.b_stage) >> 4, a16 = a_base16 + s_tap16[t], mask = s_tmask[t];
+#pragma unroll 1
+                    for (int m = 0; m < n_acc; ++m) {
+                        if (!((mask >> m) & 1u)) continue;
                         uint32_t accf = (started >> m) & 1u;
+                        const uint32_t d_tmem = tmem + m * a.n_tile, am = a16 + s_row16[m];
 #pragma unroll
                         for (int term = 0; term < TERMS; ++term) {          // hi*hi, lo*hi, hi*lo
-                            const uint32_t aa = a16 + row16[m] + (term == 1 ? a_part16 : 0), bb = b16 + (term == 2 ? b_part16 : 0);
-#pragma unroll 4
+                            uint64_t da = da0 + (am + (term == 1 ? a_part16 : 0)), db = db0 + (b16 + (term == 2 ? b_part16 : 0));
+#pragma unroll 1
                             for (int j = 0; j < ksteps; ++j) {
-                                if (leader) tc::mma_bf16_ss(tmem + m * a.n_tile, da0 + (aa + j * a_k16), db0 + (bb + j * b_k16), idesc, accf);
-                                accf = 1u;
+                                if (leader) tc::mma_bf16_ss(d_tmem, da, db, idesc, accf);
+                                accf = 1u; da += a_k16; db += b_k16;
                             }
                         }
                         started |= 1u << m;
@@ -363,9 +391,11 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
         // its pixel's whole row of n_tile channels in the (now idle) operand rings — at a pitch of 16 bytes more than the row, which
         // spreads the lanes over the banks — and hands the finished row (up to 512 contiguous bytes) to the TMA unit as one bulk
         // store: no block-wide synchronisation, no copy-out loop.
-        const int row_bytes = a.n_tile * (int)sizeof(T), pitch = row_bytes + 16;
+        // Rows are staged in segments of at most 512 bytes (256 halves / 128 floats), one bulk store each.
+        constexpr int SEG_Q = 512 / (16 * (int)sizeof(T)), PITCH = 512 + 16;         // 16-column groups per segment; row pitch in the stage
         const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
-        unsigned char* const my_row = smem + (grp * 128 + row) * pitch;
+        unsigned char* const my_row = smem + (grp * 128 + row) * PITCH;
+        bool pending = false;                                                        // a bulk store of my_row may still be reading it
 #pragma unroll 1
         for (int m = grp; m < n_acc; m += 2) {
             const int gy = y0 + tp.row_off[m] + py, gx = x0 + px;
@@ -373,7 +403,6 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
             const int oy = gy * tp.o_mul + tp.oy_off[m], ox = gx * tp.o_mul + tp.ox_off[m];
             T* dst = yout + n * a.ys_n + oy * a.ys_h + ox * a.ys_w + nt * a.n_tile;
             const float nz = (a.noise && valid) ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.noise_w + ox) : 0.0f;
-            if (staged && m >= 2) bulk_wait_read();                      // the row buffer is free once the previous bulk store has read it
             float nxt[16];
             tc::tmem_ld16(t_lane + m * a.n_tile, nxt);                   // software pipeline: the next group loads while this one is processed
 #pragma unroll 1
@@ -384,7 +413,8 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
                 for (int i = 0; i < 16; ++i) v[i] = nxt[i];
                 if (q + 1 < nq) tc::tmem_ld16(t_lane + m * a.n_tile + (q + 1) * 16, nxt);
                 if (!valid) continue;
-                const int o0 = nt * a.n_tile + q * 16;
+                const int o0 = nt * a.n_tile + q * 16, qs = q % SEG_Q;
+                if (staged && qs == 0 && pending) { bulk_wait_read(); pending = false; }      // the row buffer is free once the previous store has read it
 #pragma unroll
                 for (int i4 = 0; i4 < 4; ++i4) {
                     const float4 b4 = *reinterpret_cast<const float4*>(s_bias + q * 16 + 4 * i4);      // same address in every lane: broadcast
@@ -397,7 +427,7 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
                     }
                 }
                 if (staged || (vec_ok && o0 + 16 <= a.out_ch)) {
-                    unsigned char* out = staged ? my_row + q * 16 * (int)sizeof(T) : reinterpret_cast<unsigned char*>(dst + q * 16);
+                    unsigned char* out = staged ? my_row + qs * 16 * (int)sizeof(T) : reinterpret_cast<unsigned char*>(dst + q * 16);
                     if constexpr (PARTS == 1) {
                         uint32_t w[8];
 #pragma unroll
@@ -409,6 +439,12 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
 #pragma unroll
                         for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
                     }
+                    if (staged && (qs == SEG_Q - 1 || q == nq - 1)) {
+                        tc::fence_async_smem();             // this thread's row, written through the generic proxy, is read by the async proxy
+                        bulk_store(dst + (q - qs) * 16, my_row, (uint32_t)((qs + 1) * 16 * (int)sizeof(T)));
+                        bulk_commit();
+                        pending = true;
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 16; ++i)
@@ -416,11 +452,6 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
                             if constexpr (PARTS == 1) dst[q * 16 + i] = __float2half_rn(v[i]); else dst[q * 16 + i] = v[i];
                         }
                 }
-            }
-            if (staged && valid) {
-                tc::fence_async_smem();                     // this thread's row, written through the generic proxy, is read by the async proxy
-                bulk_store(dst, my_row, (uint32_t)row_bytes);
-                bulk_commit();
             }
         }
         if (staged) bulk_wait_all();                        // shared memory must outlive the reads, the kernel the writes
@@ -693,7 +724,7 @@ __global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArg
 
 // ---------------------------------------------------------------------------------------------- host side
 struct Plan {
-    int parts, ma, sa, n_tile, n_tiles, kc, chunks, b_stage, sb, halo;
+    int parts, ma, sa, kg, n_tile, n_tiles, kc, chunks, b_stage, sb, halo;
     long long packed_item_bytes, coef_bytes, packed_bytes, trans_bytes, total_bytes;
     int th, tw;                            // transposed-convolution intermediate (up = 2)
     int grid_h, grid_w;                    // pixel grid the windows tile
@@ -711,14 +742,19 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     pl.parts = q.dtype == NFE_DTYPE_F16 ? 1 : 2;
     // plain: two 128-pixel accumulators x 256 columns (fp16) or one x 128 (fp32 split: the operand rings are twice as wide);
     // up = 2: a 128-pixel window, four phase accumulators x 128 columns.  512 columns of tensor memory either way.
-    const int n_max = (pl.parts == 1 && q.up == 1) ? 256 : 128;
+    // N tile: 256 output channels wherever 512 columns of tensor memory allow it (an M = 128 MMA costs the same ~134+ cycles at N = 128
+    // as at N = 256, see below); up = 2 needs four phase accumulators and stays at 128
+    const int n_max = q.up == 1 ? 256 : 128;
     const int o16 = (q.out_ch + 15) / 16 * 16;
     if (o16 <= n_max) { pl.n_tile = o16; pl.n_tiles = 1; }
     else {
-        NFE_REQUIRE(q.out_ch % n_max == 0, "nfe_modulated_conv2d: out_channels above %d must be a multiple of it, got %d", n_max, q.out_ch);
-        pl.n_tile = n_max; pl.n_tiles = q.out_ch / n_max;
+        NFE_REQUIRE(q.out_ch % 128 == 0, "nfe_modulated_conv2d: out_channels above %d must be a multiple of 128, got %d", n_max, q.out_ch);
+        pl.n_tile = q.out_ch % n_max == 0 ? n_max : 128; pl.n_tiles = q.out_ch / pl.n_tile;
     }
-    pl.kc = q.in_ch % 64 == 0 ? 64 : (q.in_ch % 32 == 0 ? 32 : 16);
+    // K chunk: 64 input channels; 32 for the split (fp32) operands of a wide tile, whose hi + lo weight blocks would not leave room
+    // for a ring otherwise
+    const bool wide_split = pl.parts == 2 && pl.n_tile > 128;
+    pl.kc = (q.in_ch % 64 == 0 && !wide_split) ? 64 : (q.in_ch % 32 == 0 ? 32 : 16);
     pl.chunks = q.in_ch / pl.kc;
     pl.b_stage = pl.parts * pl.n_tile * pl.kc * 2;
     // An MMA with M = 128 costs the tensor core at least ~128 cycles (its A-operand fetch) whatever N is, so tiles of N <= 128 run
@@ -727,10 +763,14 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     const bool twin = pl.parts == 1 && q.up == 1 && pl.n_tile <= 128;
     // a layer whose 256-pixel windows would not even give every SM one CTA (the backbone's 4^2 .. 32^2 blocks) takes 128-pixel windows
     const long long ctas_256 = (long long)((q.in_h + 31) / 32) * ((q.in_w + TILE_W - 1) / TILE_W) * pl.n_tiles * q.batch;
-    pl.ma = (pl.parts == 1 && q.up == 1 && !twin && ctas_256 >= sm_count()) ? 2 : 1;
+    // two 128-pixel windows per weight stage wherever the halo stages fit beside the weight ring: fp16, and the split-operand wide
+    // tile in chunks of 32 channels (its hi + lo weight stage then feeds 12 MMAs instead of 6 and the stream stays under the TMA rate)
+    const bool split_pair = wide_split && pl.kc == 32;
+    pl.ma = (q.up == 1 && !twin && (pl.parts == 1 || split_pair) && ctas_256 >= sm_count()) ? 2 : 1;
     pl.sa = (pl.parts == 1 && q.up == 2) ? 4 : 2;
-    const int halo_h = 16 * pl.ma + 2, a_bytes = pl.sa * pl.parts * 8 * halo_h * HALO_W * 16;
-    const int budget = twin ? (SMEM_BUDGET + 1280) / 2 - 1280 - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM
+    pl.kg = (pl.parts == 2 && pl.ma == 2) ? 4 : 8;
+    const int halo_h = 16 * pl.ma + 2, a_bytes = pl.sa * pl.parts * pl.kg * halo_h * HALO_W * 16;
+    const int budget = twin ? (SMEM_BUDGET + 1408) / 2 - 1408 - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM
     pl.sb = std::min(MAX_SB, (budget - a_bytes) / pl.b_stage);
     NFE_REQUIRE(pl.sb >= 2, "nfe_modulated_conv2d: internal: weight ring does not fit");
     pl.halo = q.ksize == 3;
@@ -781,20 +821,20 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     return 0;
 }
 
-template <int PARTS, int MA, int SA>
+template <int PARTS, int MA, int SA, int KG>
 static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
-    const size_t smem = (size_t)SA * PARTS * 8 * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 256 + 256 * 4;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table
+    const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 256 + 256 * 4 + 128;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table | tap tables
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) { set_error("conv_gemm_kernel: shared memory opt-in: %s", cudaGetErrorString(e)); return 2; }
         attr_done = true;
     }
     const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)g.batch);
-    conv_gemm_kernel<PARTS, MA, SA><<<grid, THREADS, smem, stream>>>(g);
+    conv_gemm_kernel<PARTS, MA, SA, KG><<<grid, THREADS, smem, stream>>>(g);
     return check_launch("conv_gemm_kernel");
 }
 
@@ -846,8 +886,8 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     g.batch = q->batch; g.in_h = q->in_h; g.in_w = q->in_w; g.in_ch = q->in_ch; g.out_ch = q->out_ch;
     g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.halo = pl.halo;
     {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
-        const long long rings = (long long)pl.sa * pl.parts * 8 * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
-        g.stage_ok = 2ll * 128 * (pl.n_tile * (pl.parts == 1 ? 2 : 4) + 16) <= rings ? 1 : 0;
+        const long long rings = (long long)pl.sa * pl.parts * pl.kg * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
+        g.stage_ok = 2ll * 128 * (512 + 16) <= rings ? 1 : 0;            // rows are staged in segments of at most 512 bytes
     }
     g.tp = pl.tp;
     g.tiles_x = (pl.grid_w + mc::TILE_W - 1) / mc::TILE_W; g.tiles_y = (pl.grid_h + 16 * pl.ma - 1) / (16 * pl.ma);
@@ -859,8 +899,9 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
         g.y = trans; g.ys_w = q->out_ch; g.ys_h = (long long)pl.tw * q->out_ch; g.ys_n = (long long)pl.th * g.ys_h;
         g.noise = nullptr; g.noise_n = 0; g.noise_w = 0; g.bias = nullptr; g.act = 1; g.alpha = 0.0f; g.gain = 1.0f; g.clamp = -1.0f;
     }
-    int rc = pl.parts == 2 ? mc::launch_gemm<2, 1, 2>(g, pl, stream)
-             : (pl.ma == 2 ? mc::launch_gemm<1, 2, 2>(g, pl, stream) : (pl.sa == 4 ? mc::launch_gemm<1, 1, 4>(g, pl, stream) : mc::launch_gemm<1, 1, 2>(g, pl, stream)));
+    int rc = pl.parts == 2 ? (pl.ma == 2 ? mc::launch_gemm<2, 2, 2, 4>(g, pl, stream) : mc::launch_gemm<2, 1, 2, 8>(g, pl, stream))
+             : (pl.ma == 2 ? mc::launch_gemm<1, 2, 2, 8>(g, pl, stream)
+                           : (pl.sa == 4 ? mc::launch_gemm<1, 1, 4, 8>(g, pl, stream) : mc::launch_gemm<1, 1, 2, 8>(g, pl, stream)));
     if (rc) return rc;
     if (q->up == 2) {
         // conv2d_resample.py:97-101,124-131 with padding = k/2 as the layers pass it: the filter pass pads the (2H+1) image by

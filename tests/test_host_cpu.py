@@ -370,13 +370,14 @@ def test_modconv_plan_and_argument_checks_run_on_the_host(built):
     coef = up256((8 * 256 + 256 + 8) * 4)
     # fp16, plain 3x3: per item 9 taps x 256 x 256 halves of packed weights
     assert need() == coef + up256(8 * 9 * 256 * 256 * 2)
+    assert need(out_ch=384) > 0                                      # three tiles of 128
     # fp32: hi + lo parts
     assert need(dtype=0) == coef + up256(8 * 9 * 256 * 256 * 2 * 2)
     # up = 2: the same nine taps + the (2H+1)^2 intermediate in the activation type
     assert need(up=2, in_h=128, in_w=128) == coef + up256(8 * 9 * 256 * 256 * 2) + up256(8 * 257 * 257 * 256 * 2)
     # 1x1 to 3 channels (ToRGB): the output tile is padded to 16 rows
     assert need(ksize=1, out_ch=3, demodulate=0) == up256((8 * 3 + 3 + 8) * 4) + up256(8 * 16 * 256 * 2)
-    for bad in (dict(in_ch=24), dict(ksize=5), dict(up=2, ksize=1), dict(up=3), dict(dtype=2), dict(out_ch=384), dict(batch=0)):
+    for bad in (dict(in_ch=24), dict(ksize=5), dict(up=2, ksize=1), dict(up=3), dict(dtype=2), dict(out_ch=400), dict(batch=0)):
         assert need(**bad) == -1, bad
         assert lib.nfe_last_error()
 
