@@ -522,51 +522,64 @@ __global__ void __launch_bounds__(128) modconv_coef_kernel(const PackArgs a)
     }
 }
 
-// one thread per 16-byte operand slot (8 consecutive input channels of one output channel and tap): w * s * d, rounded to the
-// operand type, in the order [N tile][K chunk][tap][part][channel group][row group][row][8 channels]
+// one thread per (output channel, group of 8 input channels): w * s * d for every tap, rounded to the operand type, stored as one
+// 16-byte operand slot per tap in the order [N tile][K chunk][tap][part][channel group][row group][row][8 channels].  The thread's
+// 8 x k x k weights are one contiguous run (288 bytes for 3x3), read once from L2 and again from L1 for the other taps; a thread per
+// (slot, tap) re-fetched every 32-byte sector eight times and made the packing cost more than the small layers' convolutions.
 __global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
 {
     const int n = blockIdx.y, kk = a.ksize * a.ksize;
     const int kcores = a.kc >> 3, rows = a.n_tile;
-    long long slot = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const TapPlan& ph = a.tp;
-    const long long slots = (long long)a.n_tiles * a.chunks * ph.taps * kcores * rows;
+    // three adjacent lanes share a slot and take every third tap (more threads in flight: the kernel is latency-bound; their reads
+    // fall into the same sectors)
+    const int tg_n = ph.taps % 3 == 0 ? 3 : 1;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long slot = tid / tg_n;
+    const int tg = (int)(tid % tg_n);
+    const long long slots = (long long)a.n_tiles * a.chunks * kcores * rows;
     if (slot >= slots) return;
     const int row = (int)(slot % rows); long long r = slot / rows;
     const int k8 = (int)(r % kcores); r /= kcores;
-    const int t = (int)(r % ph.taps); r /= ph.taps;
     const int c = (int)(r % a.chunks); const int nt = (int)(r / a.chunks);
     const int o = nt * a.n_tile + row, i0 = c * a.kc + k8 * 8;
-    float v[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = 0.0f;
-    if (o < a.out_ch) {
-        const float wm = a.prenorm ? a.wmul[o] : 1.0f, sm = a.prenorm ? a.smax[n] : 1.0f, d = a.dcoef[(long long)n * a.out_ch + o];
-        const float* w = a.weight + ((long long)o * a.in_ch + i0) * kk + ph.ky[t] * a.ksize + ph.kx[t];
+    const bool real = o < a.out_ch;
+    float sd[8];                                   // style (pre-normalised) of the 8 input channels; the demodulation factor follows
+    float wm = 1.0f, d = 0.0f;
+    const float* w = a.weight + ((long long)(real ? o : 0) * a.in_ch + i0) * kk;
+    if (real) {
+        const float sm = a.prenorm ? a.smax[n] : 1.0f;
+        wm = a.prenorm ? a.wmul[o] : 1.0f;
+        d = a.dcoef[(long long)n * a.out_ch + o];
         const float* s = a.styles + (long long)n * a.in_ch + i0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float sv = a.prenorm ? __ldg(s + j) / sm : __ldg(s + j);
-            v[j] = ((__ldg(w + (long long)j * kk) * wm) * sv) * d;
-        }
+        for (int j = 0; j < 8; ++j) sd[j] = a.prenorm ? __ldg(s + j) / sm : __ldg(s + j);
     }
-    unsigned char* dst = a.packed + n * a.packed_item_stride +
-                         ((((long long)nt * a.chunks + c) * ph.taps + t) * a.b_stage) + ((long long)k8 * (rows / 8) + row / 8) * 128 + (row & 7) * 16;
-    if (a.parts == 1) {
-        uint32_t w4[4];
+    unsigned char* dst0 = a.packed + n * a.packed_item_stride + (((long long)nt * a.chunks + c) * ph.taps) * a.b_stage +
+                          ((long long)k8 * (rows / 8) + row / 8) * 128 + (row & 7) * 16;
+#pragma unroll 1
+    for (int t = tg; t < ph.taps; t += tg_n) {
+        float v[8];
+        const int wt = ph.ky[t] * a.ksize + ph.kx[t];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); w4[j] = *reinterpret_cast<const uint32_t*>(&h); }
-        *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-    } else {
-        uint32_t hi[4], lo[4];
+        for (int j = 0; j < 8; ++j) v[j] = real ? ((__ldg(w + j * kk + wt) * wm) * sd[j]) * d : 0.0f;
+        unsigned char* dst = dst0 + (long long)t * a.b_stage;
+        if (a.parts == 1) {
+            uint32_t w4[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            tc::split_bf16(v[2 * j], h0, l0); tc::split_bf16(v[2 * j + 1], h1, l1);
-            hi[j] = tc::pack_bf16(h0, h1); lo[j] = tc::pack_bf16(l0, l1);
+            for (int j = 0; j < 4; ++j) { const __half2 h = __floats2half2_rn(v[2 * j], v[2 * j + 1]); w4[j] = *reinterpret_cast<const uint32_t*>(&h); }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        } else {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                __nv_bfloat16 h0, l0, h1, l1;
+                tc::split_bf16(v[2 * j], h0, l0); tc::split_bf16(v[2 * j + 1], h1, l1);
+                hi[j] = tc::pack_bf16(h0, h1); lo[j] = tc::pack_bf16(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(dst + a.b_stage / 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
-        *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(dst + a.b_stage / 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
     }
 }
 
@@ -877,7 +890,7 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     pa.tp = pl.tp;
     mc::modconv_coef_kernel<<<dim3(q->out_ch, q->batch), 128, 0, stream>>>(pa);
     NFE_LAUNCH_CHECK("modconv_coef_kernel");
-    const long long slots = (long long)pl.n_tiles * pl.chunks * pl.tp.taps * (pl.kc / 8) * pl.n_tile;
+    const long long slots = (long long)pl.n_tiles * pl.chunks * (pl.kc / 8) * pl.n_tile * (pl.tp.taps % 3 == 0 ? 3 : 1);
     mc::modconv_pack_kernel<<<dim3((unsigned)((slots + 255) / 256), q->batch), 256, 0, stream>>>(pa);
     NFE_LAUNCH_CHECK("modconv_pack_kernel");
 

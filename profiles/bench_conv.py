@@ -58,8 +58,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=8)
     ap.add_argument("--json", default=None)
+    ap.add_argument("--backbone-only", type=int, default=-1, help="two calls of the backbone with this num_fp16_res and nothing else (launch list under ncu)")
     ap.add_argument("--sr-only", action="store_true", help="two calls of the fp16 SR head and nothing else (for a launch list under ncu)")
     a = ap.parse_args()
+    if a.backbone_only >= 0:
+        with torch.no_grad():
+            bb = synth.fill_module(net.SynthesisNetwork(512, 256, 96, num_fp16_res=a.backbone_only, conv_clamp=256 if a.backbone_only else None), 5).cuda().eval()
+            ws = torch.randn(a.batch, bb.num_ws, 512, device="cuda")
+            for _ in range(2):
+                bb(ws, noise_mode='const')
+            torch.cuda.synchronize()
+        return
     if a.sr_only:
         with torch.no_grad():
             sr = synth.fill_module(net.SuperresolutionHybrid8XDC(32, 512, 4, True), 3).cuda().eval()
