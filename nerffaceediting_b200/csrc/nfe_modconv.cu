@@ -671,59 +671,69 @@ __global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArg
 {
     constexpr int V = 16 / (int)sizeof(T);                   // channels per 16 bytes
     __shared__ __align__(16) unsigned char tile[FT_IN * FT_IN * 128];
-    __shared__ float filt[16];
-    if ((int)threadIdx.x < a.fh * a.fw) {
-        const int ky = threadIdx.x / a.fw, kx = threadIdx.x % a.fw;
-        filt[threadIdx.x] = __ldg(a.f + (a.flip ? ky : a.fh - 1 - ky) * a.fw + (a.flip ? kx : a.fw - 1 - kx)) * a.fgain;
+    __shared__ float filt[16], f_row[4], f_col[4];
+    __shared__ float s_bias[64];
+    // the filter as a zero-padded 4 x 4 table (flipped unless flip_filter, gain folded in) and, when it is an outer product — the
+    // reference's [1,3,3,1] is —, its two factors: 4 + 4 taps per output instead of 16
+    if (threadIdx.x < 16) {
+        const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+        filt[threadIdx.x] = (ky < a.fh && kx < a.fw) ? __ldg(a.f + (a.flip ? ky : a.fh - 1 - ky) * a.fw + (a.flip ? kx : a.fw - 1 - kx)) * a.fgain : 0.0f;
     }
     const int bx = blockIdx.x % tiles_x, by = blockIdx.x / tiles_x, sl = blockIdx.y % slices, n = blockIdx.y / slices;
     const int ox0 = bx * FT, oy0 = by * FT, c_base = sl * 8 * V;
     const int groups = min(8, (a.c - c_base) / V);          // 16-byte channel groups of this slice
+    if (threadIdx.x < 8 * V) s_bias[threadIdx.x] = (a.bias && c_base + (int)threadIdx.x < a.c) ? __ldg(a.bias + c_base + threadIdx.x) : 0.0f;
     const T* tin = static_cast<const T*>(a.t);
     T* yout = static_cast<T*>(a.y);
-    const int in_w = FT + a.fw - 1, in_h = FT + a.fh - 1, g = threadIdx.x & 7;
+    const int g = threadIdx.x & 7;
     if (g < groups)
-        for (int p = threadIdx.x >> 3; p < in_h * in_w; p += 32) {
-            const int iy = oy0 + p / in_w - a.pad_y0, ix = ox0 + p % in_w - a.pad_x0;
+        for (int p = threadIdx.x >> 3; p < FT_IN * FT_IN; p += 32) {
+            const int iy = oy0 + p / FT_IN - a.pad_y0, ix = ox0 + p % FT_IN - a.pad_x0;
             uint4 v = make_uint4(0u, 0u, 0u, 0u);
             if (iy >= 0 && iy < a.th && ix >= 0 && ix < a.tw)
                 v = __ldg(reinterpret_cast<const uint4*>(tin + (((long long)n * a.th + iy) * a.tw + ix) * a.c + c_base) + g);
-            *reinterpret_cast<uint4*>(tile + ((p / in_w) * FT_IN + p % in_w) * 128 + g * 16) = v;
+            *reinterpret_cast<uint4*>(tile + p * 128 + g * 16) = v;
         }
     __syncthreads();
+    bool entry_ok = true;
+    if (threadIdx.x < 16) {
+        float total = 0.0f, r = 0.0f, c = 0.0f;
+        const int ky = threadIdx.x >> 2, kx = threadIdx.x & 3;
+        for (int i = 0; i < 16; ++i) total += filt[i];
+        for (int i = 0; i < 4; ++i) { r += filt[ky * 4 + i]; c += filt[i * 4 + kx]; }
+        entry_ok = total != 0.0f && fabsf(filt[threadIdx.x] - r * c / total) <= 1e-6f * fabsf(total);
+        if (kx == 0) f_row[ky] = r;                                   // F = f_row (x) f_col with f_col = column sums / total
+        if (ky == 0) f_col[kx] = total != 0.0f ? c / total : 0.0f;
+    }
+    const bool separable = __syncthreads_and(entry_ok);
     if (g >= groups) return;
-    for (int p = threadIdx.x >> 3; p < FT * FT; p += 32) {
-        const int py = p / FT, px = p % FT, oy = oy0 + py, ox = ox0 + px;
-        if (oy >= a.oh || ox >= a.ow) continue;
-        float acc[V];
+    const int px = (threadIdx.x >> 3) & 15, half = threadIdx.x >> 7;     // this thread: column px, output rows 8 half .. 8 half + 7
+    const int ox = ox0 + px;
+    if (ox >= a.ow) return;
+    auto load8 = [&](int row, int col, float (&v)[V]) {
+        const uint4 u = *reinterpret_cast<const uint4*>(tile + (row * FT_IN + col) * 128 + g * 16);
+        if constexpr (sizeof(T) == 2) {
+            const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-        for (int j = 0; j < V; ++j) acc[j] = 0.0f;
-        for (int ky = 0; ky < a.fh; ++ky)
-            for (int kx = 0; kx < a.fw; ++kx) {
-                const float w = filt[ky * a.fw + kx];
-                const uint4 u = *reinterpret_cast<const uint4*>(tile + ((py + ky) * FT_IN + px + kx) * 128 + g * 16);
-                if constexpr (sizeof(T) == 2) {
-                    const __half2* h = reinterpret_cast<const __half2*>(&u);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) { const float2 f2 = __half22float2(h[j]); acc[2 * j] = fmaf(f2.x, w, acc[2 * j]); acc[2 * j + 1] = fmaf(f2.y, w, acc[2 * j + 1]); }
-                } else {
-                    acc[0] = fmaf(__uint_as_float(u.x), w, acc[0]); acc[1] = fmaf(__uint_as_float(u.y), w, acc[1]);
-                    acc[2] = fmaf(__uint_as_float(u.z), w, acc[2]); acc[3] = fmaf(__uint_as_float(u.w), w, acc[3]);
-                }
-            }
+            for (int j = 0; j < 4; ++j) { const float2 f2 = __half22float2(h[j]); v[2 * j] = f2.x; v[2 * j + 1] = f2.y; }
+        } else {
+            v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
+        }
+    };
+    auto finish = [&](int py, float (&acc)[V]) {
+        const int oy = oy0 + py;
+        if (oy >= a.oh) return;
         const float nz = a.noise ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.ow + ox) : 0.0f;
-        const int c0 = c_base + g * V;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             float t = acc[j];
             if constexpr (sizeof(T) == 2) t = __half2float(__float2half_rn(t));      // the reference stores the filtered image in fp16
-            t += nz;
-            if (a.bias) t += __ldg(a.bias + c0 + j);
+            t = (t + nz) + s_bias[g * V + j];
             t = act_apply<T>(t, a.act, a.alpha) * a.gain;
             if (a.clamp >= 0.0f) t = fminf(fmaxf(t, -a.clamp), a.clamp);
             acc[j] = t;
         }
-        T* dst = yout + (((long long)n * a.oh + oy) * a.ow + ox) * a.c + c0;
+        T* dst = yout + (((long long)n * a.oh + oy) * a.ow + ox) * a.c + c_base + g * V;
         if constexpr (sizeof(T) == 2) {
             uint32_t w4[4];
 #pragma unroll
@@ -731,6 +741,51 @@ __global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArg
             *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         } else {
             *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        }
+    };
+    if (separable) {
+        const float fx[4] = {f_col[0], f_col[1], f_col[2], f_col[3]}, fy[4] = {f_row[0], f_row[1], f_row[2], f_row[3]};
+        float hs[4][V];                              // horizontal sums of the last four input rows (static indices: the loop is unrolled)
+#pragma unroll
+        for (int r = 0; r < 8 + 3; ++r) {
+            float h[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) h[j] = 0.0f;
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                float v[V];
+                load8(8 * half + r, px + kx, v);
+#pragma unroll
+                for (int j = 0; j < V; ++j) h[j] = fmaf(v[j], fx[kx], h[j]);
+            }
+#pragma unroll
+            for (int j = 0; j < V; ++j) hs[r & 3][j] = h[j];
+            if (r >= 3) {
+                float acc[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+#pragma unroll
+                for (int ky = 0; ky < 4; ++ky)
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] = fmaf(hs[(r - 3 + ky) & 3][j], fy[ky], acc[j]);
+                finish(8 * half + r - 3, acc);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int py = 8 * half; py < 8 * half + 8; ++py) {
+            float acc[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+            for (int ky = 0; ky < 4; ++ky)
+                for (int kx = 0; kx < 4; ++kx) {
+                    const float w = filt[ky * 4 + kx];
+                    float v[V];
+                    load8(py + ky, px + kx, v);
+#pragma unroll
+                    for (int j = 0; j < V; ++j) acc[j] = fmaf(v[j], w, acc[j]);
+                }
+            finish(py, acc);
         }
     }
 }
