@@ -149,7 +149,7 @@ template <> struct Elem<2> { using type = float; };
 // SA = halo stages (up = 2 has little MMA work per K chunk, its loads must run several chunks ahead: four).
 // KG = channel groups of 8 a halo stage holds (8 = chunks of 64 channels; 4 = chunks of 32, the split-operand wide tile).
 template <int PARTS, int MA, int SA, int KG>
-__global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 2 : 1) conv_gemm_kernel(const GemmArgs a)
+__global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 || KG == 4)) ? 2 : 1) conv_gemm_kernel(const GemmArgs a)
 {
     using T = typename Elem<PARTS>::type;
     constexpr int HALO_H = 16 * MA + 2;
@@ -392,7 +392,8 @@ __global__ void __launch_bounds__(THREADS, (PARTS == 1 && MA == 1 && SA == 2) ? 
         // spreads the lanes over the banks — and hands the finished row (up to 512 contiguous bytes) to the TMA unit as one bulk
         // store: no block-wide synchronisation, no copy-out loop.
         // Rows are staged in segments of at most 512 bytes (256 halves / 128 floats), one bulk store each.
-        constexpr int SEG_Q = 512 / (16 * (int)sizeof(T)), PITCH = 512 + 16;         // 16-column groups per segment; row pitch in the stage
+        constexpr int SEG_Q = 512 / (16 * (int)sizeof(T));                           // 16-column groups per segment
+        const int PITCH = min(a.n_tile * (int)sizeof(T), 512) + 16;                  // row pitch in the stage
         const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
         unsigned char* const my_row = smem + (grp * 128 + row) * PITCH;
         bool pending = false;                                                        // a bulk store of my_row may still be reading it
@@ -819,24 +820,33 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
         NFE_REQUIRE(q.out_ch % 128 == 0, "nfe_modulated_conv2d: out_channels above %d must be a multiple of 128, got %d", n_max, q.out_ch);
         pl.n_tile = q.out_ch % n_max == 0 ? n_max : 128; pl.n_tiles = q.out_ch / pl.n_tile;
     }
-    // K chunk: 64 input channels; 32 for the split (fp32) operands of a wide tile, whose hi + lo weight blocks would not leave room
-    // for a ring otherwise
-    const bool wide_split = pl.parts == 2 && pl.n_tile > 128;
-    pl.kc = (q.in_ch % 64 == 0 && !wide_split) ? 64 : (q.in_ch % 32 == 0 ? 32 : 16);
+    // CTA shape.  An MMA with M = 128 costs the tensor core at least ~125 cycles (its A-operand fetch) whatever N is, so
+    //  * a tile of N <= 128 runs at half rate at best and the epilogue weighs twice as much: `twin` makes the CTA small enough (one
+    //    128-pixel window, <= 113 KB of shared memory, <= 256 columns of tensor memory) for TWO CTAs per SM, whose main loops and
+    //    epilogues overlap;
+    //  * otherwise two 128-pixel windows share every weight stage (`pair`: two accumulators), which halves the weight stream per MMA;
+    //  * a 1x1 convolution (ToRGB) has so little work per window that the per-CTA fixed cost dominates: two windows in fp16, never twin
+    //    (in fp32 the register-path halo loader is its bottleneck and 64-channel chunks with one window measured fastest);
+    //  * a layer whose 256-pixel windows would not even give every SM one CTA (the backbone's 4^2 .. 32^2 blocks) takes one window.
+    // The split (fp32) operands need chunks of 32 channels for a wide tile, for twin CTAs and for window pairs: their hi + lo halo and
+    // weight stages would not fit otherwise.
+    const bool one_by_one = q.ksize == 1;
+    const bool can32 = q.in_ch % 32 == 0;
+    const long long ctas_256 = (long long)((q.in_h + 31) / 32) * ((q.in_w + TILE_W - 1) / TILE_W) * pl.n_tiles * q.batch;
+    const bool twin = q.up == 1 && pl.n_tile <= 128 && !one_by_one && (pl.parts == 1 || can32);
+    const bool pair = q.up == 1 && !twin && ((pl.parts == 1 && (ctas_256 >= sm_count() || one_by_one)) ||
+                                             (pl.parts == 2 && can32 && !one_by_one && ctas_256 >= sm_count()));
+    const bool split32 = pl.parts == 2 && can32 && (pl.n_tile > 128 || twin || pair);
+    pl.kc = split32 ? 32 : (q.in_ch % 64 == 0 ? 64 : (can32 ? 32 : 16));
+    if (pl.parts == 2 && pl.n_tile > 128 && !split32) {        // a wide split tile without 32-channel chunks: fall back to 128 columns
+        NFE_REQUIRE(q.out_ch % 128 == 0 || o16 <= 128, "nfe_modulated_conv2d: fp32 needs in_channels to be a multiple of 32 for this out_channels");
+        pl.n_tile = o16 <= 128 ? o16 : 128; pl.n_tiles = o16 <= 128 ? 1 : q.out_ch / 128;
+    }
     pl.chunks = q.in_ch / pl.kc;
     pl.b_stage = pl.parts * pl.n_tile * pl.kc * 2;
-    // An MMA with M = 128 costs the tensor core at least ~128 cycles (its A-operand fetch) whatever N is, so tiles of N <= 128 run
-    // at half rate at best and the epilogue weighs twice as much: for those the CTA is made small enough (one 128-pixel window,
-    // <= 113 KB of shared memory, <= 256 columns of tensor memory) for TWO CTAs per SM, whose main loops and epilogues overlap.
-    const bool twin = pl.parts == 1 && q.up == 1 && pl.n_tile <= 128;
-    // a layer whose 256-pixel windows would not even give every SM one CTA (the backbone's 4^2 .. 32^2 blocks) takes 128-pixel windows
-    const long long ctas_256 = (long long)((q.in_h + 31) / 32) * ((q.in_w + TILE_W - 1) / TILE_W) * pl.n_tiles * q.batch;
-    // two 128-pixel windows per weight stage wherever the halo stages fit beside the weight ring: fp16, and the split-operand wide
-    // tile in chunks of 32 channels (its hi + lo weight stage then feeds 12 MMAs instead of 6 and the stream stays under the TMA rate)
-    const bool split_pair = wide_split && pl.kc == 32;
-    pl.ma = (q.up == 1 && !twin && (pl.parts == 1 || split_pair) && ctas_256 >= sm_count()) ? 2 : 1;
+    pl.ma = pair ? 2 : 1;
     pl.sa = (pl.parts == 1 && q.up == 2) ? 4 : 2;
-    pl.kg = (pl.parts == 2 && pl.ma == 2) ? 4 : 8;
+    pl.kg = split32 ? 4 : 8;
     const int halo_h = 16 * pl.ma + 2, a_bytes = pl.sa * pl.parts * pl.kg * halo_h * HALO_W * 16;
     const int budget = twin ? (SMEM_BUDGET + 1408) / 2 - 1408 - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM
     pl.sb = std::min(MAX_SB, (budget - a_bytes) / pl.b_stage);
@@ -955,7 +965,8 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.halo = pl.halo;
     {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
         const long long rings = (long long)pl.sa * pl.parts * pl.kg * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
-        g.stage_ok = 2ll * 128 * (512 + 16) <= rings ? 1 : 0;            // rows are staged in segments of at most 512 bytes
+        // rows are staged in segments of at most 512 bytes, one 128-row buffer per epilogue warp group that has an accumulator
+        g.stage_ok = (long long)std::min(2, pl.tp.n_acc) * 128 * (std::min(pl.n_tile * (pl.parts == 1 ? 2 : 4), 512) + 16) <= rings ? 1 : 0;
     }
     g.tp = pl.tp;
     g.tiles_x = (pl.grid_w + mc::TILE_W - 1) / mc::TILE_W; g.tiles_y = (pl.grid_h + 16 * pl.ma - 1) / (16 * pl.ma);
@@ -967,7 +978,8 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
         g.y = trans; g.ys_w = q->out_ch; g.ys_h = (long long)pl.tw * q->out_ch; g.ys_n = (long long)pl.th * g.ys_h;
         g.noise = nullptr; g.noise_n = 0; g.noise_w = 0; g.bias = nullptr; g.act = 1; g.alpha = 0.0f; g.gain = 1.0f; g.clamp = -1.0f;
     }
-    int rc = pl.parts == 2 ? (pl.ma == 2 ? mc::launch_gemm<2, 2, 2, 4>(g, pl, stream) : mc::launch_gemm<2, 1, 2, 8>(g, pl, stream))
+    int rc = pl.parts == 2 ? (pl.kg == 4 ? (pl.ma == 2 ? mc::launch_gemm<2, 2, 2, 4>(g, pl, stream) : mc::launch_gemm<2, 1, 2, 4>(g, pl, stream))
+                                         : mc::launch_gemm<2, 1, 2, 8>(g, pl, stream))
              : (pl.ma == 2 ? mc::launch_gemm<1, 2, 2, 8>(g, pl, stream)
                            : (pl.sa == 4 ? mc::launch_gemm<1, 1, 4, 8>(g, pl, stream) : mc::launch_gemm<1, 1, 2, 8>(g, pl, stream)));
     if (rc) return rc;
