@@ -642,7 +642,23 @@ def main():
                     zg = torch.randn(nb, 512, device=device)
                     cam = torch.cat([c2w.reshape(nb, 16), k.reshape(nb, 9)], dim=1).float()
                     ms_g = quick(lambda: G(zg, cam, noise_mode='const'), 5, 2)
+                    # the same through host buffers: latents and cameras up from pinned memory, the images (and the raw / semantic /
+                    # depth maps) back into pinned memory, every step
+                    z_host, cam_host = zg.cpu().pin_memory(), cam.cpu().pin_memory()
+                    outs_host = {}
+
+                    def g_e2e():
+                        zd, cd = z_host.to(device, non_blocking=True), cam_host.to(device, non_blocking=True)
+                        o_ = G(zd, cd, noise_mode='const')
+                        for kk_ in ('image', 'image_seg', 'image_raw', 'image_depth'):
+                            if kk_ not in outs_host:
+                                outs_host[kk_] = torch.empty(o_[kk_].shape, dtype=o_[kk_].dtype).pin_memory()
+                            outs_host[kk_].copy_(o_[kk_], non_blocking=True)
+                    ms_ge = quick(g_e2e, 5, 2)
+                    d2h_g = sum(v.numel() * v.element_size() for v in outs_host.values())
                 extras[tag_g] = {"value": rays_per_rank / (ms_g * 1e-3), "unit": "rays/s", "images_per_s": nb / (ms_g * 1e-3), "ms_per_step": ms_g,
+                                 "e2e": {"value": rays_per_rank / (ms_ge * 1e-3), "unit": "rays/s", "images_per_s": nb / (ms_ge * 1e-3), "ms_per_step": ms_ge,
+                                         "h2d_bytes_per_step": int(z_host.numel() * 4 + cam_host.numel() * 4), "d2h_bytes_per_step": int(d2h_g)},
                                  "workload": f"configs[1] full generator synthesis: batch {nb}, 512^2 output, 64^2 neural resolution, 48+48 samples, "
                                              f"backbone {'fp16 from 32^2 up' if g16 else 'fp32 (bf16x3 tensor-core arithmetic)'}, super-resolution fp16, "
                                              "random-init weights"}

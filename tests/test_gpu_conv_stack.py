@@ -141,3 +141,51 @@ def test_superresolution_8xdc_full_size(fp16):
     check(out[:, :, 253:259, :], g["sr8xdc.rgb_rows"], tol, "sr8xdc rows")
     mom = g["sr8xdc.moments"]
     assert abs(out.double().mean().item() - mom[0]) < tol * mom[2] and abs(out.double().std().item() - mom[1]) < tol * mom[2]
+
+
+def _torch_modconv(x, w, s, noise, up, demodulate, flip_weight, f):
+    """fp64 restatement of networks_stylegan2.py:34-91 + conv2d_resample.py:117-139 with torch's own convolutions (test oracle for the
+    shapes no fixture covers; the fixtures above pin the restatement's cases to the reference itself)."""
+    x, w, s = x.double(), w.double(), s.double()
+    n, i, h, wd = x.shape
+    o, _, k, _ = w.shape
+    wm = w.unsqueeze(0) * s.reshape(n, 1, i, 1, 1)
+    if demodulate:
+        wm = wm * (wm.square().sum(dim=[2, 3, 4], keepdim=True) + 1e-8).rsqrt()
+    outs = []
+    for b in range(n):
+        wb = wm[b] if flip_weight else wm[b].flip([2, 3])
+        if up == 1:
+            outs.append(torch.nn.functional.conv2d(x[b:b + 1], wb, padding=k // 2))
+        else:
+            t = torch.nn.functional.conv_transpose2d(x[b:b + 1], wm[b].transpose(0, 1) if not flip_weight else wm[b].flip([2, 3]).transpose(0, 1), stride=2)
+            ff = (f.double() * 4).flip([0, 1])[None, None].repeat(o, 1, 1, 1)
+            outs.append(torch.nn.functional.conv2d(torch.nn.functional.pad(t, [1, 1, 1, 1]), ff, groups=o))
+    y = torch.cat(outs)
+    return y + noise.double() if noise is not None else y
+
+
+@pytest.mark.parametrize("shape", [
+    # n, in, out, h, w, k, up        (kc = 16 / 32 / 64 chunks, ragged windows, several N tiles, twin / pair / single-window CTAs)
+    (3, 48, 24, 5, 7, 3, 1), (1, 96, 40, 33, 9, 3, 1), (2, 16, 8, 4, 4, 1, 1), (2, 64, 384, 8, 24, 3, 1), (1, 32, 128, 40, 40, 3, 1),
+    (5, 48, 16, 7, 5, 3, 2), (1, 160, 96, 16, 8, 3, 2), (2, 256, 256, 32, 32, 3, 1), (9, 128, 128, 16, 16, 3, 1), (1, 32, 3, 50, 50, 1, 1),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_modulated_conv2d_shapes_vs_torch(shape, dtype):
+    from nerffaceediting_b200 import networks as net
+    from nerffaceediting_b200 import stylegan_ops as sg
+    n, i, o, h, w, k, up = shape
+    g = torch.Generator(device="cpu").manual_seed(sum(shape))
+    x = torch.randn(n, i, h, w, generator=g).cuda()
+    wt = torch.randn(o, i, k, k, generator=g).cuda()
+    s = (1.0 + 0.3 * torch.randn(n, i, generator=g)).cuda()
+    noise = (0.3 * torch.randn(n, 1, h * up, w * up, generator=g)).cuda()
+    f = sg.setup_filter([1, 3, 3, 1]).cuda()
+    demod, flip = (k == 3), (up == 1)
+    xin = x.to(dtype)
+    ref = _torch_modconv(xin.float(), wt, s, noise, up, demod, flip, f)
+    with torch.no_grad():
+        y = net.modulated_conv2d(xin, wt, s, noise=noise, up=up, padding=k // 2, resample_filter=f if up == 2 else None, demodulate=demod, flip_weight=flip)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    e = rel_err(y.float().cpu().numpy(), ref.float().cpu().numpy())
+    assert e < tol, (shape, dtype, e)
