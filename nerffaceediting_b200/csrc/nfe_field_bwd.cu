@@ -243,6 +243,45 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
             ds[p] = dm[p] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
     };
+    // ---- tap pre-pass: ONE thread per sample turns (ray, depth) into 12 clamped texel offsets + 12 weights (kept in shared memory
+    //      for the scatter at the end of the tile).  Tile i + 1's pre-pass is COMPUTED in the shadow of tile i's first GEMM by the
+    //      upper 128 threads (which only wait there) and held in their registers until tile i's scatter has read the tables: its
+    //      dependent depth / ray loads used to sit at the head of every tile (shared memory has no room for a second table)
+    auto tap_compute = [&](int64_t tbase, TapSet& ts, int& item) {
+        const int64_t idx = tbase + (threadIdx.x & (TILE_M - 1));
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
+        item = 0;
+        if (idx < a.total) {
+            float x, y, z;
+            if (a.coords) {
+                const float* c = a.coords + idx * 3;
+                x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
+            } else {
+                const int64_t ray = idx / a.s_per_ray;
+                const float t = __ldg(a.depths + idx);
+                const float* o = a.origins + ray * 3;
+                const float* d = a.dirs + ray * 3;
+                x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
+            }
+            ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
+            item = (int)(idx / a.m);
+            const int item_off = a.plane_batch == 1 ? 0 : (int)(item * set_stride4);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
+        }
+    };
+    auto tap_store = [&](const TapSet& ts, int item) {
+        const int r = threadIdx.x & (TILE_M - 1);
+        s.tap_item[r] = item;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            *reinterpret_cast<int4*>(&s.tap_off[r][4 * q]) = make_int4(ts.off4[4 * q], ts.off4[4 * q + 1], ts.off4[4 * q + 2], ts.off4[4 * q + 3]);
+            *reinterpret_cast<float4*>(&s.tap_w[r][4 * q]) = make_float4(ts.w[4 * q], ts.w[4 * q + 1], ts.w[4 * q + 2], ts.w[4 * q + 3]);
+        }
+    };
+    TapSet next_ts;
+    int next_item = 0;
 #ifdef NFE_BWD_PROFILE
     long long prof_[16] = {};
     long long prof_t_ = clock64();
@@ -258,41 +297,10 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
             straddle = it_first != it_last;
             if (!straddle && it_first != cur_item) { flush_stats(); cur_item = it_first; }
         }
-        // ---- tap pre-pass: ONE thread per sample turns (ray, depth) into 12 clamped texel offsets + 12 weights in shared
-        //      memory (kept for the scatter at the end of the tile); the 8 lanes of a sample used to recompute them, with
-        //      the dependent depth / ray loads on every lane's critical path
-        if (threadIdx.x < TILE_M) {
-            const int r = threadIdx.x;
-            const int64_t idx = base + r;
-            TapSet ts;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) { ts.off4[i] = 0; ts.w[i] = 0.0f; }
-            int item = 0;
-            if (idx < a.total) {
-                float x, y, z;
-                if (a.coords) {
-                    const float* c = a.coords + idx * 3;
-                    x = __ldg(c); y = __ldg(c + 1); z = __ldg(c + 2);
-                } else {
-                    const int64_t ray = idx / a.s_per_ray;
-                    const float t = __ldg(a.depths + idx);
-                    const float* o = a.origins + ray * 3;
-                    const float* d = a.dirs + ray * 3;
-                    x = ray_point(__ldg(o), t, __ldg(d)); y = ray_point(__ldg(o + 1), t, __ldg(d + 1)); z = ray_point(__ldg(o + 2), t, __ldg(d + 2));
-                }
-                ts = make_tapset(taps3(__fmul_rn(a.scale, x), __fmul_rn(a.scale, y), __fmul_rn(a.scale, z), a.H, a.W), a.H, a.W);
-                item = (int)(idx / a.m);
-                const int item_off = a.plane_batch == 1 ? 0 : (int)(item * set_stride4);
-#pragma unroll
-                for (int i = 0; i < 12; ++i) ts.off4[i] += item_off;
-            }
-            s.tap_item[r] = item;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                *reinterpret_cast<int4*>(&s.tap_off[r][4 * q]) = make_int4(ts.off4[4 * q], ts.off4[4 * q + 1], ts.off4[4 * q + 2], ts.off4[4 * q + 3]);
-                *reinterpret_cast<float4*>(&s.tap_w[r][4 * q]) = make_float4(ts.w[4 * q], ts.w[4 * q + 1], ts.w[4 * q + 2], ts.w[4 * q + 3]);
-            }
+        if (tile == (int64_t)blockIdx.x) {                   // the first tile has nobody to hide behind
+            if (threadIdx.x >= TILE_M) tap_compute(base, next_ts, next_item);
         }
+        if (threadIdx.x >= TILE_M) tap_store(next_ts, next_item);
         __syncthreads();
         // ---- gather (8 lanes per sample, 32 samples per step; AFFINE: two steps' texel loads in flight together)
         auto read_taps = [&](int r, TapSet& ts) {
@@ -386,6 +394,7 @@ __global__ void __launch_bounds__(THREADS, 1) field_bwd_kernel(Args a, nfe_mlp g
                                  B1_LBO, B1_SBO, FEAT, id1);
             if (leader) tc::mma_commit(&s.bar);
         }
+        if (threadIdx.x >= TILE_M && tile + gridDim.x < n_tiles) tap_compute((tile + gridDim.x) * TILE_M, next_ts, next_item);
         // record gradients (and the saved colours) of this thread's row: requested now, consumed after the softplus loop
         const bool live = base + row < a.total;
         float4 pg[9], py[8];
