@@ -485,13 +485,15 @@ struct PackArgs {
     TapPlan tp;
 };
 
-// one block per (o, n): demodulation coefficient rsqrt(sum_{i,k} (w * s)^2 + 1e-8) (networks_stylegan2.py:59-66)
+// one block per output channel: demodulation coefficients rsqrt(sum_{i,k} (w * s)^2 + 1e-8) of every batch item
+// (networks_stylegan2.py:59-66).  sum_{i,k} (w s)^2 = sum_i s_i^2 q_i with q_i = sum_k w_ik^2: the weight row is read ONCE, folded over the
+// taps into shared memory, and contracted with each item's squared styles (a block per (o, item) re-read it for every item).
 __global__ void __launch_bounds__(128) modconv_coef_kernel(const PackArgs a)
 {
+    extern __shared__ float q_sm[];                 // [in_ch]
     __shared__ float red[4];
-    const int o = blockIdx.x, n = blockIdx.y, kk = a.ksize * a.ksize, per_o = a.in_ch * kk;
+    const int o = blockIdx.x, kk = a.ksize * a.ksize, per_o = a.in_ch * kk;
     const float* w = a.weight + (long long)o * per_o;
-    const float* s = a.styles + (long long)n * a.in_ch;
     auto block_reduce = [&](float v, bool is_max) {
         v = is_max ? warp_max(v) : warp_sum(v);
         __syncthreads();
@@ -499,27 +501,39 @@ __global__ void __launch_bounds__(128) modconv_coef_kernel(const PackArgs a)
         __syncthreads();
         return is_max ? fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3])) : (red[0] + red[1]) + (red[2] + red[3]);
     };
-    float wm = 1.0f, sm = 1.0f;
-    if (a.prenorm) {
-        float mw = 0.0f, ms = 0.0f;
+    float wm = 1.0f;
+    if (a.prenorm) {                                // networks_stylegan2.py:55-57
+        float mw = 0.0f;
         for (int i = threadIdx.x; i < per_o; i += 128) mw = fmaxf(mw, fabsf(__ldg(w + i)));
-        for (int i = threadIdx.x; i < a.in_ch; i += 128) ms = fmaxf(ms, fabsf(__ldg(s + i)));
         mw = block_reduce(mw, true);
-        ms = block_reduce(ms, true);
         wm = (float)(1.0 / sqrt((double)per_o)) / mw;
-        sm = ms;
     }
-    float acc = 0.0f;
-    if (a.demodulate)
-        for (int i = threadIdx.x; i < per_o; i += 128) {
-            const float v = (__ldg(w + i) * wm) * (a.prenorm ? __ldg(s + i / kk) / sm : __ldg(s + i / kk));
-            acc = fmaf(v, v, acc);
+    for (int i = threadIdx.x; i < a.in_ch; i += 128) {
+        float q = 0.0f;
+        for (int t = 0; t < kk; ++t) { const float v = __ldg(w + i * kk + t) * wm; q = fmaf(v, v, q); }
+        q_sm[i] = q;
+    }
+    if (threadIdx.x == 0) a.wmul[o] = wm;
+    __syncthreads();
+    for (int n = 0; n < a.batch; ++n) {
+        const float* s = a.styles + (long long)n * a.in_ch;
+        float sm = 1.0f;
+        if (a.prenorm) {
+            float ms = 0.0f;
+            for (int i = threadIdx.x; i < a.in_ch; i += 128) ms = fmaxf(ms, fabsf(__ldg(s + i)));
+            sm = block_reduce(ms, true);
         }
-    acc = block_reduce(acc, false);
-    if (threadIdx.x == 0) {
-        a.dcoef[(long long)n * a.out_ch + o] = a.demodulate ? 1.0f / sqrtf(acc + 1e-8f) : 1.0f;
-        if (n == 0) a.wmul[o] = wm;
-        if (o == 0) a.smax[n] = sm;
+        float acc = 0.0f;
+        if (a.demodulate)
+            for (int i = threadIdx.x; i < a.in_ch; i += 128) {
+                const float sv = a.prenorm ? __ldg(s + i) / sm : __ldg(s + i);
+                acc = fmaf(sv * sv, q_sm[i], acc);
+            }
+        acc = block_reduce(acc, false);
+        if (threadIdx.x == 0) {
+            a.dcoef[(long long)n * a.out_ch + o] = a.demodulate ? 1.0f / sqrtf(acc + 1e-8f) : 1.0f;
+            if (o == 0) a.smax[n] = sm;
+        }
     }
 }
 
@@ -953,7 +967,8 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     pa.prenorm = (q->dtype == NFE_DTYPE_F16 && q->demodulate) ? 1 : 0;                     // networks_stylegan2.py:55-57
     pa.parts = pl.parts; pa.n_tile = pl.n_tile; pa.n_tiles = pl.n_tiles; pa.chunks = pl.chunks; pa.kc = pl.kc; pa.b_stage = pl.b_stage;
     pa.tp = pl.tp;
-    mc::modconv_coef_kernel<<<dim3(q->out_ch, q->batch), 128, 0, stream>>>(pa);
+    NFE_REQUIRE(q->in_ch <= 8192, "nfe_modulated_conv2d: in_channels above 8192");
+    mc::modconv_coef_kernel<<<q->out_ch, 128, (size_t)q->in_ch * sizeof(float), stream>>>(pa);
     NFE_LAUNCH_CHECK("modconv_coef_kernel");
     const long long slots = (long long)pl.n_tiles * pl.chunks * (pl.kc / 8) * pl.n_tile * (pl.tp.taps % 3 == 0 ? 3 : 1);
     mc::modconv_pack_kernel<<<dim3((unsigned)((slots + 255) / 256), q->batch), 256, 0, stream>>>(pa);
