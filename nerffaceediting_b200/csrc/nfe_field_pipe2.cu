@@ -95,6 +95,17 @@ static_assert(!NFE_P2_SETMAXNREG || (2 * REGS_EPI + REGS_MISC + (GATHER_WARPS / 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float LN2 = 0.6931471805599453f;
 
+// NFE_P2_BIAS_MMA = 1: the layer-1 bias (and the log2(e) of the base-2 softplus) enter through the tensor core — log2(e) folded into W1,
+// the bias as one more K step whose A operand is a constant block of ones — so that the hidden epilogue neither reads the bias from
+// shared memory (13.8 % of the kernel's shared-memory wavefronts, the LSU being its busiest unit at 79 %) nor multiplies.  Parity green,
+// measured NEUTRAL (0.3040 vs 0.3042 ms per launch, profiles/pipe2_variants_r02.txt `bm*`): the epilogue groups only wait longer for
+// layer 2 (d2a_full 8.7 -> 15.5 %) — the gather warps pace the kernel — so the build keeps the plain epilogue.
+#ifndef NFE_P2_BIAS_MMA
+#define NFE_P2_BIAS_MMA 0
+#endif
+constexpr int ONES_LBO = 16 * 128, ONES_BYTES = 2 * ONES_LBO;            // [128 rows x 16]: column 0 = 1
+constexpr int BB_LBO = 8 * 128, BB_BYTES = 2 * BB_LBO;                   // [64 rows x 16]: column 0 = bias * log2(e)
+
 template <int KIND, bool SPLIT>
 struct Smem {
     using T = TcTraits<KIND>;
@@ -113,6 +124,10 @@ struct Smem {
     int aff_item[TAP_BUFS];
     alignas(16) unsigned char recbuf[EPI_GROUPS][TILE_M][REC_STAGE_STRIDE];   // record staging (each warp owns its 32 rows)
     float bias1[NETS][HIDDEN];     // pre-multiplied by log2(e)
+#if NFE_P2_BIAS_MMA
+    alignas(128) unsigned char ones[ONES_BYTES];
+    alignas(128) unsigned char bias_op[NETS][PARTS][BB_BYTES];
+#endif
     float bias2a[T::N_A];
     float bias2b[T::N_B];
     alignas(8) uint64_t full[2], empty[2];                                // feature ring
@@ -132,13 +147,30 @@ __device__ void load_params(Smem<KIND, SPLIT>& s, const nfe_mlp& net_a, const nf
 {
     using T = TcTraits<KIND>;
     constexpr int PARTS = SPLIT ? 2 : 1;
-    load_weights<PARTS>(s.b1[0][0], B1_BYTES, net_a.w1, net_a.wgain1, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
+    constexpr float W1_FOLD = NFE_P2_BIAS_MMA ? LOG2E : 1.0f;
+    constexpr int NETS = T::HAS_B ? 2 : 1;
+    (void)NETS;
+    load_weights<PARTS>(s.b1[0][0], B1_BYTES, net_a.w1, net_a.wgain1 * W1_FOLD, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
+#if NFE_P2_BIAS_MMA
+    for (int i = threadIdx.x; i < ONES_BYTES / 2; i += blockDim.x) {                 // element (row, k) of the ones block
+        const int row = (i >> 3) & 127, k = (i & 7) + 8 * (i >> 10);
+        *reinterpret_cast<__nv_bfloat16*>(s.ones + core_offset(row, k, ONES_LBO, 128)) = __float2bfloat16_rn(k == 0 ? 1.0f : 0.0f);
+    }
+    for (int i = threadIdx.x; i < NETS * HIDDEN * 16; i += blockDim.x) {
+        const int net = i / (HIDDEN * 16), n = (i / 16) % HIDDEN, k = i % 16;
+        const nfe_mlp& m = net ? net_b : net_a;
+        __nv_bfloat16 hi, lo;
+        tc::split_bf16(k == 0 ? folded_bias(m.b1, m.bgain1, n) * LOG2E : 0.0f, hi, lo);
+        *reinterpret_cast<__nv_bfloat16*>(s.bias_op[net][0] + core_offset(n, k, BB_LBO, 128)) = hi;
+        if (PARTS == 2) *reinterpret_cast<__nv_bfloat16*>(s.bias_op[net][PARTS - 1] + core_offset(n, k, BB_LBO, 128)) = lo;
+    }
+#endif
     // softplus runs in base 2 (see hidden_in_place): ln 2 goes into the layer-2 weights, log2(e) into the layer-1 bias
     load_weights<PARTS>(s.b2a[0], sizeof(s.b2a[0]), net_a.w2, net_a.wgain2 * LN2, T::OUT_A, T::N_A, HIDDEN, B2_LBO, B2_SBO);
     for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s.bias1[0][i] = folded_bias(net_a.b1, net_a.bgain1, i) * LOG2E;
     for (int i = threadIdx.x; i < T::N_A; i += blockDim.x) s.bias2a[i] = i < T::OUT_A ? folded_bias(net_a.b2, net_a.bgain2, i) : 0.0f;
     if constexpr (T::HAS_B) {
-        load_weights<PARTS>(s.b1[1][0], B1_BYTES, net_b.w1, net_b.wgain1, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
+        load_weights<PARTS>(s.b1[1][0], B1_BYTES, net_b.w1, net_b.wgain1 * W1_FOLD, HIDDEN, HIDDEN, FEAT, B1_LBO, B1_SBO);
         load_weights<PARTS>(s.b2b[0], sizeof(s.b2b[0]), net_b.w2, net_b.wgain2 * LN2, T::OUT_B, T::N_B, HIDDEN, B2_LBO, B2_SBO);
         for (int i = threadIdx.x; i < HIDDEN; i += blockDim.x) s.bias1[1][i] = folded_bias(net_b.b1, net_b.bgain1, i) * LOG2E;
         for (int i = threadIdx.x; i < T::N_B; i += blockDim.x) s.bias2b[i] = i < T::OUT_B ? folded_bias(net_b.b2, net_b.bgain2, i) : 0.0f;
@@ -177,10 +209,16 @@ __device__ __forceinline__ void hidden_in_place(uint32_t taddr, const float* bia
         uint32_t hi[8], lo[8];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+#if !NFE_P2_BIAS_MMA
             const float4 b4 = *reinterpret_cast<const float4*>(bias1_log2 + q * 16 + 4 * i);
+#endif
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
+#if NFE_P2_BIAS_MMA
+                const float2 t = make_float2(v[4 * i + 2 * j], v[4 * i + 2 * j + 1]);            // the accumulator already is (x W1^T + b1) * log2(e)
+#else
                 const float2 t = ffma2(make_float2(v[4 * i + 2 * j], v[4 * i + 2 * j + 1]), k2, j ? make_float2(b4.z, b4.w) : make_float2(b4.x, b4.y));
+#endif
                 float e0, e1, l0, l1;
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(-fabsf(t.x)));
                 asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(-fabsf(t.y)));
@@ -587,9 +625,20 @@ __global__ void __launch_bounds__(THREADS, 1) field_pipe2_kernel(FieldArgs a, nf
                 P2_WAIT(3, &s.full[st], (it >> 1) & 1);          // features landed
                 tc::fence_after_sync();
                 issue_gemm<SPLIT>(leader, tb + COL_D1A, s.a1[st][0][0], s.a1[st][0][P], A1_LBO, A1_SBO, s.b1[0][0], s.b1[0][P], B1_LBO, B1_SBO, FEAT, idesc1);
+#if NFE_P2_BIAS_MMA
+                auto bias_step = [&](uint32_t d, int net) {                 // D += ones * (bias_hi + bias_lo)^T, one K = 16 step each
+                    const uint64_t da = tc::make_desc(tc::smem_u32(s.ones), ONES_LBO, 128);
+                    if (leader) tc::mma_bf16_ss(d, da, tc::make_desc(tc::smem_u32(s.bias_op[net][0]), BB_LBO, 128), idesc1, 1);
+                    if (SPLIT && leader) tc::mma_bf16_ss(d, da, tc::make_desc(tc::smem_u32(s.bias_op[net][P]), BB_LBO, 128), idesc1, 1);
+                };
+                bias_step(tb + COL_D1A, 0);
+#endif
                 if (has_b)
                     issue_gemm<SPLIT>(leader, tb + COL_D1B, s.a1[st][T::SETS - 1][0], s.a1[st][T::SETS - 1][P], A1_LBO, A1_SBO, s.b1[T::HAS_B ? 1 : 0][0],
                                       s.b1[T::HAS_B ? 1 : 0][P], B1_LBO, B1_SBO, FEAT, idesc1);
+#if NFE_P2_BIAS_MMA
+                if (has_b) bias_step(tb + COL_D1B, T::HAS_B ? 1 : 0);
+#endif
                 if (leader) {
                     tc::mma_commit(&s.empty[st]);                   // ring slot reusable once these MMAs have read it
                     tc::mma_commit(&s.d1_full[st]);
