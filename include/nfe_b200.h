@@ -356,6 +356,9 @@ typedef struct nfe_modconv_args {
     int act;
     float alpha, gain, clamp;
     int dtype;
+    int64_t weight_batch_stride;   /* 0: one weight for the batch; > 0: per-item weights [batch][out_ch, in_ch, k, k], this many elements
+                                      apart — the grouped-convolution form conv2d_resample receives from a fused modulated_conv2d
+                                      (networks_stylegan2.py:84-88), whose weights are modulated already: pass styles = NULL, demodulate = 0 */
 } nfe_modconv_args;
 int64_t nfe_modconv_workspace_bytes(const nfe_modconv_args* args);
 int nfe_modulated_conv2d(const nfe_modconv_args* args, void* workspace, int64_t workspace_bytes, nfe_stream_t stream);

@@ -39,7 +39,7 @@ class NfeModconvArgs(ctypes.Structure):
     _fields_ = [("x", c_vp), ("weight", c_vp), ("styles", c_vp), ("noise", c_vp), ("noise_batch_stride", c_i64), ("bias", c_vp), ("y", c_vp),
                 ("filter", c_vp), ("fh", c_int), ("fw", c_int), ("batch", c_int), ("in_ch", c_int), ("out_ch", c_int), ("in_h", c_int),
                 ("in_w", c_int), ("ksize", c_int), ("up", c_int), ("demodulate", c_int), ("flip_weight", c_int), ("act", c_int),
-                ("alpha", c_float), ("gain", c_float), ("clamp", c_float), ("dtype", c_int)]
+                ("alpha", c_float), ("gain", c_float), ("clamp", c_float), ("dtype", c_int), ("weight_batch_stride", c_i64)]
 
 
 _MLP_P = ctypes.POINTER(NfeMlp)

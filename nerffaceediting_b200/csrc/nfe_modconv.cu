@@ -480,6 +480,7 @@ struct PackArgs {
     float* smax;                          // [N]
     unsigned char* packed;
     long long packed_item_stride;
+    long long weight_batch_stride;        // elements between the items' weights (0: shared)
     int batch, out_ch, in_ch, ksize, demodulate, prenorm, parts;
     int n_tile, n_tiles, chunks, kc, b_stage;
     TapPlan tp;
@@ -508,25 +509,29 @@ __global__ void __launch_bounds__(128) modconv_coef_kernel(const PackArgs a)
         mw = block_reduce(mw, true);
         wm = (float)(1.0 / sqrt((double)per_o)) / mw;
     }
-    for (int i = threadIdx.x; i < a.in_ch; i += 128) {
-        float q = 0.0f;
-        for (int t = 0; t < kk; ++t) { const float v = __ldg(w + i * kk + t) * wm; q = fmaf(v, v, q); }
-        q_sm[i] = q;
-    }
     if (threadIdx.x == 0) a.wmul[o] = wm;
-    __syncthreads();
     for (int n = 0; n < a.batch; ++n) {
-        const float* s = a.styles + (long long)n * a.in_ch;
+        if (n == 0 || a.weight_batch_stride) {                  // per-item weights: fold this item's row (the pre-normalisation above used item 0's:
+            __syncthreads();                                    // it only applies with demodulation, which per-item weights come without)
+            const float* wn = w + n * a.weight_batch_stride;
+            for (int i = threadIdx.x; i < a.in_ch; i += 128) {
+                float q = 0.0f;
+                for (int t = 0; t < kk; ++t) { const float v = __ldg(wn + i * kk + t) * wm; q = fmaf(v, v, q); }
+                q_sm[i] = q;
+            }
+            __syncthreads();
+        }
+        const float* s = a.styles ? a.styles + (long long)n * a.in_ch : nullptr;
         float sm = 1.0f;
         if (a.prenorm) {
             float ms = 0.0f;
-            for (int i = threadIdx.x; i < a.in_ch; i += 128) ms = fmaxf(ms, fabsf(__ldg(s + i)));
+            for (int i = threadIdx.x; i < a.in_ch; i += 128) ms = fmaxf(ms, s ? fabsf(__ldg(s + i)) : 1.0f);
             sm = block_reduce(ms, true);
         }
         float acc = 0.0f;
         if (a.demodulate)
             for (int i = threadIdx.x; i < a.in_ch; i += 128) {
-                const float sv = a.prenorm ? __ldg(s + i) / sm : __ldg(s + i);
+                const float s0 = s ? __ldg(s + i) : 1.0f, sv = a.prenorm ? s0 / sm : s0;
                 acc = fmaf(sv * sv, q_sm[i], acc);
             }
         acc = block_reduce(acc, false);
@@ -561,14 +566,14 @@ __global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
     const bool real = o < a.out_ch;
     float sd[8];                                   // style (pre-normalised) of the 8 input channels; the demodulation factor follows
     float wm = 1.0f, d = 0.0f;
-    const float* w = a.weight + ((long long)(real ? o : 0) * a.in_ch + i0) * kk;
+    const float* w = a.weight + n * a.weight_batch_stride + ((long long)(real ? o : 0) * a.in_ch + i0) * kk;
     if (real) {
         const float sm = a.prenorm ? a.smax[n] : 1.0f;
         wm = a.prenorm ? a.wmul[o] : 1.0f;
         d = a.dcoef[(long long)n * a.out_ch + o];
-        const float* s = a.styles + (long long)n * a.in_ch + i0;
+        const float* s = a.styles ? a.styles + (long long)n * a.in_ch + i0 : nullptr;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sd[j] = a.prenorm ? __ldg(s + j) / sm : __ldg(s + j);
+        for (int j = 0; j < 8; ++j) { const float s0 = s ? __ldg(s + j) : 1.0f; sd[j] = a.prenorm ? s0 / sm : s0; }
     }
     unsigned char* dst0 = a.packed + n * a.packed_item_stride + (((long long)nt * a.chunks + c) * ph.taps) * a.b_stage +
                           ((long long)k8 * (rows / 8) + row / 8) * 128 + (row & 7) * 16;
@@ -944,7 +949,8 @@ NFE_EXPORT int64_t nfe_modconv_workspace_bytes(const nfe_modconv_args* q)
 
 NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, int64_t workspace_bytes, nfe_stream_t stream_)
 {
-    NFE_REQUIRE(q && q->x && q->weight && q->styles && q->y, "nfe_modulated_conv2d: null pointer");
+    NFE_REQUIRE(q && q->x && q->weight && q->y, "nfe_modulated_conv2d: null pointer");
+    NFE_REQUIRE(q->weight_batch_stride >= 0, "nfe_modulated_conv2d: negative weight_batch_stride");
     mc::Plan pl;
     if (int rc = mc::make_plan(*q, pl)) return rc;
     NFE_REQUIRE(workspace && workspace_bytes >= pl.total_bytes, "nfe_modulated_conv2d: workspace of %lld bytes needed, %lld given",
@@ -961,7 +967,7 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     void* trans = ws + pl.coef_bytes + pl.packed_bytes;
 
     mc::PackArgs pa;
-    pa.weight = q->weight; pa.styles = q->styles; pa.dcoef = coef; pa.wmul = coef + (long long)q->batch * q->out_ch; pa.smax = pa.wmul + q->out_ch;
+    pa.weight = q->weight; pa.weight_batch_stride = q->weight_batch_stride; pa.styles = q->styles; pa.dcoef = coef; pa.wmul = coef + (long long)q->batch * q->out_ch; pa.smax = pa.wmul + q->out_ch;
     pa.packed = packed; pa.packed_item_stride = pl.packed_item_bytes;
     pa.batch = q->batch; pa.out_ch = q->out_ch; pa.in_ch = q->in_ch; pa.ksize = q->ksize; pa.demodulate = q->demodulate;
     pa.prenorm = (q->dtype == NFE_DTYPE_F16 && q->demodulate) ? 1 : 0;                     // networks_stylegan2.py:55-57

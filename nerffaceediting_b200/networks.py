@@ -35,18 +35,21 @@ def _channels_last(x):
 
 
 def _modconv(x, weight, styles, noise, up, resample_filter, demodulate, flip_weight, bias, act, gain, clamp):
-    """One call of nfe_modulated_conv2d; x [N,C,H,W] (any layout; staged channels-last), result channels-last in x.dtype."""
+    """One call of nfe_modulated_conv2d; x [N,C,H,W] (any layout; staged channels-last), result channels-last in x.dtype.
+    weight [O,I,k,k] (one for the batch) or [N,O,I,k,k] (per-item weights: the grouped form of a fused modulated_conv2d);
+    styles [N,I] or None (= ones)."""
     if not x.is_cuda:
         raise RuntimeError("modulated_conv2d: expected a CUDA tensor (this path has no CPU fallback)")
     if x.dtype not in _DT:
         raise RuntimeError(f"modulated_conv2d: activations must be float32 or float16, got {x.dtype}")
     n, c, h, w = x.shape
-    o, ci, kh, kw = weight.shape
+    o, ci, kh, kw = weight.shape[-4:]
     assert ci == c and kh == kw
-    assert styles.shape == (n, c)
+    assert weight.ndim == 4 or (weight.ndim == 5 and weight.shape[0] == n)
+    assert styles is None or styles.shape == (n, c)
     x = _channels_last(x)
     weight = weight.detach().to(torch.float32).contiguous()          # dense [O,I,k,k] whatever memory format the parameter was made in
-    styles = styles.detach().to(torch.float32).contiguous()
+    styles = styles.detach().to(torch.float32).contiguous() if styles is not None else None
     y = torch.empty((n, o, h * up, w * up), dtype=x.dtype, device=x.device, memory_format=torch.channels_last)
     nz, nz_stride = None, 0
     if noise is not None:
@@ -69,7 +72,8 @@ def _modconv(x, weight, styles, noise, up, resample_filter, demodulate, flip_wei
                                y=_ptr(y), filter=_ptr(f), fh=0 if f is None else f.shape[0], fw=0 if f is None else f.shape[1],
                                batch=n, in_ch=c, out_ch=o, in_h=h, in_w=w, ksize=kh, up=up, demodulate=int(bool(demodulate)),
                                flip_weight=int(bool(flip_weight)), act=_ACT_IDX[act], alpha=0.2 if act == 'lrelu' else 0.0, gain=float(gain),
-                               clamp=float(clamp) if clamp is not None else -1.0, dtype=_DT[x.dtype])
+                               clamp=float(clamp) if clamp is not None else -1.0, dtype=_DT[x.dtype],
+                               weight_batch_stride=o * ci * kh * kw if weight.ndim == 5 else 0)
     lib = _lib.load()
     with _Guard(x):
         need = lib.nfe_modconv_workspace_bytes(args)
@@ -90,6 +94,23 @@ def modulated_conv2d(x, weight, styles, noise=None, up=1, down=1, padding=0, res
     assert up in (1, 2)
     assert padding == weight.shape[-1] // 2, "modulated_conv2d: padding must be kernel_size // 2 (what the reference's layers pass)"
     return _modconv(x, weight, styles, noise, up, resample_filter, demodulate, flip_weight, None, 'linear', 1.0, None)
+
+
+def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight=True, flip_filter=False):
+    """torch_utils/ops/conv2d_resample.py:48-143 for the cases the generator's layers produce (inference): 3x3 / 1x1 kernels, up in
+    {1, 2}, down = 1, padding = kernel // 2, and either groups = 1 (one weight for the batch: the non-fused formulation, Conv2dLayer)
+    or the fused modulated_conv2d's grouped form — x [1, N*I, H, W], w [N*O, I, k, k], groups = N (networks_stylegan2.py:84-88), which
+    runs as N items with per-item weights.  The result has the caller's layout conventions ([N, O, H', W'] / [1, N*O, H', W'])."""
+    _no_grad(x, w)
+    kh, kw = w.shape[-2:]
+    pad = [padding] * 4 if isinstance(padding, int) else ([padding[0], padding[0], padding[1], padding[1]] if len(padding) == 2 else list(padding))
+    assert down == 1 and up in (1, 2) and kh == kw and all(p == kh // 2 for p in pad) and not flip_filter, "conv2d_resample: unsupported configuration"
+    if groups == 1:
+        return _modconv(x, w, None, None, up, f, False, flip_weight, None, 'linear', 1.0, None)
+    assert x.shape[0] == 1 and x.shape[1] % groups == 0 and w.shape[0] % groups == 0
+    n, i, o = groups, x.shape[1] // groups, w.shape[0] // groups
+    y = _modconv(x.reshape(n, i, *x.shape[2:]), w.reshape(n, o, i, kh, kw), None, None, up, f, False, flip_weight, None, 'linear', 1.0, None)
+    return y.reshape(1, n * o, *y.shape[2:])
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):

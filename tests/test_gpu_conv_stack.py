@@ -189,3 +189,33 @@ def test_modulated_conv2d_shapes_vs_torch(shape, dtype):
     tol = 1e-4 if dtype == torch.float32 else 1e-2
     e = rel_err(y.float().cpu().numpy(), ref.float().cpu().numpy())
     assert e < tol, (shape, dtype, e)
+
+
+@pytest.mark.parametrize("tag", ["3x3", "3x3_up2", "1x1_nodemod", "wide_ragged"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_shadow_conv2d_resample_serves_the_fused_modulated_conv2d(tag, dtype):
+    """shadow/torch_utils/ops/conv2d_resample.py is what an UNPICKLED generator's modulated_conv2d calls (networks_stylegan2.py:84-88:
+    x [1, N*I, H, W], per-sample weights [N*O, I, k, k], groups = N): the grouped form through the per-item-weight path of the kernel,
+    against the reference fixture of the same layer."""
+    shadow = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "shadow")
+    if shadow not in sys.path:
+        sys.path.insert(0, shadow)
+    for name in [m for m in sys.modules if m == "torch_utils" or m.startswith("torch_utils.")]:
+        del sys.modules[name]
+    from torch_utils.ops import bias_act, conv2d_resample, upfirdn2d
+    assert "shadow" in conv2d_resample.__file__ and "shadow" in bias_act.__file__ and "shadow" in upfirdn2d.__file__
+    c = cases.MODCONV[tag]
+    x, w, s, noise = (cuda(t) for t in cases.modconv_inputs(c))
+    n, o, i, k = c['n'], c['o'], c['i'], c['k']
+    f = upfirdn2d.setup_filter([1, 3, 3, 1]).cuda() if c['up'] == 2 else None
+    with torch.no_grad():
+        wm = w.unsqueeze(0) * s.reshape(n, 1, -1, 1, 1)                      # networks_stylegan2.py:59-66
+        if c['demod']:
+            wm = wm * (wm.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt().reshape(n, -1, 1, 1, 1)
+        xg = x.to(dtype).reshape(1, -1, *x.shape[2:])
+        y = conv2d_resample.conv2d_resample(x=xg, w=wm.reshape(-1, i, k, k).to(dtype), f=f, up=c['up'], padding=k // 2, groups=n, flip_weight=c['flip'])
+        y = y.reshape(n, -1, *y.shape[2:])
+        if noise is not None:
+            y = y.add_(noise.to(y.dtype))
+    assert y.shape[1] == o
+    check(y, golden("conv_stack")[f"modconv.{tag}"], TOL32 if dtype == torch.float32 else TOL16, "shadow " + tag)

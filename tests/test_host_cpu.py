@@ -359,7 +359,8 @@ def test_modconv_plan_and_argument_checks_run_on_the_host(built):
     scratch sizes of known layers and the rejected configurations, without a GPU."""
     lib = _lib.load()
     A = _lib.NfeModconvArgs
-    assert A.noise_batch_stride.offset == 4 * 8 and A.fh.offset == 8 * 8 and ctypes.sizeof(A) == 8 * 8 + 16 * 4      # 8 pointer-sized + 16 x 4 bytes
+    assert A.noise_batch_stride.offset == 4 * 8 and A.fh.offset == 8 * 8 and A.weight_batch_stride.offset == 8 * 8 + 16 * 4      # 8 pointer-sized + 16 x 4 bytes
+    assert ctypes.sizeof(A) == 8 * 8 + 16 * 4 + 8
 
     def need(**kw):
         base = dict(batch=8, in_ch=256, out_ch=256, in_h=256, in_w=256, ksize=3, up=1, demodulate=1, flip_weight=1, act=3, alpha=0.2, gain=1.0,
@@ -395,3 +396,28 @@ def test_generator_state_dict_names_are_the_reference_s():
         G = cases.make_generator(triplane.TriPlaneGenerator, which)
         keys = sorted(f"{k}:{'x'.join(map(str, v.shape))}" for k, v in G.state_dict().items())
         assert keys == sorted(g[f"keys.{which}"].tolist())
+
+
+def test_shadow_torch_utils_resolves_and_delegates_cpu_calls():
+    """shadow/torch_utils: bias_act / upfirdn2d / conv2d_resample come from the shadow, the rest of torch_utils from the reference; CPU
+    tensors go through the reference's own functions, so a reference generator still runs on CPU with the shadow on the path."""
+    if not os.path.isdir(os.path.join(REFERENCE, "torch_utils")):
+        pytest.skip("reference checkout not present")
+    code = r"""
+import sys, torch
+import training.networks_stylegan2 as ns
+from torch_utils.ops import bias_act, upfirdn2d, conv2d_resample, fma, conv2d_gradfix
+assert bias_act.__file__.startswith(sys.argv[1]) and conv2d_resample.__file__.startswith(sys.argv[1]) and upfirdn2d.__file__.startswith(sys.argv[1])
+assert fma.__file__.startswith(sys.argv[2]) and conv2d_gradfix.__file__.startswith(sys.argv[2])
+assert ns.bias_act is bias_act and ns.conv2d_resample is conv2d_resample and ns.upfirdn2d is upfirdn2d
+torch.manual_seed(0)
+block = ns.SynthesisBlock(16, 16, w_dim=8, resolution=8, img_channels=3, is_last=True).eval()
+x, img, ws = torch.randn(2, 16, 4, 4), torch.randn(2, 3, 4, 4), torch.randn(2, 3, 8)
+with torch.no_grad():
+    y, im = block(x, img, ws, noise_mode='const')
+assert y.shape == (2, 16, 8, 8) and im.shape == (2, 3, 8, 8) and torch.isfinite(im).all()
+print('ok')
+"""
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "shadow"), REFERENCE]))
+    r = subprocess.run([sys.executable, "-c", code, os.path.join(ROOT, "shadow"), REFERENCE], capture_output=True, text=True, env=env)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
