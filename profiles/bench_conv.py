@@ -49,8 +49,25 @@ def layer_bench(n, i, o, res, up, dtype):
         else:
             wt = wg.reshape(n, o, i, 3, 3).transpose(1, 2).reshape(n * i, o, 3, 3).contiguous(memory_format=torch.channels_last)
             lib = timed(lambda: torch.nn.functional.conv_transpose2d(xg, wt, stride=2, groups=n))
+        # the zero-change route of an unpickled generator: the reference's own modulated_conv2d statements
+        # (networks_stylegan2.py:59-66,84-88) around shadow/torch_utils/ops: weights folded by torch ops, the grouped per-sample
+        # convolution and the bias_act through this library, NCHW in and out
+        from nerffaceediting_b200 import stylegan_ops as sg
+
+        def shadow_route():
+            styles = layer.affine(w)
+            wm = layer.weight.unsqueeze(0) * styles.reshape(n, 1, -1, 1, 1)
+            wm = wm * (wm.square().sum(dim=[2, 3, 4]) + 1e-8).rsqrt().reshape(n, -1, 1, 1, 1)
+            y = net.conv2d_resample(x_nchw.reshape(1, -1, r, r), wm.reshape(-1, i, 3, 3).to(dtype), f=layer.resample_filter, up=up, padding=1,
+                                    groups=n, flip_weight=(up == 1))
+            y = y.reshape(n, -1, res, res).add_((layer.noise_const * layer.noise_strength).to(dtype))
+            return sg.bias_act(y, layer.bias.to(dtype), act='lrelu', gain=layer.act_gain, clamp=256)
+        x_nchw = x.contiguous()
+        with torch.no_grad():
+            shadow = timed(shadow_route)
     flop = 2.0 * n * r * r * 9 * i * o
     return {"layer": f"{i}->{o} @ {res}^2 up={up} {str(dtype).split('.')[-1]}", "ms": round(ours, 4), "tflops": round(flop / ours / 1e9, 1),
+            "shadow_route_ms": round(shadow, 4),
             "cudnn_grouped_ms": round(lib, 4), "cudnn_tflops": round(flop / lib / 1e9, 1), "gflop": round(flop / 1e9, 1)}
 
 
