@@ -7,6 +7,7 @@ S=$(date +%s)
 timeout 1500 python -m pytest tests -m gpu -q --tb=short 2>&1 | grep -v "^  \|^E    +" | tail -25 > gpurun_out/gputest_r02_full.txt
 tail -8 gpurun_out/gputest_r02_full.txt
 echo "tests t=$(( $(date +%s)-S ))s"
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py > gpurun_out/bench_r02_c2_default.json 2> gpurun_out/bench_r02_c2_default.err
 python - <<PY
 import json
