@@ -363,6 +363,11 @@ typedef struct nfe_modconv_args {
 int64_t nfe_modconv_workspace_bytes(const nfe_modconv_args* args);
 int nfe_modulated_conv2d(const nfe_modconv_args* args, void* workspace, int64_t workspace_bytes, nfe_stream_t stream);
 
+/* Layout conversion of an activation tensor between contiguous NCHW [n, c, hw] and channels-last [n, hw, c] (what
+ * `x.contiguous(memory_format=torch.channels_last)` / `.contiguous()` do around the reference's fp16_channels_last layers,
+ * networks_stylegan2.py:424-433): the convolution kernel reads and writes channels-last, the reference's own code NCHW. */
+int nfe_layout_convert(const void* src, void* dst, int64_t n, int c, int64_t hw, int dtype, int to_channels_last, nfe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

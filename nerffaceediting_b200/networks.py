@@ -30,8 +30,34 @@ def _no_grad(*tensors):
         raise RuntimeError("nerffaceediting_b200.networks: the convolution stack is forward-only; call it under torch.no_grad()")
 
 
+_LAYOUT_DT = {torch.float32: 0, torch.float16: 1, torch.bfloat16: 2}
+
+
 def _channels_last(x):
+    """x [N,C,H,W] in channels-last memory order; a contiguous-NCHW CUDA tensor goes through the library's tiled transpose
+    (nfe_layout_convert) instead of torch's strided copy."""
+    if x.is_contiguous(memory_format=torch.channels_last):
+        return x
+    if x.is_cuda and x.is_contiguous() and x.dtype in _LAYOUT_DT and x.shape[0] <= 65535 and x.numel() > 0:
+        n, c, h, w = x.shape
+        y = torch.empty_like(x, memory_format=torch.channels_last)
+        with _Guard(x):
+            _lib.check(_lib.load().nfe_layout_convert(_ptr(x), _ptr(y), n, c, h * w, _LAYOUT_DT[x.dtype], 1, _stream(x)), "nfe_layout_convert")
+        return y
     return x.contiguous(memory_format=torch.channels_last)
+
+
+def _nchw(x):
+    """x [N,C,H,W] as a contiguous-NCHW tensor (the layout the reference's own code expects back)."""
+    if x.is_contiguous():
+        return x
+    if x.is_cuda and x.is_contiguous(memory_format=torch.channels_last) and x.dtype in _LAYOUT_DT and x.shape[0] <= 65535 and x.numel() > 0:
+        n, c, h, w = x.shape
+        y = torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        with _Guard(x):
+            _lib.check(_lib.load().nfe_layout_convert(_ptr(x), _ptr(y), n, c, h * w, _LAYOUT_DT[x.dtype], 0, _stream(x)), "nfe_layout_convert")
+        return y
+    return x.contiguous()
 
 
 def _modconv(x, weight, styles, noise, up, resample_filter, demodulate, flip_weight, bias, act, gain, clamp):
@@ -110,7 +136,7 @@ def conv2d_resample(x, w, f=None, up=1, down=1, padding=0, groups=1, flip_weight
     assert x.shape[0] == 1 and x.shape[1] % groups == 0 and w.shape[0] % groups == 0
     n, i, o = groups, x.shape[1] // groups, w.shape[0] // groups
     y = _modconv(x.reshape(n, i, *x.shape[2:]), w.reshape(n, o, i, kh, kw), None, None, up, f, False, flip_weight, None, 'linear', 1.0, None)
-    return y.reshape(1, n * o, *y.shape[2:])
+    return _nchw(y).reshape(1, n * o, *y.shape[2:])
 
 
 def normalize_2nd_moment(x, dim=1, eps=1e-8):

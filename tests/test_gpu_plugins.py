@@ -138,3 +138,16 @@ def test_setup_filter_matches_the_reference_forms():
     assert f.shape == (4, 4) and abs(float(f.sum()) - 1.0) < 1e-6                     # upfirdn2d.py:95-111: outer product, normalised
     assert sg.setup_filter([1, 2, 4, 6, 6, 4, 2, 1]).ndim == 1                        # >= 8 taps stay separable
     assert sg.setup_filter(None).shape == (1, 1)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(2, 96, 33, 17), (1, 3, 64, 64), (3, 200, 5, 7), (1, 64, 128, 128)])
+def test_layout_convert_is_bit_exact(dtype, shape):
+    """nfe_layout_convert (contiguous NCHW <-> channels-last through a shared-memory tile) against torch's own copies."""
+    from nerffaceediting_b200 import networks as net
+    x = torch.randn(shape, device="cuda").to(dtype)
+    cl = net._channels_last(x)
+    assert cl.is_contiguous(memory_format=torch.channels_last) and torch.equal(cl, x)
+    assert torch.equal(cl.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous())
+    back = net._nchw(cl)
+    assert back.is_contiguous() and torch.equal(back, x)
