@@ -923,12 +923,15 @@ static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
     const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 256 + 256 * 4 + 128;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table | tap tables
-    static bool attr_done = false;
+    static unsigned long long attr_done_mask = 0;         // per device: function attributes belong to the device's context
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const bool attr_done = dev < 64 && ((attr_done_mask >> dev) & 1ull);
     if (!attr_done) {
         cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) { set_error("conv_gemm_kernel: shared memory opt-in: %s", cudaGetErrorString(e)); return 2; }
-        attr_done = true;
+        if (dev < 64) attr_done_mask |= 1ull << dev;
     }
     const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)g.batch);
     conv_gemm_kernel<PARTS, MA, SA, KG><<<grid, THREADS, smem, stream>>>(g);
