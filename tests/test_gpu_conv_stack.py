@@ -160,7 +160,9 @@ def _torch_modconv(x, w, s, noise, up, demodulate, flip_weight, f):
         else:
             t = torch.nn.functional.conv_transpose2d(x[b:b + 1], wm[b].transpose(0, 1) if not flip_weight else wm[b].flip([2, 3]).transpose(0, 1), stride=2)
             ff = (f.double() * 4).flip([0, 1])[None, None].repeat(o, 1, 1, 1)
-            outs.append(torch.nn.functional.conv2d(torch.nn.functional.pad(t, [1, 1, 1, 1]), ff, groups=o))
+            fw = f.shape[-1]
+            p0, p1 = k // 2 + (fw + 1) // 2 - (k - 1), k // 2 + (fw - 2) // 2 - (k - 2)        # conv2d_resample.py:97-101,124-127
+            outs.append(torch.nn.functional.conv2d(torch.nn.functional.pad(t, [p0, p1, p0, p1]), ff, groups=o))
     y = torch.cat(outs)
     return y + noise.double() if noise is not None else y
 
@@ -219,3 +221,50 @@ def test_shadow_conv2d_resample_serves_the_fused_modulated_conv2d(tag, dtype):
             y = y.add_(noise.to(y.dtype))
     assert y.shape[1] == o
     check(y, golden("conv_stack")[f"modconv.{tag}"], TOL32 if dtype == torch.float32 else TOL16, "shadow " + tag)
+
+
+@pytest.mark.parametrize("taps", ["1331", "121", "random4x4", "12"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_up2_resample_filters(taps, dtype):
+    """up = 2 with other resample filters than the default: a 3-tap one (different paddings), a non-separable 4 x 4 one (the filter
+    pass's direct path) and a 2-tap one, against the fp64 torch restatement."""
+    from nerffaceediting_b200 import networks as net
+    from nerffaceediting_b200 import stylegan_ops as sg
+    g = torch.Generator(device="cpu").manual_seed(11)
+    f = {"1331": sg.setup_filter([1, 3, 3, 1]), "121": sg.setup_filter([1, 2, 1]), "12": sg.setup_filter([1, 2]),
+         "random4x4": torch.rand(4, 4, generator=g) / 8}[taps].cuda()
+    n, i, o, h, w = 2, 32, 48, 9, 13
+    x = torch.randn(n, i, h, w, generator=g).cuda().to(dtype)
+    wt = torch.randn(o, i, 3, 3, generator=g).cuda()
+    s = (1.0 + 0.3 * torch.randn(n, i, generator=g)).cuda()
+    ref = _torch_modconv(x.float(), wt, s, None, 2, True, False, f)
+    with torch.no_grad():
+        y = net.modulated_conv2d(x, wt, s, up=2, padding=1, resample_filter=f, demodulate=True, flip_weight=False)
+    assert y.shape == ref.shape
+    e = rel_err(y.float().cpu().numpy(), ref.float().cpu().numpy())
+    assert e < (1e-4 if dtype == torch.float32 else 1e-2), (taps, dtype, e)
+
+
+def test_modulated_conv2d_c_abi_rejects_bad_arguments():
+    import ctypes
+    from nerffaceediting_b200 import _lib
+    lib = _lib.load()
+    x = torch.zeros(1, 8, 8, 16, device="cuda")
+    w = torch.zeros(16, 16, 3, 3, device="cuda")
+    st = torch.ones(1, 16, device="cuda")
+    y = torch.zeros(1, 8, 8, 16, device="cuda")
+    ws = torch.zeros(1 << 20, dtype=torch.uint8, device="cuda")
+
+    def call(**kw):
+        a = dict(x=x.data_ptr(), weight=w.data_ptr(), styles=st.data_ptr(), y=y.data_ptr(), batch=1, in_ch=16, out_ch=16, in_h=8, in_w=8, ksize=3,
+                 up=1, demodulate=1, flip_weight=1, act=1, gain=1.0, clamp=-1.0, dtype=0)
+        a.update(kw)
+        return lib.nfe_modulated_conv2d(_lib.NfeModconvArgs(**a), ws.data_ptr(), ws.numel(), None)
+    assert call() == 0
+    assert call(act=7) != 0 and b"act" in lib.nfe_last_error()                     # only linear / relu / lrelu are fused
+    assert call(up=2) != 0 and b"filter" in lib.nfe_last_error()                   # up = 2 without a resample filter
+    assert call(x=None) != 0
+    assert lib.nfe_modulated_conv2d(_lib.NfeModconvArgs(x=x.data_ptr(), weight=w.data_ptr(), styles=st.data_ptr(), y=y.data_ptr(), batch=1, in_ch=16,
+                                                        out_ch=16, in_h=8, in_w=8, ksize=3, up=1, demodulate=1, flip_weight=1, act=1, gain=1.0,
+                                                        clamp=-1.0, dtype=0), ws.data_ptr(), 16, None) != 0            # workspace too small
+    torch.cuda.synchronize()
