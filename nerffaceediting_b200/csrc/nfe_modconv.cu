@@ -740,28 +740,32 @@ __global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArg
             v[0] = __uint_as_float(u.x); v[1] = __uint_as_float(u.y); v[2] = __uint_as_float(u.z); v[3] = __uint_as_float(u.w);
         }
     };
+    // per-thread constants of the epilogue: this thread's V biases, the activation as one slope pair, the clamp (infinite when off)
+    float bias_r[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) bias_r[j] = s_bias[g * V + j];
+    const float neg_slope = a.act == 1 ? 1.0f : (a.act == 2 ? 0.0f : a.alpha);
+    const float gain_pos = a.gain, gain_neg = a.gain * neg_slope, clampv = a.clamp >= 0.0f ? a.clamp : __int_as_float(0x7f800000);
     auto finish = [&](int py, float (&acc)[V]) {
         const int oy = oy0 + py;
         if (oy >= a.oh) return;
         const float nz = a.noise ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.ow + ox) : 0.0f;
+        const float2 nz2 = make_float2(nz, nz);
+        uint32_t w4[V / 2];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            float t = acc[j];
-            if constexpr (sizeof(T) == 2) t = __half2float(__float2half_rn(t));      // the reference stores the filtered image in fp16
-            t = (t + nz) + s_bias[g * V + j];
-            t = act_apply<T>(t, a.act, a.alpha) * a.gain;
-            if (a.clamp >= 0.0f) t = fminf(fmaxf(t, -a.clamp), a.clamp);
-            acc[j] = t;
+        for (int j = 0; j < V / 2; ++j) {
+            float2 t = make_float2(acc[2 * j], acc[2 * j + 1]);
+            if constexpr (sizeof(T) == 2) t = __half22float2(__floats2half2_rn(t.x, t.y));      // the reference stores the filtered image in fp16
+            t = fadd2(fadd2(t, nz2), make_float2(bias_r[2 * j], bias_r[2 * j + 1]));
+            t.x *= t.x > 0.0f ? gain_pos : gain_neg;                                              // linear / relu / lrelu, then the gain
+            t.y *= t.y > 0.0f ? gain_pos : gain_neg;
+            t.x = fminf(fmaxf(t.x, -clampv), clampv); t.y = fminf(fmaxf(t.y, -clampv), clampv);
+            if constexpr (sizeof(T) == 2) { const __half2 h = __floats2half2_rn(t.x, t.y); w4[j] = *reinterpret_cast<const uint32_t*>(&h); }
+            else { acc[2 * j] = t.x; acc[2 * j + 1] = t.y; }
         }
         T* dst = yout + (((long long)n * a.oh + oy) * a.ow + ox) * a.c + c_base + g * V;
-        if constexpr (sizeof(T) == 2) {
-            uint32_t w4[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) { const __half2 h = __floats2half2_rn(acc[2 * j], acc[2 * j + 1]); w4[j] = *reinterpret_cast<const uint32_t*>(&h); }
-            *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
-        } else {
-            *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        }
+        if constexpr (sizeof(T) == 2) *reinterpret_cast<uint4*>(dst) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        else *reinterpret_cast<float4*>(dst) = make_float4(acc[0], acc[1], acc[2], acc[3]);
     };
     if (separable) {
         const float fx[4] = {f_col[0], f_col[1], f_col[2], f_col[3]}, fy[4] = {f_row[0], f_row[1], f_row[2], f_row[3]};
@@ -806,6 +810,110 @@ __global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArg
                     for (int j = 0; j < V; ++j) acc[j] = fmaf(v[j], w, acc[j]);
                 }
             finish(py, acc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- ToRGB to a handful of channels
+// 1x1 modulated convolution to at most 4 output channels (ToRGBLayer of the super-resolution blocks: 256 / 128 -> 3), without
+// demodulation: 6 FLOP per input byte — a streaming reduction, not a GEMM (through conv_gemm_kernel its windows cost more in fixed
+// overhead than in work: 0.2 ms per call against the 0.09 ms the bytes need).  One thread per pixel walks the pixel's channels in
+// 16-byte pieces; the per-sample weights w * s sit in shared memory (every lane reads the same address: broadcast).
+struct RgbArgs {
+    const void* x; const float* weight; const float* styles; const float* bias; void* y;
+    long long weight_batch_stride;
+    int batch, in_ch, out_ch; long long pixels;
+    float neg_slope_gain, gain, clamp;
+};
+
+// shared-memory stride (floats) of one 16-byte piece's weights: >= V * O, a multiple of 4 whose quarter is odd, so that the 8 lanes
+// of a pixel (8 consecutive pieces) read 8 distinct 16-byte bank groups
+__host__ __device__ constexpr int rgb_piece_stride(int v, int o) { int s = (v * o + 3) / 4; return (s | 1) * 4; }
+
+template <class T, int O>
+__global__ void __launch_bounds__(256) torgb_small_kernel(const RgbArgs a)
+{
+    extern __shared__ __align__(16) float wm[];              // [piece][O][channel in piece], pieces rgb_piece_stride apart
+    constexpr int V = 16 / (int)sizeof(T);
+    constexpr int PS = rgb_piece_stride(V, O);
+    static_assert((V * O) % 4 == 0, "piece weights are read as float4");
+    const int n = blockIdx.y;
+    for (int i = threadIdx.x; i < a.in_ch * O; i += 256) {
+        const int c = i / O, o = i % O;
+        const float w = o < a.out_ch ? __ldg(a.weight + n * a.weight_batch_stride + (long long)o * a.in_ch + c) : 0.0f;
+        wm[(c / V) * PS + o * V + (c % V)] = w * (a.styles ? __ldg(a.styles + (long long)n * a.in_ch + c) : 1.0f);
+    }
+    __syncthreads();
+    const T* xin = static_cast<const T*>(a.x) + (long long)n * a.pixels * a.in_ch;
+    T* yout = static_cast<T*>(a.y) + (long long)n * a.pixels * a.out_ch;
+    const float clampv = a.clamp >= 0.0f ? a.clamp : __int_as_float(0x7f800000);
+    // 8 lanes per pixel: a warp's load instruction covers 4 pixels x 128 contiguous bytes (4 lines, where a lane per pixel would
+    // touch 32); the lanes' partial sums meet in three shuffle steps
+    const int sub = threadIdx.x & 7;
+    const int pieces = a.in_ch / V;
+    constexpr int PIX = 2;                                   // pixels per lane group and turn: twice the loads in flight
+    const long long turn = (long long)gridDim.x * 32 * PIX;
+    for (long long base = ((long long)blockIdx.x * 8 + (threadIdx.x >> 5)) * 4 * PIX; base < a.pixels; base += turn) {
+        long long px[PIX];
+        const uint4* src[PIX];
+        float2 acc2[PIX][O];                                 // even / odd channels of the piece: packed f32x2 FMAs
+#pragma unroll
+        for (int i = 0; i < PIX; ++i) {
+            px[i] = base + 4 * i + (threadIdx.x >> 3 & 3);
+            src[i] = reinterpret_cast<const uint4*>(xin + (px[i] < a.pixels ? px[i] : 0) * a.in_ch);
+#pragma unroll
+            for (int o = 0; o < O; ++o) acc2[i][o] = make_float2(0.0f, 0.0f);
+        }
+#pragma unroll 2
+        for (int k = sub; k < pieces; k += 8) {
+            uint4 u[PIX];
+#pragma unroll
+            for (int i = 0; i < PIX; ++i) u[i] = __ldg(src[i] + k);
+            float4 w4[O][V / 4];
+#pragma unroll
+            for (int o = 0; o < O; ++o)
+#pragma unroll
+                for (int j = 0; j < V / 4; ++j) w4[o][j] = *reinterpret_cast<const float4*>(wm + k * PS + o * V + 4 * j);
+#pragma unroll
+            for (int i = 0; i < PIX; ++i) {
+                float2 v[V / 2];
+                if constexpr (sizeof(T) == 2) {
+                    const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = __half22float2(h[j]);
+                } else {
+                    v[0] = make_float2(__uint_as_float(u[i].x), __uint_as_float(u[i].y)); v[1] = make_float2(__uint_as_float(u[i].z), __uint_as_float(u[i].w));
+                }
+#pragma unroll
+                for (int o = 0; o < O; ++o) {
+#pragma unroll
+                    for (int j = 0; j < V / 4; ++j) {
+                        acc2[i][o] = ffma2(v[2 * j], make_float2(w4[o][j].x, w4[o][j].y), acc2[i][o]);
+                        acc2[i][o] = ffma2(v[2 * j + 1], make_float2(w4[o][j].z, w4[o][j].w), acc2[i][o]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < PIX; ++i) {
+            float acc[O];
+#pragma unroll
+            for (int o = 0; o < O; ++o) {
+                acc[o] = acc2[i][o].x + acc2[i][o].y;
+                acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 1);
+                acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 2);
+                acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], 4);
+            }
+            // lane `sub` finishes output channel `sub`
+            float mine = acc[0];
+#pragma unroll
+            for (int o = 1; o < O; ++o) mine = sub == o ? acc[o] : mine;
+            if (px[i] < a.pixels && sub < a.out_ch) {
+                float t = mine + (a.bias ? __ldg(a.bias + sub) : 0.0f);
+                t *= t > 0.0f ? a.gain : a.neg_slope_gain;
+                t = fminf(fmaxf(t, -clampv), clampv);
+                if constexpr (sizeof(T) == 2) yout[px[i] * a.out_ch + sub] = __float2half_rn(t); else yout[px[i] * a.out_ch + sub] = t;
+            }
         }
     }
 }
@@ -964,6 +1072,25 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     const int vec = q->dtype == NFE_DTYPE_F16 ? 8 : 4;
     NFE_REQUIRE(q->up == 1 || q->out_ch % vec == 0, "nfe_modulated_conv2d: up = 2 needs out_channels to be a multiple of %d", vec);
     cudaStream_t stream = as_stream(stream_);
+    if (q->ksize == 1 && q->up == 1 && q->out_ch <= 4 && !q->demodulate && !q->noise && q->in_ch <= 1024) {
+        // ToRGB to a few channels: the streaming kernel (in_ch % 16 == 0 is checked by the plan above, so rows are whole 16-byte pieces)
+        mc::RgbArgs r;
+        r.x = q->x; r.weight = q->weight; r.styles = q->styles; r.bias = q->bias; r.y = q->y; r.weight_batch_stride = q->weight_batch_stride;
+        r.batch = q->batch; r.in_ch = q->in_ch; r.out_ch = q->out_ch; r.pixels = (long long)q->in_h * q->in_w;
+        const float neg_slope = q->act == 1 ? 1.0f : (q->act == 2 ? 0.0f : q->alpha);
+        r.gain = q->gain; r.neg_slope_gain = q->gain * neg_slope; r.clamp = q->clamp;
+        const int v = q->dtype == NFE_DTYPE_F16 ? 8 : 4;
+        const int o = q->out_ch <= 3 ? 3 : 4;
+        const size_t smem = (size_t)(q->in_ch / v) * mc::rgb_piece_stride(v, o) * sizeof(float);     // <= 20 KB at in_ch <= 1024
+        const dim3 grid((unsigned)std::min<long long>((r.pixels + 63) / 64, (long long)sm_count() * 8 / std::max(1, std::min(q->batch, 8)) + 1), q->batch);
+        if (q->dtype == NFE_DTYPE_F16) {
+            if (o == 3) mc::torgb_small_kernel<__half, 3><<<grid, 256, smem, stream>>>(r); else mc::torgb_small_kernel<__half, 4><<<grid, 256, smem, stream>>>(r);
+        } else {
+            if (o == 3) mc::torgb_small_kernel<float, 3><<<grid, 256, smem, stream>>>(r); else mc::torgb_small_kernel<float, 4><<<grid, 256, smem, stream>>>(r);
+        }
+        NFE_LAUNCH_CHECK("torgb_small_kernel");
+        return 0;
+    }
     unsigned char* ws = static_cast<unsigned char*>(workspace);
     float* coef = reinterpret_cast<float*>(ws);
     unsigned char* packed = ws + pl.coef_bytes;
