@@ -42,6 +42,9 @@
 #include "nfe_tc.cuh"
 
 namespace nfe {
+#ifndef NFE_MC_SEG_Q
+#define NFE_MC_SEG_Q 4
+#endif
 namespace mc {
 
 #ifdef NFE_MC_EXP_ALIGNED      // timing experiment only (wrong results): window rows at a 128-byte pitch, no column shifts
@@ -107,6 +110,22 @@ __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, uint32_
 {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(tc::smem_u32(ssrc)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w)
+{
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr)
+{
+    uint4 u;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr));      // (ordered by the callers' __syncwarp)
+    return u;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c)
+{
+    float r;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));      // FMNMX3 (sm_100)
+    return r;
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
@@ -130,8 +149,10 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int fmt)
 __device__ unsigned long long g_mc_prof[16];
 #define MC_WAIT(slot, bar, par) do { const long long t0_ = clock64(); tc::mbar_wait(bar, par); prof_[slot] += clock64() - t0_; } while (0)
 #define MC_FLUSH(slot) atomicAdd(&g_mc_prof[slot], (unsigned long long)prof_[slot])
+#define MC_CLK(name) const long long name = clock64()
 #else
 #define MC_WAIT(slot, bar, par) tc::mbar_wait(bar, par)
+#define MC_CLK(name)
 #endif
 
 template <class T> __device__ __forceinline__ float act_apply(float v, int act, float alpha)
@@ -169,7 +190,7 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     uint32_t* const s_row16 = s_tmask + MAX_TAPS;                              // per accumulator: descriptor offset of its first window row
 
 #ifdef NFE_MC_PROFILE
-    long long prof_[12] = {};
+    long long prof_[16] = {};
     const long long t_cta0 = clock64();
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -382,83 +403,177 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         T* yout = static_cast<T*>(a.y);
         const float neg_slope = a.act == 1 ? 1.0f : (a.act == 2 ? 0.0f : a.alpha);
         const float gain_pos = a.gain, gain_neg = a.gain * neg_slope, clampv = a.clamp >= 0.0f ? a.clamp : __int_as_float(0x7f800000);
+        // the up = 2 intermediate leaves as it is (noise, bias, activation, gain and clamp belong to the filter pass): convert and store
+        const bool raw = !a.noise && !a.bias && a.act == 1 && a.gain == 1.0f && a.clamp < 0.0f;
         constexpr int VEC = 16 / (int)sizeof(T);
         const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
         const int nq = a.n_tile / 16;
         const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         // Stores: a thread holds 16 channels of ONE pixel at a time, so direct store instructions touch 32 different lines with 16
         // bytes each (measured: the epilogue then runs at the speed of its 8192 partial-sector stores).  Instead every thread builds
-        // its pixel's whole row of n_tile channels in the (now idle) operand rings — at a pitch of 16 bytes more than the row, which
-        // spreads the lanes over the banks — and hands the finished row (up to 512 contiguous bytes) to the TMA unit as one bulk
-        // store: no block-wide synchronisation, no copy-out loop.
-        // Rows are staged in segments of at most 512 bytes (256 halves / 128 floats), one bulk store each.
-        constexpr int SEG_Q = 512 / (16 * (int)sizeof(T));                           // 16-column groups per segment
-        const int PITCH = min(a.n_tile * (int)sizeof(T), 512) + 16;                  // row pitch in the stage
+        // its pixel's row of n_tile channels, in segments of at most 512 bytes (256 halves / 128 floats), in the (now idle) operand
+        // rings — at a pitch of 16 bytes more than the segment, which spreads the lanes over the banks — and the WARP then copies its
+        // 32 finished rows out with coalesced 16-byte stores (16 or 32 lanes per row): warp-local, no block-wide synchronisation.
+        // (Round 2 first handed each row to the TMA unit as a bulk store; a per-thread cp.async.bulk compiles to a 32-trip waterfall
+        // around a uniform-datapath UBLKCP, ~200 cycles per trip: 7 k cycles for a warp's 32 rows, most of the epilogue.
+        // -DNFE_MC_BULK_EPILOGUE keeps that variant for the A/B record, profiles/modconv_tuning_r02.txt.)
+        // Segments are short (NFE_MC_SEG_Q groups = 64 columns): an SM writes ~28 bytes per clock to global memory (measured: 16 KB per
+        // warp leave in the same ~4.8 k cycles whether 4 or 8 warps store), which is as long as the arithmetic of the groups takes —
+        // with one long segment per row the two ran back to back, with short ones a segment drains while the next is computed.
+        constexpr int SEG_Q = NFE_MC_SEG_Q;                                           // 16-column groups per segment
+        const int PITCH = min(a.n_tile, SEG_Q * 16) * (int)sizeof(T) + 16;           // row pitch in the stage
         const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
-        unsigned char* const my_row = smem + (grp * 128 + row) * PITCH;
+        const uint32_t warp_rows = tc::smem_u32(smem) + (uint32_t)((grp * 128 + (warp & 3) * 32) * PITCH);    // this warp's 32 staged rows
+        const uint32_t my_row = warp_rows + (uint32_t)(lane * PITCH);
+#ifdef NFE_MC_BULK_EPILOGUE
         bool pending = false;                                                        // a bulk store of my_row may still be reading it
+#endif
+        // The epilogue is bound by its instruction count (8 warps x n_tile / 16 groups of 16 columns; ncu: 60 % of the kernel's executed
+        // instructions at 256 x 256 channels).  Per value: (v + noise) + bias as packed f32x2 adds, the slope pair as max(t g+, t g-) —
+        // equal to t * (t > 0 ? g+ : g-) for gain > 0 and 0 <= slope <= 1 — folded with the lower clamp into one three-input max,
+        // then the upper clamp: 4 instructions instead of 7.  The 16-column groups alternate between two register arrays (the next
+        // tcgen05.ld is in flight while this group is processed, without register copies).
+        const bool fast_act = a.gain > 0.0f && neg_slope >= 0.0f && neg_slope <= 1.0f;
+        const float2 gp2 = make_float2(gain_pos, gain_pos), gn2 = make_float2(gain_neg, gain_neg);
 #pragma unroll 1
-        for (int m = grp; m < n_acc; m += 2) {
+        // two warp groups: with several accumulators they take alternate ones, with a single one they take the two halves of its
+        // columns (cut at a segment boundary) — a warp's copy-out runs at ~3.3 bytes per clock whatever the others do, so it is the
+        // number of warps storing that sets the epilogue's length
+        const int q_cut = n_acc == 1 ? min(nq, (nq / 2 + SEG_Q - 1) / SEG_Q * SEG_Q) : 0;
+        const int q0 = n_acc == 1 && grp == 1 ? q_cut : 0, q1 = n_acc == 1 && grp == 0 ? q_cut : nq;
+        for (int m = n_acc == 1 ? 0 : grp; m < n_acc; m += 2) {
             const int gy = y0 + tp.row_off[m] + py, gx = x0 + px;
             const bool valid = gy < tp.gh[m] && gx < tp.gw[m];
             const int oy = gy * tp.o_mul + tp.oy_off[m], ox = gx * tp.o_mul + tp.ox_off[m];
             T* dst = yout + n * a.ys_n + oy * a.ys_h + ox * a.ys_w + nt * a.n_tile;
+            const unsigned long long dst_bits = valid ? reinterpret_cast<unsigned long long>(dst) : 0ull;     // what the copy-out of other lanes asks for
             const float nz = (a.noise && valid) ? __ldg(a.noise + n * a.noise_n + (long long)oy * a.noise_w + ox) : 0.0f;
-            float nxt[16];
-            tc::tmem_ld16(t_lane + m * a.n_tile, nxt);                   // software pipeline: the next group loads while this one is processed
-#pragma unroll 1
-            for (int q = 0; q < nq; ++q) {
-                float v[16];
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 16; ++i) v[i] = nxt[i];
-                if (q + 1 < nq) tc::tmem_ld16(t_lane + m * a.n_tile + (q + 1) * 16, nxt);
-                if (!valid) continue;
-                const int o0 = nt * a.n_tile + q * 16, qs = q % SEG_Q;
-                if (staged && qs == 0 && pending) { bulk_wait_read(); pending = false; }      // the row buffer is free once the previous store has read it
-#pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(s_bias + q * 16 + 4 * i4);      // same address in every lane: broadcast
-                    const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float t = (v[4 * i4 + j] + nz) + bb[j];
-                        t *= t > 0.0f ? gain_pos : gain_neg;          // linear / relu / lrelu as one slope pair (bias_act.cu:66-75), then the gain
-                        v[4 * i4 + j] = fminf(fmaxf(t, -clampv), clampv);
-                    }
+            const float2 nz2 = make_float2(nz, nz);
+            // the segment just completed in the warp's staged rows goes out: (qs + 1) * 16 columns = `pieces` 16-byte pieces per row;
+            // lane i takes piece i % pieces of row i / pieces, then 32 further on, ...: a store instruction covers whole rows
+            auto copy_out = [&](const int q, const int qs) {
+#ifdef NFE_MC_BULK_EPILOGUE
+                if (valid) {
+                    tc::fence_async_smem();             // this thread's row, written through the generic proxy, is read by the async proxy
+                    bulk_store(dst + (q - qs) * 16, reinterpret_cast<const void*>(__cvta_shared_to_generic(my_row)), (uint32_t)((qs + 1) * 16 * (int)sizeof(T)));
+                    bulk_commit();
+                    pending = true;
                 }
-                if (staged || (vec_ok && o0 + 16 <= a.out_ch)) {
-                    unsigned char* out = staged ? my_row + qs * 16 * (int)sizeof(T) : reinterpret_cast<unsigned char*>(dst + q * 16);
-                    if constexpr (PARTS == 1) {
-                        uint32_t w[8];
+#else
+                const int pieces = (qs + 1) * (int)sizeof(T), shift = 31 - __clz(pieces);       // 2 .. 32
+                const bool pow2 = (pieces & (pieces - 1)) == 0;                                   // (not for e.g. 96 output channels)
+                const long long seg_off = (long long)(q - qs) * 16 * (int)sizeof(T);
+                __syncwarp();
+                // four pieces per trip: the shared-memory reads are issued together, then the stores (`pieces` is even, so 32 * pieces is a
+                // multiple of 64; the second half of a trip is guarded for the case it is not a multiple of 128)
+#pragma unroll 1
+                for (int i0 = lane; i0 < 32 * pieces; i0 += 128) {
+                    uint4 u[4];
+                    unsigned long long d[4];
+                    int pcs[4];
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) { const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&h); }
-                        uint4* d4 = reinterpret_cast<uint4*>(out);
-                        d4[0] = make_uint4(w[0], w[1], w[2], w[3]); d4[1] = make_uint4(w[4], w[5], w[6], w[7]);
-                    } else {
-                        float4* d4 = reinterpret_cast<float4*>(out);
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = i0 + 32 * k, r = pow2 ? i >> shift : i / pieces;
+                        pcs[k] = i - r * pieces;
+                        d[k] = __shfl_sync(0xffffffffu, dst_bits, r & 31);
+                        if (i >= 32 * pieces) d[k] = 0ull;
+                        u[k] = lds128(warp_rows + (uint32_t)((r & 31) * PITCH + pcs[k] * 16));
+                    }
 #pragma unroll
-                        for (int i = 0; i < 4; ++i) d4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-                    }
-                    if (staged && (qs == SEG_Q - 1 || q == nq - 1)) {
-                        tc::fence_async_smem();             // this thread's row, written through the generic proxy, is read by the async proxy
-                        bulk_store(dst + (q - qs) * 16, my_row, (uint32_t)((qs + 1) * 16 * (int)sizeof(T)));
-                        bulk_commit();
-                        pending = true;
-                    }
+                    for (int k = 0; k < 4; ++k)
+                        if (d[k]) *reinterpret_cast<uint4*>(d[k] + seg_off + pcs[k] * 16) = u[k];
+                }
+                __syncwarp();                          // the rows are rewritten by the next segment
+#endif
+            };
+            auto stage = [&](const int qs, const float (&v)[16]) {
+                // (rows outside the image are staged too and skipped by the copy-out: the warp stays converged)
+                const uint32_t out = my_row + (uint32_t)(qs * 16 * (int)sizeof(T));
+                if constexpr (PARTS == 1) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { const __half2 h = __floats2half2_rn(v[2 * i], v[2 * i + 1]); w[i] = *reinterpret_cast<const uint32_t*>(&h); }
+                    sts128(out, w[0], w[1], w[2], w[3]); sts128(out + 16, w[4], w[5], w[6], w[7]);
                 } else {
 #pragma unroll
-                    for (int i = 0; i < 16; ++i)
-                        if (o0 + i < a.out_ch) {
-                            if constexpr (PARTS == 1) dst[q * 16 + i] = __float2half_rn(v[i]); else dst[q * 16 + i] = v[i];
+                    for (int i = 0; i < 4; ++i)
+                        sts128(out + 16 * i, __float_as_uint(v[4 * i]), __float_as_uint(v[4 * i + 1]), __float_as_uint(v[4 * i + 2]), __float_as_uint(v[4 * i + 3]));
+                }
+            };
+            const uint32_t t_acc = t_lane + m * a.n_tile;
+            if (staged && (raw || fast_act)) {
+                // ---- the production path: staged rows, packed math, two register arrays
+                auto group = [&](const int q, float (&v)[16]) {
+                    const int qs = q % SEG_Q;
+#ifdef NFE_MC_BULK_EPILOGUE
+                    if (qs == 0 && pending) { bulk_wait_read(); pending = false; }      // the row buffer is free once the previous store has read it
+#endif
+                    if (!raw) {
+#pragma unroll
+                        for (int i4 = 0; i4 < 4; ++i4) {
+                            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + q * 16 + 4 * i4);      // same address in every lane: broadcast
+                            const float2 t0 = fadd2(fadd2(make_float2(v[4 * i4], v[4 * i4 + 1]), nz2), make_float2(b4.x, b4.y));
+                            const float2 t1 = fadd2(fadd2(make_float2(v[4 * i4 + 2], v[4 * i4 + 3]), nz2), make_float2(b4.z, b4.w));
+                            const float2 p0 = fmul2(t0, gp2), n0 = fmul2(t0, gn2), p1 = fmul2(t1, gp2), n1 = fmul2(t1, gn2);
+                            v[4 * i4] = fminf(fmax3(p0.x, n0.x, -clampv), clampv); v[4 * i4 + 1] = fminf(fmax3(p0.y, n0.y, -clampv), clampv);
+                            v[4 * i4 + 2] = fminf(fmax3(p1.x, n1.x, -clampv), clampv); v[4 * i4 + 3] = fminf(fmax3(p1.y, n1.y, -clampv), clampv);
                         }
+                    }
+                    stage(qs, v);
+                };
+                float ra[16], rb[16];
+                if (q0 < q1) tc::tmem_ld16(t_acc + q0 * 16, ra);
+#pragma unroll 1
+                for (int q = q0; q < q1; q += 2) {
+                    MC_CLK(t_p0);
+                    tc::tmem_ld_wait();
+                    if (q + 1 < q1) tc::tmem_ld16(t_acc + (q + 1) * 16, rb);
+                    MC_CLK(t_p1);
+                    group(q, ra);
+                    MC_CLK(t_p2);
+                    if (q + 1 < q1) {
+                        tc::tmem_ld_wait();
+                        if (q + 2 < q1) tc::tmem_ld16(t_acc + (q + 2) * 16, ra);
+                        group(q + 1, rb);
+                    }
+                    MC_CLK(t_p3);
+                    // segments hold an even number of groups: one ends with the pair's second group, or with the range
+                    const int ql = min(q + 1, q1 - 1), qls = ql % SEG_Q;
+                    if (qls == SEG_Q - 1 || ql == q1 - 1) copy_out(ql, qls);
+#ifdef NFE_MC_PROFILE
+                    { const long long t_p4 = clock64(); prof_[15] += t_p1 - t_p0; prof_[14] += t_p2 - t_p1; prof_[13] += t_p3 - t_p2; prof_[11] += t_p4 - t_p3; }
+#endif
+                }
+            } else {
+                // ---- everything else (channel counts or strides that rule out 16-byte stores, tiles past out_ch, unusual slopes): rare, so
+                //      compact rather than fast — rolled loops over a group held in local memory, direct stores
+                float v[16];
+#pragma unroll 1
+                for (int q = q0; q < q1; ++q) {
+                    tc::tmem_ld16(t_acc + q * 16, v);
+                    tc::tmem_ld_wait();
+                    const int o0 = nt * a.n_tile + q * 16;
+#pragma unroll 1
+                    for (int i = 0; i < (valid ? 16 : 0); ++i) {
+                        float t = v[i];
+                        if (!raw) {
+                            t = (t + nz) + s_bias[q * 16 + i];
+                            t *= t > 0.0f ? gain_pos : gain_neg;      // linear / relu / lrelu as one slope pair (bias_act.cu:66-75), then the gain
+                            t = fminf(fmaxf(t, -clampv), clampv);
+                        }
+                        if (o0 + i < a.out_ch) {
+                            if constexpr (PARTS == 1) dst[q * 16 + i] = __float2half_rn(t); else dst[q * 16 + i] = t;
+                        }
+                    }
                 }
             }
         }
-        if (staged) bulk_wait_all();                        // shared memory must outlive the reads, the kernel the writes
+#ifdef NFE_MC_BULK_EPILOGUE
+        if (staged) bulk_wait_read();                       // shared memory must outlive the reads; the writes complete with the kernel
+#endif
         tc::fence_before_sync();
 #ifdef NFE_MC_PROFILE
-        if (threadIdx.x == 0) { prof_[6] = clock64() - t_e1; prof_[5] = t_e1 - t_e0; atomicAdd(&g_mc_prof[5], (unsigned long long)prof_[5]); MC_FLUSH(6); }
+        if (threadIdx.x == 0) { MC_FLUSH(11); MC_FLUSH(13); MC_FLUSH(14); MC_FLUSH(15); prof_[6] = clock64() - t_e1; prof_[5] = t_e1 - t_e0; atomicAdd(&g_mc_prof[5], (unsigned long long)prof_[5]); MC_FLUSH(6); }
 #endif
     }
     __syncthreads();
@@ -686,8 +801,11 @@ __global__ void __launch_bounds__(256) upfir_finish_kernel(const FinishArgs a)
 // 16 bytes of channels per output pixel from 16-byte shared-memory reads.
 constexpr int FT = 16, FT_IN = FT + 3;
 
+#ifndef NFE_FIN_MIN_BLOCKS
+#define NFE_FIN_MIN_BLOCKS 4
+#endif
 template <class T>
-__global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArgs a, int tiles_x, int tiles_y, int slices)
+__global__ void __launch_bounds__(256, NFE_FIN_MIN_BLOCKS) upfir_finish_tiled_kernel(const FinishArgs a, int tiles_x, int tiles_y, int slices)
 {
     constexpr int V = 16 / (int)sizeof(T);                   // channels per 16 bytes
     __shared__ __align__(16) unsigned char tile[FT_IN * FT_IN * 128];
@@ -706,14 +824,16 @@ __global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArg
     const T* tin = static_cast<const T*>(a.t);
     T* yout = static_cast<T*>(a.y);
     const int g = threadIdx.x & 7;
+    // the whole input tile is requested at once with cp.async (zero fill outside the image): ~11 independent 16-byte copies per thread
+    // in flight and no staging registers, where dependent load -> store pairs left the block waiting on one latency after another
     if (g < groups)
         for (int p = threadIdx.x >> 3; p < FT_IN * FT_IN; p += 32) {
             const int iy = oy0 + p / FT_IN - a.pad_y0, ix = ox0 + p % FT_IN - a.pad_x0;
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (iy >= 0 && iy < a.th && ix >= 0 && ix < a.tw)
-                v = __ldg(reinterpret_cast<const uint4*>(tin + (((long long)n * a.th + iy) * a.tw + ix) * a.c + c_base) + g);
-            *reinterpret_cast<uint4*>(tile + p * 128 + g * 16) = v;
+            const bool ok = iy >= 0 && iy < a.th && ix >= 0 && ix < a.tw;
+            cp_async16(tile + p * 128 + g * 16, tin + (((long long)n * a.th + (ok ? iy : 0)) * a.tw + (ok ? ix : 0)) * a.c + c_base + g * V, ok ? 16 : 0);
         }
+    cp_async_commit();
+    cp_async_wait_group<0>();
     __syncthreads();
     bool entry_ok = true;
     if (threadIdx.x < 16) {
@@ -769,29 +889,40 @@ __global__ void __launch_bounds__(256) upfir_finish_tiled_kernel(const FinishArg
     };
     if (separable) {
         const float fx[4] = {f_col[0], f_col[1], f_col[2], f_col[3]}, fy[4] = {f_row[0], f_row[1], f_row[2], f_row[3]};
-        float hs[4][V];                              // horizontal sums of the last four input rows (static indices: the loop is unrolled)
+        // channel pairs as packed f32x2 (one FFMA2 per pair and tap)
+        auto load2 = [&](int row, int col, float2 (&v)[V / 2]) {
+            const uint4 u = *reinterpret_cast<const uint4*>(tile + (row * FT_IN + col) * 128 + g * 16);
+            if constexpr (sizeof(T) == 2) {
+                const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[j] = __half22float2(h[j]);
+            } else {
+                v[0] = make_float2(__uint_as_float(u.x), __uint_as_float(u.y)); v[1] = make_float2(__uint_as_float(u.z), __uint_as_float(u.w));
+            }
+        };
+        float2 hs[4][V / 2];                         // horizontal sums of the last four input rows (static indices: the loop is unrolled)
 #pragma unroll
         for (int r = 0; r < 8 + 3; ++r) {
-            float h[V];
-#pragma unroll
-            for (int j = 0; j < V; ++j) h[j] = 0.0f;
+            float2 h[V / 2];
 #pragma unroll
             for (int kx = 0; kx < 4; ++kx) {
-                float v[V];
-                load8(8 * half + r, px + kx, v);
+                float2 v[V / 2];
+                load2(8 * half + r, px + kx, v);
+                const float2 f2 = make_float2(fx[kx], fx[kx]);
 #pragma unroll
-                for (int j = 0; j < V; ++j) h[j] = fmaf(v[j], fx[kx], h[j]);
+                for (int j = 0; j < V / 2; ++j) h[j] = kx == 0 ? ffma2(v[j], f2, make_float2(0.0f, 0.0f)) : ffma2(v[j], f2, h[j]);
             }
 #pragma unroll
-            for (int j = 0; j < V; ++j) hs[r & 3][j] = h[j];
+            for (int j = 0; j < V / 2; ++j) hs[r & 3][j] = h[j];
             if (r >= 3) {
                 float acc[V];
 #pragma unroll
-                for (int j = 0; j < V; ++j) acc[j] = 0.0f;
+                for (int j = 0; j < V / 2; ++j) {
+                    float2 t = make_float2(0.0f, 0.0f);
 #pragma unroll
-                for (int ky = 0; ky < 4; ++ky)
-#pragma unroll
-                    for (int j = 0; j < V; ++j) acc[j] = fmaf(hs[(r - 3 + ky) & 3][j], fy[ky], acc[j]);
+                    for (int ky = 0; ky < 4; ++ky) t = ffma2(hs[(r - 3 + ky) & 3][j], make_float2(fy[ky], fy[ky]), t);
+                    acc[2 * j] = t.x; acc[2 * j + 1] = t.y;
+                }
                 finish(8 * half + r - 3, acc);
             }
         }
@@ -1116,8 +1247,8 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.halo = pl.halo;
     {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
         const long long rings = (long long)pl.sa * pl.parts * pl.kg * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
-        // rows are staged in segments of at most 512 bytes, one 128-row buffer per epilogue warp group that has an accumulator
-        g.stage_ok = (long long)std::min(2, pl.tp.n_acc) * 128 * (std::min(pl.n_tile * (pl.parts == 1 ? 2 : 4), 512) + 16) <= rings ? 1 : 0;
+        // rows are staged in segments of NFE_MC_SEG_Q 16-column groups, one 128-row buffer per epilogue warp group that has an accumulator
+        g.stage_ok = 2ll * 128 * (std::min(pl.n_tile, NFE_MC_SEG_Q * 16) * (pl.parts == 1 ? 2 : 4) + 16) <= rings ? 1 : 0;
     }
     g.tp = pl.tp;
     g.tiles_x = (pl.grid_w + mc::TILE_W - 1) / mc::TILE_W; g.tiles_y = (pl.grid_h + 16 * pl.ma - 1) / (16 * pl.ma);

@@ -41,3 +41,5 @@ print(f"  mma thread:  loop {buf[2] / ctas:.0f}, waits a_full {buf[0] / ctas:.0f
 print(f"  loader t0:   loading {buf[4] / ctas:.0f}, waits a_empty {buf[3] / ctas:.0f}")
 print(f"  epilogue t0: waits acc_full {buf[5] / ctas:.0f}, epilogue {buf[6] / ctas:.0f}")
 print(f"  b producer:  waits b_empty {buf[7] / ctas:.0f}")
+print(f"  epilogue t0, fast loop: tcgen05.wait::ld + next ld {buf[15] / ctas:.0f}, first group of a pair {buf[14] / ctas:.0f}, second (with its wait) {buf[13] / ctas:.0f}, "
+      f"copy-out {buf[11] / ctas:.0f}")
