@@ -460,24 +460,24 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
                     pending = true;
                 }
 #else
-                const int pieces = (qs + 1) * (int)sizeof(T), shift = 31 - __clz(pieces);       // 2 .. 32
-                const bool pow2 = (pieces & (pieces - 1)) == 0;                                   // (not for e.g. 96 output channels)
+                // (`slots` = pieces rounded up to a power of two: lanes whose slot is past the row's pieces sit a trip out — only a tile
+                //  of 48, 112, ... channels has such a segment)
+                const int pieces = (qs + 1) * (int)sizeof(T), shift = 32 - __clz(pieces - 1), slots = 1 << shift;       // pieces 2 .. 16
                 const long long seg_off = (long long)(q - qs) * 16 * (int)sizeof(T);
                 __syncwarp();
-                // four pieces per trip: the shared-memory reads are issued together, then the stores (`pieces` is even, so 32 * pieces is a
-                // multiple of 64; the second half of a trip is guarded for the case it is not a multiple of 128)
+                // four pieces per trip: the shared-memory reads are issued together, then the stores
 #pragma unroll 1
-                for (int i0 = lane; i0 < 32 * pieces; i0 += 128) {
+                for (int i0 = lane; i0 < 32 * slots; i0 += 128) {
                     uint4 u[4];
                     unsigned long long d[4];
                     int pcs[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        const int i = i0 + 32 * k, r = pow2 ? i >> shift : i / pieces;
-                        pcs[k] = i - r * pieces;
-                        d[k] = __shfl_sync(0xffffffffu, dst_bits, r & 31);
-                        if (i >= 32 * pieces) d[k] = 0ull;
-                        u[k] = lds128(warp_rows + (uint32_t)((r & 31) * PITCH + pcs[k] * 16));
+                        const int i = i0 + 32 * k, r = (i >> shift) & 31;
+                        pcs[k] = i & (slots - 1);
+                        d[k] = __shfl_sync(0xffffffffu, dst_bits, r);
+                        if (i >= 32 * slots || pcs[k] >= pieces) d[k] = 0ull;
+                        u[k] = lds128(warp_rows + (uint32_t)(r * PITCH + min(pcs[k], pieces - 1) * 16));
                     }
 #pragma unroll
                     for (int k = 0; k < 4; ++k)

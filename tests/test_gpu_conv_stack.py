@@ -171,6 +171,8 @@ def _torch_modconv(x, w, s, noise, up, demodulate, flip_weight, f):
     # n, in, out, h, w, k, up        (kc = 16 / 32 / 64 chunks, ragged windows, several N tiles, twin / pair / single-window CTAs)
     (3, 48, 24, 5, 7, 3, 1), (1, 96, 40, 33, 9, 3, 1), (2, 16, 8, 4, 4, 1, 1), (2, 64, 384, 8, 24, 3, 1), (1, 32, 128, 40, 40, 3, 1),
     (5, 48, 16, 7, 5, 3, 2), (1, 160, 96, 16, 8, 3, 2), (2, 256, 256, 32, 32, 3, 1), (9, 128, 128, 16, 16, 3, 1), (1, 32, 3, 50, 50, 1, 1),
+    # odd numbers of 16-column groups (a last staged segment of 1 or 3 groups), a channel count that rules out 16-byte stores
+    (2, 32, 48, 9, 9, 3, 1), (1, 64, 112, 12, 20, 3, 1), (1, 32, 112, 8, 8, 3, 2), (1, 32, 20, 6, 6, 3, 1), (2, 16, 16, 9, 5, 1, 1),
 ])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 def test_modulated_conv2d_shapes_vs_torch(shape, dtype):
