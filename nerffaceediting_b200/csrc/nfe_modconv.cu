@@ -415,11 +415,13 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         // rings — at a pitch of 16 bytes more than the segment, which spreads the lanes over the banks — and the WARP then copies its
         // 32 finished rows out with coalesced 16-byte stores (16 or 32 lanes per row): warp-local, no block-wide synchronisation.
         // (Round 2 first handed each row to the TMA unit as a bulk store; a per-thread cp.async.bulk compiles to a 32-trip waterfall
-        // around a uniform-datapath UBLKCP, ~200 cycles per trip: 7 k cycles for a warp's 32 rows, most of the epilogue.
-        // -DNFE_MC_BULK_EPILOGUE keeps that variant for the A/B record, profiles/modconv_tuning_r02.txt.)
-        // Segments are short (NFE_MC_SEG_Q groups = 64 columns): an SM writes ~28 bytes per clock to global memory (measured: 16 KB per
-        // warp leave in the same ~4.8 k cycles whether 4 or 8 warps store), which is as long as the arithmetic of the groups takes —
-        // with one long segment per row the two ran back to back, with short ones a segment drains while the next is computed.
+        // around a uniform-datapath UBLKCP.  Both variants take the same time — the SM's store path is the limit —; the copy-out needs
+        // no async-proxy fences and no wait before a row is reused.  -DNFE_MC_BULK_EPILOGUE keeps the bulk variant for the A/B record,
+        // profiles/modconv_tuning_r02.txt #13.)
+        // Segments are short (NFE_MC_SEG_Q groups = 64 columns): the stage then needs 144-272 bytes per row instead of 528 and fits
+        // beside every CTA shape.  (Measured: an SM's stores leave at ~28 bytes per clock — 16 KB per warp in ~4.8 k cycles with 8 warps
+        // storing — and segment length does not change the epilogue's length: the stores hold the warp, a segment does not drain
+        // behind the next one's arithmetic.  profiles/modconv_tuning_r02.txt #13.)
         constexpr int SEG_Q = NFE_MC_SEG_Q;                                           // 16-column groups per segment
         const int PITCH = min(a.n_tile, SEG_Q * 16) * (int)sizeof(T) + 16;           // row pitch in the stage
         const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
@@ -437,8 +439,8 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         const float2 gp2 = make_float2(gain_pos, gain_pos), gn2 = make_float2(gain_neg, gain_neg);
 #pragma unroll 1
         // two warp groups: with several accumulators they take alternate ones, with a single one they take the two halves of its
-        // columns (cut at a segment boundary) — a warp's copy-out runs at ~3.3 bytes per clock whatever the others do, so it is the
-        // number of warps storing that sets the epilogue's length
+        // columns (cut at a segment boundary): warps 4-7 would otherwise idle through the epilogue of every N <= 128 tile
+        // (epilogue 6.0 k -> 4.5 k cycles at 128 -> 128 channels)
         const int q_cut = n_acc == 1 ? min(nq, (nq / 2 + SEG_Q - 1) / SEG_Q * SEG_Q) : 0;
         const int q0 = n_acc == 1 && grp == 1 ? q_cut : 0, q1 = n_acc == 1 && grp == 0 ? q_cut : nq;
         for (int m = n_acc == 1 ? 0 : grp; m < n_acc; m += 2) {
