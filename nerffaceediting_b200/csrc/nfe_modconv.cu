@@ -65,6 +65,15 @@ struct TapPlan {
     int dy[MAX_TAPS], dx[MAX_TAPS];       // input pixel of tap t = window pixel + (dy, dx)
     int ky[MAX_TAPS], kx[MAX_TAPS];       // weight element of tap t
     unsigned acc_mask[MAX_TAPS];          // accumulators tap t feeds
+    // Weight blocks = what one weight stage holds and one group of MMAs consumes.  Normally a block is a tap.  Two taps that read the SAME
+    // shifted window and feed ADJACENT accumulators (up = 2: the taps of one input offset belong to neighbouring output phases) are
+    // packed as ONE block of 2 * n_tile rows and issued as ONE MMA of N = 2 * n_tile: an M = 128 MMA costs ~125 cycles whatever N is,
+    // so nine N = 128 MMAs per K step become three of N = 256 and three of N = 128.
+    int n_blk;
+    int blk_tap[MAX_TAPS];                // first tap of block u (its dy / dx / acc_mask)
+    int blk_width[MAX_TAPS];              // 1 or 2 taps
+    int blk_unit[MAX_TAPS];               // offset of block u in the chunk's packed run, in units of one tap's block
+    int tap_blk[MAX_TAPS], tap_half[MAX_TAPS];      // where tap t is packed
     int row_off[MAX_ACC];                 // first window row of the accumulator's 128 pixels
     int gh[MAX_ACC], gw[MAX_ACC];         // output grid of the accumulator
     int oy_off[MAX_ACC], ox_off[MAX_ACC]; // grid pixel (gy, gx) is written to (gy * o_mul + oy_off, gx * o_mul + ox_off)
@@ -82,7 +91,7 @@ struct GemmArgs {
     int noise_w;
     const float* bias;
     int batch, in_h, in_w, in_ch, out_ch;
-    int n_tile, n_tiles, chunks, kc, sb, b_stage, halo, stage_ok;
+    int n_tile, n_tiles, chunks, kc, sb, b_stage, b_slot, halo, stage_ok;     // b_stage: bytes of one tap's block; b_slot: bytes of a ring slot (the widest block)
     int tiles_x, tiles_y;
     int act;                              // bias_act cuda_idx: 1 linear, 2 relu, 3 lrelu
     float alpha, gain, clamp;
@@ -180,13 +189,13 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char* const sA = smem;
     unsigned char* const sB = smem + SA * A_STAGE;
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(sB + a.sb * a.b_stage);
+    uint64_t* const bars = reinterpret_cast<uint64_t*>(sB + a.sb * a.b_slot);
     uint64_t* const a_full = bars, * const a_empty = bars + MAX_SA, * const b_full = bars + 2 * MAX_SA, * const b_empty = b_full + MAX_SB;
     uint64_t* const acc_full = b_empty + MAX_SB;
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
     float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);       // this N tile's bias, zero where there is none
-    uint32_t* const s_tap16 = reinterpret_cast<uint32_t*>(s_bias + 256);      // per tap: descriptor offset of its shifted window (16-byte units)
-    uint32_t* const s_tmask = s_tap16 + MAX_TAPS;                              // per tap: accumulators it feeds
+    uint32_t* const s_tap16 = reinterpret_cast<uint32_t*>(s_bias + 256);      // per weight block: descriptor offset of its shifted window (16-byte units)
+    uint32_t* const s_tmask = s_tap16 + MAX_TAPS;                              // per weight block: accumulators it feeds (bit 8: a block of two taps)
     uint32_t* const s_row16 = s_tmask + MAX_TAPS;                              // per accumulator: descriptor offset of its first window row
 
 #ifdef NFE_MC_PROFILE
@@ -197,7 +206,7 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     const int n = blockIdx.z, nt = blockIdx.y;
     const TapPlan& tp = a.tp;
     const int x0 = (blockIdx.x % a.tiles_x) * TILE_W, y0 = (blockIdx.x / a.tiles_x) * (16 * MA);
-    const int taps = tp.taps, n_acc = tp.n_acc;
+    const int n_blk = tp.n_blk, n_acc = tp.n_acc;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < n_acc * a.n_tile) tmem_cols <<= 1;
 
@@ -210,11 +219,11 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     if (warp == 4) tc::tmem_alloc(tmem_slot, tmem_cols);
     if (threadIdx.x < MAX_TAPS) {
 #ifdef NFE_MC_EXP_ALIGNED
-        s_tap16[threadIdx.x] = (uint32_t)((1 + tp.dy[threadIdx.x]) * HALO_W);
+        s_tap16[threadIdx.x] = (uint32_t)((1 + tp.dy[tp.blk_tap[threadIdx.x]]) * HALO_W);
 #else
-        s_tap16[threadIdx.x] = (uint32_t)((1 + tp.dy[threadIdx.x]) * HALO_W + 1 + tp.dx[threadIdx.x]);
+        s_tap16[threadIdx.x] = (uint32_t)((1 + tp.dy[tp.blk_tap[threadIdx.x]]) * HALO_W + 1 + tp.dx[tp.blk_tap[threadIdx.x]]);
 #endif
-        s_tmask[threadIdx.x] = tp.acc_mask[threadIdx.x];
+        s_tmask[threadIdx.x] = tp.acc_mask[tp.blk_tap[threadIdx.x]] | (tp.blk_width[threadIdx.x] == 2 ? 0x100u : 0u);      // per BLOCK; bit 8: two taps wide
     }
     if (threadIdx.x < MAX_ACC) s_row16[threadIdx.x] = (uint32_t)(tp.row_off[threadIdx.x] * (HALO_W * 16)) >> 4;
     for (int i = threadIdx.x; i < a.n_tile; i += THREADS) {
@@ -319,6 +328,9 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
             const uint32_t b_lbo = a.n_tile * 16, b_part16 = (a.n_tile * a.kc * 2) >> 4, a_part16 = A_PART >> 4;
             const uint64_t da0 = tc::make_desc(0, A_LBO, A_SBO), db0 = tc::make_desc(0, b_lbo, 128);
             const uint32_t a_k16 = (2 * A_LBO) >> 4, b_k16 = (2 * b_lbo) >> 4;
+            // a block of two taps: 2 * n_tile rows per K core matrix column, one MMA of N = 2 * n_tile over two adjacent accumulators
+            const uint32_t idesc_w = make_idesc(128, 2 * a.n_tile, PARTS == 1 ? 0 : 1);
+            const uint64_t db0_w = tc::make_desc(0, 2 * b_lbo, 128);
             const int ksteps = a.kc >> 4;
             // The loop nest stays ROLLED (tap and accumulator tables in shared memory, filled at start-up): unrolled over taps x
             // accumulators x terms it was 16 k instructions in the split-operand build and ran out of the instruction cache — ~500
@@ -337,10 +349,13 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
                 tc::fence_after_sync();
                 const uint32_t a_base16 = tc::smem_u32(sA + s * A_STAGE) >> 4;
 #pragma unroll 1
-                for (int t = 0; t < taps; ++t) {
+                for (int t = 0; t < n_blk; ++t) {
                     MC_WAIT(1, &b_full[sb], sb_par);
                     tc::fence_after_sync();
-                    const uint32_t b16 = tc::smem_u32(sB + sb * a.b_stage) >> 4, a16 = a_base16 + s_tap16[t], mask = s_tmask[t];
+                    const uint32_t b16 = tc::smem_u32(sB + sb * a.b_slot) >> 4, a16 = a_base16 + s_tap16[t], mask = s_tmask[t];
+                    const uint32_t wide = (mask >> 8) & 1u;                  // warp-uniform
+                    const uint32_t idesc_t = wide ? idesc_w : idesc, bp16 = b_part16 << wide, bk16 = b_k16 << wide;
+                    const uint64_t db0_t = wide ? db0_w : db0;
 #pragma unroll 1
                     for (int m = 0; m < n_acc; ++m) {
                         if (!((mask >> m) & 1u)) continue;
@@ -348,14 +363,14 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
                         const uint32_t d_tmem = tmem + m * a.n_tile, am = a16 + s_row16[m];
 #pragma unroll
                         for (int term = 0; term < TERMS; ++term) {          // hi*hi, lo*hi, hi*lo
-                            uint64_t da = da0 + (am + (term == 1 ? a_part16 : 0)), db = db0 + (b16 + (term == 2 ? b_part16 : 0));
+                            uint64_t da = da0 + (am + (term == 1 ? a_part16 : 0)), db = db0_t + (b16 + (term == 2 ? bp16 : 0));
 #pragma unroll 1
                             for (int j = 0; j < ksteps; ++j) {
-                                if (leader) tc::mma_bf16_ss(d_tmem, da, db, idesc, accf);
-                                accf = 1u; da += a_k16; db += b_k16;
+                                if (leader) tc::mma_bf16_ss(d_tmem, da, db, idesc_t, accf);
+                                accf = 1u; da += a_k16; db += bk16;
                             }
                         }
-                        started |= 1u << m;
+                        started |= (1u | (wide << 1)) << m;
                     }
                     if (leader) tc::mma_commit(&b_empty[sb]);          // the weight stage is free once these MMAs have read it
                     if (++sb == a.sb) { sb = 0; sb_par ^= 1u; }
@@ -371,15 +386,17 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     } else if (warp == 5) {
         // ------------------------------------------------------------------ B stream (one thread): packed weights, one block per (chunk, tap)
         if (lane == 0) {
-            const unsigned char* src = a.packed + n * a.packed_item_stride + (long long)nt * a.chunks * taps * a.b_stage;
-            const int total = a.chunks * taps;
-            int sb = 0;
+            const unsigned char* src = a.packed + n * a.packed_item_stride + (long long)nt * a.chunks * tp.taps * a.b_stage;
+            const int total = a.chunks * n_blk;
+            int sb = 0, u = 0;
             uint32_t sb_par = 1;                    // parity of the PREVIOUS use of the stage
             for (int it = 0; it < total; ++it) {
                 if (it >= a.sb) MC_WAIT(7, &b_empty[sb], sb_par);
-                mbar_expect_tx(&b_full[sb], (uint32_t)a.b_stage);
-                bulk_copy(sB + sb * a.b_stage, src, (uint32_t)a.b_stage, &b_full[sb]);
-                src += a.b_stage;
+                const uint32_t bytes = (uint32_t)(a.b_stage * tp.blk_width[u]);         // the blocks of a chunk follow each other in issue order
+                mbar_expect_tx(&b_full[sb], bytes);
+                bulk_copy(sB + sb * a.b_slot, src, bytes, &b_full[sb]);
+                src += bytes;
+                if (++u == n_blk) u = 0;
                 if (++sb == a.sb) { sb = 0; sb_par ^= 1u; }
             }
 #ifdef NFE_MC_PROFILE
@@ -692,15 +709,16 @@ __global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float s0 = s ? __ldg(s + j) : 1.0f; sd[j] = a.prenorm ? s0 / sm : s0; }
     }
-    unsigned char* dst0 = a.packed + n * a.packed_item_stride + (((long long)nt * a.chunks + c) * ph.taps) * a.b_stage +
-                          ((long long)k8 * (rows / 8) + row / 8) * 128 + (row & 7) * 16;
+    unsigned char* const chunk0 = a.packed + n * a.packed_item_stride + (((long long)nt * a.chunks + c) * ph.taps) * a.b_stage;
 #pragma unroll 1
     for (int t = tg; t < ph.taps; t += tg_n) {
         float v[8];
         const int wt = ph.ky[t] * a.ksize + ph.kx[t];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = real ? ((__ldg(w + j * kk + wt) * wm) * sd[j]) * d : 0.0f;
-        unsigned char* dst = dst0 + (long long)t * a.b_stage;
+        // block of this tap: `width` taps side by side, [part][K core matrix column][width * rows / 8 row groups][8 rows][16 bytes]
+        const int width = ph.blk_width[ph.tap_blk[t]], rowb = ph.tap_half[t] * rows + row, rows_b = width * rows;
+        unsigned char* dst = chunk0 + (long long)ph.blk_unit[ph.tap_blk[t]] * a.b_stage + ((long long)k8 * (rows_b / 8) + rowb / 8) * 128 + (rowb & 7) * 16;
         if (a.parts == 1) {
             uint32_t w4[4];
 #pragma unroll
@@ -715,7 +733,7 @@ __global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
                 hi[j] = tc::pack_bf16(h0, h1); lo[j] = tc::pack_bf16(l0, l1);
             }
             *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(dst + a.b_stage / 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            *reinterpret_cast<uint4*>(dst + width * (a.b_stage / 2)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
         }
     }
 }
@@ -1053,7 +1071,7 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(const RgbArgs a)
 
 // ---------------------------------------------------------------------------------------------- host side
 struct Plan {
-    int parts, ma, sa, kg, n_tile, n_tiles, kc, chunks, b_stage, sb, halo;
+    int parts, ma, sa, kg, n_tile, n_tiles, kc, chunks, b_stage, b_slot, sb, halo;
     long long packed_item_bytes, coef_bytes, packed_bytes, trans_bytes, total_bytes;
     int th, tw;                            // transposed-convolution intermediate (up = 2)
     int grid_h, grid_w;                    // pixel grid the windows tile
@@ -1109,8 +1127,6 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     pl.kg = split32 ? 4 : 8;
     const int halo_h = 16 * pl.ma + 2, a_bytes = pl.sa * pl.parts * pl.kg * halo_h * HALO_W * 16;
     const int budget = twin ? (SMEM_BUDGET + 1408) / 2 - 1408 - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM
-    pl.sb = std::min(MAX_SB, (budget - a_bytes) / pl.b_stage);
-    NFE_REQUIRE(pl.sb >= 2, "nfe_modulated_conv2d: internal: weight ring does not fit");
     pl.halo = q.ksize == 3;
     TapPlan& p = pl.tp;
     p = TapPlan{};
@@ -1150,6 +1166,43 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
         p.o_mul = 2;
         pl.grid_h = q.in_h + 1; pl.grid_w = q.in_w + 1;
     }
+    // weight blocks: taps in order; a tap takes along a later one that reads the same shifted window, feeds the next accumulator (same
+    // window rows) and finds it in the same state (both fresh or both started) — see TapPlan.  $NFE_MC_MERGE=0 keeps one tap per block.
+    {
+        static const bool merge_on = [] { const char* e = getenv("NFE_MC_MERGE"); return e ? atoi(e) != 0 : true; }();
+        auto single = [](unsigned m) { return m && !(m & (m - 1)); };
+        auto bit = [](unsigned m) { int b = 0; while (!((m >> b) & 1u)) ++b; return b; };
+        bool used[MAX_TAPS] = {};
+        unsigned started = 0;
+        int unit = 0;
+        p.n_blk = 0;
+        for (int t = 0; t < p.taps; ++t) {
+            if (used[t]) continue;
+            const int u = p.n_blk++;
+            p.blk_tap[u] = t; p.blk_width[u] = 1; p.blk_unit[u] = unit; p.tap_blk[t] = u; p.tap_half[t] = 0;
+            used[t] = true;
+            if (merge_on && q.up == 2 && 2 * pl.n_tile <= 256 && single(p.acc_mask[t])) {
+                const int m = bit(p.acc_mask[t]);
+                for (int t2 = t + 1; t2 < p.taps && m + 1 < p.n_acc; ++t2) {
+                    if (used[t2] || p.dy[t2] != p.dy[t] || p.dx[t2] != p.dx[t] || p.acc_mask[t2] != (1u << (m + 1))) continue;
+                    if (p.row_off[m + 1] != p.row_off[m] || ((started >> m) & 1u) != ((started >> (m + 1)) & 1u)) continue;
+                    // the pending narrower blocks between t and t2 must not touch accumulator m + 1 first: they are issued later
+                    p.blk_width[u] = 2; p.tap_blk[t2] = u; p.tap_half[t2] = 1; used[t2] = true;
+                    started |= 1u << (m + 1);
+                    break;
+                }
+            }
+            started |= p.acc_mask[t];
+            unit += p.blk_width[u];
+        }
+    }
+    {
+        int widest = 1;
+        for (int u = 0; u < p.n_blk; ++u) widest = std::max(widest, p.blk_width[u]);
+        pl.b_slot = widest * pl.b_stage;
+        pl.sb = std::min(MAX_SB, (budget - a_bytes) / pl.b_slot);
+        NFE_REQUIRE(pl.sb >= 2, "nfe_modulated_conv2d: internal: weight ring does not fit");
+    }
     pl.packed_item_bytes = (long long)pl.n_tiles * pl.chunks * p.taps * pl.b_stage;
     auto up256 = [](long long v) { return (v + 255) / 256 * 256; };
     pl.coef_bytes = up256((long long)(q.batch * q.out_ch + q.out_ch + q.batch) * 4);
@@ -1163,7 +1216,7 @@ template <int PARTS, int MA, int SA, int KG>
 static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
-    const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_stage + 256 + 256 * 4 + 128;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table | tap tables
+    const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_slot + 256 + 256 * 4 + 128;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table | tap tables
     static unsigned long long attr_done_mask = 0;         // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1246,9 +1299,9 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     mc::GemmArgs g;
     g.x = q->x; g.packed = packed; g.packed_item_stride = pl.packed_item_bytes;
     g.batch = q->batch; g.in_h = q->in_h; g.in_w = q->in_w; g.in_ch = q->in_ch; g.out_ch = q->out_ch;
-    g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.halo = pl.halo;
+    g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.b_slot = pl.b_slot; g.halo = pl.halo;
     {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
-        const long long rings = (long long)pl.sa * pl.parts * pl.kg * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_stage;
+        const long long rings = (long long)pl.sa * pl.parts * pl.kg * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_slot;
         // rows are staged in segments of NFE_MC_SEG_Q 16-column groups, one 128-row buffer per epilogue warp group that has an accumulator
         g.stage_ok = 2ll * 128 * (std::min(pl.n_tile, NFE_MC_SEG_Q * 16) * (pl.parts == 1 ? 2 : 4) + 16) <= rings ? 1 : 0;
     }
