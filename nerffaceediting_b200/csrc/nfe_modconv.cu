@@ -1114,6 +1114,8 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     const bool twin = q.up == 1 && pl.n_tile <= 128 && !one_by_one && (pl.parts == 1 || can32);
     const bool pair = q.up == 1 && !twin && ((pl.parts == 1 && (ctas_256 >= sm_count() || one_by_one)) ||
                                              (pl.parts == 2 && can32 && !one_by_one && ctas_256 >= sm_count()));
+    // (up = 2 with split operands: blocks of two taps are 64 KB at 64-channel chunks and the ring holds two; 32-channel chunks — five
+    //  slots — measured slower: fp32 SR head 6.13 vs 5.82 ms, profiles/modconv_tuning_r02.txt #14)
     const bool split32 = pl.parts == 2 && can32 && (pl.n_tile > 128 || twin || pair);
     pl.kc = split32 ? 32 : (q.in_ch % 64 == 0 ? 64 : (can32 ? 32 : 16));
     if (pl.parts == 2 && pl.n_tile > 128 && !split32) {        // a wide split tile without 32-channel chunks: fall back to 128 columns
