@@ -23,13 +23,17 @@
 //  * roles: warps 0-3 load A during the main loop, warp 4 issues the MMAs (one elected thread, tcgen05.mma kind::f16, fp32
 //    accumulate), warp 5 streams B, tcgen05.commit releases the stages; all eight warps run the epilogue (thread = TMEM lane =
 //    pixel; warps w and w + 4 share a lane quarter and split the columns).
-//  * epilogue, fused: + noise, + bias, activation (linear / relu / lrelu), gain, clamp, conversion, channels-last store.
+//  * epilogue, fused: + noise, + bias, activation (linear / relu / lrelu), gain, clamp, conversion; rows staged in shared memory in
+//    64-column segments and copied out by their warp in coalesced 16-byte stores (channels-last).
 //  * up = 2 (conv2d_resample.py:117-134): the transposed stride-2 convolution is four phase convolutions (even/odd output rows x
 //    columns: 4 + 2 + 2 + 1 taps, i.e. the 9 taps once — no multiplication by an inserted zero).  ONE CTA computes all four phases of
 //    its window: the halo is loaded once, every tap's MMAs go to the accumulator of the tap's phase (4 accumulators x up to 128
-//    columns of tensor memory), and the epilogue writes them interleaved into the (2H+1) x (2W+1) intermediate; ONE pass then
-//    applies the low-pass filter, noise, bias, activation and clamp (upfir_finish_kernel; the reference makes four passes of it:
-//    upfirdn2d, add_, bias_act).
+//    columns of tensor memory) — two taps of the same input offset, whose phases sit in adjacent accumulators, as ONE weight block
+//    and ONE MMA of twice the width (TapPlan) — and the epilogue writes them interleaved and raw into the (2H+1) x (2W+1)
+//    intermediate; ONE pass then applies the low-pass filter, noise, bias, activation and clamp (upfir_finish_tiled_kernel; the
+//    reference makes four passes of it: upfirdn2d, add_, bias_act).
+//  * ToRGB to <= 4 channels without demodulation (the super-resolution blocks' 256 / 128 -> 3) is a streaming reduction, not a GEMM:
+//    torgb_small_kernel.
 //
 // Arithmetic: fp16 activations -> fp16 operands, one MMA per product (what the reference's fp16 layers do in cuDNN);
 // fp32 activations -> bf16 hi/lo split of both operands, three MMAs per product, fp32 accumulate (~16 significand bits per operand,
