@@ -996,7 +996,9 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(const RgbArgs a)
     for (int i = threadIdx.x; i < a.in_ch * O; i += 256) {
         const int c = i / O, o = i % O;
         const float w = o < a.out_ch ? __ldg(a.weight + n * a.weight_batch_stride + (long long)o * a.in_ch + c) : 0.0f;
-        wm[(c / V) * PS + o * V + (c % V)] = w * (a.styles ? __ldg(a.styles + (long long)n * a.in_ch + c) : 1.0f);
+        float ws = w * (a.styles ? __ldg(a.styles + (long long)n * a.in_ch + c) : 1.0f);
+        if constexpr (sizeof(T) == 2) ws = __half2float(__float2half_rn(ws));      // the reference hands cuDNN w.to(x.dtype), networks_stylegan2.py:87
+        wm[(c / V) * PS + o * V + (c % V)] = ws;
     }
     __syncthreads();
     const T* xin = static_cast<const T*>(a.x) + (long long)n * a.pixels * a.in_ch;
