@@ -182,10 +182,17 @@ template <> struct Elem<2> { using type = float; };
 // MA = window height in units of 16 rows (the window is 16 MA x 8 pixels).
 // SA = halo stages (up = 2 has little MMA work per K chunk, its loads must run several chunks ahead: four).
 // KG = channel groups of 8 a halo stage holds (8 = chunks of 64 channels; 4 = chunks of 32, the split-operand wide tile).
-template <int PARTS, int MA, int SA, int KG>
-__global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 || KG == 4)) ? 2 : 1) conv_gemm_kernel(const GemmArgs a)
+// PS = persistent: one CTA per SM walks its windows (item = blockIdx.x, + gridDim.x, ...) with dedicated roles — warps 0-3 halo loaders,
+// 4-11 epilogue, 12 MMA issue, 13 weight stream — so that the loaders and the weight stream run into the NEXT window's first stages while
+// the epilogue of the current one drains tensor memory (all 512 columns are one window's accumulators: the MMAs themselves cannot overlap
+// it).  What that removes per window: barrier / table / tensor-memory set-up and the latency of the first halo and weight stages.
+constexpr int PS_THREADS = 448;
+template <int PARTS, int MA, int SA, int KG, bool PS = false>
+__global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && SA == 2 && (PARTS == 1 || KG == 4)) ? 2 : 1) conv_gemm_kernel(const GemmArgs a)
 {
     using T = typename Elem<PARTS>::type;
+    constexpr int NTHREADS = PS ? PS_THREADS : THREADS;
+    constexpr int MMA_WARP = PS ? 12 : 4, B_WARP = PS ? 13 : 5, EPI_WARP0 = PS ? 4 : 0;
     constexpr int HALO_H = 16 * MA + 2;
     constexpr int A_LBO = HALO_H * HALO_W * 16;          // bytes between channel groups of 8 (K core matrices)
     constexpr int A_SBO = HALO_W * 16;                    // bytes between window rows (row groups of 8 pixels)
@@ -196,7 +203,8 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     uint64_t* const bars = reinterpret_cast<uint64_t*>(sB + a.sb * a.b_slot);
     uint64_t* const a_full = bars, * const a_empty = bars + MAX_SA, * const b_full = bars + 2 * MAX_SA, * const b_empty = b_full + MAX_SB;
     uint64_t* const acc_full = b_empty + MAX_SB;
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+    uint64_t* const acc_empty = acc_full + 1;                                  // PS: the epilogue warps have drained tensor memory
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
     float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);       // this N tile's bias, zero where there is none
     uint32_t* const s_tap16 = reinterpret_cast<uint32_t*>(s_bias + 256);      // per weight block: descriptor offset of its shifted window (16-byte units)
     uint32_t* const s_tmask = s_tap16 + MAX_TAPS;                              // per weight block: accumulators it feeds (bit 8: a block of two taps)
@@ -207,9 +215,20 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     const long long t_cta0 = clock64();
 #endif
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int n = blockIdx.z, nt = blockIdx.y;
     const TapPlan& tp = a.tp;
-    const int x0 = (blockIdx.x % a.tiles_x) * TILE_W, y0 = (blockIdx.x / a.tiles_x) * (16 * MA);
+    // windows of this CTA: one (grid = windows x N tiles x batch) or, persistent, every gridDim.x-th item of the flat list
+    const int tiles = a.tiles_x * a.tiles_y;
+    const int n_win = PS ? (tiles * a.n_tiles * a.batch - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 1;
+    auto window = [&](int k, int& x0, int& y0, int& n, int& nt) {
+        int tile;
+        if constexpr (PS) {
+            const int item = (int)blockIdx.x + k * (int)gridDim.x, r = item / tiles;
+            tile = item - r * tiles; nt = r % a.n_tiles; n = r / a.n_tiles;
+        } else {
+            tile = blockIdx.x; nt = blockIdx.y; n = blockIdx.z;
+        }
+        x0 = (tile % a.tiles_x) * TILE_W; y0 = (tile / a.tiles_x) * (16 * MA);
+    };
     const int n_blk = tp.n_blk, n_acc = tp.n_acc;
     uint32_t tmem_cols = 32;
     while ((int)tmem_cols < n_acc * a.n_tile) tmem_cols <<= 1;
@@ -218,9 +237,10 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         for (int i = 0; i < MAX_SA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
         tc::mbar_init(acc_full, 1);
+        tc::mbar_init(acc_empty, 8);
         tc::mbar_fence_init();
     }
-    if (warp == 4) tc::tmem_alloc(tmem_slot, tmem_cols);
+    if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, tmem_cols);
     if (threadIdx.x < MAX_TAPS) {
 #ifdef NFE_MC_EXP_ALIGNED
         s_tap16[threadIdx.x] = (uint32_t)((1 + tp.dy[tp.blk_tap[threadIdx.x]]) * HALO_W);
@@ -230,9 +250,13 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         s_tmask[threadIdx.x] = tp.acc_mask[tp.blk_tap[threadIdx.x]] | (tp.blk_width[threadIdx.x] == 2 ? 0x100u : 0u);      // per BLOCK; bit 8: two taps wide
     }
     if (threadIdx.x < MAX_ACC) s_row16[threadIdx.x] = (uint32_t)(tp.row_off[threadIdx.x] * (HALO_W * 16)) >> 4;
-    for (int i = threadIdx.x; i < a.n_tile; i += THREADS) {
-        const int o = blockIdx.y * a.n_tile + i;
-        s_bias[i] = (a.bias && o < a.out_ch) ? __ldg(a.bias + o) : 0.0f;
+    {
+        int x0_, y0_, n_, nt0;
+        window(0, x0_, y0_, n_, nt0);
+        for (int i = threadIdx.x; i < a.n_tile; i += NTHREADS) {
+            const int o = nt0 * a.n_tile + i;
+            s_bias[i] = (a.bias && o < a.out_ch) ? __ldg(a.bias + o) : 0.0f;
+        }
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -240,18 +264,22 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
     const uint32_t tmem = *tmem_slot;
 #ifdef NFE_MC_PROFILE
     const long long t_role0 = clock64();
-    if (threadIdx.x == 0) { prof_[10] = t_role0 - t_cta0; MC_FLUSH(10); atomicAdd(&g_mc_prof[9], 1ull); }
+    if (threadIdx.x == 0) { prof_[10] = t_role0 - t_cta0; MC_FLUSH(10); atomicAdd(&g_mc_prof[9], (unsigned long long)n_win); }      // per WINDOW figures
 #endif
 
     if (warp < 4) {
         // ------------------------------------------------------------------ A loader: one halo window per K chunk
         const int kcores = a.kc >> 3;
         const T* xin = static_cast<const T*>(a.x);
-        for (int c = 0; c < a.chunks; ++c) {
-            const int s = c % SA, r = c / SA;
+        // the chunks of all windows of this CTA form one stream: chunk g = window k, chunk c of it; ring stage g % SA
+        for (int k = 0, g = 0; k < n_win; ++k) {
+        int x0, y0, n, nt;
+        window(k, x0, y0, n, nt);
+        for (int c = 0; c < a.chunks; ++c, ++g) {
+            const int s = g % SA, r = g / SA;
             if constexpr (PARTS == 1) {
-                // up to SA - 1 chunks stay in flight: chunk c - (SA - 1) is handed to the MMA thread before this one is requested
-                if (c >= SA - 1) { cp_async_wait_group<SA - 2>(); tc::fence_async_smem(); tc::mbar_arrive(&a_full[(c - (SA - 1)) % SA]); }
+                // up to SA - 1 chunks stay in flight: chunk g - (SA - 1) is handed to the MMA thread before this one is requested
+                if (g >= SA - 1) { cp_async_wait_group<SA - 2>(); tc::fence_async_smem(); tc::mbar_arrive(&a_full[(g - (SA - 1)) % SA]); }
             }
             if (r > 0) MC_WAIT(3, &a_empty[s], (r - 1) & 1);
             unsigned char* const dst0 = sA + s * A_STAGE;
@@ -310,15 +338,17 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
                 tc::mbar_arrive(&a_full[s]);
             }
         }
+        }
         if constexpr (PARTS == 1) {
+            const int total = n_win * a.chunks;
             cp_async_wait_group<0>();
             tc::fence_async_smem();
-            for (int c = a.chunks > SA - 1 ? a.chunks - (SA - 1) : 0; c < a.chunks; ++c) tc::mbar_arrive(&a_full[c % SA]);
+            for (int g = total > SA - 1 ? total - (SA - 1) : 0; g < total; ++g) tc::mbar_arrive(&a_full[g % SA]);
         }
 #ifdef NFE_MC_PROFILE
         if (threadIdx.x == 0) { prof_[4] = clock64() - t_role0 - prof_[3]; MC_FLUSH(3); MC_FLUSH(4); }
 #endif
-    } else if (warp == 4) {
+    } else if (warp == MMA_WARP) {
         // ------------------------------------------------------------------ MMA issue (one thread).  The descriptors differ only in
         // their 14-bit address field (bytes >> 4), so each one is the constant part plus an add: the issuing thread stays far below
         // the tensor core's 64-128 cycles per instruction.  Every lane runs the loop; one elected lane issues.
@@ -340,16 +370,23 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
             // accumulators x terms it was 16 k instructions in the split-operand build and ran out of the instruction cache — ~500
             // cycles per MMA measured there against the 143 of the (already 7 k instruction) fp16 build.
             int sb = 0;
-            uint32_t sb_par = 0, started = 0;        // started: accumulators that hold a partial sum already
+            uint32_t sb_par = 0;
 #ifdef NFE_MC_EXP_TERMS1
             constexpr int TERMS = 1;
 #else
             constexpr int TERMS = PARTS == 2 ? 3 : 1;
 #endif
 #pragma unroll 1
-            for (int c = 0; c < a.chunks; ++c) {
-                const int s = c % SA;
-                MC_WAIT(0, &a_full[s], (c / SA) & 1);
+            for (int k = 0, g = 0; k < n_win; ++k) {
+            uint32_t started = 0;                    // accumulators that hold a partial sum already
+            if (PS && k > 0) {                       // the previous window's accumulators have been read out
+                MC_WAIT(0, acc_empty, (k - 1) & 1);
+                tc::fence_after_sync();
+            }
+#pragma unroll 1
+            for (int c = 0; c < a.chunks; ++c, ++g) {
+                const int s = g % SA;
+                MC_WAIT(0, &a_full[s], (g / SA) & 1);
                 tc::fence_after_sync();
                 const uint32_t a_base16 = tc::smem_u32(sA + s * A_STAGE) >> 4;
 #pragma unroll 1
@@ -382,19 +419,23 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
                 if (leader) tc::mma_commit(&a_empty[s]);
             }
             if (leader) tc::mma_commit(acc_full);
+            }
 #ifdef NFE_MC_PROFILE
             if (lane == 0) { prof_[2] = clock64() - t_role0; MC_FLUSH(0); MC_FLUSH(1); MC_FLUSH(2); }
 #endif
         }
         __syncwarp();
-    } else if (warp == 5) {
+    } else if (warp == B_WARP) {
         // ------------------------------------------------------------------ B stream (one thread): packed weights, one block per (chunk, tap)
         if (lane == 0) {
-            const unsigned char* src = a.packed + n * a.packed_item_stride + (long long)nt * a.chunks * tp.taps * a.b_stage;
-            const int total = a.chunks * n_blk;
+            const int per_win = a.chunks * n_blk;
             int sb = 0, u = 0;
             uint32_t sb_par = 1;                    // parity of the PREVIOUS use of the stage
-            for (int it = 0; it < total; ++it) {
+            for (int k = 0, it = 0; k < n_win; ++k) {
+            int x0, y0, n, nt;
+            window(k, x0, y0, n, nt);
+            const unsigned char* src = a.packed + n * a.packed_item_stride + (long long)nt * a.chunks * tp.taps * a.b_stage;
+            for (int j = 0; j < per_win; ++j, ++it) {
                 if (it >= a.sb) MC_WAIT(7, &b_empty[sb], sb_par);
                 const uint32_t bytes = (uint32_t)(a.b_stage * tp.blk_width[u]);         // the blocks of a chunk follow each other in issue order
                 mbar_expect_tx(&b_full[sb], bytes);
@@ -403,24 +444,41 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
                 if (++u == n_blk) u = 0;
                 if (++sb == a.sb) { sb = 0; sb_par ^= 1u; }
             }
+            }
 #ifdef NFE_MC_PROFILE
             MC_FLUSH(7);
 #endif
         }
         __syncwarp();
     }
-    {
-        // ------------------------------------------------------------------ epilogue, all eight warps: thread = TMEM lane = pixel of the
-        // window; warps w and w + 4 share a lane quarter and take alternate accumulators
+    if (!PS || (warp >= EPI_WARP0 && warp < EPI_WARP0 + 8)) {
+        // ------------------------------------------------------------------ epilogue, eight warps (all of them, or the dedicated ones of the
+        // persistent CTA): thread = TMEM lane = pixel of the window; warps w and w + 4 share a lane quarter and take alternate accumulators
+        const int ew = warp - EPI_WARP0;
+        int nt_bias;
+        { int x0_, y0_, n_; window(0, x0_, y0_, n_, nt_bias); }
+#pragma unroll 1
+        for (int k = 0; k < n_win; ++k) {
+        int x0, y0, n, nt;
+        window(k, x0, y0, n, nt);
 #ifdef NFE_MC_PROFILE
         const long long t_e0 = clock64();
 #endif
-        MC_WAIT(5, acc_full, 0);
+        MC_WAIT(5, acc_full, k & 1);
         tc::fence_after_sync();
 #ifdef NFE_MC_PROFILE
         const long long t_e1 = clock64();
 #endif
-        const int row = (warp & 3) * 32 + lane, py = row >> 3, px = row & 7, grp = warp >> 2;
+        if (PS && nt != nt_bias) {                  // (several N tiles only) the bias table follows the window's tile
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.n_tile; i += 256) {
+                const int o = nt * a.n_tile + i;
+                s_bias[i] = (a.bias && o < a.out_ch) ? __ldg(a.bias + o) : 0.0f;
+            }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            nt_bias = nt;
+        }
+        const int row = (ew & 3) * 32 + lane, py = row >> 3, px = row & 7, grp = ew >> 2;
         T* yout = static_cast<T*>(a.y);
         const float neg_slope = a.act == 1 ? 1.0f : (a.act == 2 ? 0.0f : a.alpha);
         const float gain_pos = a.gain, gain_neg = a.gain * neg_slope, clampv = a.clamp >= 0.0f ? a.clamp : __int_as_float(0x7f800000);
@@ -429,7 +487,7 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         constexpr int VEC = 16 / (int)sizeof(T);
         const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
         const int nq = a.n_tile / 16;
-        const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        const uint32_t t_lane = tmem + ((uint32_t)((ew & 3) * 32) << 16);
         // Stores: a thread holds 16 channels of ONE pixel at a time, so direct store instructions touch 32 different lines with 16
         // bytes each (measured: the epilogue then runs at the speed of its 8192 partial-sector stores).  Instead every thread builds
         // its pixel's row of n_tile channels, in segments of at most 512 bytes (256 halves / 128 floats), in the (now idle) operand
@@ -443,10 +501,12 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         // beside every CTA shape.  (Measured: an SM's stores leave at ~28 bytes per clock — 16 KB per warp in ~4.8 k cycles with 8 warps
         // storing — and segment length does not change the epilogue's length: the stores hold the warp, a segment does not drain
         // behind the next one's arithmetic.  profiles/modconv_tuning_r02.txt #13.)
-        constexpr int SEG_Q = NFE_MC_SEG_Q;                                           // 16-column groups per segment
+        constexpr int SEG_Q = NFE_MC_SEG_Q * 2 / (int)sizeof(T);                     // 16-column groups per segment: 128 bytes of a row
         const int PITCH = min(a.n_tile, SEG_Q * 16) * (int)sizeof(T) + 16;           // row pitch in the stage
         const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
-        const uint32_t warp_rows = tc::smem_u32(smem) + (uint32_t)((grp * 128 + (warp & 3) * 32) * PITCH);    // this warp's 32 staged rows
+        // (the persistent CTA's rings are busy with the next window: its stage is a region of its own behind the tables)
+        const uint32_t stage0 = tc::smem_u32(smem) + (PS ? (uint32_t)(SA * A_STAGE + a.sb * a.b_slot + 256 + 256 * 4 + 128) : 0u);
+        const uint32_t warp_rows = stage0 + (uint32_t)((grp * 128 + (ew & 3) * 32) * PITCH);    // this warp's 32 staged rows
         const uint32_t my_row = warp_rows + (uint32_t)(lane * PITCH);
 #ifdef NFE_MC_BULK_EPILOGUE
         bool pending = false;                                                        // a bulk store of my_row may still be reading it
@@ -595,12 +655,19 @@ __global__ void __launch_bounds__(THREADS, (MA == 1 && SA == 2 && (PARTS == 1 ||
         if (staged) bulk_wait_read();                       // shared memory must outlive the reads; the writes complete with the kernel
 #endif
         tc::fence_before_sync();
+        if constexpr (PS) {                                // tensor memory is free for the next window's MMAs
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(acc_empty);
+        }
 #ifdef NFE_MC_PROFILE
-        if (threadIdx.x == 0) { MC_FLUSH(11); MC_FLUSH(13); MC_FLUSH(14); MC_FLUSH(15); prof_[6] = clock64() - t_e1; prof_[5] = t_e1 - t_e0; atomicAdd(&g_mc_prof[5], (unsigned long long)prof_[5]); MC_FLUSH(6); }
+        prof_[6] += clock64() - t_e1;
+        (void)t_e0;
+        if (k == n_win - 1 && threadIdx.x == EPI_WARP0 * 32) { MC_FLUSH(5); MC_FLUSH(6); MC_FLUSH(11); MC_FLUSH(13); MC_FLUSH(14); MC_FLUSH(15); }
 #endif
+        }
     }
     __syncthreads();
-    if (warp == 4) {
+    if (warp == MMA_WARP) {
         tc::fence_after_sync();
         tc::tmem_dealloc(tmem, tmem_cols);
     }
@@ -1077,7 +1144,7 @@ __global__ void __launch_bounds__(256) torgb_small_kernel(const RgbArgs a)
 
 // ---------------------------------------------------------------------------------------------- host side
 struct Plan {
-    int parts, ma, sa, kg, n_tile, n_tiles, kc, chunks, b_stage, b_slot, sb, halo;
+    int parts, ma, sa, kg, n_tile, n_tiles, kc, chunks, b_stage, b_slot, sb, halo, persist, stage_bytes;
     long long packed_item_bytes, coef_bytes, packed_bytes, trans_bytes, total_bytes;
     int th, tw;                            // transposed-convolution intermediate (up = 2)
     int grid_h, grid_w;                    // pixel grid the windows tile
@@ -1210,6 +1277,16 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
         pl.b_slot = widest * pl.b_stage;
         pl.sb = std::min(MAX_SB, (budget - a_bytes) / pl.b_slot);
         NFE_REQUIRE(pl.sb >= 2, "nfe_modulated_conv2d: internal: weight ring does not fit");
+        // epilogue stage: two warp groups x 128 rows of one 128-byte segment (+ 16 bytes of pitch)
+        pl.stage_bytes = 2 * 128 * (std::min(pl.n_tile * (pl.parts == 1 ? 2 : 4), NFE_MC_SEG_Q * 32) + 16);
+        // Persistent CTAs (conv_gemm_kernel<..., PS = true>) where one CTA fills the SM anyway (twin CTAs overlap each other already),
+        // every SM gets several windows, and the weight ring keeps three slots beside the stage region.  $NFE_MC_PERSIST=0: never.
+        static const bool persist_on = [] { const char* e = getenv("NFE_MC_PERSIST"); return e ? atoi(e) != 0 : true; }();
+        const long long items = (long long)((q.up == 2 ? q.in_h + 1 : q.in_h) + 16 * pl.ma - 1) / (16 * pl.ma) *
+                                (((q.up == 2 ? q.in_w + 1 : q.in_w) + TILE_W - 1) / TILE_W) * pl.n_tiles * q.batch;
+        const int sb_ps = std::min(MAX_SB, (budget - a_bytes - pl.stage_bytes) / pl.b_slot);
+        pl.persist = persist_on && !twin && items >= 3ll * sm_count() && items < (1ll << 30) && sb_ps >= 3;
+        if (pl.persist) pl.sb = sb_ps;
     }
     pl.packed_item_bytes = (long long)pl.n_tiles * pl.chunks * p.taps * pl.b_stage;
     auto up256 = [](long long v) { return (v + 255) / 256 * 256; };
@@ -1220,23 +1297,29 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     return 0;
 }
 
-template <int PARTS, int MA, int SA, int KG>
+template <int PARTS, int MA, int SA, int KG, bool PS = false>
 static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
-    const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_slot + 256 + 256 * 4 + 128;   // A ring | B ring | 21 mbarriers + the TMEM slot (256 bytes reserved) | bias table | tap tables
+    // A ring | B ring | 22 mbarriers + the TMEM slot (256 bytes reserved) | bias table | tap tables | persistent: the epilogue's stage
+    const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_slot + 256 + 256 * 4 + 128 + (PS ? pl.stage_bytes : 0);
     static unsigned long long attr_done_mask = 0;         // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
     const bool attr_done = dev < 64 && ((attr_done_mask >> dev) & 1ull);
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+        cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG, PS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_gemm_kernel<PARTS, MA, SA, KG, PS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
         if (e != cudaSuccess) { set_error("conv_gemm_kernel: shared memory opt-in: %s", cudaGetErrorString(e)); return 2; }
         if (dev < 64) attr_done_mask |= 1ull << dev;
     }
-    const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)g.batch);
-    conv_gemm_kernel<PARTS, MA, SA, KG><<<grid, THREADS, smem, stream>>>(g);
+    if constexpr (PS) {
+        const long long items = (long long)g.tiles_x * g.tiles_y * pl.n_tiles * g.batch;
+        conv_gemm_kernel<PARTS, MA, SA, KG, true><<<(unsigned)std::min<long long>(items, sm_count()), PS_THREADS, smem, stream>>>(g);
+    } else {
+        const dim3 grid((unsigned)(g.tiles_x * g.tiles_y), (unsigned)pl.n_tiles, (unsigned)g.batch);
+        conv_gemm_kernel<PARTS, MA, SA, KG><<<grid, THREADS, smem, stream>>>(g);
+    }
     return check_launch("conv_gemm_kernel");
 }
 
@@ -1311,7 +1394,7 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
         const long long rings = (long long)pl.sa * pl.parts * pl.kg * (16 * pl.ma + 2) * mc::HALO_W * 16 + (long long)pl.sb * pl.b_slot;
         // rows are staged in segments of NFE_MC_SEG_Q 16-column groups, one 128-row buffer per epilogue warp group that has an accumulator
-        g.stage_ok = 2ll * 128 * (std::min(pl.n_tile, NFE_MC_SEG_Q * 16) * (pl.parts == 1 ? 2 : 4) + 16) <= rings ? 1 : 0;
+        g.stage_ok = (pl.persist || pl.stage_bytes <= rings) ? 1 : 0;
     }
     g.tp = pl.tp;
     g.tiles_x = (pl.grid_w + mc::TILE_W - 1) / mc::TILE_W; g.tiles_y = (pl.grid_h + 16 * pl.ma - 1) / (16 * pl.ma);
@@ -1323,7 +1406,14 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
         g.y = trans; g.ys_w = q->out_ch; g.ys_h = (long long)pl.tw * q->out_ch; g.ys_n = (long long)pl.th * g.ys_h;
         g.noise = nullptr; g.noise_n = 0; g.noise_w = 0; g.bias = nullptr; g.act = 1; g.alpha = 0.0f; g.gain = 1.0f; g.clamp = -1.0f;
     }
-    int rc = pl.parts == 2 ? (pl.kg == 4 ? (pl.ma == 2 ? mc::launch_gemm<2, 2, 2, 4>(g, pl, stream) : mc::launch_gemm<2, 1, 2, 4>(g, pl, stream))
+    int rc;
+    if (pl.persist)
+        rc = pl.parts == 2 ? (pl.kg == 4 ? (pl.ma == 2 ? mc::launch_gemm<2, 2, 2, 4, true>(g, pl, stream) : mc::launch_gemm<2, 1, 2, 4, true>(g, pl, stream))
+                                         : mc::launch_gemm<2, 1, 2, 8, true>(g, pl, stream))
+             : (pl.ma == 2 ? mc::launch_gemm<1, 2, 2, 8, true>(g, pl, stream)
+                           : (pl.sa == 4 ? mc::launch_gemm<1, 1, 4, 8, true>(g, pl, stream) : mc::launch_gemm<1, 1, 2, 8, true>(g, pl, stream)));
+    else
+        rc = pl.parts == 2 ? (pl.kg == 4 ? (pl.ma == 2 ? mc::launch_gemm<2, 2, 2, 4>(g, pl, stream) : mc::launch_gemm<2, 1, 2, 4>(g, pl, stream))
                                          : mc::launch_gemm<2, 1, 2, 8>(g, pl, stream))
              : (pl.ma == 2 ? mc::launch_gemm<1, 2, 2, 8>(g, pl, stream)
                            : (pl.sa == 4 ? mc::launch_gemm<1, 1, 4, 8>(g, pl, stream) : mc::launch_gemm<1, 1, 2, 8>(g, pl, stream)));
