@@ -202,9 +202,9 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
     unsigned char* const sB = smem + SA * A_STAGE;
     uint64_t* const bars = reinterpret_cast<uint64_t*>(sB + a.sb * a.b_slot);
     uint64_t* const a_full = bars, * const a_empty = bars + MAX_SA, * const b_full = bars + 2 * MAX_SA, * const b_empty = b_full + MAX_SB;
-    uint64_t* const acc_full = b_empty + MAX_SB;
-    uint64_t* const acc_empty = acc_full + 1;                                  // PS: the epilogue warps have drained tensor memory
-    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 1);
+    uint64_t* const acc_full = b_empty + MAX_SB;                               // [2]: one per accumulator set
+    uint64_t* const acc_empty = acc_full + 2;                                  // [2] PS: the epilogue warps have drained the set
+    uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);       // this N tile's bias, zero where there is none
     uint32_t* const s_tap16 = reinterpret_cast<uint32_t*>(s_bias + 256);      // per weight block: descriptor offset of its shifted window (16-byte units)
     uint32_t* const s_tmask = s_tap16 + MAX_TAPS;                              // per weight block: accumulators it feeds (bit 8: a block of two taps)
@@ -230,14 +230,17 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
         x0 = (tile % a.tiles_x) * TILE_W; y0 = (tile / a.tiles_x) * (16 * MA);
     };
     const int n_blk = tp.n_blk, n_acc = tp.n_acc;
+    // persistent CTA: when a window's accumulators take at most half of tensor memory there are TWO sets, and the MMAs of window k + 1
+    // run while the epilogue reads window k out
+    const int set_cols = n_acc * a.n_tile, n_sets = (PS && 2 * set_cols <= 512) ? 2 : 1;
     uint32_t tmem_cols = 32;
-    while ((int)tmem_cols < n_acc * a.n_tile) tmem_cols <<= 1;
+    while ((int)tmem_cols < n_sets * set_cols) tmem_cols <<= 1;
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < MAX_SA; ++i) { tc::mbar_init(&a_full[i], 128); tc::mbar_init(&a_empty[i], 1); }
         for (int i = 0; i < MAX_SB; ++i) { tc::mbar_init(&b_full[i], 1); tc::mbar_init(&b_empty[i], 1); }
-        tc::mbar_init(acc_full, 1);
-        tc::mbar_init(acc_empty, 8);
+        tc::mbar_init(&acc_full[0], 1); tc::mbar_init(&acc_full[1], 1);
+        tc::mbar_init(&acc_empty[0], 8); tc::mbar_init(&acc_empty[1], 8);
         tc::mbar_fence_init();
     }
     if (warp == MMA_WARP) tc::tmem_alloc(tmem_slot, tmem_cols);
@@ -379,8 +382,10 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
 #pragma unroll 1
             for (int k = 0, g = 0; k < n_win; ++k) {
             uint32_t started = 0;                    // accumulators that hold a partial sum already
-            if (PS && k > 0) {                       // the previous window's accumulators have been read out
-                MC_WAIT(0, acc_empty, (k - 1) & 1);
+            const int set = k % n_sets, use = k / n_sets;
+            const uint32_t tmem_set = tmem + set * set_cols;
+            if (PS && use > 0) {                     // the set's previous window has been read out
+                MC_WAIT(0, &acc_empty[set], (use - 1) & 1);
                 tc::fence_after_sync();
             }
 #pragma unroll 1
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
                     for (int m = 0; m < n_acc; ++m) {
                         if (!((mask >> m) & 1u)) continue;
                         uint32_t accf = (started >> m) & 1u;
-                        const uint32_t d_tmem = tmem + m * a.n_tile, am = a16 + s_row16[m];
+                        const uint32_t d_tmem = tmem_set + m * a.n_tile, am = a16 + s_row16[m];
 #pragma unroll
                         for (int term = 0; term < TERMS; ++term) {          // hi*hi, lo*hi, hi*lo
                             uint64_t da = da0 + (am + (term == 1 ? a_part16 : 0)), db = db0_t + (b16 + (term == 2 ? bp16 : 0));
@@ -418,7 +423,7 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
                 }
                 if (leader) tc::mma_commit(&a_empty[s]);
             }
-            if (leader) tc::mma_commit(acc_full);
+            if (leader) tc::mma_commit(&acc_full[set]);
             }
 #ifdef NFE_MC_PROFILE
             if (lane == 0) { prof_[2] = clock64() - t_role0; MC_FLUSH(0); MC_FLUSH(1); MC_FLUSH(2); }
@@ -464,7 +469,8 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
 #ifdef NFE_MC_PROFILE
         const long long t_e0 = clock64();
 #endif
-        MC_WAIT(5, acc_full, k & 1);
+        const int set = k % n_sets;
+        MC_WAIT(5, &acc_full[set], (k / n_sets) & 1);
         tc::fence_after_sync();
 #ifdef NFE_MC_PROFILE
         const long long t_e1 = clock64();
@@ -487,7 +493,7 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
         constexpr int VEC = 16 / (int)sizeof(T);
         const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
         const int nq = a.n_tile / 16;
-        const uint32_t t_lane = tmem + ((uint32_t)((ew & 3) * 32) << 16);
+        const uint32_t t_lane = tmem + set * set_cols + ((uint32_t)((ew & 3) * 32) << 16);
         // Stores: a thread holds 16 channels of ONE pixel at a time, so direct store instructions touch 32 different lines with 16
         // bytes each (measured: the epilogue then runs at the speed of its 8192 partial-sector stores).  Instead every thread builds
         // its pixel's row of n_tile channels, in segments of at most 512 bytes (256 halves / 128 floats), in the (now idle) operand
@@ -657,7 +663,7 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
         tc::fence_before_sync();
         if constexpr (PS) {                                // tensor memory is free for the next window's MMAs
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(acc_empty);
+            if (lane == 0) tc::mbar_arrive(&acc_empty[set]);
         }
 #ifdef NFE_MC_PROFILE
         prof_[6] += clock64() - t_e1;
@@ -1184,7 +1190,13 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     const bool one_by_one = q.ksize == 1;
     const bool can32 = q.in_ch % 32 == 0;
     const long long ctas_256 = (long long)((q.in_h + 31) / 32) * ((q.in_w + TILE_W - 1) / TILE_W) * pl.n_tiles * q.batch;
-    const bool twin = q.up == 1 && pl.n_tile <= 128 && !one_by_one && (pl.parts == 1 || can32);
+    //  * a LARGE fp16 layer of N <= 128 does better still as persistent window pairs (below): two 128-column accumulators are half of
+    //    tensor memory, so a persistent CTA has TWO sets and issues window k + 1 while the epilogue reads window k out — the overlap the
+    //    twin CTAs give, plus shared weight stages and no per-window start-up (128->128 at 512^2: 0.77 -> 0.64 ms; with split operands
+    //    the same change measured slower, fp32 SR head 5.64 -> 5.85 ms, so fp32 keeps the twins).  $NFE_MC_PERSIST_N128=0: twins always.
+    static const bool ps_n128_on = [] { const char* e = getenv("NFE_MC_PERSIST_N128"); return e ? atoi(e) != 0 : true; }();
+    const bool twin0 = q.up == 1 && pl.n_tile <= 128 && !one_by_one && (pl.parts == 1 || can32);
+    const bool twin = twin0 && !(ps_n128_on && pl.parts == 1 && ctas_256 >= 3ll * sm_count());
     const bool pair = q.up == 1 && !twin && ((pl.parts == 1 && (ctas_256 >= sm_count() || one_by_one)) ||
                                              (pl.parts == 2 && can32 && !one_by_one && ctas_256 >= sm_count()));
     // (up = 2 with split operands: blocks of two taps are 64 KB at 64-channel chunks and the ring holds two; 32-channel chunks — five
