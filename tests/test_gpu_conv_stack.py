@@ -195,6 +195,34 @@ def test_modulated_conv2d_shapes_vs_torch(shape, dtype):
     assert e < tol, (shape, dtype, e)
 
 
+@pytest.mark.parametrize("case", [
+    # in, out, res, up, batch   (enough windows for the persistent CTAs: several N tiles = the bias table follows the window's tile;
+    #                            N <= 128 = two accumulator sets; up = 2 = one set of four phase accumulators)
+    (32, 512, 128, 1, 4), (64, 128, 256, 1, 2), (32, 64, 256, 2, 4), (32, 256, 128, 1, 8),
+])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_synthesis_layer_large_grids_vs_torch(case, dtype):
+    """SynthesisLayer (networks_stylegan2.py:276-330) on grids of several windows per SM against an fp64 composition of the same
+    formulas: modulated convolution, noise, bias, lrelu * sqrt(2), clamp."""
+    from nerffaceediting_b200 import networks as net
+    import synth_inputs as synth
+    i, o, res, up, n = case
+    layer = synth.fill_module(net.SynthesisLayer(i, o, w_dim=64, resolution=res, up=up, conv_clamp=256), sum(case)).cuda().eval()
+    g = torch.Generator(device="cpu").manual_seed(7 + sum(case))
+    x = torch.randn(n, i, res // up, res // up, generator=g).cuda().to(dtype)
+    w = torch.randn(n, 64, generator=g).cuda()
+    with torch.no_grad():
+        y = layer(x, w, noise_mode='const')
+        styles = layer.affine(w)
+        noise = (layer.noise_const * layer.noise_strength)[None, None].expand(n, 1, res, res)
+        ref = _torch_modconv(x.float(), layer.weight, styles, noise, up, True, up == 1, layer.resample_filter)
+        ref = ref + layer.bias.double().reshape(1, -1, 1, 1)
+        ref = (torch.nn.functional.leaky_relu(ref, 0.2) * (2.0 ** 0.5)).clamp(-256, 256)
+    tol = 1e-4 if dtype == torch.float32 else 1e-2
+    e = rel_err(y.float().cpu().numpy(), ref.float().cpu().numpy())
+    assert e < tol, (case, dtype, e)
+
+
 @pytest.mark.parametrize("tag", ["3x3", "3x3_up2", "1x1_nodemod", "wide_ragged"])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
 def test_shadow_conv2d_resample_serves_the_fused_modulated_conv2d(tag, dtype):
