@@ -1268,7 +1268,10 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
             const int u = p.n_blk++;
             p.blk_tap[u] = t; p.blk_width[u] = 1; p.blk_unit[u] = unit; p.tap_blk[t] = u; p.tap_half[t] = 0;
             used[t] = true;
-            if (merge_on && q.up == 2 && 2 * pl.n_tile <= 256 && single(p.acc_mask[t])) {
+            // (split operands: a two-tap block is 64 KB at 64-channel chunks, the ring then holds two and the CTA cannot be persistent;
+            //  merging still measured faster — fp32 SR head 5.52 vs 5.58 ms, 32->256 up=2 0.49 vs 0.55 ms.  $NFE_MC_MERGE_SPLIT=0: do not)
+            static const bool merge_split = [] { const char* e = getenv("NFE_MC_MERGE_SPLIT"); return e ? atoi(e) != 0 : true; }();
+            if (merge_on && (pl.parts == 1 || merge_split) && q.up == 2 && 2 * pl.n_tile <= 256 && single(p.acc_mask[t])) {
                 const int m = bit(p.acc_mask[t]);
                 for (int t2 = t + 1; t2 < p.taps && m + 1 < p.n_acc; ++t2) {
                     if (used[t2] || p.dy[t2] != p.dy[t] || p.dx[t2] != p.dx[t] || p.acc_mask[t2] != (1u << (m + 1))) continue;
