@@ -368,6 +368,11 @@ int nfe_modulated_conv2d(const nfe_modconv_args* args, void* workspace, int64_t 
  * networks_stylegan2.py:424-433): the convolution kernel reads and writes channels-last, the reference's own code NCHW. */
 int nfe_layout_convert(const void* src, void* dst, int64_t n, int c, int64_t hw, int dtype, int to_channels_last, nfe_stream_t stream);
 
+/* Skip-image accumulation of a synthesis block: img [n, c, hw] (fp32, contiguous NCHW) += y [n, hw, c] (channels-last, NFE_DTYPE_F32 or
+ * NFE_DTYPE_F16) — replaces `y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format); img = img.add_(y)`
+ * (training/networks_stylegan2.py:456-457, training/superresolution.py:249-250) with one pass. */
+int nfe_image_accumulate(const void* y_channels_last, float* img, int64_t n, int c, int64_t hw, int dtype, nfe_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

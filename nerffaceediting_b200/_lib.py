@@ -90,6 +90,7 @@ SIGNATURES = {
     "nfe_run_model_fwd": (c_int, [_CFG_P, _MLP_P, _MLP_P, c_vp, c_vp, c_int, c_vp, c_int, c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "nfe_bias_act": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_int, c_float, c_float, c_float, c_vp]),
     "nfe_layout_convert": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_int, c_vp]),
+    "nfe_image_accumulate": (c_int, [c_vp, c_vp, c_i64, c_int, c_i64, c_int, c_vp]),
     "nfe_modconv_workspace_bytes": (c_i64, [ctypes.POINTER(NfeModconvArgs)]),
     "nfe_modulated_conv2d": (c_int, [ctypes.POINTER(NfeModconvArgs), c_vp, c_i64, c_vp]),
     "nfe_upfirdn2d": (c_int, [c_vp, c_vp, c_vp] + [c_int] * 8 + [ctypes.POINTER(c_i64), ctypes.POINTER(c_i64)] + [c_int] * 9 + [c_float, c_int, c_vp]),

@@ -47,6 +47,20 @@ def _channels_last(x):
     return x.contiguous(memory_format=torch.channels_last)
 
 
+def _accumulate_image(img, y):
+    """networks_stylegan2.py:456-457: `y = y.to(float32, contiguous_format); img = img.add_(y) if img is not None else y`, the conversion
+    and the add as one pass (nfe_image_accumulate) when y comes channels-last out of the convolution kernel."""
+    if (img is not None and y.is_cuda and y.ndim == 4 and y.dtype in (torch.float32, torch.float16) and img.dtype == torch.float32
+            and img.shape == y.shape and img.is_contiguous() and y.is_contiguous(memory_format=torch.channels_last)
+            and not y.is_contiguous() and y.shape[0] <= 65535 and y.numel() > 0):
+        n, c, h, w = y.shape
+        with _Guard(y):
+            _lib.check(_lib.load().nfe_image_accumulate(_ptr(y), _ptr(img), n, c, h * w, _LAYOUT_DT[y.dtype], _stream(y)), "nfe_image_accumulate")
+        return img
+    y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format)
+    return img.add_(y) if img is not None else y
+
+
 def _nchw(x):
     """x [N,C,H,W] as a contiguous-NCHW tensor (the layout the reference's own code expects back)."""
     if x.is_contiguous():
@@ -324,8 +338,7 @@ class SynthesisBlock(torch.nn.Module):
             img = sg.upsample2d(img, self.resample_filter)
         if self.is_last or self.architecture == 'skip':
             y = self.torgb(x, next(w_iter))
-            y = y.to(dtype=torch.float32, memory_format=torch.contiguous_format)
-            img = img.add_(y) if img is not None else y
+            img = _accumulate_image(img, y)
         assert x.dtype == dtype
         assert img is None or img.dtype == torch.float32
         return x, img

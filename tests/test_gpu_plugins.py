@@ -151,3 +151,17 @@ def test_layout_convert_is_bit_exact(dtype, shape):
     assert torch.equal(cl.permute(0, 2, 3, 1).contiguous(), x.permute(0, 2, 3, 1).contiguous())
     back = net._nchw(cl)
     assert back.is_contiguous() and torch.equal(back, x)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("shape", [(2, 96, 33, 17), (8, 3, 64, 64), (3, 200, 5, 7), (1, 4, 9, 9)])
+def test_image_accumulate_is_the_reference_s_two_steps(dtype, shape):
+    """nfe_image_accumulate == `y.to(float32, contiguous_format); img.add_(y)` (networks_stylegan2.py:456-457), bit for bit."""
+    from nerffaceediting_b200 import networks as net
+    y = torch.randn(shape, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    img = torch.randn(shape, device="cuda")
+    want = img.clone().add_(y.to(dtype=torch.float32, memory_format=torch.contiguous_format))
+    got = net._accumulate_image(img, y)
+    assert got is img and got.is_contiguous() and torch.equal(got, want)
+    first = net._accumulate_image(None, y)                      # first block: the image IS y
+    assert first.dtype == torch.float32 and first.is_contiguous() and torch.equal(first, y.float())
