@@ -453,16 +453,26 @@ __global__ void __launch_bounds__(256) image_accumulate_kernel(const T* __restri
     const T* s = src + n * (int64_t)rows * cols;
     float* d = dst + n * (int64_t)rows * cols;
     const int lx = threadIdx.x & 63, ly = threadIdx.x >> 6;
-#pragma unroll 4
-    for (int r = ly; r < 64; r += 4) {
-        const int gr = tr + r, gc = tc0 + lx;
-        if (gr < rows && gc < cols) tile[r][lx] = (float)s[(int64_t)gr * cols + gc];
+    // (all 16 loads of a thread are issued before the first use: the pass is a read-modify-write and latency-bound otherwise)
+    T in[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int gr = tr + ly + 4 * i, gc = tc0 + lx;
+        in[i] = (gr < rows && gc < cols) ? s[(int64_t)gr * cols + gc] : T(0.0f);
     }
+    float old[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int gc = tc0 + ly + 4 * i, gr = tr + lx;
+        old[i] = (gc < cols && gr < rows) ? d[(int64_t)gc * rows + gr] : 0.0f;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) tile[ly + 4 * i][lx] = (float)in[i];
     __syncthreads();
-#pragma unroll 4
-    for (int c = ly; c < 64; c += 4) {
-        const int gc = tc0 + c, gr = tr + lx;
-        if (gc < cols && gr < rows) { float* p = d + (int64_t)gc * rows + gr; *p = *p + tile[lx][c]; }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const int c = ly + 4 * i, gc = tc0 + c, gr = tr + lx;
+        if (gc < cols && gr < rows) d[(int64_t)gc * rows + gr] = old[i] + tile[lx][c];
     }
 }
 
