@@ -58,7 +58,8 @@ constexpr int HALO_W = 10;
 #endif
 constexpr int TILE_W = 8, MAX_TAPS = 9, THREADS = 256, MAX_SA = 4, MAX_SB = 6;
 
-constexpr int SMEM_BUDGET = 227 * 1024 - 256 - 1024 - 128;
+constexpr int TABLE_BYTES = 256 + 1024 + 1024 + 128;      // mbarriers + TMEM slot | bias of the N tile | output scale of the N tile | tap tables
+constexpr int SMEM_BUDGET = 227 * 1024 - TABLE_BYTES;
 
 constexpr int MAX_ACC = 4;
 
@@ -94,6 +95,11 @@ struct GemmArgs {
     long long noise_n;
     int noise_w;
     const float* bias;
+    // shared-weight form (split operands): the packed weights are the same for every item; the style multiplies the ACTIVATIONS in the
+    // halo loader and the demodulation coefficient the accumulator in the epilogue — y = d[n,o] * sum W[o,i,k] (s[n,i] x[i]), the
+    // reference's own non-fused formulation (networks_stylegan2.py:69-79).  NULL: weights are per item, modulated when packed.
+    const float* in_scale;                // [batch, in_ch]
+    const float* out_scale;               // [batch, out_ch]
     int batch, in_h, in_w, in_ch, out_ch;
     int n_tile, n_tiles, chunks, kc, sb, b_stage, b_slot, halo, stage_ok;     // b_stage: bytes of one tap's block; b_slot: bytes of a ring slot (the widest block)
     int tiles_x, tiles_y;
@@ -206,7 +212,8 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
     uint64_t* const acc_empty = acc_full + 2;                                  // [2] PS: the epilogue warps have drained the set
     uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
     float* const s_bias = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars) + 256);       // this N tile's bias, zero where there is none
-    uint32_t* const s_tap16 = reinterpret_cast<uint32_t*>(s_bias + 256);      // per weight block: descriptor offset of its shifted window (16-byte units)
+    float* const s_oscale = s_bias + 256;                                       // this (item, N tile)'s output scale (demodulation coefficients), 1 where there is none
+    uint32_t* const s_tap16 = reinterpret_cast<uint32_t*>(s_oscale + 256);      // per weight block: descriptor offset of its shifted window (16-byte units)
     uint32_t* const s_tmask = s_tap16 + MAX_TAPS;                              // per weight block: accumulators it feeds (bit 8: a block of two taps)
     uint32_t* const s_row16 = s_tmask + MAX_TAPS;                              // per accumulator: descriptor offset of its first window row
 
@@ -254,11 +261,12 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
     }
     if (threadIdx.x < MAX_ACC) s_row16[threadIdx.x] = (uint32_t)(tp.row_off[threadIdx.x] * (HALO_W * 16)) >> 4;
     {
-        int x0_, y0_, n_, nt0;
-        window(0, x0_, y0_, n_, nt0);
+        int x0_, y0_, n0, nt0;
+        window(0, x0_, y0_, n0, nt0);
         for (int i = threadIdx.x; i < a.n_tile; i += NTHREADS) {
             const int o = nt0 * a.n_tile + i;
             s_bias[i] = (a.bias && o < a.out_ch) ? __ldg(a.bias + o) : 0.0f;
+            s_oscale[i] = (a.out_scale && o < a.out_ch) ? __ldg(a.out_scale + (long long)n0 * a.out_ch + o) : 1.0f;
         }
     }
     tc::fence_before_sync();
@@ -292,6 +300,13 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
             // of them: one pixel at a time it ran at one DRAM latency per pixel (27 k cycles per chunk measured).
             const int k8 = threadIdx.x & 7;
             int hy = (threadIdx.x >> 3) / HALO_W, hx = (threadIdx.x >> 3) % HALO_W;
+            float4 sc0 = make_float4(1.f, 1.f, 1.f, 1.f), sc1 = sc0;          // styles of this thread's 8 channels (shared-weight form)
+            if constexpr (PARTS == 2) {
+                if (a.in_scale && k8 < kcores) {
+                    const float4* sp = reinterpret_cast<const float4*>(a.in_scale + (long long)n * a.in_ch + c * a.kc + k8 * 8);
+                    sc0 = __ldg(sp); sc1 = __ldg(sp + 1);
+                }
+            }
             if (k8 < kcores) {
                 constexpr int BATCH = PARTS == 1 ? 1 : 4;
                 for (int hp0 = threadIdx.x >> 3; hp0 < HALO_H * HALO_W; hp0 += 16 * BATCH) {
@@ -320,7 +335,8 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
 #pragma unroll
                         for (int b = 0; b < BATCH; ++b) {
                             if (!live[b]) continue;
-                            const float v[8] = {v0[b].x, v0[b].y, v0[b].z, v0[b].w, v1[b].x, v1[b].y, v1[b].z, v1[b].w};
+                            const float v[8] = {v0[b].x * sc0.x, v0[b].y * sc0.y, v0[b].z * sc0.z, v0[b].w * sc0.w,
+                                                v1[b].x * sc1.x, v1[b].y * sc1.y, v1[b].z * sc1.z, v1[b].w * sc1.w};
                             uint32_t hi[4], lo[4];
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
@@ -460,8 +476,8 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
         // ------------------------------------------------------------------ epilogue, eight warps (all of them, or the dedicated ones of the
         // persistent CTA): thread = TMEM lane = pixel of the window; warps w and w + 4 share a lane quarter and take alternate accumulators
         const int ew = warp - EPI_WARP0;
-        int nt_bias;
-        { int x0_, y0_, n_; window(0, x0_, y0_, n_, nt_bias); }
+        int nt_bias, n_scale;
+        { int x0_, y0_; window(0, x0_, y0_, n_scale, nt_bias); }
 #pragma unroll 1
         for (int k = 0; k < n_win; ++k) {
         int x0, y0, n, nt;
@@ -475,21 +491,22 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
 #ifdef NFE_MC_PROFILE
         const long long t_e1 = clock64();
 #endif
-        if (PS && nt != nt_bias) {                  // (several N tiles only) the bias table follows the window's tile
+        if (PS && (nt != nt_bias || (a.out_scale && n != n_scale))) {      // the bias / output-scale tables follow the window's tile and item
             asm volatile("bar.sync 1, 256;" ::: "memory");
             for (int i = threadIdx.x - EPI_WARP0 * 32; i < a.n_tile; i += 256) {
                 const int o = nt * a.n_tile + i;
                 s_bias[i] = (a.bias && o < a.out_ch) ? __ldg(a.bias + o) : 0.0f;
+                s_oscale[i] = (a.out_scale && o < a.out_ch) ? __ldg(a.out_scale + (long long)n * a.out_ch + o) : 1.0f;
             }
             asm volatile("bar.sync 1, 256;" ::: "memory");
-            nt_bias = nt;
+            nt_bias = nt; n_scale = n;
         }
         const int row = (ew & 3) * 32 + lane, py = row >> 3, px = row & 7, grp = ew >> 2;
         T* yout = static_cast<T*>(a.y);
         const float neg_slope = a.act == 1 ? 1.0f : (a.act == 2 ? 0.0f : a.alpha);
         const float gain_pos = a.gain, gain_neg = a.gain * neg_slope, clampv = a.clamp >= 0.0f ? a.clamp : __int_as_float(0x7f800000);
         // the up = 2 intermediate leaves as it is (noise, bias, activation, gain and clamp belong to the filter pass): convert and store
-        const bool raw = !a.noise && !a.bias && a.act == 1 && a.gain == 1.0f && a.clamp < 0.0f;
+        const bool raw = !a.noise && !a.bias && !a.out_scale && a.act == 1 && a.gain == 1.0f && a.clamp < 0.0f;
         constexpr int VEC = 16 / (int)sizeof(T);
         const bool vec_ok = a.out_ch % VEC == 0 && (reinterpret_cast<uintptr_t>(a.y) & 15) == 0 && a.ys_n % VEC == 0 && a.ys_h % VEC == 0 && a.ys_w % VEC == 0;
         const int nq = a.n_tile / 16;
@@ -511,7 +528,7 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
         const int PITCH = min(a.n_tile, SEG_Q * 16) * (int)sizeof(T) + 16;           // row pitch in the stage
         const bool staged = vec_ok && a.stage_ok && (nt + 1) * a.n_tile <= a.out_ch;
         // (the persistent CTA's rings are busy with the next window: its stage is a region of its own behind the tables)
-        const uint32_t stage0 = tc::smem_u32(smem) + (PS ? (uint32_t)(SA * A_STAGE + a.sb * a.b_slot + 256 + 256 * 4 + 128) : 0u);
+        const uint32_t stage0 = tc::smem_u32(smem) + (PS ? (uint32_t)(SA * A_STAGE + a.sb * a.b_slot + TABLE_BYTES) : 0u);
         const uint32_t warp_rows = stage0 + (uint32_t)((grp * 128 + (ew & 3) * 32) * PITCH);    // this warp's 32 staged rows
         const uint32_t my_row = warp_rows + (uint32_t)(lane * PITCH);
 #ifdef NFE_MC_BULK_EPILOGUE
@@ -601,8 +618,9 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
 #pragma unroll
                         for (int i4 = 0; i4 < 4; ++i4) {
                             const float4 b4 = *reinterpret_cast<const float4*>(s_bias + q * 16 + 4 * i4);      // same address in every lane: broadcast
-                            const float2 t0 = fadd2(fadd2(make_float2(v[4 * i4], v[4 * i4 + 1]), nz2), make_float2(b4.x, b4.y));
-                            const float2 t1 = fadd2(fadd2(make_float2(v[4 * i4 + 2], v[4 * i4 + 3]), nz2), make_float2(b4.z, b4.w));
+                            const float4 d4 = *reinterpret_cast<const float4*>(s_oscale + q * 16 + 4 * i4);    // 1 unless the weights are shared
+                            const float2 t0 = fadd2(ffma2(make_float2(v[4 * i4], v[4 * i4 + 1]), make_float2(d4.x, d4.y), nz2), make_float2(b4.x, b4.y));
+                            const float2 t1 = fadd2(ffma2(make_float2(v[4 * i4 + 2], v[4 * i4 + 3]), make_float2(d4.z, d4.w), nz2), make_float2(b4.z, b4.w));
                             const float2 p0 = fmul2(t0, gp2), n0 = fmul2(t0, gn2), p1 = fmul2(t1, gp2), n1 = fmul2(t1, gn2);
                             v[4 * i4] = fminf(fmax3(p0.x, n0.x, -clampv), clampv); v[4 * i4 + 1] = fminf(fmax3(p0.y, n0.y, -clampv), clampv);
                             v[4 * i4 + 2] = fminf(fmax3(p1.x, n1.x, -clampv), clampv); v[4 * i4 + 3] = fminf(fmax3(p1.y, n1.y, -clampv), clampv);
@@ -646,7 +664,7 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
                     for (int i = 0; i < (valid ? 16 : 0); ++i) {
                         float t = v[i];
                         if (!raw) {
-                            t = (t + nz) + s_bias[q * 16 + i];
+                            t = fmaf(t, s_oscale[q * 16 + i], nz) + s_bias[q * 16 + i];
                             t *= t > 0.0f ? gain_pos : gain_neg;      // linear / relu / lrelu as one slope pair (bias_act.cu:66-75), then the gain
                             t = fminf(fmaxf(t, -clampv), clampv);
                         }
@@ -693,6 +711,7 @@ struct PackArgs {
     long long packed_item_stride;
     long long weight_batch_stride;        // elements between the items' weights (0: shared)
     int batch, out_ch, in_ch, ksize, demodulate, prenorm, parts;
+    int shared;                           // pack W alone, once for the batch (the style and the demodulation travel with the GEMM)
     int n_tile, n_tiles, chunks, kc, b_stage;
     TapPlan tp;
 };
@@ -781,8 +800,8 @@ __global__ void __launch_bounds__(256) modconv_pack_kernel(const PackArgs a)
     if (real) {
         const float sm = a.prenorm ? a.smax[n] : 1.0f;
         wm = a.prenorm ? a.wmul[o] : 1.0f;
-        d = a.dcoef[(long long)n * a.out_ch + o];
-        const float* s = a.styles ? a.styles + (long long)n * a.in_ch + i0 : nullptr;
+        d = a.shared ? 1.0f : a.dcoef[(long long)n * a.out_ch + o];
+        const float* s = (a.styles && !a.shared) ? a.styles + (long long)n * a.in_ch + i0 : nullptr;
 #pragma unroll
         for (int j = 0; j < 8; ++j) { const float s0 = s ? __ldg(s + j) : 1.0f; sd[j] = a.prenorm ? s0 / sm : s0; }
     }
@@ -1213,7 +1232,7 @@ static int make_plan(const nfe_modconv_args& q, Plan& pl)
     pl.sa = (pl.parts == 1 && q.up == 2) ? 4 : 2;
     pl.kg = split32 ? 4 : 8;
     const int halo_h = 16 * pl.ma + 2, a_bytes = pl.sa * pl.parts * pl.kg * halo_h * HALO_W * 16;
-    const int budget = twin ? (SMEM_BUDGET + 1408) / 2 - 1408 - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM
+    const int budget = twin ? (SMEM_BUDGET + TABLE_BYTES) / 2 - TABLE_BYTES - 1024 : SMEM_BUDGET;       // per-CTA reservation of 1 KB when two share an SM
     pl.halo = q.ksize == 3;
     TapPlan& p = pl.tp;
     p = TapPlan{};
@@ -1317,7 +1336,7 @@ static int launch_gemm(const GemmArgs& g, const Plan& pl, cudaStream_t stream)
 {
     const int halo_h = 16 * MA + 2;
     // A ring | B ring | 22 mbarriers + the TMEM slot (256 bytes reserved) | bias table | tap tables | persistent: the epilogue's stage
-    const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_slot + 256 + 256 * 4 + 128 + (PS ? pl.stage_bytes : 0);
+    const size_t smem = (size_t)SA * PARTS * KG * halo_h * HALO_W * 16 + (size_t)pl.sb * pl.b_slot + TABLE_BYTES + (PS ? pl.stage_bytes : 0);
     static unsigned long long attr_done_mask = 0;         // per device: function attributes belong to the device's context
     int dev = 0;
     cudaGetDevice(&dev);
@@ -1395,15 +1414,23 @@ NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, 
     pa.prenorm = (q->dtype == NFE_DTYPE_F16 && q->demodulate) ? 1 : 0;                     // networks_stylegan2.py:55-57
     pa.parts = pl.parts; pa.n_tile = pl.n_tile; pa.n_tiles = pl.n_tiles; pa.chunks = pl.chunks; pa.kc = pl.kc; pa.b_stage = pl.b_stage;
     pa.tp = pl.tp;
+    // Split operands (fp32) with one weight for the batch: pack W ONCE and let the GEMM carry the style (on the activations, in the halo
+    // loader) and the demodulation coefficient (on the accumulator, in the epilogue) — the reference's non-fused formulation,
+    // networks_stylegan2.py:69-79, equal to the fused one up to fp32 rounding order.  The per-item pack wrote batch x the weight tensor
+    // (hi + lo) per layer call: 0.47 ms of a 5.2 ms fp32 backbone pass.  $NFE_MC_SHARED_W=0 keeps per-item weights.
+    static const bool shared_on = [] { const char* e = getenv("NFE_MC_SHARED_W"); return e ? atoi(e) != 0 : true; }();
+    const bool shared = shared_on && pl.parts == 2 && q->weight_batch_stride == 0 && q->batch > 1 && (reinterpret_cast<uintptr_t>(q->styles) & 15) == 0;
+    pa.shared = shared ? 1 : 0;
     NFE_REQUIRE(q->in_ch <= 8192, "nfe_modulated_conv2d: in_channels above 8192");
     mc::modconv_coef_kernel<<<q->out_ch, 128, (size_t)q->in_ch * sizeof(float), stream>>>(pa);
     NFE_LAUNCH_CHECK("modconv_coef_kernel");
     const long long slots = (long long)pl.n_tiles * pl.chunks * (pl.kc / 8) * pl.n_tile * (pl.tp.taps % 3 == 0 ? 3 : 1);
-    mc::modconv_pack_kernel<<<dim3((unsigned)((slots + 255) / 256), q->batch), 256, 0, stream>>>(pa);
+    mc::modconv_pack_kernel<<<dim3((unsigned)((slots + 255) / 256), shared ? 1 : q->batch), 256, 0, stream>>>(pa);
     NFE_LAUNCH_CHECK("modconv_pack_kernel");
 
     mc::GemmArgs g;
-    g.x = q->x; g.packed = packed; g.packed_item_stride = pl.packed_item_bytes;
+    g.x = q->x; g.packed = packed; g.packed_item_stride = shared ? 0 : pl.packed_item_bytes;
+    g.in_scale = shared ? q->styles : nullptr; g.out_scale = (shared && q->demodulate) ? coef : nullptr;
     g.batch = q->batch; g.in_h = q->in_h; g.in_w = q->in_w; g.in_ch = q->in_ch; g.out_ch = q->out_ch;
     g.n_tile = pl.n_tile; g.n_tiles = pl.n_tiles; g.chunks = pl.chunks; g.kc = pl.kc; g.sb = pl.sb; g.b_stage = pl.b_stage; g.b_slot = pl.b_slot; g.halo = pl.halo;
     {   // the epilogue stages two 128-pixel tiles in the operand rings when they fit
