@@ -1369,6 +1369,23 @@ NFE_EXPORT int64_t nfe_modconv_workspace_bytes(const nfe_modconv_args* q)
     return pl.total_bytes;
 }
 
+// Test hook (host only, no GPU needed): the CTA plan make_plan() derives for a layer, as integers —
+// [0] parts [1] ma [2] sa [3] kg [4] n_tile [5] n_tiles [6] kc [7] chunks [8] sb [9] b_stage [10] b_slot [11] persist [12] stage_bytes
+// [13] n_blk [14] taps [15] dynamic shared memory of the launch [16] CTAs per SM the kernel is built for [17 ..] width of each weight block
+NFE_EXPORT int nfe_debug_modconv_plan(const nfe_modconv_args* q, int* out, int n_out)
+{
+    mc::Plan pl;
+    if (!q || !out || n_out < 17 + mc::MAX_TAPS) return 1;
+    if (int rc = mc::make_plan(*q, pl)) return rc;
+    const int twin_shape = (!pl.persist && pl.ma == 1 && pl.sa == 2 && (pl.parts == 1 || pl.kg == 4)) ? 2 : 1;      // conv_gemm_kernel's __launch_bounds__
+    const int v[17] = {pl.parts, pl.ma, pl.sa, pl.kg, pl.n_tile, pl.n_tiles, pl.kc, pl.chunks, pl.sb, pl.b_stage, pl.b_slot, pl.persist, pl.stage_bytes,
+                       pl.tp.n_blk, pl.tp.taps,
+                       pl.sa * pl.parts * pl.kg * (16 * pl.ma + 2) * mc::HALO_W * 16 + pl.sb * pl.b_slot + mc::TABLE_BYTES + (pl.persist ? pl.stage_bytes : 0), twin_shape};
+    for (int i = 0; i < 17; ++i) out[i] = v[i];
+    for (int u = 0; u < mc::MAX_TAPS; ++u) out[17 + u] = u < pl.tp.n_blk ? pl.tp.blk_width[u] : 0;
+    return 0;
+}
+
 NFE_EXPORT int nfe_modulated_conv2d(const nfe_modconv_args* q, void* workspace, int64_t workspace_bytes, nfe_stream_t stream_)
 {
     NFE_REQUIRE(q && q->x && q->weight && q->y, "nfe_modulated_conv2d: null pointer");

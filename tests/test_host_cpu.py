@@ -383,6 +383,60 @@ def test_modconv_plan_and_argument_checks_run_on_the_host(built):
         assert lib.nfe_last_error()
 
 
+def test_modconv_cta_plans_fit_the_sm(built):
+    """The CTA plan of every layer shape of the reference's generator (and a sweep around them), read through the host-only hook
+    nfe_debug_modconv_plan: shared memory within the 227 KB a CTA may have, a weight ring of at least two slots (three beside the
+    persistent CTA's stage region), every tap in exactly one weight block, and the up = 2 blocks paired as DESIGN.md §3.6 says."""
+    lib = _lib.load()
+    A = _lib.NfeModconvArgs
+    fn = lib.nfe_debug_modconv_plan
+    fn.argtypes = [ctypes.POINTER(A), ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+    fn.restype = ctypes.c_int
+
+    def plan(**kw):
+        base = dict(batch=8, in_ch=256, out_ch=256, in_h=256, in_w=256, ksize=3, up=1, demodulate=1, flip_weight=1, act=3, alpha=0.2, gain=1.0,
+                    clamp=256.0, dtype=1)
+        base.update(kw)
+        out = (ctypes.c_int * 26)()
+        assert fn(A(**base), out, 26) == 0, (kw, lib.nfe_last_error())
+        keys = "parts ma sa kg n_tile n_tiles kc chunks sb b_stage b_slot persist stage_bytes n_blk taps smem ctas_per_sm".split()
+        d = dict(zip(keys, out[:17]))
+        d["widths"] = [w for w in out[17:] if w]
+        return d
+
+    shapes = []
+    for dtype in (0, 1):
+        for res, ch in ((4, 512), (8, 512), (16, 512), (32, 512), (64, 512), (128, 256), (256, 128), (512, 64)):      # backbone / SR ladders
+            shapes.append(dict(dtype=dtype, in_ch=ch, out_ch=ch, in_h=res, in_w=res))
+            shapes.append(dict(dtype=dtype, in_ch=min(2 * ch, 512), out_ch=ch, in_h=max(res // 2, 2), in_w=max(res // 2, 2), up=2))
+            shapes.append(dict(dtype=dtype, in_ch=ch, out_ch=96, in_h=res, in_w=res, ksize=1, demodulate=0))
+        for extra in (dict(in_ch=32, out_ch=256, in_h=128, in_w=128, up=2), dict(in_ch=256, out_ch=128, in_h=256, in_w=256, up=2),
+                      dict(in_ch=16, out_ch=8, in_h=5, in_w=7), dict(in_ch=96, out_ch=40, in_h=33, in_w=9), dict(in_ch=64, out_ch=384, in_h=8, in_w=24),
+                      dict(in_ch=48, out_ch=112, in_h=12, in_w=20, batch=1), dict(in_ch=2048, out_ch=256, in_h=64, in_w=64)):
+            shapes.append(dict(dtype=dtype, **extra))
+    seen_persist = seen_twin = seen_pairs = 0
+    for kw in shapes:
+        p = plan(**kw)
+        assert p["smem"] <= 227 * 1024, (kw, p)
+        assert p["sb"] >= (3 if p["persist"] else 2), (kw, p)
+        assert sum(p["widths"]) == p["taps"] and len(p["widths"]) == p["n_blk"], (kw, p)
+        assert p["b_slot"] == max(p["widths"]) * p["b_stage"], (kw, p)
+        assert p["b_stage"] == p["parts"] * p["n_tile"] * p["kc"] * 2 and p["chunks"] * p["kc"] == kw["in_ch"], (kw, p)
+        assert p["n_tile"] % 16 == 0 and p["n_tile"] * p["n_tiles"] >= kw["out_ch"], (kw, p)
+        n_acc = 4 if kw.get("up", 1) == 2 else p["ma"]
+        assert n_acc * p["n_tile"] <= 512, (kw, p)                                       # tensor-memory columns of one accumulator set
+        if p["ctas_per_sm"] == 2 and p["ma"] == 1 and p["n_tile"] <= 128 and kw.get("up", 1) == 1 and kw.get("ksize", 3) == 3:
+            assert 2 * (p["smem"] + 1024) <= 228 * 1024 and 2 * p["n_tile"] <= 512, (kw, p)      # twin CTAs really fit twice
+            seen_twin += 1
+        if kw.get("up", 1) == 2 and 2 * p["n_tile"] <= 256:
+            assert p["widths"] == [2, 1, 2, 1, 2, 1], (kw, p)                            # (0,0)+(0,1) | (0,2) | (1,0)+(1,1) | (1,2) | (2,0)+(2,1) | (2,2)
+            seen_pairs += 1
+        elif kw.get("up", 1) == 1:
+            assert p["widths"] == [1] * p["taps"], (kw, p)
+        seen_persist += p["persist"]
+    assert seen_persist and seen_twin and seen_pairs
+
+
 def test_generator_state_dict_names_are_the_reference_s():
     """The whole-generator mirror (BASELINE configs[1]) accepts the reference's checkpoints: names and shapes recorded from the
     reference's TriPlaneGenerator (tests/golden/make_golden_generator.py)."""
