@@ -541,7 +541,6 @@ __global__ void __launch_bounds__(PS ? PS_THREADS : THREADS, (!PS && MA == 1 && 
         // tcgen05.ld is in flight while this group is processed, without register copies).
         const bool fast_act = a.gain > 0.0f && neg_slope >= 0.0f && neg_slope <= 1.0f;
         const float2 gp2 = make_float2(gain_pos, gain_pos), gn2 = make_float2(gain_neg, gain_neg);
-#pragma unroll 1
         // two warp groups: with several accumulators they take alternate ones, with a single one they take the two halves of its
         // columns (cut at a segment boundary): warps 4-7 would otherwise idle through the epilogue of every N <= 128 tile
         // (epilogue 6.0 k -> 4.5 k cycles at 128 -> 128 channels)
