@@ -19,7 +19,7 @@
 //    once per 9 taps.
 //  * B operand (weights): packed by the packing kernel in exactly the shared-memory operand order, one contiguous block per
 //    (K chunk, tap), streamed by ONE thread with cp.async.bulk (the TMA unit's bulk copy, completion on an mbarrier with
-//    complete_tx) through a ring of up to 4 stages.
+//    complete_tx) through a ring of up to 6 slots (a slot holds the widest block of the plan).
 //  * roles: warps 0-3 load A during the main loop, warp 4 issues the MMAs (one elected thread, tcgen05.mma kind::f16, fp32
 //    accumulate), warp 5 streams B, tcgen05.commit releases the stages; all eight warps run the epilogue (thread = TMEM lane =
 //    pixel; warps w and w + 4 share a lane quarter and split the columns).
